@@ -1,0 +1,222 @@
+/* ntpoly_b200 — C ABI of the B200-native NTPoly hot path (libntpoly_b200.so).
+ *
+ * Drop-in boundary: the symbols in sections 1-8 are exactly the `*_wrp` entry
+ * points NTPoly's own C ABI exposes for this path (reference headers under
+ * /root/reference/Source/C/, Fortran shims under Source/Wrapper/): same names,
+ * same argument order, everything by pointer, opaque `int ih[SIZE_wrp]` handles
+ * (SIZE_wrp = 12, Source/C/Wrapper.h:4). NTPoly's C++ classes (Source/CPlusPlus)
+ * and its SWIG Python module bind these symbols unchanged.
+ *
+ * Behavioural contract kept from the reference: no error returns (a failure
+ * prints and aborts, Source/Fortran/ErrorModule.F90:193-205); every `_ps_` call
+ * is collective over the matrix's process grid; handles own heap objects that
+ * Construct* allocates and Destruct* frees.
+ *
+ * What differs: matrices live in GPU memory (one CSC block per GPU) between
+ * calls; `world_comm` arguments (Fortran MPI communicator integers) are accepted
+ * and ignored — the rank layout comes from ntb_world_init() or the RANK /
+ * WORLD_SIZE / LOCAL_RANK environment (one process per GPU, NCCL underneath).
+ *
+ * Section 9 lists the `ntb_` extensions (bootstrap, bulk triplet transfer,
+ * counters) that have no counterpart in the reference.
+ */
+#ifndef NTPOLY_B200_H
+#define NTPOLY_B200_H
+
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTB_SIZE_wrp 12
+
+/* ---- 1. process grid (Source/C/ProcessGrid_c.h:4-39; ProcessGridModule_wrp.F90) */
+void ConstructGlobalProcessGrid_wrp(const int *world_comm, const int *process_rows,
+                                    const int *process_columns, const int *process_slices);
+void ConstructGlobalProcessGrid_onlyslice_wrp(const int *world_comm, const int *process_slices);
+void ConstructGlobalProcessGrid_default_wrp(const int *world_comm);
+void CopyProcessGrid_wrp(const int *ih_old_grid, int *ih_new_grid);
+int GetGlobalMySlice_wrp(void);
+int GetGlobalMyColumn_wrp(void);
+int GetGlobalMyRow_wrp(void);
+bool GetGlobalIsRoot_wrp(void);
+int GetGlobalNumSlices_wrp(void);
+int GetGlobalNumColumns_wrp(void);
+int GetGlobalNumRows_wrp(void);
+void WriteGlobalProcessGridInfo_wrp(void);
+void DestructGlobalProcessGrid_wrp(void);
+void ConstructProcessGrid_wrp(int *ih_grid, const int *world_comm, const int *process_rows,
+                              const int *process_columns, const int *process_slices);
+void ConstructProcessGrid_onlyslice_wrp(int *ih_grid, const int *world_comm, const int *process_slices);
+void ConstructProcessGrid_default_wrp(int *ih_grid, const int *world_comm);
+int GetMySlice_wrp(const int *ih_grid);
+int GetMyColumn_wrp(const int *ih_grid);
+int GetMyRow_wrp(const int *ih_grid);
+int GetNumSlices_wrp(const int *ih_grid);
+int GetNumColumns_wrp(const int *ih_grid);
+int GetNumRows_wrp(const int *ih_grid);
+void WriteProcessGridInfo_wrp(const int *ih_grid);
+void DestructProcessGrid_wrp(int *ih_grid);
+
+/* ---- 2. triplet lists (Source/C/TripletList_c.h:4-38) */
+void ConstructTripletList_r_wrp(int *ih_this, const int *size);
+void ResizeTripletList_r_wrp(int *ih_this, const int *size);
+void AppendToTripletList_r_wrp(int *ih_this, const int *index_column, const int *index_row,
+                               const double *point_value);
+void SetTripletAt_r_wrp(int *ih_this, const int *index, const int *index_column, const int *index_row,
+                        const double *point_value);
+void GetTripletAt_r_wrp(const int *ih_this, const int *index, int *index_column, int *index_row,
+                        double *point_value);
+void DestructTripletList_r_wrp(int *ih_this);
+int GetTripletListSize_r_wrp(const int *ih_this);
+void ConstructTripletList_c_wrp(int *ih_this, const int *size);
+void ResizeTripletList_c_wrp(int *ih_this, const int *size);
+void AppendToTripletList_c_wrp(int *ih_this, const int *index_column, const int *index_row,
+                               const double *point_value_real, const double *point_value_imag);
+void SetTripletAt_c_wrp(int *ih_this, const int *index, const int *index_column, const int *index_row,
+                        const double *point_value_real, const double *point_value_imag);
+void GetTripletAt_c_wrp(const int *ih_this, const int *index, int *index_column, int *index_row,
+                        double *point_value_real, double *point_value_imag);
+void DestructTripletList_c_wrp(int *ih_this);
+int GetTripletListSize_c_wrp(const int *ih_this);
+
+/* ---- 3. distributed matrix container (Source/C/PSMatrix_c.h:4-49; PSMatrixModule_wrp.F90) */
+void ConstructEmptyMatrix_ps_wrp(int *ih_this, const int *matrix_dim);
+void ConstructEmptyMatrixPG_ps_wrp(int *ih_this, const int *matrix_dim, const int *ih_grid);
+void CopyMatrix_ps_wrp(const int *ih_matA, int *ih_matB);
+void DestructMatrix_ps_wrp(int *ih_this);
+void ConstructMatrixFromMatrixMarket_ps_wrp(int *ih_this, const char *file_name, const int *name_size);
+void ConstructMatrixFromMatrixMarketPG_ps_wrp(int *ih_this, const char *file_name, const int *name_size,
+                                              const int *ih_grid);
+void WriteMatrixToMatrixMarket_ps_wrp(const int *ih_this, const char *file_name, const int *name_size);
+void FillMatrixFromTripletList_psr_wrp(const int *ih_this, const int *ih_triplet_list);
+void FillMatrixFromTripletList_psc_wrp(const int *ih_this, const int *ih_triplet_list);
+void FillMatrixPermutation_ps_wrp(int *ih_this, const int *ih_permutation, const bool *permuterows);
+void FillMatrixIdentity_ps_wrp(int *ih_this);
+void GetMatrixActualDimension_ps_wrp(const int *ih_this, int *size);
+void GetMatrixLogicalDimension_ps_wrp(const int *ih_this, int *size);
+void GetMatrixSize_ps_wrp(const int *ih_this, long int *size);
+void GetMatrixTripletList_psr_wrp(const int *ih_this, int *ih_triplet_list);
+void GetMatrixTripletList_psc_wrp(const int *ih_this, int *ih_triplet_list);
+void TransposeMatrix_ps_wrp(const int *ih_matA, int *ih_transmat);
+void ConjugateMatrix_ps_wrp(int *ih_matA);
+void GetMatrixProcessGrid_ps_wrp(const int *ih_this, int *ih_grid);
+int IsIdentity_ps_wrp(const int *ih_this);
+
+/* ---- 4. THE HOT PATH: distributed algebra (Source/C/PSMatrix_c.h:51-68;
+ *         PSMatrixAlgebraModule_wrp.F90:29-198 -> PSMatrixAlgebraModule.F90) */
+void MatrixMultiply_ps_wrp(const int *ih_matA, const int *ih_matB, int *ih_matC, const double *alpha_in,
+                           const double *beta_in, const double *threshold_in, int *ih_memory_pool_in);
+void IncrementMatrix_ps_wrp(const int *ih_matA, int *ih_matB, const double *alpha_in,
+                            const double *threshold_in);
+void ScaleMatrix_ps_wrp(int *ih_this, const double *constant);
+void MatrixTrace_ps_wrp(const int *ih_this, double *trace_val);
+double MatrixNorm_ps_wrp(const int *ih_this);
+void DotMatrix_psr_wrp(const int *ih_matA, const int *ih_matB, double *product);
+void DotMatrix_psc_wrp(const int *ih_matA, const int *ih_matB, double *product_real, double *product_imag);
+void MatrixPairwiseMultiply_ps_wrp(const int *ih_matA, const int *ih_matB, int *ih_matC);
+double MeasureAsymmetry_ps_wrp(const int *ih_this);
+void SymmetrizeMatrix_ps_wrp(int *ih_this);
+
+/* ---- 5. memory pool (Source/C/PMatrixMemoryPool_c.h:4-5) */
+void ConstructMatrixMemoryPool_p_wrp(int *ih_this, const int *ih_matrix);
+void DestructMatrixMemoryPool_p_wrp(int *ih_this);
+
+/* ---- 6. solver parameters / permutation / load balancer
+ *         (Source/C/SolverParameters_c.h, Permutation_c.h, LoadBalancer_c.h) */
+void ConstructSolverParameters_wrp(int *ih_this);
+void SetParametersConvergeDiff_wrp(int *ih_this, const double *new_value);
+void SetParametersMaxIterations_wrp(int *ih_this, const int *new_value);
+void SetParametersBeVerbose_wrp(int *ih_this, const bool *new_value);
+void SetParametersThreshold_wrp(int *ih_this, const double *new_value);
+void SetParametersLoadBalance_wrp(int *ih_this, const int *ih_permutation);
+void SetParametersStepThreshold_wrp(int *ih_this, const double *new_value);
+void SetParametersMonitorConvergence_wrp(int *ih_this, const bool *new_value);
+void DestructSolverParameters_wrp(int *ih_this);
+void ConstructDefaultPermutation_wrp(int *ih_this, const int *matrix_dimension);
+void ConstructReversePermutation_wrp(int *ih_this, const int *matrix_dimension);
+void ConstructRandomPermutation_wrp(int *ih_this, const int *matrix_dimension);
+void DestructPermutation_wrp(int *ih_this);
+void PermuteMatrix_wrp(const int *ih_mat_in, int *ih_mat_out, const int *ih_permutation, int *ih_memorypool);
+void UndoPermuteMatrix_wrp(const int *ih_mat_in, int *ih_mat_out, const int *ih_permutation,
+                           int *ih_memorypool);
+
+/* ---- 7. drivers that iterate on the hot path (signatures frozen)
+ *         Source/C/DensityMatrixSolvers_c.h, SignSolvers_c.h, InverseSolvers_c.h,
+ *         SquareRootSolvers_c.h, ExponentialSolvers_c.h, EigenBounds_c.h.
+ *         (the reference headers mark energy/chemical potential `const double*`
+ *          although the Fortran side writes them; they are outputs.) */
+void TRS2_wrp(const int *ih_Hamiltonian, const int *ih_InverseSquareRoot, const double *trace,
+              int *ih_Density, double *energy_value_out, double *chemical_potential_out,
+              const int *ih_solver_parameters);
+void TRS4_wrp(const int *ih_Hamiltonian, const int *ih_InverseSquareRoot, const double *trace,
+              int *ih_Density, double *energy_value_out, double *chemical_potential_out,
+              const int *ih_solver_parameters);
+void PM_wrp(const int *ih_Hamiltonian, const int *ih_InverseSquareRoot, const double *trace,
+            int *ih_Density, double *energy_value_out, double *chemical_potential_out,
+            const int *ih_solver_parameters);
+void HPCP_wrp(const int *ih_Hamiltonian, const int *ih_InverseSquareRoot, const double *trace,
+              int *ih_Density, double *energy_value_out, double *chemical_potential_out,
+              const int *ih_solver_parameters);
+void EnergyDensityMatrix_wrp(const int *ih_Hamiltonian, const int *ih_Density, int *ih_EnergyDensity,
+                             const double *threshold);
+void McWeenyStep_wrp(const int *ih_D, int *ih_DOut, const double *threshold);
+void McWeenyStepS_wrp(const int *ih_D, int *ih_DOut, const int *ih_S, const double *threshold);
+void SignFunction_wrp(const int *ih_mat1, int *ih_signmat, const int *ih_solver_parameters);
+void PolarDecomposition_wrp(const int *ih_mat1, int *ih_umat, int *ih_hmat, const int *ih_solver_parameters);
+void Invert_wrp(const int *ih_Hamiltonian, int *ih_Inverse, const int *ih_solver_parameters);
+void SquareRoot_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters);
+void InverseSquareRoot_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters);
+void ComputeExponential_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters);
+void GershgorinBounds_wrp(const int *ih_Hamiltonian, double *max_value, double *min_value);
+void PowerBounds_wrp(const int *ih_Hamiltonian, double *max_value, const int *ih_solver_parameters);
+
+/* ---- 9. ntb_ extensions (no counterpart in the reference) ------------------- */
+/* bootstrap: rank/size of this process and, for size>1, the 128-byte ncclUniqueId that
+ * rank 0 obtained from ntb_nccl_unique_id() and the host broadcast (e.g. torch.distributed). */
+void ntb_nccl_unique_id(void *out128);
+void ntb_world_init(int rank, int size, const void *nccl_unique_id_128);
+int ntb_world_rank(void);
+int ntb_world_size(void);
+/* run the hot path on a caller-owned CUDA stream (cudaStream_t passed as void*) */
+void ntb_set_stream(void *cuda_stream);
+void ntb_synchronize(void);
+/* bulk triplet transfer: 1-based global indices, n entries */
+void ntb_TripletList_r_set(int *ih_this, long long n, const int *rows, const int *cols, const double *vals);
+void ntb_TripletList_r_get(const int *ih_this, int *rows, int *cols, double *vals);
+void ntb_TripletList_c_set(int *ih_this, long long n, const int *rows, const int *cols,
+                           const double *vals_interleaved_re_im);
+void ntb_TripletList_c_get(const int *ih_this, int *rows, int *cols, double *vals_interleaved_re_im);
+/* host arrays straight into / out of a matrix (skips the triplet-list object) */
+void ntb_FillMatrixFromArrays_ps(int *ih_this, long long n, const int *rows, const int *cols,
+                                 const double *vals, int is_complex_interleaved);
+long long ntb_GetMatrixLocalSize_ps(const int *ih_this);
+void ntb_GetMatrixArrays_ps(const int *ih_this, int *rows, int *cols, double *vals);
+void ntb_ConstructEmptyMatrixComplex_ps(int *ih_this, const int *matrix_dim, const int *is_complex);
+int ntb_MatrixIsComplex_ps(const int *ih_this);
+void ntb_FilterMatrix_ps(int *ih_this, const double *threshold);
+void ntb_ScaleMatrixComplex_ps(int *ih_this, const double *re, const double *im);
+/* solver variants the reference exposes only through Fortran optional arguments */
+void ntb_InverseSquareRootOrder_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters,
+                                    const int *order);
+void ntb_SquareRootOrder_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters,
+                             const int *order);
+void ntb_ConstructRandomPermutationSeeded(int *ih_this, const int *matrix_dimension, const long long *seed);
+void ntb_SetPermutation(int *ih_this, const int *matrix_dimension, const int *index_lookup_1based);
+/* counters: [0] kernels launched by this library, [1] multiplies, [2] useful flops,
+ *           [3] block pairs that used the dense-branch rule */
+void ntb_get_counters(double *out4);
+void ntb_reset_counters(void);
+/* record of the last solver call: [0] loop counter at exit, [1] last monitored value,
+ *                                 [2] energy, [3] multiplies, [4] useful flops */
+void ntb_last_solve(double *out5);
+/* bytes of this rank's local block as counted for the roofline:
+ * nnz*(sizeof(value)+4) + (cols+1)*4    */
+long long ntb_MatrixAlgorithmicBytes_ps(const int *ih_this);
+const char *ntb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTPOLY_B200_H */

@@ -1,0 +1,393 @@
+// extern "C" surface: NTPoly's `*_wrp` symbols over the CUDA hot path.
+// See include/ntpoly_b200.h for the per-section reference citations.
+#include "../../include/ntpoly_b200.h"
+#include "ops.cuh"
+#include "solvers.h"
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+
+using namespace ntb;
+
+namespace {
+// opaque handle = caller-owned int[12]; first 8 bytes carry the object pointer
+// (the reference TRANSFERs a derived type holding one POINTER, WrapperModule.F90:8)
+template <typename T> T* get(const int* ih) {
+  T* p;
+  std::memcpy(&p, ih, sizeof(p));
+  NTB_CHECK(p != nullptr, "null handle passed to ntpoly_b200");
+  return p;
+}
+template <typename T> void put(int* ih, T* p) {
+  std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int));
+  std::memcpy(ih, &p, sizeof(p));
+}
+SolverParameters default_params;
+const SolverParameters& params_of(const int* ih) { return *get<SolverParameters>(ih); }
+
+// ---- MatrixMarket (host side; PSMatrixModule.F90:351-570, WriteToMatrixMarket.f90)
+struct MMData {
+  int n = 0;
+  bool is_complex = false;
+  std::vector<int> rows, cols;
+  std::vector<double> re, im;
+};
+MMData read_matrix_market(const std::string& path, int rank, int size) {
+  std::ifstream f(path);
+  NTB_CHECK(f.good(), "cannot open MatrixMarket file");
+  std::string line;
+  std::getline(f, line);
+  std::string lower = line;
+  std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
+  MMData d;
+  d.is_complex = lower.find("complex") != std::string::npos;
+  const bool pattern = lower.find("pattern") != std::string::npos;
+  const bool symmetric = lower.find(" symmetric") != std::string::npos;
+  const bool skew = lower.find("skew-symmetric") != std::string::npos;
+  const bool hermitian = lower.find("hermitian") != std::string::npos;
+  while (std::getline(f, line)) if (!line.empty() && line[0] != '%') break;
+  long long nr, nc, nnz;
+  { std::istringstream ss(line); ss >> nr >> nc >> nnz; }
+  d.n = (int)nr;
+  for (long long i = 0; i < nnz; ++i) {
+    int r, c;
+    double vr = 1.0, vi = 0.0;
+    f >> r >> c;
+    if (!pattern) { f >> vr; if (d.is_complex) f >> vi; }
+    if ((i % size) != rank) continue;  // every rank parses, each keeps a disjoint share
+    d.rows.push_back(r); d.cols.push_back(c); d.re.push_back(vr); d.im.push_back(vi);
+    if ((symmetric || skew || hermitian) && r != c) {
+      d.rows.push_back(c); d.cols.push_back(r);
+      d.re.push_back(skew ? -vr : vr);
+      d.im.push_back(hermitian ? -vi : (skew ? -vi : vi));
+    }
+  }
+  return d;
+}
+void construct_from_mm(int* ih_this, const char* file_name, int name_size, ProcessGrid* grid) {
+  std::string path(file_name, (size_t)name_size);
+  world_init_from_env();
+  MMData d = read_matrix_market(path, world().rank, world().size);
+  auto* M = new Matrix();
+  mat_construct_empty(*M, d.n, grid, d.is_complex);
+  const long long n = (long long)d.rows.size();
+  if (d.is_complex) {
+    std::vector<cplx> v((size_t)n);
+    for (long long i = 0; i < n; ++i) v[i] = cplx{d.re[i], d.im[i]};
+    mat_fill_from_triplets(*M, d.rows.data(), d.cols.data(), nullptr, v.data(), n, false, false);
+  } else {
+    mat_fill_from_triplets(*M, d.rows.data(), d.cols.data(), d.re.data(), nullptr, n, false, false);
+  }
+  put(ih_this, M);
+}
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- 1. process grid
+void ConstructGlobalProcessGrid_wrp(const int*, const int* r, const int* c, const int* s) { grid_construct(global_grid(), *r, *c, *s); }
+void ConstructGlobalProcessGrid_onlyslice_wrp(const int*, const int* s) { grid_construct_onlyslice(global_grid(), *s); }
+void ConstructGlobalProcessGrid_default_wrp(const int*) { grid_construct_default(global_grid()); }
+void CopyProcessGrid_wrp(const int* ih_old, int* ih_new) { auto* g = new ProcessGrid(); grid_copy(*get<ProcessGrid>(ih_old), *g); put(ih_new, g); }
+int GetGlobalMySlice_wrp(void) { return global_grid().my_slice; }
+int GetGlobalMyColumn_wrp(void) { return global_grid().my_col; }
+int GetGlobalMyRow_wrp(void) { return global_grid().my_row; }
+bool GetGlobalIsRoot_wrp(void) { return global_grid().rank == 0; }
+int GetGlobalNumSlices_wrp(void) { return global_grid().S; }
+int GetGlobalNumColumns_wrp(void) { return global_grid().C; }
+int GetGlobalNumRows_wrp(void) { return global_grid().R; }
+static void write_grid(const ProcessGrid& g) {
+  if (g.rank != 0) return;
+  std::printf("Process Grid:\n  - Process Rows: %d\n  - Process Columns: %d\n  - Process Slices: %d\n  - Column Blocks: %d\n  - Row Blocks: %d\n",
+              g.R, g.C, g.S, g.nbc, g.nbr);
+}
+void WriteGlobalProcessGridInfo_wrp(void) { write_grid(global_grid()); }
+void DestructGlobalProcessGrid_wrp(void) { grid_destruct(global_grid()); }
+void ConstructProcessGrid_wrp(int* ih, const int*, const int* r, const int* c, const int* s) { auto* g = new ProcessGrid(); grid_construct(*g, *r, *c, *s); put(ih, g); }
+void ConstructProcessGrid_onlyslice_wrp(int* ih, const int*, const int* s) { auto* g = new ProcessGrid(); grid_construct_onlyslice(*g, *s); put(ih, g); }
+void ConstructProcessGrid_default_wrp(int* ih, const int*) { auto* g = new ProcessGrid(); grid_construct_default(*g); put(ih, g); }
+int GetMySlice_wrp(const int* ih) { return get<ProcessGrid>(ih)->my_slice; }
+int GetMyColumn_wrp(const int* ih) { return get<ProcessGrid>(ih)->my_col; }
+int GetMyRow_wrp(const int* ih) { return get<ProcessGrid>(ih)->my_row; }
+int GetNumSlices_wrp(const int* ih) { return get<ProcessGrid>(ih)->S; }
+int GetNumColumns_wrp(const int* ih) { return get<ProcessGrid>(ih)->C; }
+int GetNumRows_wrp(const int* ih) { return get<ProcessGrid>(ih)->R; }
+void WriteProcessGridInfo_wrp(const int* ih) { write_grid(*get<ProcessGrid>(ih)); }
+void DestructProcessGrid_wrp(int* ih) { auto* g = get<ProcessGrid>(ih); grid_destruct(*g); delete g; std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int)); }
+
+// ---------------------------------------------------------------- 2. triplet lists
+void ConstructTripletList_r_wrp(int* ih, const int* size) { auto* t = new TripletList_r(); t->data.resize((size_t)*size); put(ih, t); }
+void ResizeTripletList_r_wrp(int* ih, const int* size) { get<TripletList_r>(ih)->data.resize((size_t)*size); }
+void AppendToTripletList_r_wrp(int* ih, const int* col, const int* row, const double* v) { get<TripletList_r>(ih)->data.push_back(Triplet_r{*col, *row, *v}); }
+void SetTripletAt_r_wrp(int* ih, const int* index, const int* col, const int* row, const double* v) { get<TripletList_r>(ih)->data.at((size_t)*index - 1) = Triplet_r{*col, *row, *v}; }
+void GetTripletAt_r_wrp(const int* ih, const int* index, int* col, int* row, double* v) {
+  const Triplet_r& t = get<TripletList_r>(ih)->data.at((size_t)*index - 1);
+  *col = t.index_column; *row = t.index_row; *v = t.point_value;
+}
+void DestructTripletList_r_wrp(int* ih) { delete get<TripletList_r>(ih); std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int)); }
+int GetTripletListSize_r_wrp(const int* ih) { return (int)get<TripletList_r>(ih)->data.size(); }
+void ConstructTripletList_c_wrp(int* ih, const int* size) { auto* t = new TripletList_c(); t->data.resize((size_t)*size); put(ih, t); }
+void ResizeTripletList_c_wrp(int* ih, const int* size) { get<TripletList_c>(ih)->data.resize((size_t)*size); }
+void AppendToTripletList_c_wrp(int* ih, const int* col, const int* row, const double* re, const double* im) { get<TripletList_c>(ih)->data.push_back(Triplet_c{*col, *row, *re, *im}); }
+void SetTripletAt_c_wrp(int* ih, const int* index, const int* col, const int* row, const double* re, const double* im) { get<TripletList_c>(ih)->data.at((size_t)*index - 1) = Triplet_c{*col, *row, *re, *im}; }
+void GetTripletAt_c_wrp(const int* ih, const int* index, int* col, int* row, double* re, double* im) {
+  const Triplet_c& t = get<TripletList_c>(ih)->data.at((size_t)*index - 1);
+  *col = t.index_column; *row = t.index_row; *re = t.re; *im = t.im;
+}
+void DestructTripletList_c_wrp(int* ih) { delete get<TripletList_c>(ih); std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int)); }
+int GetTripletListSize_c_wrp(const int* ih) { return (int)get<TripletList_c>(ih)->data.size(); }
+
+// ---------------------------------------------------------------- 3. matrix container
+void ConstructEmptyMatrix_ps_wrp(int* ih, const int* n) { auto* M = new Matrix(); mat_construct_empty(*M, *n, nullptr, false); put(ih, M); }
+void ConstructEmptyMatrixPG_ps_wrp(int* ih, const int* n, const int* ih_grid) { auto* M = new Matrix(); mat_construct_empty(*M, *n, get<ProcessGrid>(ih_grid), false); put(ih, M); }
+void CopyMatrix_ps_wrp(const int* ih_a, int* ih_b) { mat_copy(*get<Matrix>(ih_a), *get<Matrix>(ih_b)); }
+void DestructMatrix_ps_wrp(int* ih) { delete get<Matrix>(ih); std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int)); }
+void ConstructMatrixFromMatrixMarket_ps_wrp(int* ih, const char* file_name, const int* name_size) { construct_from_mm(ih, file_name, *name_size, nullptr); }
+void ConstructMatrixFromMatrixMarketPG_ps_wrp(int* ih, const char* file_name, const int* name_size, const int* ih_grid) { construct_from_mm(ih, file_name, *name_size, get<ProcessGrid>(ih_grid)); }
+void WriteMatrixToMatrixMarket_ps_wrp(const int* ih, const char* file_name, const int* name_size) {
+  const Matrix& M = *get<Matrix>(ih);
+  NTB_CHECK(M.grid->size == 1 || true, "");
+  // every rank of slice 0 appends its block in turn is not possible without host messaging;
+  // the blocks are therefore collected on the device side and written by global rank 0.
+  std::string path(file_name, (size_t)*name_size);
+  const long long nloc = mat_get_triplets(M, nullptr, nullptr, nullptr, nullptr);
+  std::vector<int> rows((size_t)nloc), cols((size_t)nloc);
+  std::vector<double> vr;
+  std::vector<cplx> vc;
+  if (M.is_complex) { vc.resize((size_t)nloc); mat_get_triplets(M, rows.data(), cols.data(), nullptr, vc.data()); }
+  else { vr.resize((size_t)nloc); mat_get_triplets(M, rows.data(), cols.data(), vr.data(), nullptr); }
+  if (M.grid->size > 1) {
+    // gather (row, col, value) of all ranks in the slice through the device
+    const int np = comm_size(M.grid->within_slice);
+    std::vector<long long> cnt(np);
+    {
+      DevBuf<long long> a(1), b((size_t)np);
+      h2d(a.get(), &nloc, 1);
+      comm_allgather_bytes(M.grid->within_slice, a.get(), b.get(), sizeof(long long));
+      d2h(cnt.data(), b.get(), (size_t)np);
+    }
+    long long tot = 0;
+    std::vector<long long> off(np + 1, 0);
+    for (int q = 0; q < np; ++q) { off[q + 1] = off[q] + cnt[q]; }
+    tot = off[np];
+    const size_t vsz = M.is_complex ? sizeof(cplx) : sizeof(double);
+    DevBuf<int> drow((size_t)nloc), dcol((size_t)nloc), arow((size_t)tot), acol((size_t)tot);
+    DevBuf<unsigned char> dval((size_t)nloc * vsz), aval((size_t)tot * vsz);
+    if (nloc) {
+      h2d(drow.get(), rows.data(), (size_t)nloc); h2d(dcol.get(), cols.data(), (size_t)nloc);
+      CUDA_CHECK(cudaMemcpyAsync(dval.get(), M.is_complex ? (const void*)vc.data() : (const void*)vr.data(), (size_t)nloc * vsz, cudaMemcpyHostToDevice, rt().stream));
+    }
+    comm_group_start();
+    for (int q = 0; q < np; ++q) {
+      comm_broadcast_bytes(M.grid->within_slice, drow.get(), arow.get() + off[q], (size_t)cnt[q] * sizeof(int), q);
+      comm_broadcast_bytes(M.grid->within_slice, dcol.get(), acol.get() + off[q], (size_t)cnt[q] * sizeof(int), q);
+      comm_broadcast_bytes(M.grid->within_slice, dval.get(), aval.get() + (size_t)off[q] * vsz, (size_t)cnt[q] * vsz, q);
+    }
+    comm_group_end();
+    rows.resize((size_t)tot); cols.resize((size_t)tot);
+    d2h(rows.data(), arow.get(), (size_t)tot); d2h(cols.data(), acol.get(), (size_t)tot);
+    if (M.is_complex) { vc.resize((size_t)tot); d2h((unsigned char*)vc.data(), aval.get(), (size_t)tot * vsz); }
+    else { vr.resize((size_t)tot); d2h((unsigned char*)vr.data(), aval.get(), (size_t)tot * vsz); }
+  }
+  if (M.grid->rank != 0) return;
+  std::FILE* f = std::fopen(path.c_str(), "w");
+  NTB_CHECK(f != nullptr, "cannot open output MatrixMarket file");
+  std::fprintf(f, "%%%%MatrixMarket matrix coordinate %s general\n%%\n", M.is_complex ? "complex" : "real");
+  std::fprintf(f, "%d %d %lld\n", M.actual_dim, M.actual_dim, (long long)rows.size());
+  for (size_t i = 0; i < rows.size(); ++i) {
+    if (M.is_complex) std::fprintf(f, "%d %d %.17e %.17e\n", rows[i], cols[i], vc[i].x, vc[i].y);
+    else std::fprintf(f, "%d %d %.17e\n", rows[i], cols[i], vr[i]);
+  }
+  std::fclose(f);
+}
+void FillMatrixFromTripletList_psr_wrp(const int* ih, const int* ih_tl) {
+  const auto& d = get<TripletList_r>(ih_tl)->data;
+  std::vector<int> rows(d.size()), cols(d.size());
+  std::vector<double> vals(d.size());
+  for (size_t i = 0; i < d.size(); ++i) { rows[i] = d[i].index_row; cols[i] = d[i].index_column; vals[i] = d[i].point_value; }
+  Matrix& M = *get<Matrix>(ih);
+  if (M.is_complex) { Matrix t; mat_construct_empty(t, M.actual_dim, M.grid, false); M = std::move(t); }
+  mat_fill_from_triplets(M, rows.data(), cols.data(), vals.data(), nullptr, (long long)d.size(), false, false);
+}
+void FillMatrixFromTripletList_psc_wrp(const int* ih, const int* ih_tl) {
+  const auto& d = get<TripletList_c>(ih_tl)->data;
+  std::vector<int> rows(d.size()), cols(d.size());
+  std::vector<cplx> vals(d.size());
+  for (size_t i = 0; i < d.size(); ++i) { rows[i] = d[i].index_row; cols[i] = d[i].index_column; vals[i] = cplx{d[i].re, d[i].im}; }
+  Matrix& M = *get<Matrix>(ih);
+  if (!M.is_complex) { Matrix t; mat_construct_empty(t, M.actual_dim, M.grid, true); M = std::move(t); }  // FillMatrixFromTripletList_psc converts
+  mat_fill_from_triplets(M, rows.data(), cols.data(), nullptr, vals.data(), (long long)d.size(), false, false);
+}
+void FillMatrixPermutation_ps_wrp(int* ih, const int* ih_perm, const bool* permuterows) { mat_fill_permutation(*get<Matrix>(ih), get<Permutation>(ih_perm)->index_lookup.data(), *permuterows); }
+void FillMatrixIdentity_ps_wrp(int* ih) { mat_fill_identity(*get<Matrix>(ih)); }
+void GetMatrixActualDimension_ps_wrp(const int* ih, int* size) { *size = get<Matrix>(ih)->actual_dim; }
+void GetMatrixLogicalDimension_ps_wrp(const int* ih, int* size) { *size = get<Matrix>(ih)->logical_dim; }
+void GetMatrixSize_ps_wrp(const int* ih, long int* size) { *size = (long int)mat_global_nnz(*get<Matrix>(ih)); }
+void GetMatrixTripletList_psr_wrp(const int* ih, int* ih_tl) {
+  const Matrix& M = *get<Matrix>(ih);
+  NTB_CHECK(!M.is_complex, "GetMatrixTripletList_psr on a complex matrix");
+  const long long n = M.local_nnz();
+  std::vector<int> rows((size_t)n), cols((size_t)n);
+  std::vector<double> vals((size_t)n);
+  mat_get_triplets(M, rows.data(), cols.data(), vals.data(), nullptr);
+  auto& d = get<TripletList_r>(ih_tl)->data;
+  d.resize((size_t)n);
+  for (long long i = 0; i < n; ++i) d[i] = Triplet_r{cols[i], rows[i], vals[i]};
+}
+void GetMatrixTripletList_psc_wrp(const int* ih, int* ih_tl) {
+  const Matrix& M = *get<Matrix>(ih);
+  NTB_CHECK(M.is_complex, "GetMatrixTripletList_psc on a real matrix");
+  const long long n = M.local_nnz();
+  std::vector<int> rows((size_t)n), cols((size_t)n);
+  std::vector<cplx> vals((size_t)n);
+  mat_get_triplets(M, rows.data(), cols.data(), nullptr, vals.data());
+  auto& d = get<TripletList_c>(ih_tl)->data;
+  d.resize((size_t)n);
+  for (long long i = 0; i < n; ++i) d[i] = Triplet_c{cols[i], rows[i], vals[i].x, vals[i].y};
+}
+void TransposeMatrix_ps_wrp(const int* ih_a, int* ih_t) { mat_transpose(*get<Matrix>(ih_a), *get<Matrix>(ih_t)); }
+void ConjugateMatrix_ps_wrp(int* ih) { mat_conjugate(*get<Matrix>(ih)); }
+void GetMatrixProcessGrid_ps_wrp(const int* ih, int* ih_grid) { put(ih_grid, get<Matrix>(ih)->grid); }
+int IsIdentity_ps_wrp(const int* ih) { return mat_is_identity(*get<Matrix>(ih)) ? 1 : 0; }
+
+// ---------------------------------------------------------------- 4. hot path
+void MatrixMultiply_ps_wrp(const int* ih_a, const int* ih_b, int* ih_c, const double* alpha, const double* beta,
+                           const double* threshold, int* ih_pool) {
+  MemoryPool* pool = nullptr;
+  if (ih_pool) { std::memcpy(&pool, ih_pool, sizeof(pool)); }
+  mat_multiply(*get<Matrix>(ih_a), *get<Matrix>(ih_b), *get<Matrix>(ih_c), *alpha, *beta, *threshold, pool);
+}
+void IncrementMatrix_ps_wrp(const int* ih_a, int* ih_b, const double* alpha, const double* threshold) { mat_increment(*get<Matrix>(ih_a), *get<Matrix>(ih_b), *alpha, *threshold); }
+void ScaleMatrix_ps_wrp(int* ih, const double* c) { mat_scale(*get<Matrix>(ih), *c); }
+void MatrixTrace_ps_wrp(const int* ih, double* out) { *out = mat_trace(*get<Matrix>(ih)); }
+double MatrixNorm_ps_wrp(const int* ih) { return mat_norm(*get<Matrix>(ih)); }
+void DotMatrix_psr_wrp(const int* ih_a, const int* ih_b, double* product) { double im; mat_dot(*get<Matrix>(ih_a), *get<Matrix>(ih_b), product, &im); }
+void DotMatrix_psc_wrp(const int* ih_a, const int* ih_b, double* re, double* im) { mat_dot(*get<Matrix>(ih_a), *get<Matrix>(ih_b), re, im); }
+void MatrixPairwiseMultiply_ps_wrp(const int* ih_a, const int* ih_b, int* ih_c) { mat_pairwise(*get<Matrix>(ih_a), *get<Matrix>(ih_b), *get<Matrix>(ih_c)); }
+double MeasureAsymmetry_ps_wrp(const int* ih) { return mat_measure_asymmetry(*get<Matrix>(ih)); }
+void SymmetrizeMatrix_ps_wrp(int* ih) { mat_symmetrize(*get<Matrix>(ih)); }
+
+// ---------------------------------------------------------------- 5. memory pool
+void ConstructMatrixMemoryPool_p_wrp(int* ih, const int* ih_matrix) {
+  auto* p = new MemoryPool();
+  const Matrix& M = *get<Matrix>(ih_matrix);
+  p->rows = M.local_rows; p->cols = M.local_cols; p->is_complex = M.is_complex; p->constructed = true;
+  put(ih, p);
+}
+void DestructMatrixMemoryPool_p_wrp(int* ih) { delete get<MemoryPool>(ih); std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int)); }
+
+// ---------------------------------------------------------------- 6. parameters etc.
+void ConstructSolverParameters_wrp(int* ih) { put(ih, new SolverParameters()); }
+void SetParametersConvergeDiff_wrp(int* ih, const double* v) { get<SolverParameters>(ih)->converge_diff = *v; }
+void SetParametersMaxIterations_wrp(int* ih, const int* v) { get<SolverParameters>(ih)->max_iterations = *v; }
+void SetParametersBeVerbose_wrp(int* ih, const bool* v) { get<SolverParameters>(ih)->be_verbose = *v; }
+void SetParametersThreshold_wrp(int* ih, const double* v) { get<SolverParameters>(ih)->threshold = *v; }
+void SetParametersLoadBalance_wrp(int* ih, const int* ih_perm) {
+  auto* p = get<SolverParameters>(ih);
+  p->do_load_balancing = true;
+  p->balance_permutation = *get<Permutation>(ih_perm);
+}
+void SetParametersStepThreshold_wrp(int* ih, const double* v) { get<SolverParameters>(ih)->step_thresh = *v; }
+void SetParametersMonitorConvergence_wrp(int* ih, const bool* v) { get<SolverParameters>(ih)->monitor_convergence = *v; }
+void DestructSolverParameters_wrp(int* ih) { delete get<SolverParameters>(ih); std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int)); }
+void ConstructDefaultPermutation_wrp(int* ih, const int* n) { auto* p = new Permutation(); permutation_default(*p, *n); put(ih, p); }
+void ConstructReversePermutation_wrp(int* ih, const int* n) { auto* p = new Permutation(); permutation_reverse(*p, *n); put(ih, p); }
+void ConstructRandomPermutation_wrp(int* ih, const int* n) { auto* p = new Permutation(); permutation_random(*p, *n, 0); put(ih, p); }
+void DestructPermutation_wrp(int* ih) { delete get<Permutation>(ih); std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int)); }
+static MemoryPool* opt_pool(int* ih) { MemoryPool* p = nullptr; if (ih) std::memcpy(&p, ih, sizeof(p)); return p; }
+void PermuteMatrix_wrp(const int* ih_in, int* ih_out, const int* ih_perm, int* ih_pool) { permute_matrix(*get<Matrix>(ih_in), *get<Matrix>(ih_out), *get<Permutation>(ih_perm), opt_pool(ih_pool)); }
+void UndoPermuteMatrix_wrp(const int* ih_in, int* ih_out, const int* ih_perm, int* ih_pool) { undo_permute_matrix(*get<Matrix>(ih_in), *get<Matrix>(ih_out), *get<Permutation>(ih_perm), opt_pool(ih_pool)); }
+
+// ---------------------------------------------------------------- 7. drivers
+void TRS2_wrp(const int* H, const int* ISQ, const double* trace, int* K, double* e, double* mu, const int* sp) { solve_trs2(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), e, mu, params_of(sp)); }
+void TRS4_wrp(const int* H, const int* ISQ, const double* trace, int* K, double* e, double* mu, const int* sp) { solve_trs4(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), e, mu, params_of(sp)); }
+void PM_wrp(const int* H, const int* ISQ, const double* trace, int* K, double* e, double* mu, const int* sp) { solve_pm(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), e, mu, params_of(sp)); }
+void HPCP_wrp(const int* H, const int* ISQ, const double* trace, int* K, double* e, double* mu, const int* sp) { solve_hpcp(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), e, mu, params_of(sp)); }
+void EnergyDensityMatrix_wrp(const int* H, const int* D, int* ED, const double* thr) { energy_density_matrix(*get<Matrix>(H), *get<Matrix>(D), *get<Matrix>(ED), *thr); }
+void McWeenyStep_wrp(const int* D, int* Dout, const double* thr) { mcweeny_step(*get<Matrix>(D), *get<Matrix>(Dout), nullptr, *thr); }
+void McWeenyStepS_wrp(const int* D, int* Dout, const int* S, const double* thr) { mcweeny_step(*get<Matrix>(D), *get<Matrix>(Dout), get<Matrix>(S), *thr); }
+void SignFunction_wrp(const int* in, int* out, const int* sp) { solve_sign(*get<Matrix>(in), *get<Matrix>(out), params_of(sp)); }
+void PolarDecomposition_wrp(const int* in, int* u, int* h, const int* sp) { solve_polar(*get<Matrix>(in), *get<Matrix>(u), h ? get<Matrix>(h) : nullptr, params_of(sp)); }
+void Invert_wrp(const int* in, int* out, const int* sp) { solve_invert(*get<Matrix>(in), *get<Matrix>(out), params_of(sp)); }
+void SquareRoot_wrp(const int* in, int* out, const int* sp) { solve_sqrt(*get<Matrix>(in), *get<Matrix>(out), params_of(sp), false, 5); }
+void InverseSquareRoot_wrp(const int* in, int* out, const int* sp) { solve_sqrt(*get<Matrix>(in), *get<Matrix>(out), params_of(sp), true, 5); }
+void ComputeExponential_wrp(const int* in, int* out, const int* sp) { solve_exponential(*get<Matrix>(in), *get<Matrix>(out), params_of(sp)); }
+void GershgorinBounds_wrp(const int* ih, double* max_value, double* min_value) {
+  // NB the C header names the outputs (max_value, min_value) but the Fortran shim forwards them
+  // positionally to GershgorinBounds(this, min_value, max_value): the FIRST pointer receives the
+  // minimum (EigenBoundsModule_wrp.F90). Kept bug-for-bug so existing callers see the same values.
+  double mn, mx;
+  mat_gershgorin(*get<Matrix>(ih), &mn, &mx);
+  *max_value = mn;
+  *min_value = mx;
+}
+void PowerBounds_wrp(const int* ih, double* max_value, const int* sp) { solve_power_bounds(*get<Matrix>(ih), max_value, params_of(sp), false); }
+
+// ---------------------------------------------------------------- 9. extensions
+void ntb_nccl_unique_id(void* out128) { world_get_unique_id(out128); }
+void ntb_world_init(int rank, int size, const void* id) { world_init_explicit(rank, size, id); }
+int ntb_world_rank(void) { return world().rank; }
+int ntb_world_size(void) { return world().size; }
+void ntb_set_stream(void* s) { set_stream((cudaStream_t)s); }
+void ntb_synchronize(void) { ensure_init(); stream_sync(); }
+void ntb_TripletList_r_set(int* ih, long long n, const int* rows, const int* cols, const double* vals) {
+  auto& d = get<TripletList_r>(ih)->data;
+  d.resize((size_t)n);
+  for (long long i = 0; i < n; ++i) d[i] = Triplet_r{cols[i], rows[i], vals[i]};
+}
+void ntb_TripletList_r_get(const int* ih, int* rows, int* cols, double* vals) {
+  const auto& d = get<TripletList_r>(ih)->data;
+  for (size_t i = 0; i < d.size(); ++i) { rows[i] = d[i].index_row; cols[i] = d[i].index_column; vals[i] = d[i].point_value; }
+}
+void ntb_TripletList_c_set(int* ih, long long n, const int* rows, const int* cols, const double* v) {
+  auto& d = get<TripletList_c>(ih)->data;
+  d.resize((size_t)n);
+  for (long long i = 0; i < n; ++i) d[i] = Triplet_c{cols[i], rows[i], v[2 * i], v[2 * i + 1]};
+}
+void ntb_TripletList_c_get(const int* ih, int* rows, int* cols, double* v) {
+  const auto& d = get<TripletList_c>(ih)->data;
+  for (size_t i = 0; i < d.size(); ++i) { rows[i] = d[i].index_row; cols[i] = d[i].index_column; v[2 * i] = d[i].re; v[2 * i + 1] = d[i].im; }
+}
+void ntb_FillMatrixFromArrays_ps(int* ih, long long n, const int* rows, const int* cols, const double* vals, int is_complex) {
+  Matrix& M = *get<Matrix>(ih);
+  if ((is_complex != 0) != M.is_complex) { Matrix t; mat_construct_empty(t, M.actual_dim, M.grid, is_complex != 0); M = std::move(t); }
+  if (is_complex) mat_fill_from_triplets(M, rows, cols, nullptr, reinterpret_cast<const cplx*>(vals), n, false, false);
+  else mat_fill_from_triplets(M, rows, cols, vals, nullptr, n, false, false);
+}
+long long ntb_GetMatrixLocalSize_ps(const int* ih) { return get<Matrix>(ih)->local_nnz(); }
+void ntb_GetMatrixArrays_ps(const int* ih, int* rows, int* cols, double* vals) {
+  const Matrix& M = *get<Matrix>(ih);
+  if (M.is_complex) mat_get_triplets(M, rows, cols, nullptr, reinterpret_cast<cplx*>(vals));
+  else mat_get_triplets(M, rows, cols, vals, nullptr);
+}
+void ntb_ConstructEmptyMatrixComplex_ps(int* ih, const int* n, const int* is_complex) { auto* M = new Matrix(); mat_construct_empty(*M, *n, nullptr, *is_complex != 0); put(ih, M); }
+int ntb_MatrixIsComplex_ps(const int* ih) { return get<Matrix>(ih)->is_complex ? 1 : 0; }
+void ntb_FilterMatrix_ps(int* ih, const double* thr) { mat_filter(*get<Matrix>(ih), *thr); }
+void ntb_ScaleMatrixComplex_ps(int* ih, const double* re, const double* im) { mat_scale_c(*get<Matrix>(ih), cplx{*re, *im}); }
+void ntb_InverseSquareRootOrder_wrp(const int* in, int* out, const int* sp, const int* order) { solve_sqrt(*get<Matrix>(in), *get<Matrix>(out), params_of(sp), true, *order); }
+void ntb_SquareRootOrder_wrp(const int* in, int* out, const int* sp, const int* order) { solve_sqrt(*get<Matrix>(in), *get<Matrix>(out), params_of(sp), false, *order); }
+void ntb_ConstructRandomPermutationSeeded(int* ih, const int* n, const long long* seed) { auto* p = new Permutation(); permutation_random(*p, *n, (unsigned long long)*seed); put(ih, p); }
+void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
+  auto* p = new Permutation();
+  p->index_lookup.assign(lookup, lookup + *n);
+  p->reverse_index_lookup.resize((size_t)*n);
+  for (int i = 0; i < *n; ++i) p->reverse_index_lookup[(size_t)lookup[i] - 1] = i + 1;
+  put(ih, p);
+}
+void ntb_get_counters(double* out4) {
+  out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
+}
+void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; }
+void ntb_last_solve(double* out5) {
+  const SolveRecord& r = last_solve();
+  out5[0] = r.loop_counter; out5[1] = r.last_value; out5[2] = r.energy; out5[3] = (double)r.multiplies; out5[4] = r.flops;
+}
+long long ntb_MatrixAlgorithmicBytes_ps(const int* ih) {
+  const Matrix& M = *get<Matrix>(ih);
+  return (long long)(M.is_complex ? M.c.bytes() : M.r.bytes());
+}
+const char* ntb_version(void) { return "ntpoly_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// Runtime plumbing: the library stream, stream-ordered allocation, launch
+// accounting and device-wide scans used by every kernel family.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace ntb {
+
+struct Runtime {
+  int device = -1;
+  cudaStream_t stream = nullptr;   // all kernels of the hot path are issued here
+  bool owns_stream = false;
+  bool inited = false;
+  unsigned long long launches = 0; // kernels launched by this library (bench: gpu_launches)
+  double flops_useful = 0.0;       // 2*sum_{(i,k) in A} nnz(B(k,:)) accumulated over multiplies
+  unsigned long long multiplies = 0;
+  unsigned long long dense_rule_blocks = 0;
+};
+Runtime& rt();
+void ensure_init();
+void set_stream(cudaStream_t s);
+
+void* dmalloc(size_t bytes);
+void dfree(void* p);
+void stream_sync();
+
+// RAII device array on the library stream
+template <typename T> struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    p = static_cast<T*>(dmalloc((count ? count : 1) * sizeof(T)));
+  }
+  void release() { if (p) { dfree(p); p = nullptr; n = 0; } }
+  void zero() { CUDA_CHECK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), rt().stream)); }
+  T* get() const { return p; }
+};
+
+template <typename T> inline void d2h(T* host, const T* dev, size_t count) {
+  CUDA_CHECK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, rt().stream));
+  stream_sync();
+}
+template <typename T> inline void h2d(T* dev, const T* host, size_t count) {
+  CUDA_CHECK(cudaMemcpyAsync(dev, host, count * sizeof(T), cudaMemcpyHostToDevice, rt().stream));
+}
+template <typename T> inline void d2d(T* dst, const T* src, size_t count) {
+  if (count) CUDA_CHECK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToDevice, rt().stream));
+}
+
+#define NTB_LAUNCH(kernel, grid, block, smem, ...)                              \
+  do {                                                                          \
+    kernel<<<(grid), (block), (smem), ::ntb::rt().stream>>>(__VA_ARGS__);       \
+    ::ntb::rt().launches++;                                                     \
+    CUDA_CHECK(cudaGetLastError());                                             \
+  } while (0)
+
+// out[0..n] = exclusive prefix sums of in[0..n-1] (out has n+1 entries; out[n] = total).
+void exclusive_scan(const int* in, int* out, int n);
+void exclusive_scan(const int* in, long long* out, int n);
+
+}  // namespace ntb

@@ -1,0 +1,697 @@
+#include "psmatrix.h"
+#include "ops.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace ntb {
+
+// ===========================================================================
+// process grid
+// ===========================================================================
+static ProcessGrid g_global_grid;
+ProcessGrid& global_grid() { return g_global_grid; }
+
+void compute_grid_size(int total, int slices, int* rows, int* cols) {
+  *rows = 1; *cols = 1;
+  const int slice_size = total / slices;
+  for (int ii = (int)std::floor(std::sqrt((float)slice_size)); ii >= 1; --ii) {
+    if (slice_size % ii == 0) { *rows = ii; *cols = slice_size / ii; break; }
+  }
+}
+
+int compute_num_slices(int total) {
+  for (int slices = std::min(4, total); slices >= 2; --slices) {
+    const int slice_size = total / slices;
+    if (slice_size * slices != total) continue;
+    int d = (int)std::floor(std::sqrt((float)slice_size));
+    if (d * d == slice_size) return slices;
+    d = (int)std::floor(std::sqrt((float)(slice_size / 2)));
+    if (d * d * 2 == slice_size) return slices;
+  }
+  return 1;
+}
+
+void grid_destruct(ProcessGrid& g) {
+  if (!g.constructed) return;
+  comm_free(g.row); comm_free(g.column); comm_free(g.within_slice); comm_free(g.between_slice);
+  // g.global aliases the world communicator: not freed here
+  g = ProcessGrid();
+}
+
+void grid_construct(ProcessGrid& g, int rows, int cols, int slices) {
+  world_init_from_env();
+  grid_destruct(g);
+  World& w = world();
+  g.R = rows; g.C = cols; g.S = slices;
+  g.size = w.size; g.rank = w.rank;
+  NTB_CHECK(rows * cols * slices == g.size, "you did not specify a consistent process grid size");
+  if (slices > 1)
+    NTB_CHECK(std::max(rows, cols) % std::min(rows, cols) == 0,
+              "if slices >1, either rows or columns must be a multiple of the other.");
+  g.slice_size = g.size / slices;
+  g.my_slice = g.rank / g.slice_size;                       // ProcessGridModule.F90:180-183
+  g.my_row = (g.rank % g.slice_size) / cols;
+  g.my_col = g.rank % cols;
+  g.within_slice_rank = g.rank % g.slice_size;
+  g.between_slice_rank = g.my_slice;
+  // blocking (ProcessGridModule.F90:200-235) with one host thread driving the GPU
+  int cbm = (rows / cols) * slices; if (cbm == 0) cbm = slices;
+  int rbm = (cols / rows) * slices; if (rbm == 0) rbm = slices;
+  g.block_multiplier = 1;
+  g.nbc = cbm; g.nbr = rbm;
+  g.global = w.comm;
+  if (w.comm) {
+    g.within_slice = comm_split(w.comm, g.my_slice, g.rank);
+    comm_set_shape(g.within_slice, g.slice_size, g.within_slice_rank);
+    g.between_slice = comm_split(w.comm, g.within_slice_rank, g.rank);
+    comm_set_shape(g.between_slice, slices, g.my_slice);
+    g.row = comm_split(w.comm, g.my_slice * rows + g.my_row, g.rank);
+    comm_set_shape(g.row, cols, g.my_col);
+    g.column = comm_split(w.comm, g.my_slice * cols + g.my_col, g.rank);
+    comm_set_shape(g.column, rows, g.my_row);
+  }
+  g.constructed = true;
+}
+
+void grid_construct_onlyslice(ProcessGrid& g, int slices) {
+  world_init_from_env();
+  int r, c;
+  compute_grid_size(world().size, slices, &r, &c);
+  grid_construct(g, r, c, slices);
+}
+void grid_construct_default(ProcessGrid& g) {
+  world_init_from_env();
+  grid_construct_onlyslice(g, compute_num_slices(world().size));
+}
+void grid_copy(const ProcessGrid& src, ProcessGrid& dst) { grid_construct(dst, src.R, src.C, src.S); }
+
+// ===========================================================================
+// construction
+// ===========================================================================
+int scaled_dimension(const ProcessGrid& g, int n) {
+  const int lcm = g.block_multiplier * g.S * g.C * g.R;
+  const int q = n / lcm;
+  return (q * lcm == n) ? n : (q + 1) * lcm;
+}
+
+void mat_destruct(Matrix& M) {
+  M.r = LocalCsc<double>();
+  M.c = LocalCsc<cplx>();
+  M.constructed = false;
+}
+
+void mat_construct_empty(Matrix& M, int n, ProcessGrid* grid, bool is_complex) {
+  mat_destruct(M);
+  ensure_init();
+  if (!grid) grid = &global_grid();
+  if (!grid->constructed) grid_construct_default(*grid);
+  M.grid = grid;
+  M.is_complex = is_complex;
+  M.actual_dim = n;
+  M.logical_dim = scaled_dimension(*grid, n);
+  M.local_rows = M.logical_dim / grid->R;
+  M.local_cols = M.logical_dim / grid->C;
+  M.start_row = M.local_rows * grid->my_row;
+  M.start_col = M.local_cols * grid->my_col;
+  if (is_complex) M.c.init_empty(M.local_rows, M.local_cols);
+  else M.r.init_empty(M.local_rows, M.local_cols);
+  M.constructed = true;
+}
+
+void mat_construct_like(Matrix& M, const Matrix& ref) {
+  mat_construct_empty(M, ref.actual_dim, ref.grid, ref.is_complex);
+}
+
+void mat_copy(const Matrix& A, Matrix& B) {
+  if (&A == &B) return;
+  B.actual_dim = A.actual_dim; B.logical_dim = A.logical_dim; B.grid = A.grid; B.is_complex = A.is_complex;
+  B.local_rows = A.local_rows; B.local_cols = A.local_cols; B.start_row = A.start_row; B.start_col = A.start_col;
+  if (A.is_complex) { B.c.copy_from(A.c); B.r = LocalCsc<double>(); }
+  else { B.r.copy_from(A.r); B.c = LocalCsc<cplx>(); }
+  B.constructed = true;
+}
+
+void mat_to_complex(const Matrix& in, Matrix& out) {
+  if (in.is_complex) { mat_copy(in, out); return; }
+  Matrix res;
+  mat_construct_empty(res, in.actual_dim, in.grid, true);
+  csc_to_complex(in.r, res.c);
+  out = std::move(res);
+}
+void mat_to_real(const Matrix& in, Matrix& out) {
+  if (!in.is_complex) { mat_copy(in, out); return; }
+  Matrix res;
+  mat_construct_empty(res, in.actual_dim, in.grid, false);
+  csc_to_real(in.c, res.r);
+  out = std::move(res);
+}
+
+// ---------------------------------------------------------------------------
+// gathers of variable-size CSC blocks over a communicator
+// ---------------------------------------------------------------------------
+static std::vector<long long> exchange_counts(CommHandle* comm, long long mine) {
+  const int n = comm_size(comm);
+  std::vector<long long> all(n, mine);
+  if (n == 1) return all;
+  DevBuf<long long> d_mine(1), d_all((size_t)n);
+  h2d(d_mine.get(), &mine, 1);
+  comm_allgather_bytes(comm, d_mine.get(), d_all.get(), sizeof(long long));
+  d2h(all.data(), d_all.get(), (size_t)n);
+  return all;
+}
+
+// every rank of `comm` contributes one block of identical shape; result = the blocks
+// as separate CSC objects (own block is NOT copied: parts[me] stays empty, views[me] aliases local)
+template <typename T>
+static void gather_parts(const LocalCsc<T>& local, CommHandle* comm, std::vector<LocalCsc<T>>& parts,
+                         std::vector<CscView<T>>& views) {
+  const int n = comm_size(comm), me = comm_rank(comm);
+  parts.clear(); parts.resize(n);
+  views.assign(n, local.view());
+  if (n == 1) return;
+  std::vector<long long> nnz = exchange_counts(comm, local.nnz);
+  for (int q = 0; q < n; ++q) {
+    if (q == me) continue;
+    parts[q].rows = local.rows; parts[q].cols = local.cols;
+    parts[q].outer.alloc((size_t)local.cols + 1);
+    parts[q].alloc_entries(nnz[q]);
+    views[q] = parts[q].view();
+  }
+  comm_group_start();
+  for (int q = 0; q < n; ++q) {
+    const LocalCsc<T>& dst = (q == me) ? local : parts[q];
+    comm_broadcast_bytes(comm, local.outer.get(), dst.outer.get(), ((size_t)local.cols + 1) * sizeof(int), q);
+    comm_broadcast_bytes(comm, local.inner.get(), dst.inner.get(), (size_t)nnz[q] * sizeof(int), q);
+    comm_broadcast_bytes(comm, local.val.get(), dst.val.get(), (size_t)nnz[q] * sizeof(T), q);
+  }
+  comm_group_end();
+}
+
+__global__ void __launch_bounds__(256) k_concat_outer(const int* __restrict__ all_outer, int cols, int nparts,
+                                                      const long long* __restrict__ nnz_off, int* __restrict__ out_outer) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)cols * nparts;
+  if (i < total) {
+    const int q = (int)(i / cols), j = (int)(i - (long long)q * cols);
+    out_outer[i] = all_outer[(size_t)q * (cols + 1) + j] + (int)nnz_off[q];
+  } else if (i == total) {
+    out_outer[i] = (int)nnz_off[nparts];
+  }
+}
+
+// blocks side by side (ComposeMatrixColumns over the row communicator): entries land
+// directly at their final offset, only the outer index needs a fix-up pass
+// (reference comm_includes/ReduceAndComposeMatrixCleanup.f90:6-13).
+template <typename T>
+static void gather_concat_cols(const LocalCsc<T>& local, CommHandle* comm, LocalCsc<T>& out) {
+  const int n = comm_size(comm);
+  NTB_CHECK(n > 1, "gather_concat_cols on a single rank");
+  std::vector<long long> nnz = exchange_counts(comm, local.nnz);
+  std::vector<long long> off(n + 1, 0);
+  for (int q = 0; q < n; ++q) off[q + 1] = off[q] + nnz[q];
+  NTB_CHECK(off[n] < (1ll << 31), "gathered panel exceeds 2^31 entries");
+  out.rows = local.rows; out.cols = local.cols * n;
+  out.outer.alloc((size_t)out.cols + 1);
+  out.alloc_entries(off[n]);
+  DevBuf<int> all_outer((size_t)n * (local.cols + 1));
+  comm_allgather_bytes(comm, local.outer.get(), all_outer.get(), ((size_t)local.cols + 1) * sizeof(int));
+  comm_group_start();
+  for (int q = 0; q < n; ++q) {
+    comm_broadcast_bytes(comm, local.inner.get(), out.inner.get() + off[q], (size_t)nnz[q] * sizeof(int), q);
+    comm_broadcast_bytes(comm, local.val.get(), out.val.get() + off[q], (size_t)nnz[q] * sizeof(T), q);
+  }
+  comm_group_end();
+  DevBuf<long long> d_off((size_t)n + 1);
+  h2d(d_off.get(), off.data(), (size_t)n + 1);
+  const long long total = (long long)local.cols * n + 1;
+  NTB_LAUNCH(k_concat_outer, div_up(total, 256), 256, 0, all_outer.get(), local.cols, n, d_off.get(), out.outer.get());
+  stream_sync();  // off (host vector) was the h2d source
+}
+
+// between-slice "gather and sum" (comm_includes/ReduceAndSumMatrixCleanup.f90:11-32)
+template <typename T>
+static void reduce_and_sum(LocalCsc<T>& block, CommHandle* comm, double threshold, int rb) {
+  const int n = comm_size(comm);
+  if (n == 1) return;
+  std::vector<LocalCsc<T>> parts;
+  std::vector<CscView<T>> views;
+  gather_parts(block, comm, parts, views);
+  LocalCsc<T> sum;
+  sum.init_empty(block.rows, block.cols);
+  for (int q = 0; q < n; ++q) csc_increment<T>(views[q], sum, 1.0, (q == n - 1) ? threshold : 0.0, rb);
+  block.swap(sum);
+}
+
+template <typename T> static LocalCsc<T>& loc(Matrix& M);
+template <> LocalCsc<double>& loc<double>(Matrix& M) { return M.r; }
+template <> LocalCsc<cplx>& loc<cplx>(Matrix& M) { return M.c; }
+template <typename T> static const LocalCsc<T>& loc(const Matrix& M);
+template <> const LocalCsc<double>& loc<double>(const Matrix& M) { return M.r; }
+template <> const LocalCsc<cplx>& loc<cplx>(const Matrix& M) { return M.c; }
+
+// ===========================================================================
+// ingest / egress
+// ===========================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_local_filter(const int* __restrict__ row, const int* __restrict__ col, long long n,
+                                                      int r0, int r1, int c0, int c1, int* __restrict__ flag) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    flag[i] = (row[i] >= r0 && row[i] < r1 && col[i] >= c0 && col[i] < c1) ? 1 : 0;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_local_take(const int* __restrict__ row, const int* __restrict__ col,
+                                                    const T* __restrict__ val, long long n, const int* __restrict__ flag,
+                                                    const int* __restrict__ pos, int r0, int c0, int* __restrict__ orow,
+                                                    int* __restrict__ ocol, T* __restrict__ oval) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (flag[i]) { const int o = pos[i]; orow[o] = row[i] - r0; ocol[o] = col[i] - c0; oval[o] = val[i]; }
+}
+
+// d_row/d_col: GLOBAL 0-based indices on device. Keeps what belongs to this rank's block.
+template <typename T>
+static void build_local_from_global_triplets(Matrix& M, const int* d_row, const int* d_col, const T* d_val, long long n) {
+  LocalCsc<T>& L = loc<T>(M);
+  if (n == 0) { L.init_empty(M.local_rows, M.local_cols); return; }
+  NTB_CHECK(n < (1ll << 31), "too many triplets");
+  DevBuf<int> flag((size_t)n), pos((size_t)n + 1);
+  const int g = std::min(div_up(n, 256), kNumSMs * 16);
+  NTB_LAUNCH((k_local_filter<T>), g, 256, 0, d_row, d_col, n, M.start_row, M.start_row + M.local_rows, M.start_col,
+             M.start_col + M.local_cols, flag.get());
+  exclusive_scan(flag.get(), pos.get(), (int)n);
+  int m = 0;
+  d2h(&m, pos.get() + n, 1);
+  DevBuf<int> lrow((size_t)m), lcol((size_t)m);
+  DevBuf<T> lval((size_t)m);
+  NTB_LAUNCH((k_local_take<T>), g, 256, 0, d_row, d_col, d_val, n, flag.get(), pos.get(), M.start_row, M.start_col,
+             lrow.get(), lcol.get(), lval.get());
+  csc_from_device_triplets<T>(M.local_rows, M.local_cols, lrow.get(), lcol.get(), lval.get(), m, L);
+}
+
+// all ranks of `comm` end up with the concatenation of everyone's (row,col,val) arrays
+template <typename T>
+static long long allgather_triplets(CommHandle* comm, DevBuf<int>& row, DevBuf<int>& col, DevBuf<T>& val, long long n) {
+  const int np = comm_size(comm);
+  if (np == 1) return n;
+  std::vector<long long> cnt = exchange_counts(comm, n);
+  std::vector<long long> off(np + 1, 0);
+  for (int q = 0; q < np; ++q) off[q + 1] = off[q] + cnt[q];
+  DevBuf<int> arow((size_t)off[np]), acol((size_t)off[np]);
+  DevBuf<T> aval((size_t)off[np]);
+  comm_group_start();
+  for (int q = 0; q < np; ++q) {
+    comm_broadcast_bytes(comm, row.get(), arow.get() + off[q], (size_t)cnt[q] * sizeof(int), q);
+    comm_broadcast_bytes(comm, col.get(), acol.get() + off[q], (size_t)cnt[q] * sizeof(int), q);
+    comm_broadcast_bytes(comm, val.get(), aval.get() + off[q], (size_t)cnt[q] * sizeof(T), q);
+  }
+  comm_group_end();
+  row = std::move(arow); col = std::move(acol); val = std::move(aval);
+  return off[np];
+}
+
+template <typename T>
+static void fill_from_triplets_t(Matrix& M, const int* rows, const int* cols, const T* vals, long long n,
+                                 bool preduplicated, bool prepartitioned) {
+  // host: 1-based global -> 0-based global
+  std::vector<int> r0((size_t)n), c0((size_t)n);
+  for (long long i = 0; i < n; ++i) { r0[i] = rows[i] - 1; c0[i] = cols[i] - 1; }
+  DevBuf<int> d_row((size_t)n), d_col((size_t)n);
+  DevBuf<T> d_val((size_t)n);
+  if (n) { h2d(d_row.get(), r0.data(), (size_t)n); h2d(d_col.get(), c0.data(), (size_t)n); h2d(d_val.get(), vals, (size_t)n); }
+  stream_sync();
+  long long total = n;
+  if (!prepartitioned) total = allgather_triplets<T>(M.grid->within_slice, d_row, d_col, d_val, n);
+  build_local_from_global_triplets<T>(M, d_row.get(), d_col.get(), d_val.get(), total);
+  if (!prepartitioned && !preduplicated && M.grid->S > 1)   // FillMatrixFromTripletList.f90:37-42
+    reduce_and_sum<T>(loc<T>(M), M.grid->between_slice, 0.0, M.row_block());
+}
+
+void mat_fill_from_triplets(Matrix& M, const int* rows, const int* cols, const double* vals_r, const cplx* vals_c,
+                            long long n, bool preduplicated, bool prepartitioned) {
+  NTB_CHECK(M.constructed, "FillMatrixFromTripletList on an unconstructed matrix");
+  if (M.is_complex) {
+    std::vector<cplx> tmp;
+    if (!vals_c) { tmp.resize((size_t)n); for (long long i = 0; i < n; ++i) tmp[i] = cplx{vals_r[i], 0.0}; vals_c = tmp.data(); }
+    fill_from_triplets_t<cplx>(M, rows, cols, vals_c, n, preduplicated, prepartitioned);
+  } else {
+    NTB_CHECK(vals_r != nullptr, "complex triplets into a real matrix");
+    fill_from_triplets_t<double>(M, rows, cols, vals_r, n, preduplicated, prepartitioned);
+  }
+}
+
+long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r, cplx* vals_c) {
+  const long long nnz = M.local_nnz();
+  if (!rows) return nnz;
+  if (nnz == 0) return 0;
+  DevBuf<int> d_row((size_t)nnz), d_col((size_t)nnz);
+  if (M.is_complex) csc_to_device_triplets<cplx>(M.c.view(), nnz, d_row.get(), d_col.get());
+  else csc_to_device_triplets<double>(M.r.view(), nnz, d_row.get(), d_col.get());
+  CUDA_CHECK(cudaMemcpyAsync(rows, d_row.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  CUDA_CHECK(cudaMemcpyAsync(cols, d_col.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  if (M.is_complex) {
+    NTB_CHECK(vals_c != nullptr, "complex matrix needs a complex value buffer");
+    CUDA_CHECK(cudaMemcpyAsync(vals_c, M.c.val.get(), nnz * sizeof(cplx), cudaMemcpyDeviceToHost, rt().stream));
+  } else {
+    NTB_CHECK(vals_r != nullptr, "real matrix needs a real value buffer");
+    CUDA_CHECK(cudaMemcpyAsync(vals_r, M.r.val.get(), nnz * sizeof(double), cudaMemcpyDeviceToHost, rt().stream));
+  }
+  stream_sync();
+  for (long long i = 0; i < nnz; ++i) { rows[i] += M.start_row + 1; cols[i] += M.start_col + 1; }
+  return nnz;
+}
+
+void mat_fill_identity(Matrix& M) {
+  // distributed_includes/FillMatrixIdentity.f90:9-22: only indices <= actual dimension
+  std::vector<int> rows, cols;
+  std::vector<double> vals;
+  for (int jj = M.start_row; jj < M.start_row + M.local_rows; ++jj)
+    if (jj >= M.start_col && jj < M.start_col + M.local_cols && jj < M.actual_dim) {
+      rows.push_back(jj + 1); cols.push_back(jj + 1); vals.push_back(1.0);
+    }
+  mat_fill_from_triplets(M, rows.data(), cols.data(), vals.data(), nullptr, (long long)rows.size(), true, true);
+}
+
+void mat_fill_permutation(Matrix& M, const int* lookup, bool permute_rows) {
+  // distributed_includes/FillMatrixPermutation.f90 (lookup is 1-based, over the logical dimension)
+  std::vector<int> rows, cols;
+  std::vector<double> vals;
+  if (permute_rows) {
+    for (int ii = M.start_row; ii < M.start_row + M.local_rows; ++ii) {
+      const int pc = lookup[ii] - 1;
+      if (pc >= M.start_col && pc < M.start_col + M.local_cols) { rows.push_back(ii + 1); cols.push_back(pc + 1); vals.push_back(1.0); }
+    }
+  } else {
+    for (int ii = M.start_col; ii < M.start_col + M.local_cols; ++ii) {
+      const int pr = lookup[ii] - 1;
+      if (pr >= M.start_row && pr < M.start_row + M.local_rows) { rows.push_back(pr + 1); cols.push_back(ii + 1); vals.push_back(1.0); }
+    }
+  }
+  mat_fill_from_triplets(M, rows.data(), cols.data(), vals.data(), nullptr, (long long)rows.size(), true, true);
+}
+
+__global__ void __launch_bounds__(256) k_shift_swap(int* __restrict__ row, int* __restrict__ col, long long n, int roff, int coff) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = row[i] + roff, c = col[i] + coff;
+    row[i] = c; col[i] = r;   // transposed global position
+  }
+}
+
+template <typename T> static void transpose_t(const Matrix& A, Matrix& out) {
+  Matrix res;
+  mat_construct_empty(res, A.actual_dim, A.grid, A.is_complex);
+  const LocalCsc<T>& L = loc<T>(A);
+  if (comm_size(A.grid->within_slice) == 1) {
+    csc_transpose<T>(L.view(), loc<T>(res));
+  } else {
+    // every slice transposes its own replica: global triplets, swap, regroup inside the slice
+    // (the reference routes this through triplet redistribution as well,
+    //  distributed_includes/TransposeMatrix.f90)
+    const long long n = L.nnz;
+    DevBuf<int> d_row((size_t)n), d_col((size_t)n);
+    DevBuf<T> d_val((size_t)n);
+    csc_to_device_triplets<T>(L.view(), n, d_row.get(), d_col.get());
+    d2d(d_val.get(), L.val.get(), (size_t)n);
+    if (n) NTB_LAUNCH(k_shift_swap, std::min(div_up(n, 256), kNumSMs * 16), 256, 0, d_row.get(), d_col.get(), n,
+                      A.start_row, A.start_col);
+    const long long total = allgather_triplets<T>(A.grid->within_slice, d_row, d_col, d_val, n);
+    build_local_from_global_triplets<T>(res, d_row.get(), d_col.get(), d_val.get(), total);
+  }
+  out = std::move(res);
+}
+void mat_transpose(const Matrix& A, Matrix& out) {
+  if (A.is_complex) transpose_t<cplx>(A, out); else transpose_t<double>(A, out);
+}
+
+void mat_conjugate(Matrix& M) { if (M.is_complex) csc_conjugate<cplx>(M.c); }
+
+void mat_filter(Matrix& M, double threshold) {
+  if (M.is_complex) csc_filter<cplx>(M.c, threshold); else csc_filter<double>(M.r, threshold);
+}
+
+static void allreduce_host(CommHandle* comm, double* vals, int n, RedOp op) {
+  if (comm_size(comm) == 1) return;
+  DevBuf<double> d((size_t)n);
+  h2d(d.get(), vals, (size_t)n);
+  comm_allreduce_f64(comm, d.get(), (size_t)n, op);
+  d2h(vals, d.get(), (size_t)n);
+}
+
+long long mat_global_nnz(const Matrix& M) {
+  double v = (double)M.local_nnz();
+  allreduce_host(M.grid->within_slice, &v, 1, RedOp::Sum);
+  return (long long)(v + 0.5);
+}
+
+bool mat_is_identity(const Matrix& M) {
+  DevBuf<double> d(2);
+  if (M.is_complex) csc_identity_check<cplx>(M.c.view(), M.start_row, M.start_col, d.get());
+  else csc_identity_check<double>(M.r.view(), M.start_row, M.start_col, d.get());
+  comm_allreduce_f64(M.grid->within_slice, d.get(), 2, RedOp::Sum);
+  double h[2];
+  d2h(h, d.get(), 2);
+  return h[0] == 0.0 && (long long)(h[1] + 0.5) == (long long)M.actual_dim;
+}
+
+// ===========================================================================
+// algebra
+// ===========================================================================
+void mat_scale(Matrix& M, double c) {
+  if (M.is_complex) csc_scale<cplx>(M.c, cplx{c, 0.0}); else csc_scale<double>(M.r, c);
+}
+void mat_scale_c(Matrix& M, cplx c) {
+  if (!M.is_complex) { Matrix t; mat_to_complex(M, t); M = std::move(t); }   // PSMatrixAlgebraModule.F90:483-504
+  csc_scale<cplx>(M.c, c);
+}
+
+void mat_increment(const Matrix& A, Matrix& B, double alpha, double threshold) {
+  NTB_CHECK(A.constructed && B.constructed, "IncrementMatrix on an unconstructed matrix");
+  NTB_CHECK(A.logical_dim == B.logical_dim, "IncrementMatrix: dimension mismatch");
+  if (A.is_complex && !B.is_complex) { Matrix t; mat_to_complex(B, t); B = std::move(t); }  // :436-439
+  if (!A.is_complex && B.is_complex) {
+    Matrix t;
+    mat_to_complex(A, t);
+    csc_increment<cplx>(t.c.view(), B.c, alpha, threshold, B.row_block());
+    return;
+  }
+  if (A.is_complex) csc_increment<cplx>(A.c.view(), B.c, alpha, threshold, B.row_block());
+  else csc_increment<double>(A.r.view(), B.r, alpha, threshold, B.row_block());
+}
+
+double mat_trace(const Matrix& M) {
+  DevBuf<double> d(1);
+  if (M.is_complex) csc_trace<cplx>(M.c.view(), M.start_row, M.start_col, d.get());
+  else csc_trace<double>(M.r.view(), M.start_row, M.start_col, d.get());
+  comm_allreduce_f64(M.grid->within_slice, d.get(), 1, RedOp::Sum);
+  double h;
+  d2h(&h, d.get(), 1);
+  return h;
+}
+
+double mat_norm(const Matrix& M) {
+  // distributed_algebra_includes/MatrixNorm.f90: column sums over the process column, max over the row
+  DevBuf<double> colsum((size_t)M.local_cols), d(1);
+  if (M.is_complex) csc_col_abs_sums<cplx>(M.c.view(), colsum.get());
+  else csc_col_abs_sums<double>(M.r.view(), colsum.get());
+  comm_allreduce_f64(M.grid->column, colsum.get(), (size_t)M.local_cols, RedOp::Sum);
+  reduce_max(colsum.get(), M.local_cols, d.get());
+  comm_allreduce_f64(M.grid->row, d.get(), 1, RedOp::Max);
+  double h;
+  d2h(&h, d.get(), 1);
+  return h;
+}
+
+double mat_sigma(const Matrix& M) {
+  const double n = mat_norm(M);
+  return 1.0 / (n * n);
+}
+
+void mat_gershgorin(const Matrix& M, double* e_min, double* e_max) {
+  DevBuf<double> dmin((size_t)M.local_cols), dmax((size_t)M.local_cols), d(2);
+  if (M.is_complex) csc_gershgorin_cols<cplx>(M.c.view(), M.start_row, M.start_col, dmin.get(), dmax.get());
+  else csc_gershgorin_cols<double>(M.r.view(), M.start_row, M.start_col, dmin.get(), dmax.get());
+  comm_allreduce_f64(M.grid->column, dmin.get(), (size_t)M.local_cols, RedOp::Sum);
+  comm_allreduce_f64(M.grid->column, dmax.get(), (size_t)M.local_cols, RedOp::Sum);
+  reduce_min(dmin.get(), M.local_cols, d.get());
+  reduce_max(dmax.get(), M.local_cols, d.get() + 1);
+  comm_allreduce_f64(M.grid->row, d.get(), 1, RedOp::Min);
+  comm_allreduce_f64(M.grid->row, d.get() + 1, 1, RedOp::Max);
+  double h[2];
+  d2h(h, d.get(), 2);
+  *e_min = h[0];
+  *e_max = h[1];
+}
+
+void mat_dot(const Matrix& A, const Matrix& B, double* re, double* im) {
+  DevBuf<double> d(2);
+  if (A.is_complex || B.is_complex) {
+    Matrix ta, tb;
+    const Matrix* pa = &A; const Matrix* pb = &B;
+    if (!A.is_complex) { mat_to_complex(A, ta); pa = &ta; }
+    if (!B.is_complex) { mat_to_complex(B, tb); pb = &tb; }
+    csc_dot<cplx>(pa->c.view(), pb->c.view(), d.get());
+  } else {
+    csc_dot<double>(A.r.view(), B.r.view(), d.get());
+  }
+  comm_allreduce_f64(A.grid->within_slice, d.get(), 2, RedOp::Sum);
+  double h[2];
+  d2h(h, d.get(), 2);
+  *re = h[0];
+  if (im) *im = h[1];
+}
+
+void mat_pairwise(const Matrix& A, const Matrix& B, Matrix& C) {
+  Matrix res;
+  const bool cx = A.is_complex || B.is_complex;
+  mat_construct_empty(res, A.actual_dim, A.grid, cx);
+  if (cx) {
+    Matrix ta, tb;
+    const Matrix* pa = &A; const Matrix* pb = &B;
+    if (!A.is_complex) { mat_to_complex(A, ta); pa = &ta; }
+    if (!B.is_complex) { mat_to_complex(B, tb); pb = &tb; }
+    csc_pairwise<cplx>(pa->c.view(), pb->c.view(), res.c);
+  } else {
+    csc_pairwise<double>(A.r.view(), B.r.view(), res.r);
+  }
+  C = std::move(res);
+}
+
+double mat_measure_asymmetry(const Matrix& M) {       // PSMatrixAlgebraModule.F90:569-583
+  Matrix t;
+  mat_transpose(M, t);
+  mat_conjugate(t);
+  mat_increment(M, t, -1.0, 0.0);
+  return mat_norm(t);
+}
+
+void mat_symmetrize(Matrix& M) {                       // PSMatrixAlgebraModule.F90:586-599
+  Matrix t;
+  mat_transpose(M, t);
+  mat_conjugate(t);
+  mat_increment(t, M, 1.0, 0.0);
+  mat_scale(M, 0.5);
+}
+
+// ---------------------------------------------------------------------------
+// the distributed multiply (distributed_algebra_includes/MatrixMultiply.f90)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rowblock_nnz(const int* __restrict__ inner, long long nnz, int rb,
+                                                      unsigned long long* __restrict__ counts) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&counts[inner[i] / rb], 1ull);
+}
+
+template <typename T>
+static void multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold) {
+  ProcessGrid& g = *A.grid;
+  const int S = g.S;
+  const double wthr = (S > 1) ? threshold / (S * 1000) : threshold;      // MatrixMultiply.f90:25-29
+  const LocalCsc<T>& Al = loc<T>(A);
+  const LocalCsc<T>& Bl = loc<T>(B);
+  const int rb = A.row_block(), cb = A.col_block();
+
+  // ---- A task: my slice's column blocks, gathered along the process row (:94-145)
+  LocalCsc<T> Asel, Ypanel;
+  const LocalCsc<T>* Ysrc = &Al;
+  if (S > 1) { csc_select_col_blocks<T>(Al.view(), cb, S, g.my_slice, Asel); Ysrc = &Asel; }
+  if (comm_size(g.row) > 1) { gather_concat_cols<T>(*Ysrc, g.row, Ypanel); Ysrc = &Ypanel; }
+  // ---- B task: my slice's row blocks, gathered along the process column (:154-193)
+  LocalCsc<T> Bsel, Xpanel;
+  const LocalCsc<T>* Xsrc = &Bl;
+  if (S > 1) { csc_select_row_blocks<T>(Bl.view(), rb, S, g.my_slice, Bsel); Xsrc = &Bsel; }
+  if (comm_size(g.column) > 1) {
+    std::vector<LocalCsc<T>> parts;
+    std::vector<CscView<T>> views;
+    gather_parts<T>(*Xsrc, g.column, parts, views);
+    std::vector<int> roff(views.size());
+    for (size_t q = 0; q < views.size(); ++q) roff[q] = (int)q * Xsrc->rows;
+    csc_stack_rows<T>(views.data(), roff.data(), (int)views.size(), Xsrc->rows * (int)views.size(), Xpanel);
+    Xsrc = &Xpanel;
+  }
+  const CscView<T> Y = Ysrc->view();   // A panel: rows = my rows, cols = inner index
+  const CscView<T> X = Xsrc->view();   // B panel: rows = inner index, cols = my columns
+  NTB_CHECK(Y.cols == X.rows, "multiply: gathered panels disagree on the inner dimension");
+
+  // ---- per local block pair: dense or sparse threshold rule (GemmMatrix.f90:49-61)
+  const int nI = g.nbr, nJ = g.nbc;
+  std::vector<unsigned char> rule((size_t)nI * nJ, 0);
+  {
+    std::vector<double> fa(nI), fb(nJ);
+    const double inner_dim = (double)X.rows;
+    if (nI == 1) fa[0] = (double)Ysrc->nnz / ((double)rb * inner_dim);
+    else {
+      DevBuf<unsigned long long> cnt((size_t)nI);
+      cnt.zero();
+      if (Ysrc->nnz) NTB_LAUNCH(k_rowblock_nnz, std::min(div_up(Ysrc->nnz, 256), kNumSMs * 8), 256, 0, Y.inner, Ysrc->nnz, rb, cnt.get());
+      std::vector<unsigned long long> h(nI);
+      d2h(h.data(), cnt.get(), (size_t)nI);
+      for (int i = 0; i < nI; ++i) fa[i] = (double)h[i] / ((double)rb * inner_dim);
+    }
+    if (nJ == 1) fb[0] = (double)Xsrc->nnz / ((double)cb * inner_dim);
+    else {
+      std::vector<int> marks(nJ + 1);
+      for (int j = 0; j <= nJ; ++j) CUDA_CHECK(cudaMemcpyAsync(&marks[j], X.outer + (size_t)j * cb, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+      stream_sync();
+      for (int j = 0; j < nJ; ++j) fb[j] = (double)(marks[j + 1] - marks[j]) / ((double)cb * inner_dim);
+    }
+    for (int i = 0; i < nI; ++i)
+      for (int j = 0; j < nJ; ++j) {
+        rule[(size_t)i * nJ + j] = (std::min(fa[i], fb[j]) > 0.1) ? 1 : 0;
+        if (rule[(size_t)i * nJ + j]) rt().dense_rule_blocks++;
+      }
+  }
+  DevBuf<unsigned char> d_rule;
+  RuleView rv;
+  if (std::any_of(rule.begin(), rule.end(), [](unsigned char c) { return c != 0; })) {
+    d_rule.alloc(rule.size());
+    h2d(d_rule.get(), rule.data(), rule.size());
+    rv.tbl = d_rule.get(); rv.rb = rb; rv.cb = cb; rv.nJ = nJ;
+  }
+
+  // ---- local product
+  Matrix AB;
+  mat_construct_empty(AB, A.actual_dim, A.grid, scalar_traits<T>::is_complex);
+  GemmStats st;
+  spgemm<T>(X, Y, alpha, wthr, rv, loc<T>(AB), &st);
+  rt().flops_useful += st.flops;
+  rt().multiplies++;
+  stream_sync();  // rule (host vector) was an h2d source
+
+  // ---- between-slice sum (:234-261)
+  if (S > 1) reduce_and_sum<T>(loc<T>(AB), g.between_slice, threshold, rb);
+
+  // ---- C = AB  or  C = beta*C + AB (:324-329)
+  if (std::fabs(beta) < 2.2250738585072014e-308 || !C.constructed) {
+    C = std::move(AB);
+  } else {
+    mat_scale(C, beta);
+    mat_increment(AB, C, 1.0, 0.0);
+  }
+}
+
+void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
+                  MemoryPool* pool) {
+  NTB_CHECK(A.constructed && B.constructed, "MatrixMultiply on an unconstructed matrix");
+  NTB_CHECK(A.logical_dim == B.logical_dim && A.grid == B.grid, "MatrixMultiply: operands live on different grids/sizes");
+  if (pool) { pool->rows = A.local_rows; pool->cols = A.local_cols; pool->is_complex = A.is_complex || B.is_complex; pool->constructed = true; }
+  // A, B may alias C: results are built in a temporary and moved in at the end.
+  if (A.is_complex || B.is_complex) {                                    // PSMatrixAlgebraModule.F90:171-205
+    Matrix ta, tb;
+    const Matrix* pa = &A; const Matrix* pb = &B;
+    if (!A.is_complex) { mat_to_complex(A, ta); pa = &ta; }
+    if (!B.is_complex) { mat_to_complex(B, tb); pb = &tb; }
+    if (C.constructed && !C.is_complex && std::fabs(beta) > 0) { Matrix tc; mat_to_complex(C, tc); C = std::move(tc); }
+    multiply_t<cplx>(*pa, *pb, C, alpha, beta, threshold);
+  } else {
+    multiply_t<double>(A, B, C, alpha, beta, threshold);
+  }
+}
+
+void mat_similarity_transform(const Matrix& A, const Matrix& P, const Matrix& PInv, Matrix& Res, MemoryPool* pool,
+                              double threshold) {
+  if (mat_is_identity(P)) { mat_copy(A, Res); return; }       // PSMatrixAlgebraModule.F90:633-634
+  Matrix tmp;
+  mat_multiply(P, A, tmp, 1.0, 0.0, threshold, pool);
+  mat_multiply(tmp, PInv, Res, 1.0, 0.0, threshold, pool);
+}
+
+}  // namespace ntb

@@ -1,0 +1,104 @@
+// Host-side mirror of NTPoly's distributed layer: ProcessGrid_t, Matrix_ps,
+// MatrixMemoryPool_p and the PSMatrixAlgebraModule operations, with every
+// matrix DEVICE-RESIDENT (one CSC block per GPU) between calls.
+// Reference: Source/Fortran/ProcessGridModule.F90, PSMatrixModule.F90,
+// PSMatrixAlgebraModule.F90, PMatrixMemoryPoolModule.F90.
+#pragma once
+#include "comm.h"
+#include "csc.cuh"
+#include <vector>
+
+namespace ntb {
+
+// ---- ProcessGrid_t (ProcessGridModule.F90:15-56, 130-264) -----------------------
+struct ProcessGrid {
+  int R = 1, C = 1, S = 1;
+  int rank = 0, size = 1, slice_size = 1;
+  int my_slice = 0, my_row = 0, my_col = 0;
+  int within_slice_rank = 0, between_slice_rank = 0;
+  int block_multiplier = 1, nbr = 1, nbc = 1;  // number_of_blocks_rows / columns per rank
+  CommHandle* global = nullptr;
+  CommHandle* within_slice = nullptr;
+  CommHandle* between_slice = nullptr;
+  CommHandle* row = nullptr;      // same (slice,row): size C, my rank = my_col
+  CommHandle* column = nullptr;   // same (slice,col): size R, my rank = my_row
+  bool constructed = false;
+};
+void grid_construct(ProcessGrid& g, int rows, int cols, int slices);
+void grid_construct_onlyslice(ProcessGrid& g, int slices);
+void grid_construct_default(ProcessGrid& g);
+void grid_destruct(ProcessGrid& g);
+void grid_copy(const ProcessGrid& src, ProcessGrid& dst);
+ProcessGrid& global_grid();
+void compute_grid_size(int total, int slices, int* rows, int* cols);   // ProcessGridModule.F90:576-601
+int compute_num_slices(int total);                                    // ProcessGridModule.F90:606-638
+
+// ---- host triplet lists (TripletModule.F90:13-26; TripletListModule.F90) ---------
+struct Triplet_r { int index_column; int index_row; double point_value; };
+struct Triplet_c { int index_column; int index_row; double re; double im; };
+struct TripletList_r { std::vector<Triplet_r> data; };
+struct TripletList_c { std::vector<Triplet_c> data; };
+
+// ---- Matrix_ps (PSMatrixModule.F90:33-51) -----------------------------------------
+struct Matrix {
+  int actual_dim = 0;
+  int logical_dim = 0;
+  ProcessGrid* grid = nullptr;
+  bool is_complex = false;
+  int local_rows = 0, local_cols = 0;
+  int start_row = 0, start_col = 0;   // 0-based first global row / column held here
+  LocalCsc<double> r;
+  LocalCsc<cplx> c;
+  bool constructed = false;
+  long long local_nnz() const { return is_complex ? c.nnz : r.nnz; }
+  int row_block() const { return local_rows / grid->nbr; }
+  int col_block() const { return local_cols / grid->nbc; }
+};
+
+// MatrixMemoryPool_p (PMatrixMemoryPoolModule.F90:12-49). On the GPU the scratch of the
+// multiply lives in the stream-ordered allocator's cache; the handle keeps the API and
+// remembers the shape it was built for (CheckMemoryPoolValidity).
+struct MemoryPool {
+  int rows = 0, cols = 0;
+  bool is_complex = false;
+  bool constructed = false;
+};
+
+int scaled_dimension(const ProcessGrid& g, int n);                      // PSMatrixModule.F90:1596-1618
+void mat_construct_empty(Matrix& M, int n, ProcessGrid* grid, bool is_complex);
+void mat_construct_like(Matrix& M, const Matrix& ref);
+void mat_destruct(Matrix& M);
+void mat_copy(const Matrix& A, Matrix& B);
+void mat_fill_identity(Matrix& M);
+void mat_fill_permutation(Matrix& M, const int* index_lookup_1based, bool permute_rows);
+// global 1-based triplets; mirrors FillMatrixFromTripletList (preduplicated / prepartitioned flags)
+void mat_fill_from_triplets(Matrix& M, const int* rows, const int* cols, const double* vals_r,
+                            const cplx* vals_c, long long n, bool preduplicated, bool prepartitioned);
+// local block as global 1-based triplets, column-major order. Call with nullptrs to get the count.
+long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r, cplx* vals_c);
+void mat_transpose(const Matrix& A, Matrix& out);
+void mat_conjugate(Matrix& M);
+void mat_to_complex(const Matrix& in, Matrix& out);
+void mat_to_real(const Matrix& in, Matrix& out);
+void mat_filter(Matrix& M, double threshold);
+long long mat_global_nnz(const Matrix& M);
+bool mat_is_identity(const Matrix& M);
+
+// PSMatrixAlgebraModule
+void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
+                  MemoryPool* pool);
+void mat_increment(const Matrix& A, Matrix& B, double alpha, double threshold);
+void mat_scale(Matrix& M, double c);
+void mat_scale_c(Matrix& M, cplx c);
+double mat_trace(const Matrix& M);
+double mat_norm(const Matrix& M);
+double mat_sigma(const Matrix& M);
+void mat_dot(const Matrix& A, const Matrix& B, double* re, double* im);
+void mat_pairwise(const Matrix& A, const Matrix& B, Matrix& C);
+void mat_gershgorin(const Matrix& M, double* e_min, double* e_max);
+double mat_measure_asymmetry(const Matrix& M);
+void mat_symmetrize(Matrix& M);
+void mat_similarity_transform(const Matrix& A, const Matrix& P, const Matrix& PInv, Matrix& Res, MemoryPool* pool,
+                              double threshold);
+
+}  // namespace ntb

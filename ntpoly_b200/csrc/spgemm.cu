@@ -1,0 +1,363 @@
+// Local thresholded SpGEMM for sm_100a — the B200 replacement of NTPoly's
+// MultiplyBlock + PruneList (reference Source/Fortran/sparse_includes/
+// MultiplyBlock.f90:9-36, PruneList.f90:8-38) and of the memory pool scratch
+// (dense_includes/ConstructMatrixMemoryPool.f90:10-30).
+//
+// Formulation. NTPoly stores CSC; C = A*B column by column is
+//     C(:,j) = sum_k  B(k,j) * A(:,k)          (k ascending, like the reference)
+// so with X := B and Y := A every output column is a Gustavson "row" and no
+// operand ever has to be transposed (the reference transposes both, every call).
+//
+// Pipeline (all on the library stream):
+//   k_bounds     per output column: product count ub, reachable row window [lo,lo+w)
+//   k_binlists   columns -> bins by window size (accumulator kind), chunk-contiguous
+//   numeric      bin 1-4: one WARP per column, dense window accumulator in shared memory
+//                bin 5  : one CTA per column, shared-memory window up to ~200 KB
+//                bin 6  : one CTA per column, window in a per-CTA global slab (L2 resident)
+//                each: accumulate in k order, then sweep the window in row order applying
+//                the drop rule (|alpha*v|>thr or dense-branch |v|>thr) -> sorted, filtered,
+//                alpha-scaled entries written to a staging area at a bound-derived offset
+//   scan + k_compact   exact CSC of the kept entries
+// The window sweep makes sort and filter free: no hash tables, no atomics, and the
+// summation order per element is the reference's (k ascending).
+#include "csc.cuh"
+
+namespace ntb {
+
+constexpr int NBINS = 7;       // 0: empty column, 1..4 warp windows, 5 CTA window, 6 global slab
+constexpr int WARPS = 8;       // warps per CTA in the warp-window kernels
+constexpr int CTA_T = 256;     // threads per CTA in the CTA-window kernels
+constexpr size_t SMEM_BUDGET = 200 * 1024;
+
+struct BinCfg { int wmax[NBINS]; };
+
+__device__ __forceinline__ bool keep_entry(double mag_scaled, double mag_raw, double thr, bool dense_rule) {
+  return (dense_rule ? mag_raw : mag_scaled) > thr;
+}
+
+__device__ __forceinline__ bool rule_for(const RuleView& r, int inner_idx, int outer_idx) {
+  if (r.tbl == nullptr) return false;
+  return r.tbl[(inner_idx / r.rb) * r.nJ + (outer_idx / r.cb)] != 0;
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_bounds(CscView<T> X, CscView<T> Y, int* __restrict__ lo,
+                                                int* __restrict__ wid, int* __restrict__ cap,
+                                                int* __restrict__ binid, BinCfg cfg,
+                                                unsigned long long* __restrict__ flops) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long my_flops = 0;
+  for (int j = gw; j < X.cols; j += nw) {
+    unsigned long long ub = 0;
+    int mn = INT_MAX, mx = -1;
+    for (int p = X.outer[j] + lane; p < X.outer[j + 1]; p += 32) {
+      int k = X.inner[p];
+      int s = Y.outer[k], e = Y.outer[k + 1];
+      if (e > s) {
+        ub += (unsigned long long)(e - s);
+        mn = min(mn, Y.inner[s]);
+        mx = max(mx, Y.inner[e - 1]);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      ub += __shfl_xor_sync(0xffffffffu, ub, d);
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if (lane == 0) {
+      int w = (ub > 0) ? (mx - mn + 1) : 0;
+      lo[j] = (ub > 0) ? mn : 0;
+      wid[j] = w;
+      cap[j] = (int)min((unsigned long long)w, ub);
+      int b = 0;
+      if (w > 0) {
+        b = NBINS - 1;
+#pragma unroll
+        for (int t = NBINS - 2; t >= 1; --t)
+          if (w <= cfg.wmax[t]) b = t;
+      }
+      binid[j] = b;
+      my_flops += ub;
+    }
+  }
+  if (lane == 0 && my_flops) atomicAdd(flops, my_flops);
+}
+
+// chunk-contiguous bin lists: 32 consecutive columns stay adjacent inside a bin so
+// that the columns one CTA works on share their Y columns in L1/L2.
+__global__ void __launch_bounds__(256) k_binlists(const int* __restrict__ binid, int n, int* __restrict__ lists,
+                                                  int* __restrict__ bin_count) {
+  const int lane = threadIdx.x & 31;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = (j < n) ? binid[j] : -1;
+#pragma unroll
+  for (int t = 1; t < NBINS; ++t) {
+    unsigned m = __ballot_sync(0xffffffffu, b == t);
+    if (m == 0) continue;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&bin_count[t], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (b == t) lists[(size_t)t * n + base + __popc(m & ((1u << lane) - 1))] = j;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bins 1..4: one warp per output column, window accumulator in shared memory
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+k_numeric_warp(CscView<T> X, CscView<T> Y, const int* __restrict__ list, const int* __restrict__ nlist_p,
+               const int* __restrict__ lo, const int* __restrict__ wid,
+               const long long* __restrict__ tmp_off, double alpha, double thr, RuleView rules,
+               int* __restrict__ tmp_idx, T* __restrict__ tmp_val, int* __restrict__ cnt, int wmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* acc = reinterpret_cast<T*>(smem_raw) + (size_t)warp * wmax;
+  const int nlist = *nlist_p;
+  for (int li = blockIdx.x * WARPS + warp; li < nlist; li += gridDim.x * WARPS) {
+    const int j = list[li];
+    const int base = lo[j];
+    const int w = wid[j];
+    for (int t = lane; t < w; t += 32) acc[t] = zero_of<T>();
+    __syncwarp();
+    const int xs = X.outer[j], xe = X.outer[j + 1];
+    for (int p0 = xs; p0 < xe; p0 += 32) {
+      const int p = p0 + lane;
+      int ys = 0, ye = 0;
+      T xv = zero_of<T>();
+      if (p < xe) {
+        const int k = X.inner[p];
+        xv = X.val[p];
+        ys = Y.outer[k];
+        ye = Y.outer[k + 1];
+      }
+      const int nv = min(32, xe - p0);
+      for (int t = 0; t < nv; ++t) {
+        const int s = shfl(ys, t), e = shfl(ye, t);
+        const T b = shfl(xv, t);
+        for (int q = s + lane; q < e; q += 32) {
+          const int c = Y.inner[q] - base;
+          acc[c] = s_fma(Y.val[q], b, acc[c]);
+        }
+        __syncwarp();
+      }
+    }
+    // ordered sweep: filter + alpha + emit (sorted by construction)
+    const long long off = tmp_off[j];
+    int count = 0;
+    for (int t0 = 0; t0 < w; t0 += 32) {
+      const int t = t0 + lane;
+      bool keep = false;
+      T v = zero_of<T>();
+      if (t < w) {
+        v = acc[t];
+        const T sv = s_scale(alpha, v);
+        keep = keep_entry(s_abs(sv), s_abs(v), thr, rule_for(rules, base + t, j));
+        v = sv;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const long long pos = off + count + __popc(m & ((1u << lane) - 1));
+        tmp_idx[pos] = base + t;
+        tmp_val[pos] = v;
+      }
+      count += __popc(m);
+    }
+    if (lane == 0) cnt[j] = count;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bins 5/6: one CTA per output column; window in shared memory (bin 5) or in a
+// per-CTA global slab kept all-zero between columns (bin 6).
+template <typename T, bool GLOBAL_SLAB>
+__global__ void __launch_bounds__(CTA_T)
+k_numeric_cta(CscView<T> X, CscView<T> Y, const int* __restrict__ list, const int* __restrict__ nlist_p,
+              const int* __restrict__ lo, const int* __restrict__ wid,
+              const long long* __restrict__ tmp_off, double alpha, double thr, RuleView rules,
+              int* __restrict__ tmp_idx, T* __restrict__ tmp_val, int* __restrict__ cnt, T* __restrict__ slab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_warp_cnt[CTA_T / 32];
+  __shared__ int s_running;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nlist = *nlist_p;
+  for (int li = blockIdx.x; li < nlist; li += gridDim.x) {
+    const int j = list[li];
+    const int base = lo[j];
+    const int w = wid[j];
+    T* acc = GLOBAL_SLAB ? (slab + (size_t)blockIdx.x * Y.rows + base) : reinterpret_cast<T*>(smem_raw);
+    if (!GLOBAL_SLAB) {
+      for (int t = threadIdx.x; t < w; t += CTA_T) acc[t] = zero_of<T>();
+    }
+    __syncthreads();
+    const int xs = X.outer[j], xe = X.outer[j + 1];
+    for (int p = xs; p < xe; ++p) {
+      const int k = X.inner[p];
+      const T b = X.val[p];
+      const int s = Y.outer[k], e = Y.outer[k + 1];
+      for (int q = s + threadIdx.x; q < e; q += CTA_T) {
+        const int c = Y.inner[q] - base;
+        acc[c] = s_fma(Y.val[q], b, acc[c]);
+      }
+      __syncthreads();
+    }
+    const long long off = tmp_off[j];
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < w; t0 += CTA_T) {
+      const int t = t0 + threadIdx.x;
+      bool keep = false;
+      T v = zero_of<T>();
+      if (t < w) {
+        v = acc[t];
+        if (GLOBAL_SLAB) acc[t] = zero_of<T>();
+        const T sv = s_scale(alpha, v);
+        keep = keep_entry(s_abs(sv), s_abs(v), thr, rule_for(rules, base + t, j));
+        v = sv;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_warp_cnt[warp] = __popc(m);
+      __syncthreads();
+      int before = s_running;
+      for (int ww = 0; ww < warp; ++ww) before += s_warp_cnt[ww];
+      if (keep) {
+        const long long pos = off + before + __popc(m & ((1u << lane) - 1));
+        tmp_idx[pos] = base + t;
+        tmp_val[pos] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int ww = 0; ww < CTA_T / 32; ++ww) tot += s_warp_cnt[ww];
+        s_running += tot;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) cnt[j] = s_running;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_compact(int ncols, const long long* __restrict__ tmp_off,
+                                                 const int* __restrict__ cnt, const int* __restrict__ outer,
+                                                 const int* __restrict__ tmp_idx, const T* __restrict__ tmp_val,
+                                                 int* __restrict__ inner, T* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int j = gw; j < ncols; j += nw) {
+    const long long src = tmp_off[j];
+    const int dst = outer[j];
+    const int n = cnt[j];
+    for (int t = lane; t < n; t += 32) {
+      inner[dst + t] = tmp_idx[src + t];
+      val[dst + t] = tmp_val[src + t];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, const RuleView& rules,
+            LocalCsc<T>& Z, GemmStats* stats) {
+  NTB_CHECK(X.rows == Y.cols, "spgemm: inner dimensions differ");
+  const int ncols = X.cols;
+  const int nrows = Y.rows;
+  Z.rows = nrows;
+  Z.cols = ncols;
+  Z.outer.alloc((size_t)ncols + 1);
+  if (ncols == 0) { Z.alloc_entries(0); return; }
+
+  // bin configuration by scalar width (bytes of shared memory per window)
+  BinCfg cfg;
+  const int per_warp_elems[5] = {0, (int)(4096 / sizeof(T)), (int)(8192 / sizeof(T)),
+                                 (int)(16384 / sizeof(T)), (int)(24576 / sizeof(T))};
+  cfg.wmax[0] = 0;
+  for (int b = 1; b <= 4; ++b) cfg.wmax[b] = per_warp_elems[b];
+  cfg.wmax[5] = (int)(SMEM_BUDGET / sizeof(T));
+  cfg.wmax[6] = INT_MAX;
+
+  DevBuf<int> lo(ncols), wid(ncols), cap(ncols), binid(ncols), cnt(ncols);
+  DevBuf<int> lists((size_t)NBINS * ncols);
+  DevBuf<int> bin_count(NBINS);
+  DevBuf<unsigned long long> flops(1);
+  DevBuf<long long> tmp_off((size_t)ncols + 1);
+  bin_count.zero();
+  flops.zero();
+  cnt.zero();
+
+  {
+    int blocks = min(div_up((long long)ncols * 32, 256), kNumSMs * 16);
+    NTB_LAUNCH((k_bounds<T>), blocks, 256, 0, X, Y, lo.get(), wid.get(), cap.get(), binid.get(), cfg, flops.get());
+    NTB_LAUNCH(k_binlists, div_up(ncols, 256), 256, 0, binid.get(), ncols, lists.get(), bin_count.get());
+  }
+  exclusive_scan(cap.get(), tmp_off.get(), ncols);
+
+  // one small read-back: bin populations, staging size, flop count
+  int h_bins[NBINS];
+  long long h_tmp_total = 0;
+  unsigned long long h_flops = 0;
+  CUDA_CHECK(cudaMemcpyAsync(h_bins, bin_count.get(), sizeof(h_bins), cudaMemcpyDeviceToHost, rt().stream));
+  CUDA_CHECK(cudaMemcpyAsync(&h_tmp_total, tmp_off.get() + ncols, sizeof(long long), cudaMemcpyDeviceToHost, rt().stream));
+  CUDA_CHECK(cudaMemcpyAsync(&h_flops, flops.get(), sizeof(h_flops), cudaMemcpyDeviceToHost, rt().stream));
+  stream_sync();
+
+  DevBuf<int> tmp_idx((size_t)h_tmp_total);
+  DevBuf<T> tmp_val((size_t)h_tmp_total);
+
+  for (int b = 1; b <= 4; ++b) {
+    if (h_bins[b] == 0) continue;
+    const size_t smem = (size_t)WARPS * cfg.wmax[b] * sizeof(T);
+    CUDA_CHECK(cudaFuncSetAttribute(k_numeric_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
+    int blocks = min(div_up(h_bins[b], WARPS), kNumSMs * per_sm);
+    NTB_LAUNCH((k_numeric_warp<T>), blocks, WARPS * 32, smem, X, Y, lists.get() + (size_t)b * ncols,
+               bin_count.get() + b, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
+               tmp_val.get(), cnt.get(), cfg.wmax[b]);
+  }
+  if (h_bins[5] > 0) {
+    CUDA_CHECK(cudaFuncSetAttribute((k_numeric_cta<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    int blocks = min(h_bins[5], kNumSMs * 4);
+    NTB_LAUNCH((k_numeric_cta<T, false>), blocks, CTA_T, SMEM_BUDGET, X, Y, lists.get() + (size_t)5 * ncols,
+               bin_count.get() + 5, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
+               tmp_val.get(), cnt.get(), (T*)nullptr);
+  }
+  DevBuf<T> slab;
+  if (h_bins[6] > 0) {
+    int blocks = min(h_bins[6], kNumSMs * 2);
+    slab.alloc((size_t)blocks * nrows);
+    slab.zero();
+    NTB_LAUNCH((k_numeric_cta<T, true>), blocks, CTA_T, 0, X, Y, lists.get() + (size_t)6 * ncols,
+               bin_count.get() + 6, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
+               tmp_val.get(), cnt.get(), slab.get());
+  }
+
+  exclusive_scan(cnt.get(), Z.outer.get(), ncols);
+  int h_nnz = 0;
+  d2h(&h_nnz, Z.outer.get() + ncols, 1);
+  Z.alloc_entries(h_nnz);
+  if (h_nnz > 0) {
+    int blocks = min(div_up((long long)ncols * 32, 256), kNumSMs * 16);
+    NTB_LAUNCH((k_compact<T>), blocks, 256, 0, ncols, tmp_off.get(), cnt.get(), Z.outer.get(), tmp_idx.get(),
+               tmp_val.get(), Z.inner.get(), Z.val.get());
+  }
+  if (stats) {
+    stats->flops = 2.0 * (double)h_flops * (scalar_traits<T>::is_complex ? 4.0 : 1.0);
+    stats->tmp_entries = h_tmp_total;
+    for (int b = 0; b < NBINS; ++b) stats->bins[b] = h_bins[b];
+  }
+}
+
+template void spgemm<double>(const CscView<double>&, const CscView<double>&, double, double, const RuleView&,
+                             LocalCsc<double>&, GemmStats*);
+template void spgemm<cplx>(const CscView<cplx>&, const CscView<cplx>&, double, double, const RuleView&,
+                           LocalCsc<cplx>&, GemmStats*);
+
+}  // namespace ntb

@@ -1,0 +1,122 @@
+"""Parity of the CUDA hot path (through the C ABI) with the CPU oracle.
+Mirrors reference UnitTests/test_psmatrixalgebra.py (sizes/fills :74,:103-107) and adds the
+threshold / alpha / beta cases the reference never tests."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from util import banded, compare_sparse, random_sparse
+
+pytestmark = pytest.mark.gpu
+
+
+def to_gpu(nt, m, n=None):
+    n = n or m.shape[0]
+    M = nt.Matrix_ps(n, is_complex=np.iscomplexobj(m.data))
+    M.fill_from_scipy(m)
+    return M
+
+
+@pytest.mark.parametrize("fill", [1.0, 0.2, 0.0])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_multiply_reference_sizes(nt, oracle, fill, cplx):
+    n = 33
+    a = random_sparse(n, fill, 1, cplx)
+    b = random_sparse(n, fill, 2, cplx)
+    A, B, C = to_gpu(nt, a), to_gpu(nt, b), nt.Matrix_ps(n)
+    pool = nt.PMatrixMemoryPool(A)
+    C.Gemm(A, B, pool)
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a, is_complex=cplx), oracle.PSMatrix.from_scipy(b, is_complex=cplx))
+    compare_sparse(C.to_scipy(), ref.to_scipy())
+    # and against scipy the way the reference tests do (THRESHOLD 1e-4, helpers.py:13)
+    assert abs(C.to_scipy() - a @ b).sum() < 1e-4
+
+
+@pytest.mark.parametrize("pair", [(1.0, 0.0), (0.0, 1.0)])
+def test_multiply_empty_operand(nt, oracle, pair):
+    n = 33
+    a = random_sparse(n, pair[0], 3)
+    b = random_sparse(n, pair[1], 4)
+    A, B, C = to_gpu(nt, a), to_gpu(nt, b), nt.Matrix_ps(n)
+    C.Gemm(A, B)
+    assert C.GetSize() == 0
+
+
+@pytest.mark.parametrize("n,fill,thr,alpha", [
+    (257, 0.03, 0.0, 1.0), (257, 0.03, 1e-3, 1.0), (512, 0.05, 1e-2, 0.5), (512, 0.3, 5e-2, -2.0),
+    (1000, 0.004, 1e-4, 1.7)])
+def test_multiply_threshold_alpha(nt, oracle, n, fill, thr, alpha):
+    a = random_sparse(n, fill, 11)
+    b = random_sparse(n, fill, 12)
+    A, B, C = to_gpu(nt, a), to_gpu(nt, b), nt.Matrix_ps(n)
+    C.Gemm(A, B, None, alpha=alpha, threshold=thr)
+    st = oracle.MultiplyStats()
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(b), alpha=alpha, thr=thr, stats=st)
+    compare_sparse(C.to_scipy(), ref.to_scipy(), thr)
+    assert C.GetSize() == pytest.approx(ref.nnz(), abs=max(3, ref.nnz() * 1e-4))
+
+
+def test_multiply_beta(nt, oracle):
+    n = 300
+    a, b, c = random_sparse(n, 0.02, 21), random_sparse(n, 0.02, 22), random_sparse(n, 0.02, 23)
+    A, B, C = to_gpu(nt, a), to_gpu(nt, b), to_gpu(nt, c)
+    C.Gemm(A, B, None, alpha=0.7, beta=-1.3, threshold=1e-3)
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(b),
+                          C=oracle.PSMatrix.from_scipy(c), alpha=0.7, beta=-1.3, thr=1e-3)
+    compare_sparse(C.to_scipy(), ref.to_scipy(), 1e-3)
+
+
+def test_multiply_mixed_real_complex(nt, oracle):
+    n = 120
+    a = random_sparse(n, 0.05, 31, True)
+    b = random_sparse(n, 0.05, 32, False)
+    A, B, C, D = to_gpu(nt, a), to_gpu(nt, b), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    C.Gemm(A, B)
+    D.Gemm(B, A)
+    compare_sparse(C.to_scipy(), oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(b)).to_scipy())
+    compare_sparse(D.to_scipy(), oracle.multiply(oracle.PSMatrix.from_scipy(b), oracle.PSMatrix.from_scipy(a)).to_scipy())
+
+
+def test_multiply_banded_config1_small(nt, oracle):
+    """config 1 shape (banded, 165 nnz/row, thr 1e-8) at a size the oracle finishes in seconds"""
+    n = 2048
+    a = banded(n)
+    A, C = to_gpu(nt, a), nt.Matrix_ps(n)
+    nt.reset_counters()
+    C.Gemm(A, A, None, threshold=1e-8)
+    st = oracle.MultiplyStats()
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(a), thr=1e-8, stats=st)
+    compare_sparse(C.to_scipy(), ref.to_scipy(), 1e-8)
+    assert nt.counters()["flops"] == pytest.approx(st.flops, rel=1e-12)
+    assert nt.counters()["launches"] > 0
+
+
+def test_multiply_wide_rows_use_cta_and_slab_bins(nt, oracle):
+    """windows wider than a warp window / than shared memory exercise bins 5 and 6"""
+    n = 40000
+    rng = np.random.default_rng(5)
+    rows = rng.integers(0, n, 6000)
+    cols = rng.integers(0, n, 6000)
+    a = sp.coo_matrix((rng.standard_normal(6000), (rows, cols)), shape=(n, n)).tocsc()
+    a.sum_duplicates()
+    A, C = to_gpu(nt, a), nt.Matrix_ps(n)
+    C.Gemm(A, A)
+    compare_sparse(C.to_scipy(), a @ a)
+
+
+def test_dense_rule_is_applied_before_alpha(nt, oracle):
+    """dense branch keeps |v|>thr then scales; sparse branch tests |alpha*v| (DenseBranch.f90:14-15, PruneList.f90:27)"""
+    n = 64
+    a = random_sparse(n, 0.5, 41)
+    b = random_sparse(n, 0.5, 42)
+    A, B, C = to_gpu(nt, a), to_gpu(nt, b), nt.Matrix_ps(n)
+    thr, alpha = 0.5, 0.25
+    C.Gemm(A, B, None, alpha=alpha, threshold=thr)
+    st = oracle.MultiplyStats()
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(b), alpha=alpha, thr=thr, stats=st)
+    assert set(st.branches) == {2}
+    compare_sparse(C.to_scipy(), ref.to_scipy(), thr)
+    assert C.GetSize() == ref.nnz()
+    # the sparse rule would have kept far fewer entries
+    full = (a @ b).toarray()
+    assert ref.nnz() == int((abs(full) > thr).sum()) > int((abs(alpha * full) > thr).sum())
