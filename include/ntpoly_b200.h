@@ -1,6 +1,6 @@
 /* ntpoly_b200 — C ABI of the B200-native NTPoly hot path (libntpoly_b200.so).
  *
- * Drop-in boundary: the symbols in sections 1-8 are exactly the `*_wrp` entry
+ * Drop-in boundary: the symbols in sections 1-7 are exactly the `*_wrp` entry
  * points NTPoly's own C ABI exposes for this path (reference headers under
  * /root/reference/Source/C/, Fortran shims under Source/Wrapper/): same names,
  * same argument order, everything by pointer, opaque `int ih[SIZE_wrp]` handles
@@ -17,7 +17,7 @@
  * and ignored — the rank layout comes from ntb_world_init() or the RANK /
  * WORLD_SIZE / LOCAL_RANK environment (one process per GPU, NCCL underneath).
  *
- * Section 9 lists the `ntb_` extensions (bootstrap, bulk triplet transfer,
+ * Section 8 lists the `ntb_` extensions (bootstrap, bulk triplet transfer,
  * counters) that have no counterpart in the reference.
  */
 #ifndef NTPOLY_B200_H
@@ -172,7 +172,7 @@ void ComputeExponential_wrp(const int *ih_Input, int *ih_Output, const int *ih_s
 void GershgorinBounds_wrp(const int *ih_Hamiltonian, double *max_value, double *min_value);
 void PowerBounds_wrp(const int *ih_Hamiltonian, double *max_value, const int *ih_solver_parameters);
 
-/* ---- 9. ntb_ extensions (no counterpart in the reference) ------------------- */
+/* ---- 8. ntb_ extensions (no counterpart in the reference) ------------------- */
 /* bootstrap: rank/size of this process and, for size>1, the 128-byte ncclUniqueId that
  * rank 0 obtained from ntb_nccl_unique_id() and the host broadcast (e.g. torch.distributed). */
 void ntb_nccl_unique_id(void *out128);
@@ -208,6 +208,13 @@ void ntb_SetPermutation(int *ih_this, const int *matrix_dimension, const int *in
  *           [3] block pairs that used the dense-branch rule */
 void ntb_get_counters(double *out4);
 void ntb_reset_counters(void);
+/* compulsory bytes bytes(A)+bytes(B)+bytes(C_kept) accumulated over the local products since the
+ * last reset (A counted once when A and B are the same matrix) */
+double ntb_algorithmic_bytes(void);
+/* device timing of the numeric SpGEMM kernels (CUDA events on the library stream):
+ * enable, run, then read out2 = {total ms, number of timed products}; reading clears the record */
+void ntb_profile_enable(int on);
+void ntb_profile_read(double *out2);
 /* record of the last solver call: [0] loop counter at exit, [1] last monitored value,
  *                                 [2] energy, [3] multiplies, [4] useful flops */
 void ntb_last_solve(double *out5);

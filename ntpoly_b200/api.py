@@ -62,7 +62,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_reset_counters ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_reset_counters ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -81,6 +81,7 @@ def lib():
         L.ntb_GetMatrixLocalSize_ps.restype = c_longlong
         L.ntb_MatrixAlgorithmicBytes_ps.restype = c_longlong
         L.ntb_version.restype = c_char_p
+        L.ntb_algorithmic_bytes.restype = c_double
         L.ntb_set_stream.argtypes = [c_void_p]
         L.ntb_world_init.argtypes = [c_int, c_int, c_void_p]
         L.ntb_nccl_unique_id.argtypes = [c_void_p]
@@ -655,6 +656,20 @@ def counters():
 
 def reset_counters():
     lib().ntb_reset_counters()
+
+
+def algorithmic_bytes():
+    return float(lib().ntb_algorithmic_bytes())
+
+
+def profile_enable(on=True):
+    lib().ntb_profile_enable(c_int(1 if on else 0))
+
+
+def profile_read():
+    out = (c_double * 2)()
+    lib().ntb_profile_read(out)
+    return {"numeric_ms": float(out[0]), "products": int(out[1])}
 
 
 def last_solve():

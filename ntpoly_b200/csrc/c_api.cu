@@ -379,7 +379,24 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; }
+double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }
+void ntb_profile_enable(int on) { ensure_init(); rt().profile = on != 0; }
+void ntb_profile_read(double* out2) {
+  ensure_init();
+  stream_sync();
+  double ms = 0.0;
+  for (auto& pr : rt().prof_events) {
+    float t = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&t, pr.first, pr.second));
+    ms += t;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  out2[0] = ms;
+  out2[1] = (double)rt().prof_events.size();
+  rt().prof_events.clear();
+}
 void ntb_last_solve(double* out5) {
   const SolveRecord& r = last_solve();
   out5[0] = r.loop_counter; out5[1] = r.last_value; out5[2] = r.energy; out5[3] = (double)r.multiplies; out5[4] = r.flops;

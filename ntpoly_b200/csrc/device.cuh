@@ -2,6 +2,7 @@
 // accounting and device-wide scans used by every kernel family.
 #pragma once
 #include "common.cuh"
+#include <utility>
 #include <vector>
 
 namespace ntb {
@@ -15,6 +16,10 @@ struct Runtime {
   double flops_useful = 0.0;       // 2*sum_{(i,k) in A} nnz(B(k,:)) accumulated over multiplies
   unsigned long long multiplies = 0;
   unsigned long long dense_rule_blocks = 0;
+  double alg_bytes = 0.0;          // compulsory bytes of the local products: bytes(A)+bytes(B)+bytes(C_kept)
+  // optional device timing of the dominant (numeric SpGEMM) kernels, for bench.py's roofline
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 Runtime& rt();
 void ensure_init();

@@ -312,6 +312,13 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
   DevBuf<int> tmp_idx((size_t)h_tmp_total);
   DevBuf<T> tmp_val((size_t)h_tmp_total);
 
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (rt().profile) {
+    CUDA_CHECK(cudaEventCreate(&ev0));
+    CUDA_CHECK(cudaEventCreate(&ev1));
+    CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
+  }
+
   for (int b = 1; b <= 4; ++b) {
     if (h_bins[b] == 0) continue;
     const size_t smem = (size_t)WARPS * cfg.wmax[b] * sizeof(T);
@@ -339,6 +346,10 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
                tmp_val.get(), cnt.get(), slab.get());
   }
 
+  if (rt().profile) {
+    CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
+    rt().prof_events.emplace_back(ev0, ev1);
+  }
   exclusive_scan(cnt.get(), Z.outer.get(), ncols);
   int h_nnz = 0;
   d2h(&h_nnz, Z.outer.get() + ncols, 1);
@@ -347,6 +358,16 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
     int blocks = min(div_up((long long)ncols * 32, 256), kNumSMs * 16);
     NTB_LAUNCH((k_compact<T>), blocks, 256, 0, ncols, tmp_off.get(), cnt.get(), Z.outer.get(), tmp_idx.get(),
                tmp_val.get(), Z.inner.get(), Z.val.get());
+  }
+  {
+    auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
+    int h_nx = 0, h_ny = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h_nx, X.outer + X.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+    CUDA_CHECK(cudaMemcpyAsync(&h_ny, Y.outer + Y.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+    stream_sync();
+    double b = csc_bytes(h_nx, X.cols) + csc_bytes(h_nnz, ncols);
+    if (Y.val != X.val) b += csc_bytes(h_ny, Y.cols);   // A counted once when A == B
+    rt().alg_bytes += b;
   }
   if (stats) {
     stats->flops = 2.0 * (double)h_flops * (scalar_traits<T>::is_complex ? 4.0 : 1.0);

@@ -1,0 +1,166 @@
+"""Solver drivers on the CUDA path vs the oracle and vs the reference's golden density:
+identical iteration counts, energy within 1e-8 relative (north_star tolerances)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.io as sio
+import scipy.sparse as sp
+
+from util import banded, compare_sparse, random_sparse
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def to_gpu(nt, m):
+    M = nt.Matrix_ps(m.shape[0], is_complex=np.iscomplexobj(m.data))
+    M.fill_from_scipy(m)
+    return M
+
+
+def params(nt, conv, thr, monitor=True, maxit=None):
+    sp_ = nt.SolverParameters()
+    sp_.SetConvergeDiff(conv)
+    sp_.SetThreshold(thr)
+    sp_.SetMonitorConvergence(monitor)
+    if maxit:
+        sp_.SetMaxIterations(maxit)
+    return sp_
+
+
+def test_premade_matrix_density_golden(nt, oracle):
+    """BASELINE config 2: Examples/PremadeMatrix — NS inverse square root then TRS2; the density must
+    reproduce Density-Reference.mtx, Tr(KH) within 1e-8 relative of the oracle, iteration counts equal."""
+    H = nt.Matrix_ps(os.path.join(GOLD, "premade_Hamiltonian.mtx"))
+    S = nt.Matrix_ps(os.path.join(GOLD, "premade_Overlap.mtx"))
+    D = sio.mmread(os.path.join(GOLD, "premade_Density-Reference.mtx")).toarray()
+    trace = json.load(open(os.path.join(GOLD, "premade_oracle_trace.json")))
+    n = H.GetActualDimension()
+    ISQ, K = nt.Matrix_ps(n), nt.Matrix_ps(n)
+    p = params(nt, 1e-3, 1e-6)
+    nt.reset_counters()
+    nt.SquareRootSolvers.InverseSquareRoot(S, ISQ, p)
+    assert nt.last_solve()["loop_counter"] == trace["isq_loop_counter"]
+    assert nt.counters()["dense_rule_blocks"] > 0            # 7x7 dense inputs take the dense-branch rule
+    p.SetConvergeDiff(1e-5)
+    for name, fn in (("trs2", nt.DensityMatrixSolvers.TRS2), ("trs4", nt.DensityMatrixSolvers.TRS4),
+                     ("pm", nt.DensityMatrixSolvers.PM)):
+        e, mu = fn(H, ISQ, 5.0, K, p)
+        rec = nt.last_solve()
+        assert rec["loop_counter"] == trace[name]["loop_counter"], name
+        assert e == pytest.approx(trace[name]["energy"], rel=1e-8), name
+        assert mu == pytest.approx(trace[name]["mu"], rel=1e-8), name
+        assert np.linalg.norm(K.to_scipy().toarray() - D) <= 1e-4, name
+
+
+def test_premade_with_load_balancing_permutation(nt):
+    """every reference example runs with a random permutation: results are permutation invariant up to
+    threshold effects"""
+    H = nt.Matrix_ps(os.path.join(GOLD, "premade_Hamiltonian.mtx"))
+    S = nt.Matrix_ps(os.path.join(GOLD, "premade_Overlap.mtx"))
+    D = sio.mmread(os.path.join(GOLD, "premade_Density-Reference.mtx")).toarray()
+    n = H.GetActualDimension()
+    perm = nt.Permutation(H.GetLogicalDimension())
+    perm.SetRandomPermutation(seed=3)
+    p = params(nt, 1e-3, 1e-6)
+    p.SetLoadBalance(perm)
+    ISQ, K = nt.Matrix_ps(n), nt.Matrix_ps(n)
+    nt.SquareRootSolvers.InverseSquareRoot(S, ISQ, p)
+    p.SetConvergeDiff(1e-5)
+    e, mu = nt.DensityMatrixSolvers.TRS2(H, ISQ, 5.0, K, p)
+    assert np.linalg.norm(K.to_scipy().toarray() - D) <= 1e-4
+    assert e == pytest.approx(-22.97196, abs=1e-4)
+
+
+def spd_banded(n, w=6, seed=0):
+    rng = np.random.default_rng(seed)
+    a = sp.diags([rng.uniform(0.05, 0.2, n - d) for d in range(1, w + 1)], list(range(1, w + 1)), shape=(n, n))
+    m = a + a.T + sp.identity(n) * 2.0
+    return sp.csc_matrix(m)
+
+
+@pytest.mark.parametrize("thr", [0.0, 1e-7])
+def test_sign_function_iterations_and_result(nt, oracle, thr):
+    n = 600
+    m = sp.csc_matrix(spd_banded(n) - sp.identity(n) * 2.0 + sp.diags(np.where(np.arange(n) % 2 == 0, 1.5, -1.5)))
+    M, Out = to_gpu(nt, m), nt.Matrix_ps(n)
+    p = params(nt, 1e-8, thr)
+    nt.SignSolvers.ComputeSign(M, Out, p)
+    rec = nt.last_solve()
+    ref, info = oracle.sign_function(oracle.PSMatrix.from_scipy(m), oracle.SolverParameters(converge_diff=1e-8, threshold=thr))
+    assert rec["loop_counter"] == info.iterations
+    compare_sparse(Out.to_scipy(), ref.to_scipy(), thr, tol=1e-9)
+    s2 = Out.to_scipy() @ Out.to_scipy()
+    assert abs(s2 - sp.identity(n)).max() < 1e-5               # sign(M)^2 = I
+
+
+@pytest.mark.parametrize("order", [2, 3, 5])
+def test_inverse_square_root_orders(nt, oracle, order):
+    n = 400
+    m = spd_banded(n, seed=1)
+    M, Out = to_gpu(nt, m), nt.Matrix_ps(n)
+    thr = 1e-9
+    p = params(nt, 1e-7, thr)
+    nt.SquareRootSolvers.InverseSquareRoot(M, Out, p, order=order)
+    rec = nt.last_solve()
+    ref, info = oracle.inverse_square_root(oracle.PSMatrix.from_scipy(m), oracle.SolverParameters(converge_diff=1e-7, threshold=thr), order=order)
+    assert rec["loop_counter"] == info.iterations
+    compare_sparse(Out.to_scipy(), ref.to_scipy(), thr, tol=1e-8)
+    z = Out.to_scipy()
+    assert abs(z @ m @ z - sp.identity(n)).max() < 1e-5
+
+
+def test_square_root_and_invert(nt, oracle):
+    n = 300
+    m = spd_banded(n, seed=2)
+    M, R, Inv = to_gpu(nt, m), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    p = params(nt, 1e-8, 1e-10)
+    nt.SquareRootSolvers.SquareRoot(M, R, p)
+    r = R.to_scipy()
+    assert abs(r @ r - m).max() < 1e-6
+    nt.InverseSolvers.Invert(M, Inv, p)
+    rec = nt.last_solve()
+    ref, info = oracle.invert(oracle.PSMatrix.from_scipy(m), oracle.SolverParameters(converge_diff=1e-8, threshold=1e-10))
+    assert rec["loop_counter"] == info.iterations
+    compare_sparse(Inv.to_scipy(), ref.to_scipy(), 1e-10, tol=1e-8)
+    assert abs(Inv.to_scipy() @ m - sp.identity(n)).max() < 1e-6
+
+
+def test_complex_hermitian_invert_and_exponential(nt):
+    """config 5 at the shipped size: Examples/ComplexMatrix/input.mtx (512x512 Hermitian, complex path)"""
+    import scipy.linalg as la
+    g = sp.csc_matrix(sio.mmread(os.path.join(GOLD, "complex_input.mtx")))
+    n = g.shape[0]
+    assert abs(g - g.conj().T).max() < 1e-14
+    shift = float(np.asarray(abs(g).sum(axis=0)).max()) + 1.0
+    m = sp.csc_matrix(g + sp.identity(n) * shift)
+    M, Inv, E = to_gpu(nt, m), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    p = params(nt, 1e-9, 1e-12)
+    nt.InverseSolvers.Invert(M, Inv, p)
+    assert Inv.IsComplex()
+    assert abs(Inv.to_scipy() @ m - sp.identity(n)).max() < 1e-7
+    G = to_gpu(nt, sp.csc_matrix(0.05 * g))
+    pe = params(nt, 1e-9, 1e-10)
+    nt.ExponentialSolvers.ComputeExponential(G, E, pe)
+    expect = la.expm(0.05 * g.toarray())
+    assert np.linalg.norm(E.to_scipy().toarray() - expect) / np.linalg.norm(expect) < 1e-6
+
+
+def test_trs2_banded_medium(nt, oracle):
+    """a sparse-branch purification (banded Hamiltonian, identity overlap): iteration count + energy vs oracle"""
+    n = 1024
+    h = banded(n, half_bandwidth=12, scale=0.2)
+    thr = 1e-7
+    H, ISQ, K = to_gpu(nt, h), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    ISQ.FillIdentity()
+    p = params(nt, 1e-6, thr)
+    e, mu = nt.DensityMatrixSolvers.TRS2(H, ISQ, n // 2, K, p)
+    rec = nt.last_solve()
+    OH = oracle.PSMatrix.from_scipy(h)
+    Kref, info = oracle.trs2(OH, oracle.identity(OH), n // 2, oracle.SolverParameters(converge_diff=1e-6, threshold=thr))
+    assert rec["loop_counter"] == info.iterations
+    assert e == pytest.approx(info.energy, rel=1e-8)
+    assert K.Trace() == pytest.approx(n // 2, abs=1e-3)
+    compare_sparse(K.to_scipy(), Kref.to_scipy(), thr, tol=1e-7)
