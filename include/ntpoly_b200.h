@@ -211,6 +211,10 @@ void ntb_reset_counters(void);
 /* compulsory bytes bytes(A)+bytes(B)+bytes(C_kept) accumulated over the local products since the
  * last reset (A counted once when A and B are the same matrix) */
 double ntb_algorithmic_bytes(void);
+/* out2 = {local products that ran on the FP64 tensor-core tile path, DMMA.8x8x4 instructions issued} */
+void ntb_get_tile_counters(double *out2);
+/* 1 (default): locally dense real products run on the FP64 tensor-core tile path; 0: scalar kernels only */
+void ntb_set_tile_path(int on);
 /* device timing of the numeric SpGEMM kernels (CUDA events on the library stream):
  * enable, run, then read out2 = {total ms, number of timed products}; reading clears the record */
 void ntb_profile_enable(int on);

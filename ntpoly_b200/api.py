@@ -62,7 +62,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_reset_counters ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -656,6 +656,16 @@ def counters():
 
 def reset_counters():
     lib().ntb_reset_counters()
+
+
+def set_tile_path(on=True):
+    lib().ntb_set_tile_path(c_int(1 if on else 0))
+
+
+def tile_counters():
+    out = (c_double * 2)()
+    lib().ntb_get_tile_counters(out)
+    return {"tile_products": int(out[0]), "dmma": float(out[1])}
 
 
 def algorithmic_bytes():

@@ -16,6 +16,8 @@ struct Runtime {
   double flops_useful = 0.0;       // 2*sum_{(i,k) in A} nnz(B(k,:)) accumulated over multiplies
   unsigned long long multiplies = 0;
   unsigned long long dense_rule_blocks = 0;
+  unsigned long long tile_products = 0;  // local products that ran on the DMMA tile path
+  double dmma_issued = 0.0;              // DMMA.8x8x4 instructions (x256 FMAs) issued by the tile path
   double alg_bytes = 0.0;          // compulsory bytes of the local products: bytes(A)+bytes(B)+bytes(C_kept)
   // optional device timing of the dominant (numeric SpGEMM) kernels, for bench.py's roofline
   bool profile = false;

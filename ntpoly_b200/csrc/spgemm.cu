@@ -24,6 +24,16 @@
 
 namespace ntb {
 
+bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alpha, double thr, const RuleView& rules,
+                 LocalCsc<double>& Z, double useful_products, long long nnzX, long long nnzY);
+
+static int g_tile_mode = -1;   // -1: read NTB_TILE once; 0 off; 1 on
+void set_tile_path(int on) { g_tile_mode = on ? 1 : 0; }
+static bool tile_path_enabled() {
+  if (g_tile_mode < 0) { const char* e = std::getenv("NTB_TILE"); g_tile_mode = (e && e[0] == '0') ? 0 : 1; }
+  return g_tile_mode == 1;
+}
+
 constexpr int NBINS = 7;       // 0: empty column, 1..4 warp windows, 5 CTA window, 6 global slab
 constexpr int WARPS = 8;       // warps per CTA in the warp-window kernels
 constexpr int CTA_T = 256;     // threads per CTA in the CTA-window kernels
@@ -309,6 +319,37 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
   CUDA_CHECK(cudaMemcpyAsync(&h_flops, flops.get(), sizeof(h_flops), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
 
+  auto account = [&](long long nnz_out) {
+    auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
+    int h_nx = 0, h_ny = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h_nx, X.outer + X.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+    CUDA_CHECK(cudaMemcpyAsync(&h_ny, Y.outer + Y.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+    stream_sync();
+    double b = csc_bytes(h_nx, X.cols) + csc_bytes(nnz_out, ncols);
+    if (Y.val != X.val) b += csc_bytes(h_ny, Y.cols);   // A counted once when A == B (SURVEY 8d)
+    rt().alg_bytes += b;
+    if (stats) {
+      stats->flops = 2.0 * (double)h_flops * (scalar_traits<T>::is_complex ? 4.0 : 1.0);
+      stats->tmp_entries = h_tmp_total;
+      for (int b2 = 0; b2 < NBINS; ++b2) stats->bins[b2] = h_bins[b2];
+    }
+  };
+
+  if constexpr (!scalar_traits<T>::is_complex) {
+    if (tile_path_enabled() && h_flops > 0) {
+      int h_nx = 0, h_ny = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&h_nx, X.outer + X.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+      CUDA_CHECK(cudaMemcpyAsync(&h_ny, Y.outer + Y.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+      stream_sync();
+      // worth it only when columns are long enough to fill tiles
+      if ((double)h_flops >= 16.0 * (double)ncols &&
+          spgemm_tile(X, Y, alpha, thr, rules, Z, (double)h_flops, h_nx, h_ny)) {
+        account(Z.nnz);
+        return;
+      }
+    }
+  }
+
   DevBuf<int> tmp_idx((size_t)h_tmp_total);
   DevBuf<T> tmp_val((size_t)h_tmp_total);
 
@@ -359,21 +400,7 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
     NTB_LAUNCH((k_compact<T>), blocks, 256, 0, ncols, tmp_off.get(), cnt.get(), Z.outer.get(), tmp_idx.get(),
                tmp_val.get(), Z.inner.get(), Z.val.get());
   }
-  {
-    auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
-    int h_nx = 0, h_ny = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&h_nx, X.outer + X.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-    CUDA_CHECK(cudaMemcpyAsync(&h_ny, Y.outer + Y.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-    stream_sync();
-    double b = csc_bytes(h_nx, X.cols) + csc_bytes(h_nnz, ncols);
-    if (Y.val != X.val) b += csc_bytes(h_ny, Y.cols);   // A counted once when A == B (SURVEY 8d)
-    rt().alg_bytes += b;
-  }
-  if (stats) {
-    stats->flops = 2.0 * (double)h_flops * (scalar_traits<T>::is_complex ? 4.0 : 1.0);
-    stats->tmp_entries = h_tmp_total;
-    for (int b = 0; b < NBINS; ++b) stats->bins[b] = h_bins[b];
-  }
+  account(h_nnz);
 }
 
 template void spgemm<double>(const CscView<double>&, const CscView<double>&, double, double, const RuleView&,

@@ -120,3 +120,46 @@ def test_dense_rule_is_applied_before_alpha(nt, oracle):
     # the sparse rule would have kept far fewer entries
     full = (a @ b).toarray()
     assert ref.nnz() == int((abs(full) > thr).sum()) > int((abs(alpha * full) > thr).sum())
+
+
+@pytest.mark.parametrize("n,hb,thr,alpha", [(2048, 82, 1e-8, 1.0), (3000, 20, 1e-6, -0.7), (1531, 9, 0.0, 1.0)])
+def test_tile_path_matches_scalar_path_and_oracle(nt, oracle, n, hb, thr, alpha):
+    """the FP64 tensor-core tile path (DMMA) and the scalar window kernels must agree with the oracle and
+    with each other on locally dense (banded) operands, including sizes that are not tile multiples"""
+    a = banded(n, half_bandwidth=hb)
+    A, C1, C2 = to_gpu(nt, a), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    nt.set_tile_path(True)
+    nt.reset_counters()
+    C1.Gemm(A, A, None, alpha=alpha, threshold=thr)
+    assert nt.tile_counters()["tile_products"] == 1, "banded product did not take the tile path"
+    nt.set_tile_path(False)
+    nt.reset_counters()
+    C2.Gemm(A, A, None, alpha=alpha, threshold=thr)
+    assert nt.tile_counters()["tile_products"] == 0
+    nt.set_tile_path(True)
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(a), alpha=alpha, thr=thr)
+    compare_sparse(C1.to_scipy(), ref.to_scipy(), thr)
+    compare_sparse(C2.to_scipy(), ref.to_scipy(), thr)
+    compare_sparse(C1.to_scipy(), C2.to_scipy(), thr)
+
+
+def test_tile_path_block_sparse(nt, oracle):
+    from ntpoly_b200.workloads import block_sparse
+    n = 2048
+    a = block_sparse(n, block=32, neighbours=6, band_blocks=8, seed=3)
+    A, C = to_gpu(nt, a), nt.Matrix_ps(n)
+    nt.reset_counters()
+    C.Gemm(A, A, None, threshold=1e-9)
+    assert nt.tile_counters()["tile_products"] == 1
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(a), thr=1e-9)
+    compare_sparse(C.to_scipy(), ref.to_scipy(), 1e-9)
+
+
+def test_scattered_product_stays_on_scalar_path(nt):
+    n = 4096
+    a = random_sparse(n, 0.002, 77)
+    A, C = to_gpu(nt, a), nt.Matrix_ps(n)
+    nt.reset_counters()
+    C.Gemm(A, A)
+    assert nt.tile_counters()["tile_products"] == 0
+    compare_sparse(C.to_scipy(), a @ a)
