@@ -380,7 +380,6 @@ void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
 void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; }
-namespace ntb { void set_tile_path(int on); }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_get_tile_counters(double* out2) { out2[0] = (double)rt().tile_products; out2[1] = rt().dmma_issued; }
 double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }

@@ -71,4 +71,7 @@ template <typename T>
 void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr,
             const RuleView& rules, LocalCsc<T>& Z, GemmStats* stats);
 
+// 1: locally dense real products may run on the DMMA tile path (default), 0: scalar kernels only
+void set_tile_path(int on);
+
 }  // namespace ntb
