@@ -22,7 +22,6 @@ namespace ntb {
 constexpr int BM_WORDS = 64;                 // bitmap words per warp: 2048 tiles of reach per tile column
 constexpr int BM_BITS = BM_WORDS * 32;
 constexpr int TW = 8;                        // warps per CTA
-constexpr int META_CAP = 192;                // K tiles of one J staged in shared memory per pass
 
 struct TileCsc {
   int tr = 0, tc = 0;                        // tile rows x cols (8x4 for A, 4x8 for B)
@@ -142,15 +141,19 @@ static bool build_tiles(const CscView<double>& M, TileCsc& T) {
 }
 
 struct TileView {
-  const int* tptr; const int* tid; const int* first; const int* last; const double* tval; int ntc;
+  const int* tptr; const int* tid; const int4* meta; const double* tval; int ntc;
 };
-static TileView view_of(const TileCsc& T) {
-  return TileView{T.tptr.get(), T.tid.get(), T.first.get(), T.last.get(), T.tval.get(), T.ntc};
+
+// per tile column: {offset of its first tile, tile count, first tile id, last tile id}
+__global__ void __launch_bounds__(256) k_tile_meta(int ntc, const int* __restrict__ tptr, const int* __restrict__ first,
+                                                   const int* __restrict__ last, int4* __restrict__ meta) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < ntc) meta[q] = make_int4(tptr[q], tptr[q + 1] - tptr[q], first[q], last[q]);
 }
 
-// per output tile column J: row-tile window [imin, imax] and the number of DMMAs
-__global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int* __restrict__ imin, int* __restrict__ nI,
-                                                     int* __restrict__ stg64, unsigned long long* __restrict__ ndmma) {
+// per output tile column J: row-tile window aligned to blocks of 8 row tiles, and the DMMA count
+__global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int* __restrict__ imin8, int* __restrict__ nI8,
+                                                     unsigned long long* __restrict__ ndmma) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -158,9 +161,8 @@ __global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int
   for (int J = gw; J < B.ntc; J += nw) {
     int mn = INT_MAX, mx = -1;
     for (int t = B.tptr[J] + lane; t < B.tptr[J + 1]; t += 32) {
-      const int K = B.tid[t];
-      const int cnt = A.tptr[K + 1] - A.tptr[K];
-      if (cnt > 0) { mn = min(mn, A.first[K]); mx = max(mx, A.last[K]); mine += (unsigned long long)cnt; }
+      const int4 m = A.meta[B.tid[t]];
+      if (m.y > 0) { mn = min(mn, m.z); mx = max(mx, m.w); mine += (unsigned long long)m.y; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -168,10 +170,8 @@ __global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int
       mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     }
     if (lane == 0) {
-      const int n = (mx >= 0) ? (mx - mn + 1) : 0;
-      imin[J] = (mx >= 0) ? mn : 0;
-      nI[J] = n;
-      stg64[J] = n;   // staging size in units of 64 doubles (8 columns x 8 rows per row tile)
+      if (mx >= 0) { imin8[J] = (mn >> 3) << 3; nI8[J] = (((mx >> 3) + 1) << 3) - ((mn >> 3) << 3); }
+      else { imin8[J] = 0; nI8[J] = 0; }
     }
   }
 #pragma unroll
@@ -179,69 +179,79 @@ __global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int
   if (lane == 0 && mine) atomicAdd(ndmma, mine);
 }
 
+// groups of 8 tile columns (64 output columns): union of their 64-row block ranges
+__global__ void __launch_bounds__(256) k_group_bounds(int nJ, int nG, const int* __restrict__ imin8, const int* __restrict__ nI8,
+                                                      int* __restrict__ gbmin, int* __restrict__ gnb) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nG) return;
+  int mn = INT_MAX, mx = -1;
+  for (int J = g * 8; J < min(nJ, g * 8 + 8); ++J)
+    if (nI8[J] > 0) { mn = min(mn, imin8[J] >> 3); mx = max(mx, ((imin8[J] + nI8[J]) >> 3) - 1); }
+  gbmin[g] = (mx >= 0) ? mn : 0;
+  gnb[g] = (mx >= 0) ? (mx - mn + 1) : 0;
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// one warp per task = (J, slice of its row-tile window)
+// CTA task = (group of 8 tile columns, block of 8 row tiles) = a 64x64 output block;
+// warp w owns tile column 8g+w: a 64x8 strip with its 8 accumulator tiles in registers.
+// Loop order: B tiles of the column outermost (each loaded once), the <=8 A tiles that meet
+// the strip innermost (consecutive in memory); the 8 warps walk the same A tiles, so they
+// are served by L1 after the first touch.
 __global__ void __launch_bounds__(TW * 32)
-k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin, const int* __restrict__ nI,
-               const long long* __restrict__ stg_off, int nsplit, double* __restrict__ stg) {
-  __shared__ int s_first[TW][META_CAP], s_last[TW][META_CAP], s_base[TW][META_CAP];
+k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int* __restrict__ nI8,
+               const long long* __restrict__ stg_off, const int* __restrict__ gbmin, const int* __restrict__ gtask_off,
+               int nG, double* __restrict__ stg) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int* f = s_first[warp]; int* l = s_last[warp]; int* bs = s_base[warp];
-  const long long ntasks = (long long)B.ntc * nsplit;
-  for (long long task = (long long)blockIdx.x * TW + warp; task < ntasks; task += (long long)gridDim.x * TW) {
-    const int J = (int)(task / nsplit), sp = (int)(task - (long long)J * nsplit);
-    const int n = nI[J];
-    if (n == 0) continue;
-    const int per = (n + nsplit - 1) / nsplit;
-    const int ia = imin[J] + sp * per, ib = min(imin[J] + n, ia + per);
-    if (ia >= ib) continue;
+  const int ntasks = gtask_off[nG];
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    int lo_g = 0, hi_g = nG;               // upper_bound(gtask_off, task) - 1
+    while (lo_g < hi_g) { const int mid = (lo_g + hi_g) >> 1; if (gtask_off[mid + 1] <= task) lo_g = mid + 1; else hi_g = mid; }
+    const int g = lo_g;
+    const int J = g * 8 + warp;
+    if (J >= B.ntc) continue;
+    const int I0 = (gbmin[g] + (task - gtask_off[g])) << 3;
+    const int iw0 = imin8[J], iw1 = iw0 + nI8[J];
+    if (I0 < iw0 || I0 >= iw1) continue;
     const int xb = B.tptr[J], nK = B.tptr[J + 1] - xb;
-    const int wlen = n * 8;
-    double* out = stg + stg_off[J] * 64;
-    for (int k0 = 0; k0 < nK; k0 += META_CAP) {
-      const int kc = min(META_CAP, nK - k0);
-      __syncwarp();
-      for (int t = lane; t < kc; t += 32) {
-        const int K = B.tid[xb + k0 + t];
-        const int yb = A.tptr[K], cnt = A.tptr[K + 1] - yb;
-        const int fi = A.first[K], la = A.last[K];
-        f[t] = fi; l[t] = (cnt > 0) ? la : fi - 1;
-        // contiguous run of row tiles: position = yb + (I - first); otherwise ~yb flags "search the id list"
-        bs[t] = (la - fi + 1 == cnt) ? yb : ~yb;
+    double acc[8][2];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
+    for (int t = 0; t < nK; ++t) {
+      const int4 m = A.meta[B.tid[xb + t]];
+      const int lo = max(m.z, I0), hi = min(m.w, I0 + 7);
+      if (m.y == 0 || lo > hi) continue;
+      unsigned mask;
+      int base;
+      if (m.w - m.z + 1 == m.y) {          // one contiguous run of row tiles
+        mask = ((2u << (hi - I0)) - 1u) & ~((1u << (lo - I0)) - 1u);
+        base = m.x + (lo - m.z);
+      } else {                             // several runs: locate the block inside the sorted id list
+        int l2 = 0, h2 = m.y;
+        while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.tid[m.x + mid] < I0) l2 = mid + 1; else h2 = mid; }
+        const int id = (lane < 8 && l2 + lane < m.y) ? A.tid[m.x + l2 + lane] : INT_MAX;
+        mask = __reduce_or_sync(0xffffffffu, (id < I0 + 8) ? (1u << (id - I0)) : 0u);
+        if (mask == 0u) continue;
+        base = m.x + l2;
       }
-      __syncwarp();
-      for (int I = ia; I < ib; ++I) {
-        double c0 = 0.0, c1 = 0.0;
-#pragma unroll 4
-        for (int t = 0; t < kc; ++t) {
-          if (I < f[t] || I > l[t]) continue;
-          int pos;
-          const int b = bs[t];
-          if (b >= 0) pos = b + (I - f[t]);
-          else {
-            const int yb = ~b;
-            const int K = B.tid[xb + k0 + t];
-            const int cnt = A.tptr[K + 1] - yb;
-            int lo = 0, hi = cnt;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.tid[yb + mid] < I) lo = mid + 1; else hi = mid; }
-            if (lo >= cnt || A.tid[yb + lo] != I) continue;
-            pos = yb + lo;
-          }
-          const double av = A.tval[(size_t)pos * 32 + lane];
-          const double bv = B.tval[(size_t)(xb + k0 + t) * 32 + lane];
-          dmma884(c0, c1, av, bv);
+      const double bv = B.tval[(size_t)(xb + t) * 32 + lane];
+      const double* ap = A.tval + (size_t)base * 32 + lane;
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii)
+        if ((mask >> ii) & 1u) {
+          const double av = ap[(size_t)__popc(mask & ((1u << ii) - 1u)) * 32];
+          dmma884(acc[ii][0], acc[ii][1], av, bv);
         }
-        // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per J
-        const int r = lane >> 2, cc = (lane & 3) * 2;
-        double* o0 = out + (size_t)cc * wlen + (size_t)(I - imin[J]) * 8 + r;
-        double* o1 = o0 + wlen;
-        if (k0 == 0) { *o0 = c0; *o1 = c1; } else { *o0 += c0; *o1 += c1; }
-      }
     }
+    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column
+    const int wlen = nI8[J] * 8;
+    const int r = lane >> 2, cc = (lane & 3) * 2;
+    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) { o[ii * 8] = acc[ii][0]; o[wlen + ii * 8] = acc[ii][1]; }
   }
 }
 
@@ -253,7 +263,7 @@ __device__ __forceinline__ bool tile_rule(const RuleView& r, int inner_idx, int 
 // kept entries per output column (EMIT=false) / ordered emit into CSC (EMIT=true)
 template <bool EMIT>
 __global__ void __launch_bounds__(256)
-k_tile_emit(int ncols, int nrows, const int* __restrict__ imin, const int* __restrict__ nI,
+k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __restrict__ nI8,
             const long long* __restrict__ stg_off, const double* __restrict__ stg, double alpha, double thr,
             RuleView rules, int* __restrict__ cnt, const int* __restrict__ outer, int* __restrict__ inner,
             double* __restrict__ val) {
@@ -262,8 +272,8 @@ k_tile_emit(int ncols, int nrows, const int* __restrict__ imin, const int* __res
   const int nw = (gridDim.x * blockDim.x) >> 5;
   for (int j = gw; j < ncols; j += nw) {
     const int J = j >> 3, jj = j & 7;
-    const int wlen = nI[J] * 8;
-    const int base = imin[J] * 8;
+    const int wlen = nI8[J] * 8;
+    const int base = imin8[J] * 8;
     const double* src = stg + stg_off[J] * 64 + (size_t)jj * wlen;
     int count = 0;
     const int dst = EMIT ? outer[j] : 0;
@@ -299,19 +309,26 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
   if ((double)nnzY < 0.20 * 32.0 * (double)A.ntiles) return false;   // tiles mostly padding
   if (!build_tiles<4, 8>(X, B)) return false;
   if ((double)nnzX < 0.20 * 32.0 * (double)B.ntiles) return false;
-  const int nJ = B.ntc;
-  DevBuf<int> imin((size_t)nJ), nI((size_t)nJ), stg64((size_t)nJ);
+  const int nJ = B.ntc, nG = div_up(nJ, 8);
+  DevBuf<int4> metaA((size_t)A.ntc);
+  NTB_LAUNCH(k_tile_meta, div_up(A.ntc, 256), 256, 0, A.ntc, A.tptr.get(), A.first.get(), A.last.get(), metaA.get());
+  const TileView Av{A.tptr.get(), A.tid.get(), metaA.get(), A.tval.get(), A.ntc};
+  const TileView Bv{B.tptr.get(), B.tid.get(), nullptr, B.tval.get(), B.ntc};
+  DevBuf<int> imin8((size_t)nJ), nI8((size_t)nJ), gbmin((size_t)nG), gnb((size_t)nG), gtask_off((size_t)nG + 1);
   DevBuf<long long> stg_off((size_t)nJ + 1);
   DevBuf<unsigned long long> ndmma(1);
   ndmma.zero();
-  const TileView Av = view_of(A), Bv = view_of(B);
-  NTB_LAUNCH(k_tile_bounds, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, imin.get(),
-             nI.get(), stg64.get(), ndmma.get());
-  exclusive_scan(stg64.get(), stg_off.get(), nJ);
+  NTB_LAUNCH(k_tile_bounds, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, imin8.get(),
+             nI8.get(), ndmma.get());
+  NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), gbmin.get(), gnb.get());
+  exclusive_scan(nI8.get(), stg_off.get(), nJ);        // staging in units of 64 doubles (8 cols x 8 rows per row tile)
+  exclusive_scan(gnb.get(), gtask_off.get(), nG);
   long long h_stg = 0;
   unsigned long long h_ndmma = 0;
+  int h_tasks = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_stg, stg_off.get() + nJ, sizeof(long long), cudaMemcpyDeviceToHost, rt().stream));
   CUDA_CHECK(cudaMemcpyAsync(&h_ndmma, ndmma.get(), sizeof(h_ndmma), cudaMemcpyDeviceToHost, rt().stream));
+  CUDA_CHECK(cudaMemcpyAsync(&h_tasks, gtask_off.get() + nG, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
   // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
   if ((double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
@@ -323,21 +340,16 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
     CUDA_CHECK(cudaEventCreate(&ev1));
     CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
   }
-  {
-    int nsplit = 1;
-    const long long want = (long long)kNumSMs * TW * 8;
-    if ((long long)nJ < want) nsplit = (int)min((long long)8, (want + nJ - 1) / nJ);
-    const long long ntasks = (long long)nJ * nsplit;
-    const int grid = (int)max(1ll, min((ntasks + TW - 1) / TW, (long long)kNumSMs * 8));
-    NTB_LAUNCH(k_tile_numeric, grid, TW * 32, 0, Av, Bv, imin.get(), nI.get(), stg_off.get(), nsplit, stg.get());
-  }
+  if (h_tasks > 0)
+    NTB_LAUNCH(k_tile_numeric, min(h_tasks, kNumSMs * 8), TW * 32, 0, Av, Bv, imin8.get(), nI8.get(), stg_off.get(),
+               gbmin.get(), gtask_off.get(), nG, stg.get());
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
     rt().prof_events.emplace_back(ev0, ev1);
   }
   DevBuf<int> cnt((size_t)ncols);
   const int egrid = max(1, min(div_up((long long)ncols * 32, 256), kNumSMs * 16));
-  NTB_LAUNCH((k_tile_emit<false>), egrid, 256, 0, ncols, nrows, imin.get(), nI.get(), stg_off.get(), stg.get(), alpha,
+  NTB_LAUNCH((k_tile_emit<false>), egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(), alpha,
              thr, rules, cnt.get(), (const int*)nullptr, (int*)nullptr, (double*)nullptr);
   Z.rows = nrows; Z.cols = ncols;
   Z.outer.alloc((size_t)ncols + 1);
@@ -346,7 +358,7 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
   d2h(&h_nnz, Z.outer.get() + ncols, 1);
   Z.alloc_entries(h_nnz);
   if (h_nnz > 0)
-    NTB_LAUNCH((k_tile_emit<true>), egrid, 256, 0, ncols, nrows, imin.get(), nI.get(), stg_off.get(), stg.get(),
+    NTB_LAUNCH((k_tile_emit<true>), egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(),
                alpha, thr, rules, (int*)nullptr, Z.outer.get(), Z.inner.get(), Z.val.get());
   rt().tile_products++;
   rt().dmma_issued += (double)h_ndmma;
