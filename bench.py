@@ -197,7 +197,10 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
     R, C, S = GRIDS[world]
     nt.ConstructGlobalProcessGrid(R, C, S)
-    nt.set_stream(torch.cuda.current_stream().cuda_stream)
+    bench_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(bench_stream)
+    if not os.environ.get('BENCH_OWN_STREAM'):
+        nt.set_stream(bench_stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,7 +247,8 @@ def main():
     barrier()
     nt.reset_counters()
     nt.profile_enable(True)
-    sampler.start()
+    if not os.environ.get('BENCH_NO_SAMPLER'):
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -1,4 +1,6 @@
 #include "device.cuh"
+#include <map>
+#include <unordered_map>
 
 namespace ntb {
 
@@ -21,32 +23,73 @@ void ensure_init() {
     CUDA_CHECK(cudaStreamCreateWithFlags(&g_rt.stream, cudaStreamNonBlocking));
     g_rt.owns_stream = true;
   }
-  // keep freed blocks cached in the stream-ordered pool: the per-iteration
-  // temporaries of the solvers then never hit cudaMalloc again.
-  cudaMemPool_t pool;
-  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t thresh = UINT64_MAX;
-  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
   g_rt.inited = true;
 }
 
 void set_stream(cudaStream_t s) {
   ensure_init();
   if (g_rt.stream) CUDA_CHECK(cudaStreamSynchronize(g_rt.stream));
+  CUDA_CHECK(cudaDeviceSynchronize());   // cached arena blocks may still be in use on the old stream
   if (g_rt.owns_stream && g_rt.stream) CUDA_CHECK(cudaStreamDestroy(g_rt.stream));
   g_rt.stream = s;
   g_rt.owns_stream = false;
 }
 
+// ---------------------------------------------------------------------------
+// Device arena: NTPoly's memory pool idea (scratch that survives across multiplies,
+// reference MatrixMemoryPoolModule.F90 / PMatrixMemoryPoolModule.F90) applied to every
+// temporary of the hot path. All work is ordered on ONE stream, so a block handed back
+// by dfree() can be reused by the next dmalloc() without any synchronisation; after the
+// first iterations of a solver no call reaches cudaMalloc any more.
+// ---------------------------------------------------------------------------
+namespace {
+struct Arena {
+  std::multimap<size_t, void*> free_blocks;          // capacity -> block
+  std::unordered_map<void*, size_t> capacity;        // every live or cached block
+  size_t bytes_reserved = 0;
+  void release_cached() {
+    for (auto& kv : free_blocks) { cudaFree(kv.second); capacity.erase(kv.second); bytes_reserved -= kv.first; }
+    free_blocks.clear();
+  }
+} g_arena;
+
+size_t round_size(size_t bytes) {
+  if (bytes < 512) return 512;
+  if (bytes < (1u << 20)) return (bytes + 511) & ~size_t(511);
+  return (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);   // 2 MiB granules for large blocks
+}
+}  // namespace
+
 void* dmalloc(size_t bytes) {
   ensure_init();
+  const size_t need = round_size(bytes);
+  auto it = g_arena.free_blocks.lower_bound(need);
+  // accept a cached block unless it would waste more than half of itself (keeps the big
+  // staging buffers from being burnt on small requests)
+  if (it != g_arena.free_blocks.end() && (it->first <= 2 * need || it->first - need <= (size_t(4) << 20))) {
+    void* p = it->second;
+    g_arena.free_blocks.erase(it);
+    return p;
+  }
   void* p = nullptr;
-  CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, g_rt.stream));
+  cudaError_t e = cudaMalloc(&p, need);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    CUDA_CHECK(cudaStreamSynchronize(g_rt.stream));
+    g_arena.release_cached();
+    CUDA_CHECK(cudaMalloc(&p, need));
+  }
+  g_arena.capacity[p] = need;
+  g_arena.bytes_reserved += need;
   return p;
 }
 void dfree(void* p) {
-  if (p) CUDA_CHECK(cudaFreeAsync(p, g_rt.stream));
+  if (!p) return;
+  auto it = g_arena.capacity.find(p);
+  NTB_CHECK(it != g_arena.capacity.end(), "dfree of a pointer the arena does not own");
+  g_arena.free_blocks.emplace(it->second, p);
 }
+size_t arena_bytes_reserved() { return g_arena.bytes_reserved; }
 void stream_sync() { CUDA_CHECK(cudaStreamSynchronize(g_rt.stream)); }
 
 // ---------------------------------------------------------------------------

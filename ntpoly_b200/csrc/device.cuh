@@ -30,6 +30,7 @@ void set_stream(cudaStream_t s);
 void* dmalloc(size_t bytes);
 void dfree(void* p);
 void stream_sync();
+size_t arena_bytes_reserved();
 
 // RAII device array on the library stream
 template <typename T> struct DevBuf {
