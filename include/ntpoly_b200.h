@@ -225,6 +225,12 @@ void ntb_last_solve(double *out5);
 /* bytes of this rank's local block as counted for the roofline:
  * nnz*(sizeof(value)+4) + (cols+1)*4    */
 long long ntb_MatrixAlgorithmicBytes_ps(const int *ih_this);
+/* pure host arithmetic, usable without a GPU: the block rank `rank` owns on a rows x cols x slices grid.
+ * out12 = {my_slice, my_row, my_col, logical_dim, local_rows, local_cols, start_row, start_col (0-based),
+ *          row blocks, column blocks, row-communicator colour, column-communicator colour} */
+void ntb_grid_layout(int rank, int size, int rows, int cols, int slices, int matrix_dim, int *out12);
+/* NTPoly's automatic grid for `size` processes: out3 = {rows, cols, slices} (ProcessGridModule.F90:576-638) */
+void ntb_default_grid(int size, int *out3);
 const char *ntb_version(void);
 
 #ifdef __cplusplus

@@ -62,7 +62,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -687,6 +687,21 @@ def last_solve():
     lib().ntb_last_solve(out)
     return {"loop_counter": int(out[0]), "last_value": float(out[1]), "energy": float(out[2]),
             "multiplies": int(out[3]), "flops": float(out[4])}
+
+
+def grid_layout(rank, size, rows, cols, slices, matrix_dim):
+    """Pure host arithmetic (no GPU needed): ownership of `rank` on a rows x cols x slices grid."""
+    out = (c_int * 12)()
+    lib().ntb_grid_layout(c_int(rank), c_int(size), c_int(rows), c_int(cols), c_int(slices), c_int(matrix_dim), out)
+    keys = ["my_slice", "my_row", "my_col", "logical_dim", "local_rows", "local_cols", "start_row", "start_col",
+            "row_blocks", "col_blocks", "row_comm_colour", "col_comm_colour"]
+    return dict(zip(keys, list(out)))
+
+
+def default_grid(size):
+    out = (c_int * 3)()
+    lib().ntb_default_grid(c_int(size), out)
+    return tuple(out)
 
 
 def set_stream(cuda_stream_ptr: int):

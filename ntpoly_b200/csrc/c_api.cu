@@ -407,6 +407,32 @@ long long ntb_MatrixAlgorithmicBytes_ps(const int* ih) {
   const Matrix& M = *get<Matrix>(ih);
   return (long long)(M.is_complex ? M.c.bytes() : M.r.bytes());
 }
+void ntb_grid_layout(int rank, int size, int rows, int cols, int slices, int matrix_dim, int* out12) {
+  // pure host arithmetic (no CUDA, no NCCL): what rank `rank` of a rows x cols x slices grid owns.
+  // ProcessGridModule.F90:180-235, PSMatrixModule.F90:220-234,1596-1618
+  NTB_CHECK(rows * cols * slices == size, "you did not specify a consistent process grid size");
+  ProcessGrid g;
+  g.R = rows; g.C = cols; g.S = slices; g.size = size; g.rank = rank;
+  g.slice_size = size / slices;
+  g.my_slice = rank / g.slice_size;
+  g.my_row = (rank % g.slice_size) / cols;
+  g.my_col = rank % cols;
+  int cbm = (rows / cols) * slices; if (cbm == 0) cbm = slices;
+  int rbm = (cols / rows) * slices; if (rbm == 0) rbm = slices;
+  g.block_multiplier = 1; g.nbc = cbm; g.nbr = rbm;
+  const int N = scaled_dimension(g, matrix_dim);
+  out12[0] = g.my_slice; out12[1] = g.my_row; out12[2] = g.my_col;
+  out12[3] = N; out12[4] = N / rows; out12[5] = N / cols;
+  out12[6] = (N / rows) * g.my_row; out12[7] = (N / cols) * g.my_col;
+  out12[8] = g.nbr; out12[9] = g.nbc;
+  out12[10] = g.my_slice * rows + g.my_row;      // colour of the row communicator
+  out12[11] = g.my_slice * cols + g.my_col;      // colour of the column communicator
+}
+void ntb_default_grid(int size, int* out3) {
+  const int s = compute_num_slices(size);
+  compute_grid_size(size, s, &out3[0], &out3[1]);
+  out3[2] = s;
+}
 const char* ntb_version(void) { return "ntpoly_b200 0.1 (sm_100a)"; }
 
 }  // extern "C"
