@@ -334,7 +334,7 @@ void mat_fill_from_triplets(Matrix& M, const int* rows, const int* cols, const d
     if (!vals_c) { tmp.resize((size_t)n); for (long long i = 0; i < n; ++i) tmp[i] = cplx{vals_r[i], 0.0}; vals_c = tmp.data(); }
     fill_from_triplets_t<cplx>(M, rows, cols, vals_c, n, preduplicated, prepartitioned);
   } else {
-    NTB_CHECK(vals_r != nullptr, "complex triplets into a real matrix");
+    NTB_CHECK(vals_r != nullptr || n == 0, "complex triplets into a real matrix");
     fill_from_triplets_t<double>(M, rows, cols, vals_r, n, preduplicated, prepartitioned);
   }
 }
