@@ -220,15 +220,26 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
     double acc[8][2];
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
+    int4 m_next = (nK > 0) ? A.meta[B.tid[xb]] : make_int4(0, 0, 0, -1);
     for (int t = 0; t < nK; ++t) {
-      const int4 m = A.meta[B.tid[xb + t]];
+      const int4 m = m_next;
+      if (t + 1 < nK) m_next = A.meta[B.tid[xb + t + 1]];   // prefetch: hides the tid -> meta dependency
       const int lo = max(m.z, I0), hi = min(m.w, I0 + 7);
       if (m.y == 0 || lo > hi) continue;
       unsigned mask;
       int base;
-      if (m.w - m.z + 1 == m.y) {          // one contiguous run of row tiles
-        mask = ((2u << (hi - I0)) - 1u) & ~((1u << (lo - I0)) - 1u);
-        base = m.x + (lo - m.z);
+      if (m.w - m.z + 1 == m.y) {          // one contiguous run of row tiles: tile ii sits at a fixed offset
+        const double bv = B.tval[(size_t)(xb + t) * 32 + lane];
+        const double* ap = A.tval + ((long long)m.x + (I0 - m.z)) * 32 + lane;   // tile I0 (may precede the run)
+        const int l0 = lo - I0, h0 = hi - I0;
+        double av[8];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii)
+          if (ii >= l0 && ii <= h0) av[ii] = ap[ii * 32];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii)
+          if (ii >= l0 && ii <= h0) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
+        continue;
       } else {                             // several runs: locate the block inside the sorted id list
         int l2 = 0, h2 = m.y;
         while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.tid[m.x + mid] < I0) l2 = mid + 1; else h2 = mid; }
