@@ -233,6 +233,13 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
         const double* ap = A.tval + ((long long)m.x + (I0 - m.z)) * 32 + lane;   // tile I0 (may precede the run)
         const int l0 = lo - I0, h0 = hi - I0;
         double av[8];
+        if (l0 == 0 && h0 == 7) {            // the run covers the whole 64-row strip: no predicates at all
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) av[ii] = ap[ii * 32];
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
+          continue;
+        }
 #pragma unroll
         for (int ii = 0; ii < 8; ++ii)
           if (ii >= l0 && ii <= h0) av[ii] = ap[ii * 32];
