@@ -179,16 +179,37 @@ __global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int
   if (lane == 0 && mine) atomicAdd(ndmma, mine);
 }
 
-// groups of 8 tile columns (64 output columns): union of their 64-row block ranges
+__device__ __forceinline__ bool tile_rule(const RuleView& r, int inner_idx, int outer_idx) {
+  if (r.tbl == nullptr) return false;
+  return r.tbl[(inner_idx / r.rb) * r.nJ + (outer_idx / r.cb)] != 0;
+}
+
+// groups of 8 tile columns (64 output columns): union of their 64-row block ranges, and the
+// range of inner tile indices K their B tiles span
 __global__ void __launch_bounds__(256) k_group_bounds(int nJ, int nG, const int* __restrict__ imin8, const int* __restrict__ nI8,
-                                                      int* __restrict__ gbmin, int* __restrict__ gnb) {
+                                                      const int4* __restrict__ metaB, int* __restrict__ gbmin,
+                                                      int* __restrict__ gnb, int2* __restrict__ gk) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nG) return;
-  int mn = INT_MAX, mx = -1;
+  int mn = INT_MAX, mx = -1, kmn = INT_MAX, kmx = -1;
   for (int J = g * 8; J < min(nJ, g * 8 + 8); ++J)
-    if (nI8[J] > 0) { mn = min(mn, imin8[J] >> 3); mx = max(mx, ((imin8[J] + nI8[J]) >> 3) - 1); }
+    if (nI8[J] > 0) {
+      mn = min(mn, imin8[J] >> 3); mx = max(mx, ((imin8[J] + nI8[J]) >> 3) - 1);
+      const int4 m = metaB[J];
+      kmn = min(kmn, m.z); kmx = max(kmx, m.w);
+    }
   gbmin[g] = (mx >= 0) ? mn : 0;
   gnb[g] = (mx >= 0) ? (mx - mn + 1) : 0;
+  gk[g] = (kmx >= 0) ? make_int2(kmn, kmx - kmn + 1) : make_int2(0, 0);
+}
+
+// task t = (group g, first row tile of a 64-row block)
+__global__ void __launch_bounds__(256) k_task_table(int nG, const int* __restrict__ gbmin, const int* __restrict__ gtask_off,
+                                                    int2* __restrict__ tasks) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nG) return;
+  const int t0 = gtask_off[g], n = gtask_off[g + 1] - t0;
+  for (int b = 0; b < n; ++b) tasks[t0 + b] = make_int2(g, (gbmin[g] + b) << 3);
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -196,95 +217,268 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// CTA task = (group of 8 tile columns, block of 8 row tiles) = a 64x64 output block;
-// warp w owns tile column 8g+w: a 64x8 strip with its 8 accumulator tiles in registers.
-// Loop order: B tiles of the column outermost (each loaded once), the <=8 A tiles that meet
-// the strip innermost (consecutive in memory); the 8 warps walk the same A tiles, so they
-// are served by L1 after the first touch.
-__global__ void __launch_bounds__(TW * 32)
-k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int* __restrict__ nI8,
-               const long long* __restrict__ stg_off, const int* __restrict__ gbmin, const int* __restrict__ gtask_off,
-               int nG, double* __restrict__ stg) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ntasks = gtask_off[nG];
-  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    int lo_g = 0, hi_g = nG;               // upper_bound(gtask_off, task) - 1
-    while (lo_g < hi_g) { const int mid = (lo_g + hi_g) >> 1; if (gtask_off[mid + 1] <= task) lo_g = mid + 1; else hi_g = mid; }
-    const int g = lo_g;
-    const int J = g * 8 + warp;
-    if (J >= B.ntc) continue;
-    const int I0 = (gbmin[g] + (task - gtask_off[g])) << 3;
-    const int iw0 = imin8[J], iw1 = iw0 + nI8[J];
-    if (I0 < iw0 || I0 >= iw1) continue;
-    const int xb = B.tptr[J], nK = B.tptr[J + 1] - xb;
-    double acc[8][2];
-#pragma unroll
-    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
-    int4 m_next = (nK > 0) ? A.meta[B.tid[xb]] : make_int4(0, 0, 0, -1);
-    for (int t = 0; t < nK; ++t) {
-      const int4 m = m_next;
-      if (t + 1 < nK) m_next = A.meta[B.tid[xb + t + 1]];   // prefetch: hides the tid -> meta dependency
-      const int lo = max(m.z, I0), hi = min(m.w, I0 + 7);
-      if (m.y == 0 || lo > hi) continue;
-      unsigned mask;
-      int base;
-      if (m.w - m.z + 1 == m.y) {          // one contiguous run of row tiles: tile ii sits at a fixed offset
-        const double bv = B.tval[(size_t)(xb + t) * 32 + lane];
-        const double* ap = A.tval + ((long long)m.x + (I0 - m.z)) * 32 + lane;   // tile I0 (may precede the run)
-        const int l0 = lo - I0, h0 = hi - I0;
-        double av[8];
-        if (l0 == 0 && h0 == 7) {            // the run covers the whole 64-row strip: no predicates at all
-#pragma unroll
-          for (int ii = 0; ii < 8; ++ii) av[ii] = ap[ii * 32];
-#pragma unroll
-          for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
-          continue;
-        }
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii)
-          if (ii >= l0 && ii <= h0) av[ii] = ap[ii * 32];
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii)
-          if (ii >= l0 && ii <= h0) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
-        continue;
-      } else {                             // several runs: locate the block inside the sorted id list
-        int l2 = 0, h2 = m.y;
-        while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.tid[m.x + mid] < I0) l2 = mid + 1; else h2 = mid; }
-        const int id = (lane < 8 && l2 + lane < m.y) ? A.tid[m.x + l2 + lane] : INT_MAX;
-        mask = __reduce_or_sync(0xffffffffu, (id < I0 + 8) ? (1u << (id - I0)) : 0u);
-        if (mask == 0u) continue;
-        base = m.x + l2;
-      }
-      const double bv = B.tval[(size_t)(xb + t) * 32 + lane];
-      const double* ap = A.tval + (size_t)base * 32 + lane;
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii)
-        if ((mask >> ii) & 1u) {
-          const double av = ap[(size_t)__popc(mask & ((1u << ii) - 1u)) * 32];
-          dmma884(acc[ii][0], acc[ii][1], av, bv);
-        }
+// ---- mbarrier + bulk-copy (TMA, 1-D) primitives; SASS: SYNCS.*, UBLKCP.S.G
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int KC = 8;                         // inner tiles (of 4 indices) per pipeline stage
+constexpr int NSTAGE = 3;
+constexpr int STAGE_DOUBLES = 2 * KC * 8 * 32;               // A slab [KC][8 row tiles] + B slab [8 tile cols][KC]
+constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;               // 32 KB
+constexpr int META_BYTES = 32;                               // maskA[8] maskB[8] flags g I0 pad
+constexpr int NUMERIC_SMEM = NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES + 2 * NSTAGE * 8;
+constexpr int NUMERIC_THREADS = (TW + 1) * 32;               // 8 DMMA warps + 1 copy warp
+
+// tiles whose ids are the set bits of `mask` lie consecutively in memory from tile `src`; copy those also set in
+// `want` to their natural slots (slot = bit) with as few bulk copies as the id runs allow. Returns nothing: the
+// byte count was announced to the barrier beforehand (256 B per bit of mask & want).
+__device__ __forceinline__ void copy_runs(unsigned mask, unsigned want, long long src, const double* __restrict__ tval,
+                                          unsigned dst_slot0, unsigned bar) {
+  while (mask) {
+    const int b = __ffs(mask) - 1;
+    const int len = __ffs(~(mask >> b)) - 1;             // run of consecutive ids
+    const unsigned runbits = ((1u << len) - 1u) << b;
+    unsigned w = want & runbits;
+    while (w) {
+      const int wb = __ffs(w) - 1;
+      const int wl = __ffs(~(w >> wb)) - 1;
+      bulk_g2s(dst_slot0 + wb * 256, tval + (src + (wb - b)) * 32, wl * 256, bar);
+      w &= ~(((1u << wl) - 1u) << wb);
     }
-    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column
-    const int wlen = nI8[J] * 8;
-    const int r = lane >> 2, cc = (lane & 3) * 2;
-    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
-#pragma unroll
-    for (int ii = 0; ii < 8; ++ii) { o[ii * 8] = acc[ii][0]; o[wlen + ii * 8] = acc[ii][1]; }
+    src += len;
+    mask &= ~runbits;
   }
 }
 
-__device__ __forceinline__ bool tile_rule(const RuleView& r, int inner_idx, int outer_idx) {
-  if (r.tbl == nullptr) return false;
-  return r.tbl[(inner_idx / r.rb) * r.nJ + (outer_idx / r.cb)] != 0;
+// Persistent CTAs; task = 64x64 output block (8 tile columns x 8 row tiles), handed out by an atomic counter.
+// Warp 8 (copy warp): for every chunk of KC inner tiles it works out which A tiles (rows of the block) and which
+// B tiles (columns of the group) exist, publishes the two 8x8 presence masks, and moves the tiles with 1-D bulk
+// copies (TMA) into a 3-stage shared-memory ring guarded by full/empty mbarriers. Warps 0-7: warp w owns tile
+// column 8g+w, i.e. a 64x8 strip with its 8 accumulator tiles in registers, and issues one DMMA.8x8x4 per
+// (present A tile, present B tile) pair from conflict-free 256-byte shared-memory fragments. The strip is
+// written to the dense staging window and the kept-entry counts of its 8 columns are accumulated on the fly
+// (threshold rule fused), so the emit pass is a single sweep.
+__global__ void __launch_bounds__(NUMERIC_THREADS, 2)
+k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int* __restrict__ nI8,
+               const long long* __restrict__ stg_off, const int2* __restrict__ gk, const int2* __restrict__ tasks,
+               int ntasks, int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
+               int nrows, int ncols, double alpha, double thr, RuleView rules) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* slab = reinterpret_cast<double*>(smem);
+  unsigned char* meta = smem + NSTAGE * STAGE_BYTES;
+  const unsigned bar0 = smem_u32(smem + NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES);   // full[s] at +8s, empty[s] at +8(NSTAGE+s)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * (NSTAGE + s), TW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  int st = 0;
+  unsigned ph = 0;
+  if (warp == TW) {
+    // ------------------------------------------------------------------ copy warp
+    for (;;) {
+      int task = 0;
+      if (lane == 0) task = atomicAdd(task_counter, 1);
+      task = __shfl_sync(0xffffffffu, task, 0);
+      const bool done = task >= ntasks;
+      int g = 0, I0 = 0, kmin = 0, nk = 0;
+      if (!done) {
+        const int2 tk = tasks[task];
+        g = tk.x; I0 = tk.y;
+        const int2 k2 = gk[g];
+        kmin = k2.x; nk = k2.y;
+      }
+      // B role (lanes 8..15): tile column J = 8g + lane - 8
+      int4 mb4 = make_int4(0, 0, 0, -1);
+      if (!done && lane >= 8 && lane < 16) {
+        const int J = g * 8 + lane - 8;
+        if (J < B.ntc) {
+          const int iw0 = imin8[J], iw1 = iw0 + nI8[J];
+          if (I0 >= iw0 && I0 < iw1) mb4 = B.meta[J];     // outside the strip's row window: nothing to do
+        }
+      }
+      long long pB = mb4.x;
+      const long long endB = (long long)mb4.x + mb4.y;
+      const bool contigB = (mb4.w - mb4.z + 1 == mb4.y);
+      const int nch = done ? 1 : max(1, (nk + KC - 1) / KC);
+      for (int c = 0; c < nch; ++c) {
+        const int K0 = kmin + c * KC, Kend = min(K0 + KC, kmin + nk);
+        const bool last = (c == nch - 1);
+        unsigned mask = 0;
+        long long src = 0;
+        if (!done) {
+          if (lane < 8) {
+            const int K = K0 + lane;
+            if (K < Kend) {
+              const int4 m = A.meta[K];
+              if (m.y > 0 && m.z <= I0 + 7 && m.w >= I0) {
+                if (m.w - m.z + 1 == m.y) {
+                  const int lo = max(m.z, I0), hi = min(m.w, I0 + 7);
+                  mask = ((1u << (hi - lo + 1)) - 1u) << (lo - I0);
+                  src = (long long)m.x + (lo - m.z);
+                } else {
+                  int l2 = 0, h2 = m.y;
+                  while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.tid[m.x + mid] < I0) l2 = mid + 1; else h2 = mid; }
+                  src = (long long)m.x + l2;
+                  for (int p = l2; p < m.y; ++p) {
+                    const int id = A.tid[m.x + p];
+                    if (id >= I0 + 8) break;
+                    mask |= 1u << (id - I0);
+                  }
+                }
+              }
+            }
+          } else if (lane < 16 && mb4.y > 0) {
+            if (contigB) {
+              const int lo = max(mb4.z, K0), hi = min(mb4.w, Kend - 1);
+              if (lo <= hi) { mask = ((1u << (hi - lo + 1)) - 1u) << (lo - K0); src = (long long)mb4.x + (lo - mb4.z); }
+            } else {
+              src = pB;
+              while (pB < endB) {
+                const int id = B.tid[pB];
+                if (id >= Kend) break;
+                mask |= 1u << (id - K0);
+                ++pB;
+              }
+            }
+          }
+        }
+        // inner tiles that have both an A tile in the block and a B tile in the group
+        const unsigned kA = __ballot_sync(0xffffffffu, lane < 8 && mask != 0u) & 0xffu;
+        const unsigned kB = __reduce_or_sync(0xffffffffu, (lane >= 8 && lane < 16) ? mask : 0u);
+        const unsigned live = kA & kB;
+        if (live == 0u && !last) continue;
+        unsigned want = 0;
+        if (lane < 8) want = ((live >> lane) & 1u) ? mask : 0u;
+        else if (lane < 16) want = mask & live;
+        const unsigned bytes = __reduce_add_sync(0xffffffffu, (unsigned)__popc(want) * 256u);
+        mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
+        unsigned char* mt = meta + st * META_BYTES;
+        if (lane < 16) mt[lane] = (unsigned char)want;
+        if (lane == 16) {
+          int* mi = reinterpret_cast<int*>(mt + 16);
+          mi[0] = (last ? 1 : 0) | (done ? 2 : 0);
+          mi[1] = g;
+          mi[2] = I0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(bar0 + 8 * st, bytes);
+        __syncwarp();
+        if (want) {
+          const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
+          if (lane < 8) copy_runs(mask, want, src, A.tval, slab_s + lane * (8 * 256), bar0 + 8 * st);
+          else copy_runs(mask, want, src, B.tval, slab_s + KC * 8 * 256 + (lane - 8) * (KC * 256), bar0 + 8 * st);
+        }
+        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+      }
+      if (done) break;
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- DMMA warps
+  for (;;) {
+    double acc[8][2];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
+    int g = 0, I0 = 0;
+    unsigned fl = 0;
+    do {
+      mbar_wait(bar0 + 8 * st, ph);
+      const unsigned char* mt = meta + st * META_BYTES;
+      const uint4 mm = *reinterpret_cast<const uint4*>(mt);               // maskA[0..7], maskB[0..7]
+      const int4 mi = *reinterpret_cast<const int4*>(mt + 16);
+      fl = (unsigned)mi.x; g = mi.y; I0 = mi.z;
+      const unsigned mb = ((warp < 4 ? mm.z >> (8 * warp) : mm.w >> (8 * (warp - 4)))) & 0xffu;
+      if (mb) {
+        const double* As = slab + (size_t)st * STAGE_DOUBLES + lane;
+        const double* Bs = As + KC * 8 * 32 + warp * (KC * 32);
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+          const unsigned ma = ((kk < 4 ? mm.x >> (8 * kk) : mm.y >> (8 * (kk - 4)))) & 0xffu;
+          if (((mb >> kk) & 1u) == 0u || ma == 0u) continue;
+          const double bv = Bs[kk * 32];
+          const double* ap = As + kk * (8 * 32);
+          if (ma == 0xffu) {
+            double av[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) av[ii] = ap[ii * 32];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
+          } else {
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii)
+              if ((ma >> ii) & 1u) dmma884(acc[ii][0], acc[ii][1], ap[ii * 32], bv);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (NSTAGE + st));
+      if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+    } while ((fl & 1u) == 0u);
+    if (fl & 2u) break;
+    const int J = g * 8 + warp;
+    if (J >= B.ntc) continue;
+    const int iw0 = imin8[J], nI = nI8[J];
+    if (I0 < iw0 || I0 >= iw0 + nI) continue;
+    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column
+    const int wlen = nI * 8;
+    const int r = lane >> 2, cc = (lane & 3) * 2;
+    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
+    const int j0 = J * 8 + cc;
+    int c0 = 0, c1 = 0;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const double v0 = acc[ii][0], v1 = acc[ii][1];
+      o[ii * 8] = v0;
+      o[wlen + ii * 8] = v1;
+      const int row = (I0 + ii) * 8 + r;
+      if (row < nrows) {
+        if (j0 < ncols) c0 += ((tile_rule(rules, row, j0) ? fabs(v0) : fabs(alpha * v0)) > thr) ? 1 : 0;
+        if (j0 + 1 < ncols) c1 += ((tile_rule(rules, row, j0 + 1) ? fabs(v1) : fabs(alpha * v1)) > thr) ? 1 : 0;
+      }
+    }
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+    }
+    if (lane < 4) {
+      if (c0) atomicAdd(&cnt[j0], c0);
+      if (c1) atomicAdd(&cnt[j0 + 1], c1);
+    }
+  }
 }
 
-// kept entries per output column (EMIT=false) / ordered emit into CSC (EMIT=true)
-template <bool EMIT>
+// ordered emit of the kept entries of every output column into CSC (counts came from the numeric kernel)
 __global__ void __launch_bounds__(256)
 k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __restrict__ nI8,
             const long long* __restrict__ stg_off, const double* __restrict__ stg, double alpha, double thr,
-            RuleView rules, int* __restrict__ cnt, const int* __restrict__ outer, int* __restrict__ inner,
-            double* __restrict__ val) {
+            RuleView rules, const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -294,7 +488,7 @@ k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __re
     const int base = imin8[J] * 8;
     const double* src = stg + stg_off[J] * 64 + (size_t)jj * wlen;
     int count = 0;
-    const int dst = EMIT ? outer[j] : 0;
+    const int dst = outer[j];
     for (int t0 = 0; t0 < wlen; t0 += 32) {
       const int t = t0 + lane;
       bool keep = false;
@@ -305,14 +499,13 @@ k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __re
         keep = (tile_rule(rules, base + t, j) ? fabs(v) : fabs(sv)) > thr;
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (EMIT && keep) {
+      if (keep) {
         const int pos = dst + count + __popc(m & ((1u << lane) - 1));
         inner[pos] = base + t;
         val[pos] = sv;
       }
       count += __popc(m);
     }
-    if (!EMIT && lane == 0) cnt[j] = count;
   }
 }
 
@@ -321,24 +514,27 @@ k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __re
 bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alpha, double thr, const RuleView& rules,
                  LocalCsc<double>& Z, double useful_products, long long nnzX, long long nnzY) {
   const int ncols = X.cols, nrows = Y.rows;
-  if (ncols == 0 || nnzX == 0 || nnzY == 0) return false;
+  if (ncols == 0 || nnzX == 0 || nnzY == 0 || !(thr >= 0.0)) return false;
   TileCsc A, B;
   if (!build_tiles<8, 4>(Y, A)) return false;
   if ((double)nnzY < 0.20 * 32.0 * (double)A.ntiles) return false;   // tiles mostly padding
   if (!build_tiles<4, 8>(X, B)) return false;
   if ((double)nnzX < 0.20 * 32.0 * (double)B.ntiles) return false;
   const int nJ = B.ntc, nG = div_up(nJ, 8);
-  DevBuf<int4> metaA((size_t)A.ntc);
+  DevBuf<int4> metaA((size_t)A.ntc), metaB((size_t)nJ);
   NTB_LAUNCH(k_tile_meta, div_up(A.ntc, 256), 256, 0, A.ntc, A.tptr.get(), A.first.get(), A.last.get(), metaA.get());
+  NTB_LAUNCH(k_tile_meta, div_up(nJ, 256), 256, 0, nJ, B.tptr.get(), B.first.get(), B.last.get(), metaB.get());
   const TileView Av{A.tptr.get(), A.tid.get(), metaA.get(), A.tval.get(), A.ntc};
-  const TileView Bv{B.tptr.get(), B.tid.get(), nullptr, B.tval.get(), B.ntc};
+  const TileView Bv{B.tptr.get(), B.tid.get(), metaB.get(), B.tval.get(), B.ntc};
   DevBuf<int> imin8((size_t)nJ), nI8((size_t)nJ), gbmin((size_t)nG), gnb((size_t)nG), gtask_off((size_t)nG + 1);
+  DevBuf<int2> gk((size_t)nG);
   DevBuf<long long> stg_off((size_t)nJ + 1);
   DevBuf<unsigned long long> ndmma(1);
   ndmma.zero();
   NTB_LAUNCH(k_tile_bounds, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, imin8.get(),
              nI8.get(), ndmma.get());
-  NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), gbmin.get(), gnb.get());
+  NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), metaB.get(), gbmin.get(),
+             gnb.get(), gk.get());
   exclusive_scan(nI8.get(), stg_off.get(), nJ);        // staging in units of 64 doubles (8 cols x 8 rows per row tile)
   exclusive_scan(gnb.get(), gtask_off.get(), nG);
   long long h_stg = 0;
@@ -352,23 +548,33 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
   if ((double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
 
   DevBuf<double> stg((size_t)h_stg * 64);
+  DevBuf<int2> tasks((size_t)max(h_tasks, 1));
+  DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
+  cnt.zero();
+  task_counter.zero();
+  if (h_tasks > 0)
+    NTB_LAUNCH(k_task_table, div_up(nG, 256), 256, 0, nG, gbmin.get(), gtask_off.get(), tasks.get());
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (rt().profile) {
     CUDA_CHECK(cudaEventCreate(&ev0));
     CUDA_CHECK(cudaEventCreate(&ev1));
     CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
   }
-  if (h_tasks > 0)
-    NTB_LAUNCH(k_tile_numeric, min(h_tasks, kNumSMs * 8), TW * 32, 0, Av, Bv, imin8.get(), nI8.get(), stg_off.get(),
-               gbmin.get(), gtask_off.get(), nG, stg.get());
+  if (h_tasks > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_tile_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, NUMERIC_SMEM));
+      attr_set = true;
+    }
+    NTB_LAUNCH(k_tile_numeric, min(h_tasks, kNumSMs * 2), NUMERIC_THREADS, NUMERIC_SMEM, Av, Bv, imin8.get(), nI8.get(),
+               stg_off.get(), gk.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(), nrows, ncols,
+               alpha, thr, rules);
+  }
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
     rt().prof_events.emplace_back(ev0, ev1);
   }
-  DevBuf<int> cnt((size_t)ncols);
   const int egrid = max(1, min(div_up((long long)ncols * 32, 256), kNumSMs * 16));
-  NTB_LAUNCH((k_tile_emit<false>), egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(), alpha,
-             thr, rules, cnt.get(), (const int*)nullptr, (int*)nullptr, (double*)nullptr);
   Z.rows = nrows; Z.cols = ncols;
   Z.outer.alloc((size_t)ncols + 1);
   exclusive_scan(cnt.get(), Z.outer.get(), ncols);
@@ -376,8 +582,8 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
   d2h(&h_nnz, Z.outer.get() + ncols, 1);
   Z.alloc_entries(h_nnz);
   if (h_nnz > 0)
-    NTB_LAUNCH((k_tile_emit<true>), egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(),
-               alpha, thr, rules, (int*)nullptr, Z.outer.get(), Z.inner.get(), Z.val.get());
+    NTB_LAUNCH(k_tile_emit, egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(),
+               alpha, thr, rules, Z.outer.get(), Z.inner.get(), Z.val.get());
   rt().tile_products++;
   rt().dmma_issued += (double)h_ndmma;
   return true;
