@@ -203,13 +203,38 @@ __global__ void __launch_bounds__(256) k_group_bounds(int nJ, int nG, const int*
   gk[g] = (kmx >= 0) ? make_int2(kmn, kmx - kmn + 1) : make_int2(0, 0);
 }
 
-// task t = (group g, first row tile of a 64-row block)
-__global__ void __launch_bounds__(256) k_task_table(int nG, const int* __restrict__ gbmin, const int* __restrict__ gtask_off,
-                                                    int2* __restrict__ tasks) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// task t = (group g, 64-row block): {g, first row tile I0, first live inner tile, live inner tile count | window mask << 24}
+// "live" = the range of inner tiles K whose A tile column meets the rows of the block (dead chunks at both ends of
+// the group's K range are never visited); window mask bit jj = block lies inside the row window of tile column 8g+jj.
+// One warp per group, lanes over its row blocks; the A.meta reads are warp-uniform.
+__global__ void __launch_bounds__(256) k_task_table(int nG, int nJ, const int* __restrict__ gbmin, const int* __restrict__ gtask_off,
+                                                    const int2* __restrict__ gk, const int4* __restrict__ metaA,
+                                                    const int* __restrict__ imin8, const int* __restrict__ nI8,
+                                                    int4* __restrict__ tasks) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= nG) return;
   const int t0 = gtask_off[g], n = gtask_off[g + 1] - t0;
-  for (int b = 0; b < n; ++b) tasks[t0 + b] = make_int2(g, (gbmin[g] + b) << 3);
+  if (n == 0) return;
+  const int2 k2 = gk[g];
+  const int b0 = gbmin[g];
+  for (int bb = 0; bb < n; bb += 32) {
+    const int b = bb + lane;
+    const int I0 = (b0 + b) << 3;
+    int klo = INT_MAX, khi = -1;
+    for (int k = 0; k < k2.y; ++k) {
+      const int4 m = metaA[k2.x + k];
+      if (m.y > 0 && m.z <= I0 + 7 && m.w >= I0) { klo = min(klo, k); khi = k; }
+    }
+    unsigned win = 0;
+    for (int jj = 0; jj < 8; ++jj) {
+      const int J = g * 8 + jj;
+      if (J < nJ) { const int iw0 = imin8[J]; if (I0 >= iw0 && I0 < iw0 + nI8[J]) win |= 1u << jj; }
+    }
+    if (b < n)
+      tasks[t0 + b] = (khi >= 0) ? make_int4(g, I0, k2.x + klo, (khi - klo + 1) | (int)(win << 24))
+                                 : make_int4(g, I0, k2.x, 0 | (int)(win << 24));
+  }
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -242,13 +267,16 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-constexpr int KC = 8;                         // inner tiles (of 4 indices) per pipeline stage
-constexpr int NSTAGE = 3;
-constexpr int STAGE_DOUBLES = 2 * KC * 8 * 32;               // A slab [KC][8 row tiles] + B slab [8 tile cols][KC]
-constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;               // 32 KB
+// pipeline shape: KC inner tiles (of 4 indices) per stage, NSTAGE stages; a stage holds the A slab
+// [KC][8 row tiles] and the B slab [8 tile columns][KC] (KC * 4 KB), 96 KB per CTA, two CTAs per SM
 constexpr int META_BYTES = 32;                               // maskA[8] maskB[8] flags g I0 pad
-constexpr int NUMERIC_SMEM = NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES + 2 * NSTAGE * 8;
-constexpr int NUMERIC_THREADS = (TW + 1) * 32;               // 8 DMMA warps + 1 copy warp
+template <int KC, int NSTAGE> struct PipeCfg {
+  static constexpr int STAGE_DOUBLES = 2 * KC * 8 * 32;
+  static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+  static constexpr int SMEM = NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES + 2 * NSTAGE * 8;
+};
+constexpr int CW = 16;                                       // DMMA warps: 8 tile columns x 2 halves of the row block
+constexpr int NUMERIC_THREADS = (CW + 1) * 32;               // + 1 copy warp
 
 // tiles whose ids are the set bits of `mask` lie consecutively in memory from tile `src`; copy those also set in
 // `want` to their natural slots (slot = bit) with as few bulk copies as the id runs allow. Returns nothing: the
@@ -279,18 +307,21 @@ __device__ __forceinline__ void copy_runs(unsigned mask, unsigned want, long lon
 // (present A tile, present B tile) pair from conflict-free 256-byte shared-memory fragments. The strip is
 // written to the dense staging window and the kept-entry counts of its 8 columns are accumulated on the fly
 // (threshold rule fused), so the emit pass is a single sweep.
+template <int KC, int NSTAGE>
 __global__ void __launch_bounds__(NUMERIC_THREADS, 2)
 k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int* __restrict__ nI8,
-               const long long* __restrict__ stg_off, const int2* __restrict__ gk, const int2* __restrict__ tasks,
+               const long long* __restrict__ stg_off, const int4* __restrict__ tasks,
                int ntasks, int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
                int nrows, int ncols, double alpha, double thr, RuleView rules) {
+  constexpr int STAGE_DOUBLES = PipeCfg<KC, NSTAGE>::STAGE_DOUBLES;
+  constexpr int STAGE_BYTES = PipeCfg<KC, NSTAGE>::STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem[];
   double* slab = reinterpret_cast<double*>(smem);
   unsigned char* meta = smem + NSTAGE * STAGE_BYTES;
   const unsigned bar0 = smem_u32(smem + NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES);   // full[s] at +8s, empty[s] at +8(NSTAGE+s)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * (NSTAGE + s), TW); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * (NSTAGE + s), CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -298,72 +329,71 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
 
   int st = 0;
   unsigned ph = 0;
-  if (warp == TW) {
+  if (warp == CW) {
     // ------------------------------------------------------------------ copy warp
+    const int4 none = make_int4(0, 0, 0, -1);
+    int task = 0;
+    if (lane == 0) task = atomicAdd(task_counter, 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    int4 tk = (task < ntasks) ? tasks[task] : make_int4(0, 0, 0, 0);
     for (;;) {
-      int task = 0;
-      if (lane == 0) task = atomicAdd(task_counter, 1);
-      task = __shfl_sync(0xffffffffu, task, 0);
       const bool done = task >= ntasks;
-      int g = 0, I0 = 0, kmin = 0, nk = 0;
-      if (!done) {
-        const int2 tk = tasks[task];
-        g = tk.x; I0 = tk.y;
-        const int2 k2 = gk[g];
-        kmin = k2.x; nk = k2.y;
-      }
-      // B role (lanes 8..15): tile column J = 8g + lane - 8
-      int4 mb4 = make_int4(0, 0, 0, -1);
-      if (!done && lane >= 8 && lane < 16) {
-        const int J = g * 8 + lane - 8;
-        if (J < B.ntc) {
-          const int iw0 = imin8[J], iw1 = iw0 + nI8[J];
-          if (I0 >= iw0 && I0 < iw1) mb4 = B.meta[J];     // outside the strip's row window: nothing to do
-        }
-      }
+      const int g = tk.x, I0 = tk.y, kmin = tk.z, nk = tk.w & 0xffffff;
+      const unsigned win = (unsigned)tk.w >> 24;
+      // claim the next task now; its table entry is read after this task's chunks are under way
+      int task_n = 0;
+      if (!done && lane == 0) task_n = atomicAdd(task_counter, 1);
+      // B role (lanes 8..15): tile column J = 8g + lane - 8, skipped when the block is outside its row window
+      int4 mb4 = none;
+      if (!done && lane >= 8 && lane < 16 && ((win >> (lane - 8)) & 1u)) mb4 = B.meta[g * 8 + lane - 8];
+      int4 ma_next = (!done && lane < KC && lane < nk) ? A.meta[kmin + lane] : none;
       long long pB = mb4.x;
       const long long endB = (long long)mb4.x + mb4.y;
       const bool contigB = (mb4.w - mb4.z + 1 == mb4.y);
+      if (!contigB) {                               // skip the tiles below the live range
+        while (pB < endB && B.tid[pB] < kmin) ++pB;
+      }
       const int nch = done ? 1 : max(1, (nk + KC - 1) / KC);
+      int4 tk_n = make_int4(0, 0, 0, 0);
       for (int c = 0; c < nch; ++c) {
         const int K0 = kmin + c * KC, Kend = min(K0 + KC, kmin + nk);
         const bool last = (c == nch - 1);
+        const int4 m = ma_next;
+        ma_next = (lane < KC && K0 + KC + lane < kmin + nk) ? A.meta[K0 + KC + lane] : none;
+        if (c == 0 && !done) {
+          task_n = __shfl_sync(0xffffffffu, task_n, 0);
+          tk_n = (task_n < ntasks) ? tasks[task_n] : make_int4(0, 0, 0, 0);
+        }
         unsigned mask = 0;
         long long src = 0;
-        if (!done) {
-          if (lane < 8) {
-            const int K = K0 + lane;
-            if (K < Kend) {
-              const int4 m = A.meta[K];
-              if (m.y > 0 && m.z <= I0 + 7 && m.w >= I0) {
-                if (m.w - m.z + 1 == m.y) {
-                  const int lo = max(m.z, I0), hi = min(m.w, I0 + 7);
-                  mask = ((1u << (hi - lo + 1)) - 1u) << (lo - I0);
-                  src = (long long)m.x + (lo - m.z);
-                } else {
-                  int l2 = 0, h2 = m.y;
-                  while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.tid[m.x + mid] < I0) l2 = mid + 1; else h2 = mid; }
-                  src = (long long)m.x + l2;
-                  for (int p = l2; p < m.y; ++p) {
-                    const int id = A.tid[m.x + p];
-                    if (id >= I0 + 8) break;
-                    mask |= 1u << (id - I0);
-                  }
-                }
+        if (lane < 8) {
+          if (m.y > 0 && m.z <= I0 + 7 && m.w >= I0) {
+            if (m.w - m.z + 1 == m.y) {
+              const int lo = max(m.z, I0), hi = min(m.w, I0 + 7);
+              mask = ((1u << (hi - lo + 1)) - 1u) << (lo - I0);
+              src = (long long)m.x + (lo - m.z);
+            } else {
+              int l2 = 0, h2 = m.y;
+              while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.tid[m.x + mid] < I0) l2 = mid + 1; else h2 = mid; }
+              src = (long long)m.x + l2;
+              for (int p = l2; p < m.y; ++p) {
+                const int id = A.tid[m.x + p];
+                if (id >= I0 + 8) break;
+                mask |= 1u << (id - I0);
               }
             }
-          } else if (lane < 16 && mb4.y > 0) {
-            if (contigB) {
-              const int lo = max(mb4.z, K0), hi = min(mb4.w, Kend - 1);
-              if (lo <= hi) { mask = ((1u << (hi - lo + 1)) - 1u) << (lo - K0); src = (long long)mb4.x + (lo - mb4.z); }
-            } else {
-              src = pB;
-              while (pB < endB) {
-                const int id = B.tid[pB];
-                if (id >= Kend) break;
-                mask |= 1u << (id - K0);
-                ++pB;
-              }
+          }
+        } else if (lane < 16 && mb4.y > 0) {
+          if (contigB) {
+            const int lo = max(mb4.z, K0), hi = min(mb4.w, Kend - 1);
+            if (lo <= hi) { mask = ((1u << (hi - lo + 1)) - 1u) << (lo - K0); src = (long long)mb4.x + (lo - mb4.z); }
+          } else {
+            src = pB;
+            while (pB < endB) {
+              const int id = B.tid[pB];
+              if (id >= Kend) break;
+              mask |= 1u << (id - K0);
+              ++pB;
             }
           }
         }
@@ -396,15 +426,18 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
         if (++st == NSTAGE) { st = 0; ph ^= 1u; }
       }
       if (done) break;
+      task = task_n;
+      tk = tk_n;
     }
     return;
   }
 
   // -------------------------------------------------------------------- DMMA warps
+  const int wj = warp & 7, half = warp >> 3;        // tile column of the group, upper/lower 4 row tiles of the block
   for (;;) {
-    double acc[8][2];
+    double acc[4][2];
 #pragma unroll
-    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
+    for (int ii = 0; ii < 4; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
     int g = 0, I0 = 0;
     unsigned fl = 0;
     do {
@@ -413,26 +446,47 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
       const uint4 mm = *reinterpret_cast<const uint4*>(mt);               // maskA[0..7], maskB[0..7]
       const int4 mi = *reinterpret_cast<const int4*>(mt + 16);
       fl = (unsigned)mi.x; g = mi.y; I0 = mi.z;
-      const unsigned mb = ((warp < 4 ? mm.z >> (8 * warp) : mm.w >> (8 * (warp - 4)))) & 0xffu;
-      if (mb) {
-        const double* As = slab + (size_t)st * STAGE_DOUBLES + lane;
-        const double* Bs = As + KC * 8 * 32 + warp * (KC * 32);
+      const unsigned mb = ((wj < 4 ? mm.z >> (8 * wj) : mm.w >> (8 * (wj - 4)))) & 0xffu;
+      // this warp's 4 row tiles: nibble `half` of every maskA byte
+      const unsigned mlo = (mm.x >> (4 * half)) & 0x0f0f0f0fu, mhi = (mm.y >> (4 * half)) & 0x0f0f0f0fu;
+      if (mb && (mlo | mhi)) {
+        const double* As = slab + (size_t)st * STAGE_DOUBLES + half * (4 * 32) + lane;
+        const double* Bs = slab + (size_t)st * STAGE_DOUBLES + KC * 8 * 32 + wj * (KC * 32) + lane;
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
-          const unsigned ma = ((kk < 4 ? mm.x >> (8 * kk) : mm.y >> (8 * (kk - 4)))) & 0xffu;
+          const unsigned ma = ((kk < 4 ? mlo >> (8 * kk) : mhi >> (8 * (kk - 4)))) & 0xfu;
           if (((mb >> kk) & 1u) == 0u || ma == 0u) continue;
           const double bv = Bs[kk * 32];
           const double* ap = As + kk * (8 * 32);
-          if (ma == 0xffu) {
-            double av[8];
+          if (ma == 0xfu) {
+            double av[4];
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) av[ii] = ap[ii * 32];
+            for (int ii = 0; ii < 4; ++ii) av[ii] = ap[ii * 32];
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
+            for (int ii = 0; ii < 4; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
           } else {
+            // a predicated-off DMMA still occupies the FP64 tensor pipe for its full 16 cycles (measured,
+            // scripts/micro/dmma_shapes.cu), so absent tiles are skipped with real branches: enter the
+            // unrolled sequence at the first tile of each id run, leave it after the last.
+            double av[4];
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii)
-              if ((ma >> ii) & 1u) dmma884(acc[ii][0], acc[ii][1], ap[ii * 32], bv);
+            for (int ii = 0; ii < 4; ++ii)
+              if ((ma >> ii) & 1u) av[ii] = ap[ii * 32];
+            unsigned m = ma;
+#define NTB_RUN_STEP(i) dmma884(acc[i][0], acc[i][1], av[i], bv); if (h0 == i) break;
+            do {
+              const int l0 = __ffs(m) - 1;
+              const int len = __ffs(~(m >> l0)) - 1;
+              const int h0 = l0 + len - 1;
+              m &= ~(((1u << len) - 1u) << l0);
+              switch (l0) {
+                case 0: NTB_RUN_STEP(0)
+                case 1: NTB_RUN_STEP(1)
+                case 2: NTB_RUN_STEP(2)
+                default: dmma884(acc[3][0], acc[3][1], av[3], bv);
+              }
+            } while (m);
+#undef NTB_RUN_STEP
           }
         }
       }
@@ -441,25 +495,39 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
       if (++st == NSTAGE) { st = 0; ph ^= 1u; }
     } while ((fl & 1u) == 0u);
     if (fl & 2u) break;
-    const int J = g * 8 + warp;
+    const int J = g * 8 + wj;
     if (J >= B.ntc) continue;
     const int iw0 = imin8[J], nI = nI8[J];
     if (I0 < iw0 || I0 >= iw0 + nI) continue;
     // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column
     const int wlen = nI * 8;
     const int r = lane >> 2, cc = (lane & 3) * 2;
-    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
+    const int Ih = I0 + 4 * half;
+    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(Ih - iw0) * 8 + r;
     const int j0 = J * 8 + cc;
     int c0 = 0, c1 = 0;
+    if (rules.tbl == nullptr) {                 // sparse rule everywhere: |alpha*v| > thr
+      const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
 #pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {
-      const double v0 = acc[ii][0], v1 = acc[ii][1];
-      o[ii * 8] = v0;
-      o[wlen + ii * 8] = v1;
-      const int row = (I0 + ii) * 8 + r;
-      if (row < nrows) {
-        if (j0 < ncols) c0 += ((tile_rule(rules, row, j0) ? fabs(v0) : fabs(alpha * v0)) > thr) ? 1 : 0;
-        if (j0 + 1 < ncols) c1 += ((tile_rule(rules, row, j0 + 1) ? fabs(v1) : fabs(alpha * v1)) > thr) ? 1 : 0;
+      for (int ii = 0; ii < 4; ++ii) {
+        const double v0 = acc[ii][0], v1 = acc[ii][1];
+        o[ii * 8] = v0;
+        o[wlen + ii * 8] = v1;
+        const bool rin = (Ih + ii) * 8 + r < nrows;
+        c0 += (rin && in0 && fabs(alpha * v0) > thr) ? 1 : 0;
+        c1 += (rin && in1 && fabs(alpha * v1) > thr) ? 1 : 0;
+      }
+    } else {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const double v0 = acc[ii][0], v1 = acc[ii][1];
+        o[ii * 8] = v0;
+        o[wlen + ii * 8] = v1;
+        const int row = (Ih + ii) * 8 + r;
+        if (row < nrows) {
+          if (j0 < ncols) c0 += ((tile_rule(rules, row, j0) ? fabs(v0) : fabs(alpha * v0)) > thr) ? 1 : 0;
+          if (j0 + 1 < ncols) c1 += ((tile_rule(rules, row, j0 + 1) ? fabs(v1) : fabs(alpha * v1)) > thr) ? 1 : 0;
+        }
       }
     }
 #pragma unroll
@@ -548,12 +616,13 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
   if ((double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
 
   DevBuf<double> stg((size_t)h_stg * 64);
-  DevBuf<int2> tasks((size_t)max(h_tasks, 1));
+  DevBuf<int4> tasks((size_t)max(h_tasks, 1));
   DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
   cnt.zero();
   task_counter.zero();
   if (h_tasks > 0)
-    NTB_LAUNCH(k_task_table, div_up(nG, 256), 256, 0, nG, gbmin.get(), gtask_off.get(), tasks.get());
+    NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, nJ, gbmin.get(), gtask_off.get(), gk.get(), metaA.get(),
+               imin8.get(), nI8.get(), tasks.get());
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (rt().profile) {
     CUDA_CHECK(cudaEventCreate(&ev0));
@@ -561,14 +630,21 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
     CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
   }
   if (h_tasks > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_CHECK(cudaFuncSetAttribute(k_tile_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, NUMERIC_SMEM));
-      attr_set = true;
+    static int shape = -1;
+    if (shape < 0) {
+      const char* e = std::getenv("NTB_TILE_PIPE");      // developer knob: 0 = 8x3, 1 = 4x6, 2 = 2x12
+      shape = e ? std::atoi(e) : 0;
+      CUDA_CHECK(cudaFuncSetAttribute((k_tile_numeric<8, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<8, 3>::SMEM));
+      CUDA_CHECK(cudaFuncSetAttribute((k_tile_numeric<4, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<4, 6>::SMEM));
+      CUDA_CHECK(cudaFuncSetAttribute((k_tile_numeric<2, 12>), cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<2, 12>::SMEM));
     }
-    NTB_LAUNCH(k_tile_numeric, min(h_tasks, kNumSMs * 2), NUMERIC_THREADS, NUMERIC_SMEM, Av, Bv, imin8.get(), nI8.get(),
-               stg_off.get(), gk.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(), nrows, ncols,
-               alpha, thr, rules);
+    const int grid = min(h_tasks, kNumSMs * 2);
+#define NTB_NUMERIC_ARGS Av, Bv, imin8.get(), nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), \
+                         cnt.get(), nrows, ncols, alpha, thr, rules
+    if (shape == 0) NTB_LAUNCH((k_tile_numeric<8, 3>), grid, NUMERIC_THREADS, (PipeCfg<8, 3>::SMEM), NTB_NUMERIC_ARGS);
+    else if (shape == 2) NTB_LAUNCH((k_tile_numeric<2, 12>), grid, NUMERIC_THREADS, (PipeCfg<2, 12>::SMEM), NTB_NUMERIC_ARGS);
+    else NTB_LAUNCH((k_tile_numeric<4, 6>), grid, NUMERIC_THREADS, (PipeCfg<4, 6>::SMEM), NTB_NUMERIC_ARGS);
+#undef NTB_NUMERIC_ARGS
   }
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));

@@ -34,6 +34,25 @@ __global__ void __launch_bounds__(256) k(double* out, int iters) {
   for (int i = 0; i < CHAINS; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// 8 live DMMAs + 8 DMMAs under a warp-uniform predicate that is false at run time: do they cost pipe time?
+__global__ void __launch_bounds__(256) kpred(double* out, int iters, int flag) {
+  double a[1] = {threadIdx.x * 1e-3}, b[1] = {1.0 + threadIdx.x * 1e-6};
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = i; c[i][1] = -i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mma884(c[i], a, b);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %4, 0;\n\t@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n\t}"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a[0]), "d"(b[0]), "r"(flag));
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <typename F> float timeit(F f) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   f(); cudaDeviceSynchronize();
@@ -55,6 +74,12 @@ int main() {
     for (int s = 0; s < 4; ++s)
       printf("%s chains=8 blocks/SM=%d: %.3f ms %.2f TFLOP/s  (%.1f clk/inst/SMSP @1.965GHz)\n", nm[s], bps, ms[s],
              2.0 * fma[s] * 8 * iters * blocks * 8 / ms[s] / 1e9, ms[s] * 1e-3 * 1.965e9 / (8.0 * iters * bps * 2));
+  }
+  {
+    float t0 = timeit([&] { k<0, 8><<<148, 256>>>(out, iters); });
+    float t1 = timeit([&] { kpred<<<148, 256>>>(out, iters, 0); });
+    float t2 = timeit([&] { kpred<<<148, 256>>>(out, iters, 1); });
+    printf("8 DMMA: %.3f ms; 8 DMMA + 8 predicated-off: %.3f ms; 8 + 8 predicated-on: %.3f ms\n", t0, t1, t2);
   }
   float m1 = timeit([&] { k<0, 1><<<148, 128>>>(out, iters); });
   printf("m8n8k4 1 chain 1 warp/SMSP: dependent latency %.1f clk\n", m1 * 1e-3 * 1.965e9 / iters);
