@@ -215,6 +215,19 @@ double ntb_algorithmic_bytes(void);
 void ntb_get_tile_counters(double *out2);
 /* 1 (default): locally dense real products run on the FP64 tensor-core tile path; 0: scalar kernels only */
 void ntb_set_tile_path(int on);
+/* 1 (default): MatrixMultiplyShift fuses the identity shift into the product's emit pass; 0: two reference calls */
+void ntb_set_fused_shift(int on);
+/* CSC -> tile-form conversions since the last reset (0 per product once operands carry their tile forms) */
+double ntb_tile_builds(void);
+/* C = alpha*A*B (thresholded), then IncrementMatrix(Identity, C, sigma) with threshold 0 — the call pair of
+ * SignSolversModule.F90:226-229 / SquareRootSolversModule.F90 as one entry point. */
+void ntb_MatrixMultiplyShift_ps(const int *ih_matA, const int *ih_matB, int *ih_matC, const double *alpha,
+                                const double *threshold, const double *sigma, const int *ih_identity,
+                                int *ih_memory_pool);
+/* One pass of the loop body of SignFunction (SignSolversModule.F90:213-234), exactly as the SignFunction_wrp driver
+ * runs it: X advances in place, T1/T2 are work matrices, the return value is ||X_new - X_old||. */
+double ntb_SignIteration(int *ih_X, const int *ih_identity, int *ih_T1, int *ih_T2, const double *alpha_k,
+                         const double *threshold, int *ih_memory_pool);
 /* device timing of the numeric SpGEMM kernels (CUDA events on the library stream):
  * enable, run, then read out2 = {total ms, number of timed products}; reading clears the record */
 void ntb_profile_enable(int on);

@@ -62,7 +62,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_set_fused_shift ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -76,6 +76,8 @@ def lib():
                 "(there is no CPU fallback)")
         L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
         L.MatrixNorm_ps_wrp.restype = c_double
+        L.ntb_tile_builds.restype = c_double
+        L.ntb_SignIteration.restype = c_double
         L.MeasureAsymmetry_ps_wrp.restype = c_double
         L.GetGlobalIsRoot_wrp.restype = c_bool
         L.ntb_GetMatrixLocalSize_ps.restype = c_longlong
@@ -485,6 +487,12 @@ class Matrix_ps:
         lib().MatrixMultiply_ps_wrp(matA.ih, matB.ih, self.ih, _d(alpha), _d(beta), _d(threshold),
                                     memory_pool.ih if memory_pool is not None else None)
 
+    def GemmShift(self, matA, matB, identity, sigma, memory_pool: PMatrixMemoryPool | None = None, alpha=1.0,
+                  threshold=0.0):
+        """this = alpha*matA*matB (thresholded), then this += sigma*identity (the drivers' Gemm + Increment pair)"""
+        lib().ntb_MatrixMultiplyShift_ps(matA.ih, matB.ih, self.ih, _d(alpha), _d(threshold), _d(sigma), identity.ih,
+                                         memory_pool.ih if memory_pool is not None else None)
+
     def Scale(self, constant):
         if isinstance(constant, complex):
             lib().ntb_ScaleMatrixComplex_ps(self.ih, _d(constant.real), _d(constant.imag))
@@ -666,6 +674,20 @@ def tile_counters():
     out = (c_double * 2)()
     lib().ntb_get_tile_counters(out)
     return {"tile_products": int(out[0]), "dmma": float(out[1])}
+
+
+def tile_builds():
+    return int(lib().ntb_tile_builds())
+
+
+def set_fused_shift(on=True):
+    lib().ntb_set_fused_shift(c_int(1 if on else 0))
+
+
+def sign_iteration(X, identity, T1, T2, alpha_k, threshold, memory_pool=None):
+    """one pass of the SignFunction driver's loop body; X advances in place, returns ||X_new - X_old||"""
+    return float(lib().ntb_SignIteration(X.ih, identity.ih, T1.ih, T2.ih, _d(alpha_k), _d(threshold),
+                                         memory_pool.ih if memory_pool is not None else None))
 
 
 def algorithmic_bytes():

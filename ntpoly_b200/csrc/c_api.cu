@@ -379,9 +379,30 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
+void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
+// C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when
+// the product runs on the tile path)
+void ntb_MatrixMultiplyShift_ps(const int* ih_a, const int* ih_b, int* ih_c, const double* alpha, const double* threshold,
+                                const double* sigma, const int* ih_identity, int* ih_pool) {
+  MemoryPool* pool = nullptr;
+  if (ih_pool) { std::memcpy(&pool, ih_pool, sizeof(pool)); }
+  mat_multiply_shift(*get<Matrix>(ih_a), *get<Matrix>(ih_b), *get<Matrix>(ih_c), *alpha, *threshold, *sigma,
+                     *get<Matrix>(ih_identity), pool);
+}
+// one pass of the loop body of SignFunction (the driver's own code, solvers.cu: sign_iteration): X is advanced in
+// place to the next iterate, the returned value is the convergence norm ||X_new - X_old||
+double ntb_SignIteration(int* ih_x, const int* ih_identity, int* ih_t1, int* ih_t2, const double* alpha_k,
+                         const double* threshold, int* ih_pool) {
+  MemoryPool* pool = nullptr;
+  if (ih_pool) { std::memcpy(&pool, ih_pool, sizeof(pool)); }
+  Matrix unused;
+  return sign_iteration(*get<Matrix>(ih_x), *get<Matrix>(ih_identity), *get<Matrix>(ih_t1), *get<Matrix>(ih_t2), unused,
+                        *alpha_k, *threshold, false, pool);
+}
 void ntb_get_tile_counters(double* out2) { out2[0] = (double)rt().tile_products; out2[1] = rt().dmma_issued; }
+double ntb_tile_builds(void) { return (double)rt().tile_builds; }
 double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }
 void ntb_profile_enable(int on) { ensure_init(); rt().profile = on != 0; }
 void ntb_profile_read(double* out2) {

@@ -3,8 +3,27 @@
 // inside a column. nnz is always known on the host.
 #pragma once
 #include "device.cuh"
+#include <memory>
 
 namespace ntb {
+
+// Chunked-tile form of a real local block (spgemm_tile.cu): 8x4 (left operand) or 4x8 (right operand) tiles in
+// DMMA fragment order, grouped into 64x32 / 32x64 super-tiles whose present tiles are contiguous in memory.
+struct ChunkTiles {
+  int ncc = 0;                               // chunk columns: left form ceil(cols/32), right form ceil(cols/64)
+  int nsuper = 0;
+  long long ntiles = 0;
+  DevBuf<int4> colmeta;                      // [ncc]   {first entry, entry count, first id, last id}
+  DevBuf<int4> ent;                          // [nsuper] {id, first tile, mask lo, mask hi}; id = row block (left) / inner chunk (right)
+  DevBuf<double> tval;                       // [ntiles*32] fragment-ordered values
+  DevBuf<int4> kmeta;                        // left form only: per inner tile K {0, tile count, first row tile, last row tile}
+};
+// Both forms of one matrix, built on first use as a product operand or emitted together with a product's result.
+// Immutable once built, so copies of a matrix share them; any change of the entries drops them.
+struct TileForms {
+  ChunkTiles left, right;                    // as the A (Y) operand / as the B (X) operand
+  int has_left = 0, has_right = 0;           // 0 not built, 1 built, -1 cannot be built (pattern reach overflow)
+};
 
 template <typename T> struct LocalCsc {
   int rows = 0;
@@ -13,8 +32,10 @@ template <typename T> struct LocalCsc {
   DevBuf<int> outer;  // [cols+1]
   DevBuf<int> inner;  // [nnz]
   DevBuf<T> val;      // [nnz]
+  mutable std::shared_ptr<TileForms> forms;   // cached tile forms of these very entries (real blocks only)
 
   void init_empty(int r, int c) {
+    forms.reset();
     rows = r; cols = c; nnz = 0;
     outer.alloc((size_t)c + 1);
     outer.zero();
@@ -22,6 +43,7 @@ template <typename T> struct LocalCsc {
     val.alloc(0);
   }
   void alloc_entries(long long count) {
+    forms.reset();
     nnz = count;
     inner.alloc((size_t)count);
     val.alloc((size_t)count);
@@ -35,10 +57,12 @@ template <typename T> struct LocalCsc {
     val.alloc((size_t)nnz);
     d2d(inner.get(), o.inner.get(), (size_t)nnz);
     d2d(val.get(), o.val.get(), (size_t)nnz);
+    forms = o.forms;
   }
   void swap(LocalCsc<T>& o) {
     std::swap(rows, o.rows); std::swap(cols, o.cols); std::swap(nnz, o.nnz);
     std::swap(outer, o.outer); std::swap(inner, o.inner); std::swap(val, o.val);
+    std::swap(forms, o.forms);
   }
   size_t bytes() const {  // algorithmic bytes of this block
     return (size_t)nnz * (sizeof(T) + 4) + ((size_t)cols + 1) * 4;
@@ -62,14 +86,25 @@ struct GemmStats {
   double flops = 0.0;        // 2 * sum over x-entries of len(Y[k]) (real flops; x4 for complex)
   long long tmp_entries = 0; // staging entries written before compaction
   int bins[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool shift_applied = false;  // the DiagShift was fused into the product (tile path only)
 };
 
 // Z = alpha * (Y-columns combined by X): for every outer index j of X,
 // Z(:,j) = sum_k X(k,j) * Y(:,k), entries kept by the threshold rule, sorted.
 // In NTPoly terms (C = A*B in CSC): X = B panel, Y = A panel, Z = C block.
+// Optional fused diagonal shift (the drivers' "Gemm then IncrementMatrix(Identity, C, sigma)" with threshold 0,
+// reference sparse_includes/AddSparseVectors.f90): after thresholding, sigma is added at local positions
+// row == col + dd for col < ncols_diag; a shifted entry is kept iff it is non-zero.
+struct DiagShift {
+  double sigma = 0.0;
+  int dd = 0;            // local row of the diagonal entry of local column 0
+  int ncols_diag = 0;    // local columns whose global index is below the actual (unpadded) dimension
+};
 template <typename T>
-void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr,
-            const RuleView& rules, LocalCsc<T>& Z, GemmStats* stats);
+void spgemm(const LocalCsc<T>& X, const LocalCsc<T>& Y, double alpha, double thr,
+            const RuleView& rules, LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift = nullptr);
+// true when spgemm can apply a DiagShift to this product (real operands on the tile path decide at run time:
+// the caller must check GemmStats::shift_applied)
 
 // 1: locally dense real products may run on the DMMA tile path (default), 0: scalar kernels only
 void set_tile_path(int on);

@@ -166,6 +166,19 @@ template <typename T> __global__ void __launch_bounds__(256) k_scale(T* __restri
 template <typename T> void csc_scale(LocalCsc<T>& M, T c) {
   if (M.nnz == 0) return;
   NTB_LAUNCH((k_scale<T>), min(div_up(M.nnz, 256), kNumSMs * 16), 256, 0, M.val.get(), M.nnz, c);
+  // cached tile forms: scaled in place when this matrix is their only owner, dropped otherwise
+  if constexpr (!scalar_traits<T>::is_complex) {
+    if (M.forms && M.forms.use_count() == 1) {
+      for (ChunkTiles* t : {&M.forms->left, &M.forms->right}) {
+        const int has = (t == &M.forms->left) ? M.forms->has_left : M.forms->has_right;
+        const long long n = t->ntiles * 32;
+        if (has == 1 && n > 0)
+          NTB_LAUNCH((k_scale<double>), min(div_up(n, 256), kNumSMs * 16), 256, 0, t->tval.get(), n, c);
+      }
+      return;
+    }
+  }
+  M.forms.reset();
 }
 __global__ void __launch_bounds__(256) k_conj(cplx* __restrict__ v, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -175,6 +188,7 @@ template <> void csc_conjugate<double>(LocalCsc<double>&) {}
 template <> void csc_conjugate<cplx>(LocalCsc<cplx>& M) {
   if (M.nnz == 0) return;
   NTB_LAUNCH(k_conj, min(div_up(M.nnz, 256), kNumSMs * 16), 256, 0, M.val.get(), M.nnz);
+  M.forms.reset();
 }
 
 // ---------------------------------------------------------------------------

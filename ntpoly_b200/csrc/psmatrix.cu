@@ -580,8 +580,17 @@ __global__ void __launch_bounds__(256) k_rowblock_nnz(const int* __restrict__ in
     atomicAdd(&counts[inner[i] / rb], 1ull);
 }
 
+static int g_fused_shift = -1;
+void set_fused_shift(int on) { g_fused_shift = on ? 1 : 0; }
+static bool fused_shift_enabled() {
+  if (g_fused_shift < 0) { const char* e = std::getenv("NTB_FUSED_SHIFT"); g_fused_shift = (e && e[0] == '0') ? 0 : 1; }
+  return g_fused_shift == 1;
+}
+
+// returns true when the optional diagonal shift `sigma` (C = alpha*A*B + sigma*I, see DiagShift) was fused
 template <typename T>
-static void multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold) {
+static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
+                       double sigma = 0.0) {
   ProcessGrid& g = *A.grid;
   const int S = g.S;
   const double wthr = (S > 1) ? threshold / (S * 1000) : threshold;      // MatrixMultiply.f90:25-29
@@ -651,7 +660,14 @@ static void multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
   Matrix AB;
   mat_construct_empty(AB, A.actual_dim, A.grid, scalar_traits<T>::is_complex);
   GemmStats st;
-  spgemm<T>(X, Y, alpha, wthr, rv, loc<T>(AB), &st);
+  DiagShift ds;
+  const bool want_shift = sigma != 0.0 && S == 1 && std::fabs(beta) < 2.2250738585072014e-308;
+  if (want_shift) {
+    ds.sigma = sigma;
+    ds.dd = A.start_col - A.start_row;        // same block coordinates for A, B and the product
+    ds.ncols_diag = std::max(0, std::min(A.local_cols, A.actual_dim - A.start_col));
+  }
+  spgemm<T>(*Xsrc, *Ysrc, alpha, wthr, rv, loc<T>(AB), &st, want_shift ? &ds : nullptr);
   rt().flops_useful += st.flops;
   rt().multiplies++;
   stream_sync();  // rule (host vector) was an h2d source
@@ -666,6 +682,7 @@ static void multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
     mat_scale(C, beta);
     mat_increment(AB, C, 1.0, 0.0);
   }
+  return st.shift_applied;
 }
 
 void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
@@ -684,6 +701,22 @@ void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, dou
   } else {
     multiply_t<double>(A, B, C, alpha, beta, threshold);
   }
+}
+
+// C = alpha*A*B (thresholded) followed by IncrementMatrix(Identity, C, sigma) with threshold 0 — the pair every
+// Newton-Schulz style driver issues (e.g. SignSolversModule.F90:226-229). The shift is fused into the product's
+// emit pass when the product runs on the tile path; otherwise the two reference calls are made.
+void mat_multiply_shift(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double threshold, double sigma,
+                        const Matrix& Identity, MemoryPool* pool) {
+  NTB_CHECK(A.constructed && B.constructed, "MatrixMultiply on an unconstructed matrix");
+  if (!A.is_complex && !B.is_complex && sigma != 0.0 && fused_shift_enabled()) {
+    NTB_CHECK(A.logical_dim == B.logical_dim && A.grid == B.grid, "MatrixMultiply: operands live on different grids/sizes");
+    if (pool) { pool->rows = A.local_rows; pool->cols = A.local_cols; pool->is_complex = false; pool->constructed = true; }
+    if (multiply_t<double>(A, B, C, alpha, 0.0, threshold, sigma)) return;
+  } else {
+    mat_multiply(A, B, C, alpha, 0.0, threshold, pool);
+  }
+  mat_increment(Identity, C, sigma, 0.0);
 }
 
 void mat_similarity_transform(const Matrix& A, const Matrix& P, const Matrix& PInv, Matrix& Res, MemoryPool* pool,

@@ -411,6 +411,24 @@ void mcweeny_step(const Matrix& D, Matrix& Dout, const Matrix* S, double thresho
 
 // ---------------------------------------------------------------------------
 // sign function / polar decomposition core (SignSolversModule.F90:150-258)
+// One pass of the loop body (:213-234): X <- 0.5*a*X*(3I - a^2 X^T X); returns ||X_new - X_old||.
+// "Gemm then IncrementMatrix(Identity, T1, 3)" is issued as one fused product (mat_multiply_shift).
+double sign_iteration(Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& T2, Matrix& OutT, double alpha_k,
+                      double threshold, bool needs_transpose, MemoryPool* pool) {
+  if (needs_transpose) {
+    mat_transpose(X, OutT);
+    if (OutT.is_complex) mat_conjugate(OutT);
+    mat_multiply_shift(OutT, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool);
+  } else {
+    mat_multiply_shift(X, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool);   // T1 = 3I - a^2 X^2
+  }
+  mat_multiply(X, T1, T2, 0.5 * alpha_k, 0.0, threshold, pool);
+  mat_increment(T2, X, -1.0, 0.0);
+  const double norm_value = mat_norm(X);
+  mat_copy(T2, X);
+  return norm_value;
+}
+
 static void sign_core(const Matrix& In, Matrix& Out, const SolverParameters& p, bool needs_transpose) {
   const double alpha = 1.69770248526;
   Monitor mon;
@@ -433,18 +451,7 @@ static void sign_core(const Matrix& In, Matrix& Out, const SolverParameters& p, 
   for (II = 1; II <= p.max_iterations; ++II) {
     const double alpha_k = std::min(std::sqrt(3.0 / (1.0 + xk + xk * xk)), alpha);
     xk = 0.5 * alpha_k * xk * (3.0 - (alpha_k * alpha_k) * xk * xk);
-    if (needs_transpose) {
-      mat_transpose(X, OutT);
-      if (OutT.is_complex) mat_conjugate(OutT);
-      mat_multiply(OutT, X, T1, -1.0 * alpha_k * alpha_k, 0.0, p.threshold, &pool);
-    } else {
-      mat_multiply(X, X, T1, -1.0 * alpha_k * alpha_k, 0.0, p.threshold, &pool);
-    }
-    mat_increment(Identity, T1, 3.0, 0.0);
-    mat_multiply(X, T1, T2, 0.5 * alpha_k, 0.0, p.threshold, &pool);
-    mat_increment(T2, X, -1.0, 0.0);
-    const double norm_value = mat_norm(X);
-    mat_copy(T2, X);
+    const double norm_value = sign_iteration(X, Identity, T1, T2, OutT, alpha_k, p.threshold, needs_transpose, &pool);
     mon.append(norm_value);
     g_last.last_value = norm_value;
     if (mon.converged(p.be_verbose)) break;
@@ -575,8 +582,7 @@ static void ns_isr_taylor(const Matrix& In, Matrix& Out, const SolverParameters&
   }
   int II = 1;
   for (II = 1; II <= p.max_iterations; ++II) {
-    mat_multiply(Z, Y, X, 1.0, 0.0, p.threshold, &pool);
-    mat_increment(Identity, X, -1.0, 0.0);
+    mat_multiply_shift(Z, Y, X, 1.0, p.threshold, -1.0, Identity, &pool);      // X = Z*Y - I
     const double norm_value = mat_norm(X);
     if (order == 3) {
       mat_multiply(X, X, T, 1.0, 0.0, p.threshold, &pool);
@@ -596,8 +602,7 @@ static void ns_isr_taylor(const Matrix& In, Matrix& Out, const SolverParameters&
       mat_increment(X, T2, 1.0, 0.0);
       mat_increment(T, T2, 1.0, 0.0);
       mat_increment(Identity, T, c, 0.0);
-      mat_multiply(T2, T, X, 1.0, 0.0, p.threshold, &pool);
-      mat_increment(Identity, X, d, 0.0);
+      mat_multiply_shift(T2, T, X, 1.0, p.threshold, d, Identity, &pool);
       mat_scale(X, 35.0 / 128.0);
     }
     // any other order falls through the reference's SELECT CASE without a polynomial step

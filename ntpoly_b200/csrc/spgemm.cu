@@ -24,8 +24,8 @@
 
 namespace ntb {
 
-bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alpha, double thr, const RuleView& rules,
-                 LocalCsc<double>& Z, double useful_products, long long nnzX, long long nnzY);
+bool spgemm_tile(const LocalCsc<double>& X, const LocalCsc<double>& Y, double alpha, double thr, const RuleView& rules,
+                 LocalCsc<double>& Z, double useful_products, const DiagShift* shift);
 
 static int g_tile_mode = -1;   // -1: read NTB_TILE once; 0 off; 1 on
 void set_tile_path(int on) { g_tile_mode = on ? 1 : 0; }
@@ -275,9 +275,11 @@ __global__ void __launch_bounds__(256) k_compact(int ncols, const long long* __r
 
 // ---------------------------------------------------------------------------
 template <typename T>
-void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, const RuleView& rules,
-            LocalCsc<T>& Z, GemmStats* stats) {
+void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double thr, const RuleView& rules,
+            LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift) {
+  const CscView<T> X = Xl.view(), Y = Yl.view();
   NTB_CHECK(X.rows == Y.cols, "spgemm: inner dimensions differ");
+  if (stats) stats->shift_applied = false;
   const int ncols = X.cols;
   const int nrows = Y.rows;
   Z.rows = nrows;
@@ -321,12 +323,8 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
 
   auto account = [&](long long nnz_out) {
     auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
-    int h_nx = 0, h_ny = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&h_nx, X.outer + X.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-    CUDA_CHECK(cudaMemcpyAsync(&h_ny, Y.outer + Y.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-    stream_sync();
-    double b = csc_bytes(h_nx, X.cols) + csc_bytes(nnz_out, ncols);
-    if (Y.val != X.val) b += csc_bytes(h_ny, Y.cols);   // A counted once when A == B
+    double b = csc_bytes(Xl.nnz, X.cols) + csc_bytes(nnz_out, ncols);
+    if (Y.val != X.val) b += csc_bytes(Yl.nnz, Y.cols);   // A counted once when A == B
     rt().alg_bytes += b;
     if (stats) {
       stats->flops = 2.0 * (double)h_flops * (scalar_traits<T>::is_complex ? 4.0 : 1.0);
@@ -337,13 +335,10 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
 
   if constexpr (!scalar_traits<T>::is_complex) {
     if (tile_path_enabled() && h_flops > 0) {
-      int h_nx = 0, h_ny = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&h_nx, X.outer + X.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-      CUDA_CHECK(cudaMemcpyAsync(&h_ny, Y.outer + Y.cols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-      stream_sync();
       // worth it only when columns are long enough to fill tiles
       if ((double)h_flops >= 16.0 * (double)ncols &&
-          spgemm_tile(X, Y, alpha, thr, rules, Z, (double)h_flops, h_nx, h_ny)) {
+          spgemm_tile(Xl, Yl, alpha, thr, rules, Z, (double)h_flops, shift)) {
+        if (stats && shift && shift->sigma != 0.0) stats->shift_applied = true;
         account(Z.nnz);
         return;
       }
@@ -403,9 +398,9 @@ void spgemm(const CscView<T>& X, const CscView<T>& Y, double alpha, double thr, 
   account(h_nnz);
 }
 
-template void spgemm<double>(const CscView<double>&, const CscView<double>&, double, double, const RuleView&,
-                             LocalCsc<double>&, GemmStats*);
-template void spgemm<cplx>(const CscView<cplx>&, const CscView<cplx>&, double, double, const RuleView&,
-                           LocalCsc<cplx>&, GemmStats*);
+template void spgemm<double>(const LocalCsc<double>&, const LocalCsc<double>&, double, double, const RuleView&,
+                             LocalCsc<double>&, GemmStats*, const DiagShift*);
+template void spgemm<cplx>(const LocalCsc<cplx>&, const LocalCsc<cplx>&, double, double, const RuleView&,
+                           LocalCsc<cplx>&, GemmStats*, const DiagShift*);
 
 }  // namespace ntb

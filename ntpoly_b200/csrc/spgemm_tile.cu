@@ -5,169 +5,221 @@
 //
 //   C(:,J) = sum_K  A(:,K) * B(K,J)        J: 8 output columns, K: 4 inner indices
 //
-//   A (the Y operand)  -> tile-CSC of 8x4 tiles, stored in DMMA A-fragment order
-//   B (the X operand)  -> tile-CSC of 4x8 tiles, stored in DMMA B-fragment order
+// Operand layout ("chunked tiles", built per product from CSC):
+//   A (the Y operand): 8x4 tiles in DMMA A-fragment order, grouped into SUPER-TILES of
+//       64 rows x 32 columns (8 row tiles x 8 inner tiles). The present tiles of a super-tile are
+//       contiguous in memory in (inner tile kk, row tile ii) order and described by one
+//       64-bit mask (bit kk*8+ii). Super-tiles are listed per chunk column (32 matrix
+//       columns), row block ascending.
+//   B (the X operand): 4x8 tiles in DMMA B-fragment order, super-tiles of 32 rows x 64
+//       columns (8 inner tiles x 8 tile columns), (tile column jj, inner tile kk) order, mask bit
+//       jj*8+kk, listed per group of 64 output columns, inner chunk ascending.
+//   => the operands of one pipeline stage of the numeric kernel (64x64 output block, 32
+//      inner indices) are exactly TWO contiguous byte ranges: one 1-D bulk copy (TMA) each.
 //   every (row tile I, K, J) triple with both tiles present = ONE mma.sync.m8n8k4.f64
-//   (256 FMAs for 2 coalesced 256-byte loads, accumulators in registers).
+//   (256 FMAs), accumulators in registers.
 //
-// Pipeline: k_tile_count / k_tile_fill (CSC -> tiles, bitmap ranked), k_tile_bounds
-// (row-tile window per J), k_tile_numeric (DMMA), k_tile_kept + scan + k_tile_emit
-// (threshold rule, alpha, ordered compaction into CSC). Exact zeros introduced by tile
-// padding never survive the strict |v| > thr test, so results equal the scalar path up
-// to summation order.
+// Pipeline: k_ct_build (CSC -> chunked tiles, bitmap ranked, 2 passes), k_tile_bounds
+// (row-tile window per J), k_tile_numeric (TMA-fed DMMA, threshold counts fused), scan,
+// k_tile_emit (threshold rule, alpha, ordered compaction into CSC). Exact zeros introduced
+// by tile padding never survive the strict |v| > thr test, so results equal the scalar
+// path up to summation order.
 #include "csc.cuh"
 
 namespace ntb {
 
-constexpr int BM_WORDS = 64;                 // bitmap words per warp: 2048 tiles of reach per tile column
-constexpr int BM_BITS = BM_WORDS * 32;
-constexpr int TW = 8;                        // warps per CTA
+constexpr int TW = 8;                        // warps per CTA in the build kernels
+constexpr int MAXR = 256;                    // super-tiles of reach per chunk column (bitmap words per warp)
+constexpr int IPL = MAXR / 32;               // bitmap words owned by a lane
 
-struct TileCsc {
-  int tr = 0, tc = 0;                        // tile rows x cols (8x4 for A, 4x8 for B)
-  int ntc = 0;                               // number of tile columns
-  long long ntiles = 0;
-  DevBuf<int> tptr;                          // [ntc+1]
-  DevBuf<int> tid;                           // [ntiles] row-tile ids, ascending per tile column
-  DevBuf<int> first, last;                   // [ntc] first / last tile id (last < first when empty)
-  DevBuf<double> tval;                       // [ntiles*32] fragment-ordered values
+struct CtView {
+  const int4* colmeta; const int4* ent; const double* tval; const int4* kmeta; int ncc;
 };
 
-template <int TR, int TC> __device__ __forceinline__ int frag_pos(int r, int c) {
-  // A fragment (8x4): lane = r*4 + c ; B fragment (4x8): lane = c*4 + r
-  return (TR == 8) ? (r * 4 + c) : (c * 4 + r);
-}
+// A: super-tile id = row/64, bit = ((col%32)/4)*8 + (row/8)%8, fragment lane = (row%8)*4 + col%4
+// B: super-tile id = row/32, bit = ((col%64)/8)*8 + (row/4)%8, fragment lane = (col%8)*4 + row%4
+template <bool ISA> struct CtGeom {
+  static constexpr int CW = ISA ? 32 : 64;   // matrix columns per chunk column
+  static constexpr int RB = ISA ? 64 : 32;   // matrix rows per super-tile
+  __device__ static __forceinline__ int bit(int r, int c) {
+    return ISA ? (((c & 31) >> 2) * 8 + ((r >> 3) & 7)) : (((c & 63) >> 3) * 8 + ((r >> 2) & 7));
+  }
+  __device__ static __forceinline__ int frag(int r, int c) { return ISA ? ((r & 7) * 4 + (c & 3)) : ((c & 7) * 4 + (r & 3)); }
+};
 
-// pass 1 (FILL=false): tiles per tile column; pass 2 (FILL=true): ids + values
-template <int TR, int TC, bool FILL>
+__device__ __forceinline__ int popc64(unsigned long long v) { return __popcll(v); }
+
+// pass 1 (FILL=false): super-tile and tile counts per chunk column (+ per-K meta for A);
+// pass 2 (FILL=true): entries + values. One warp per chunk column.
+template <bool ISA, bool FILL>
 __global__ void __launch_bounds__(TW * 32)
-k_tile_build(CscView<double> M, int ntc, int* __restrict__ tcount, int* __restrict__ first, int* __restrict__ last,
-             int* __restrict__ overflow, const int* __restrict__ tptr, int* __restrict__ tid, double* __restrict__ tval) {
-  __shared__ unsigned bm[TW][BM_WORDS];
+k_ct_build(CscView<double> M, int ncc, int* __restrict__ scount, int* __restrict__ tcount, int4* __restrict__ colmeta,
+           int4* __restrict__ kmeta, int nk, int* __restrict__ overflow, const int* __restrict__ sptr,
+           const int* __restrict__ tptr, int4* __restrict__ ent, double* __restrict__ tval) {
+  using G = CtGeom<ISA>;
+  __shared__ unsigned long long bm[TW][MAXR];
+  __shared__ int pre[TW][MAXR];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned* b = bm[warp];
-  for (int q = blockIdx.x * TW + warp; q < ntc; q += gridDim.x * TW) {
-    const int c0 = q * TC, c1 = min(M.cols, c0 + TC);
+  unsigned long long* b = bm[warp];
+  for (int q = blockIdx.x * TW + warp; q < ncc; q += gridDim.x * TW) {
+    const int c0 = q * G::CW, c1 = min(M.cols, c0 + G::CW);
     int rmin = INT_MAX, rmax = -1;
-    if (lane < c1 - c0) {
-      const int s = M.outer[c0 + lane], e = M.outer[c0 + lane + 1];
-      if (e > s) { rmin = M.inner[s]; rmax = M.inner[e - 1]; }
+    for (int c = c0 + lane; c < c1; c += 32) {
+      const int s = M.outer[c], e = M.outer[c + 1];
+      if (e > s) { rmin = min(rmin, M.inner[s]); rmax = max(rmax, M.inner[e - 1]); }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, d));
       rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, d));
     }
-    if (rmax < 0) {
-      if (!FILL && lane == 0) { tcount[q] = 0; first[q] = 0; last[q] = -1; }
-      continue;
-    }
-    const int tmin = rmin / TR, tmax = rmax / TR;
-    if (tmax - tmin + 1 > BM_BITS) {
-      if (!FILL && lane == 0) { tcount[q] = 0; first[q] = 0; last[q] = -1; atomicExch(overflow, 1); }
-      continue;
-    }
-    b[lane] = 0; b[lane + 32] = 0;
-    __syncwarp();
-    for (int c = c0; c < c1; ++c)
-      for (int p = M.outer[c] + lane; p < M.outer[c + 1]; p += 32) {
-        const int t = M.inner[p] / TR - tmin;
-        atomicOr(&b[t >> 5], 1u << (t & 31));
+    const bool empty = rmax < 0;
+    const int idmin = empty ? 0 : rmin / G::RB, idmax = empty ? -1 : rmax / G::RB;
+    const bool over = (idmax - idmin + 1 > MAXR);
+    if (empty || over) {
+      if (!FILL) {
+        if (lane == 0) { scount[q] = 0; tcount[q] = 0; colmeta[q] = make_int4(0, 0, 0, -1); if (over) atomicExch(overflow, 1); }
+        if (ISA && lane < 8 && q * 8 + lane < nk) kmeta[q * 8 + lane] = make_int4(0, 0, 0, -1);
       }
-    __syncwarp();
-    // exclusive prefix of popcounts over the 64 words (2 per lane)
-    const unsigned w0 = b[2 * lane], w1 = b[2 * lane + 1];
-    const int mine = __popc(w0) + __popc(w1);
-    int inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += o;
-    }
-    const int total = __shfl_sync(0xffffffffu, inc, 31);
-    if (!FILL) {
-      if (lane == 0) { tcount[q] = total; first[q] = tmin; last[q] = tmax; }
-      __syncwarp();
       continue;
     }
-    const int base = tptr[q];
-    // tile ids
-    int rank = base + inc - mine;
-    unsigned w = w0;
-    while (w) { const int bit = __ffs(w) - 1; w &= w - 1; tid[rank++] = tmin + 2 * lane * 32 + bit; }
-    w = w1;
-    while (w) { const int bit = __ffs(w) - 1; w &= w - 1; tid[rank++] = tmin + (2 * lane + 1) * 32 + bit; }
-    // word-exclusive prefix back into shared memory (reuse: store prefix in a second array via shuffles)
-    __syncwarp();
-    __shared__ int pre[TW][BM_WORDS];
-    pre[warp][2 * lane] = inc - mine;
-    pre[warp][2 * lane + 1] = inc - mine + __popc(w0);
+#pragma unroll
+    for (int w = 0; w < IPL; ++w) b[lane * IPL + w] = 0ull;
     __syncwarp();
     for (int c = c0; c < c1; ++c)
       for (int p = M.outer[c] + lane; p < M.outer[c + 1]; p += 32) {
         const int r = M.inner[p];
-        const int t = r / TR - tmin;
-        const int rk = pre[warp][t >> 5] + __popc(b[t >> 5] & ((1u << (t & 31)) - 1));
-        tval[((size_t)(base + rk)) * 32 + frag_pos<TR, TC>(r - (r / TR) * TR, c - c0)] = M.val[p];
+        const int bit = G::bit(r, c);           // native 32-bit shared-memory atomics on the two halves of the word
+        atomicOr(reinterpret_cast<unsigned*>(&b[r / G::RB - idmin]) + (bit >> 5), 1u << (bit & 31));
+      }
+    __syncwarp();
+    // lane owns IPL consecutive ids: prefix of non-empty super-tiles and of tiles
+    int ns = 0, nt = 0;
+#pragma unroll
+    for (int w = 0; w < IPL; ++w) { const unsigned long long m = b[lane * IPL + w]; ns += (m != 0ull); nt += popc64(m); }
+    int is = ns, it = nt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int os = __shfl_up_sync(0xffffffffu, is, d), ot = __shfl_up_sync(0xffffffffu, it, d);
+      if (lane >= d) { is += os; it += ot; }
+    }
+    const int tot_s = __shfl_sync(0xffffffffu, is, 31), tot_t = __shfl_sync(0xffffffffu, it, 31);
+    if (!FILL) {
+      if (lane == 0) { scount[q] = tot_s; tcount[q] = tot_t; }
+      if (ISA) {
+        // per inner tile kk of this chunk column: tile count, first and last row tile
+        for (int kk = 0; kk < 8; ++kk) {
+          int cntk = 0, fk = INT_MAX, lk = -1;
+#pragma unroll
+          for (int w = 0; w < IPL; ++w) {
+            const unsigned byte = (unsigned)(b[lane * IPL + w] >> (kk * 8)) & 0xffu;
+            if (byte) {
+              const int base = (idmin + lane * IPL + w) * 8;
+              cntk += __popc(byte);
+              fk = min(fk, base + __ffs(byte) - 1);
+              lk = max(lk, base + 31 - __clz(byte));
+            }
+          }
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            cntk += __shfl_xor_sync(0xffffffffu, cntk, d);
+            fk = min(fk, __shfl_xor_sync(0xffffffffu, fk, d));
+            lk = max(lk, __shfl_xor_sync(0xffffffffu, lk, d));
+          }
+          if (lane == 0 && q * 8 + kk < nk) kmeta[q * 8 + kk] = (cntk > 0) ? make_int4(0, cntk, fk, lk) : make_int4(0, 0, 0, -1);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    const int base_s = sptr[q], base_t = tptr[q];
+    if (lane == 0) colmeta[q] = make_int4(base_s, tot_s, idmin, idmax);
+    int rs = base_s + is - ns, rt_ = it - nt;
+#pragma unroll
+    for (int w = 0; w < IPL; ++w) {
+      const unsigned long long m = b[lane * IPL + w];
+      pre[warp][lane * IPL + w] = rt_;
+      if (m != 0ull) {
+        ent[rs++] = make_int4(idmin + lane * IPL + w, base_t + rt_, (int)(unsigned)(m & 0xffffffffull), (int)(unsigned)(m >> 32));
+        rt_ += popc64(m);
+      }
+    }
+    __syncwarp();
+    for (int c = c0; c < c1; ++c)
+      for (int p = M.outer[c] + lane; p < M.outer[c + 1]; p += 32) {
+        const int r = M.inner[p];
+        const int id = r / G::RB - idmin;
+        const int bit = G::bit(r, c);
+        const int rk = pre[warp][id] + popc64(b[id] & ((1ull << bit) - 1ull));
+        tval[((size_t)(base_t + rk)) * 32 + G::frag(r, c)] = M.val[p];
       }
     __syncwarp();
   }
 }
 
-template <int TR, int TC>
-static bool build_tiles(const CscView<double>& M, TileCsc& T) {
-  T.tr = TR; T.tc = TC;
-  T.ntc = div_up(M.cols, TC);
-  const int ntc = T.ntc;
-  DevBuf<int> tcount((size_t)ntc), overflow(1);
-  T.first.alloc((size_t)ntc); T.last.alloc((size_t)ntc); T.tptr.alloc((size_t)ntc + 1);
+template <bool ISA>
+static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
+  using G = CtGeom<ISA>;
+  T.ncc = div_up(M.cols, G::CW);
+  const int ncc = T.ncc;
+  const int nk = ISA ? div_up(M.cols, 4) : 0;
+  DevBuf<int> scount((size_t)ncc), tcount((size_t)ncc), sptr((size_t)ncc + 1), tptr((size_t)ncc + 1), overflow(1);
+  T.colmeta.alloc((size_t)ncc);
+  if (ISA) T.kmeta.alloc((size_t)nk);
   overflow.zero();
-  const int grid = max(1, min(div_up(ntc, TW), kNumSMs * 8));
-  NTB_LAUNCH((k_tile_build<TR, TC, false>), grid, TW * 32, 0, M, ntc, tcount.get(), T.first.get(), T.last.get(),
-             overflow.get(), (const int*)nullptr, (int*)nullptr, (double*)nullptr);
-  exclusive_scan(tcount.get(), T.tptr.get(), ntc);
-  int h[2] = {0, 0};
-  CUDA_CHECK(cudaMemcpyAsync(&h[0], T.tptr.get() + ntc, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-  CUDA_CHECK(cudaMemcpyAsync(&h[1], overflow.get(), sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  const int grid = max(1, min(div_up(ncc, TW), kNumSMs * 8));
+  NTB_LAUNCH((k_ct_build<ISA, false>), grid, TW * 32, 0, M, ncc, scount.get(), tcount.get(), T.colmeta.get(),
+             ISA ? T.kmeta.get() : (int4*)nullptr, nk, overflow.get(), (const int*)nullptr, (const int*)nullptr,
+             (int4*)nullptr, (double*)nullptr);
+  exclusive_scan(scount.get(), sptr.get(), ncc);
+  exclusive_scan(tcount.get(), tptr.get(), ncc);
+  int h[3] = {0, 0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(&h[0], sptr.get() + ncc, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  CUDA_CHECK(cudaMemcpyAsync(&h[1], tptr.get() + ncc, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  CUDA_CHECK(cudaMemcpyAsync(&h[2], overflow.get(), sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
-  if (h[1]) return false;
-  T.ntiles = h[0];
-  T.tid.alloc((size_t)T.ntiles);
+  if (h[2]) return false;
+  T.nsuper = h[0];
+  T.ntiles = h[1];
+  T.ent.alloc((size_t)max(T.nsuper, 1));
   T.tval.alloc((size_t)T.ntiles * 32);
   T.tval.zero();
-  NTB_LAUNCH((k_tile_build<TR, TC, true>), grid, TW * 32, 0, M, ntc, (int*)nullptr, (int*)nullptr, (int*)nullptr,
-             (int*)nullptr, T.tptr.get(), T.tid.get(), T.tval.get());
+  NTB_LAUNCH((k_ct_build<ISA, true>), grid, TW * 32, 0, M, ncc, (int*)nullptr, (int*)nullptr, T.colmeta.get(),
+             (int4*)nullptr, nk, (int*)nullptr, sptr.get(), tptr.get(), T.ent.get(), T.tval.get());
   return true;
 }
 
-struct TileView {
-  const int* tptr; const int* tid; const int4* meta; const double* tval; int ntc;
-};
-
-// per tile column: {offset of its first tile, tile count, first tile id, last tile id}
-__global__ void __launch_bounds__(256) k_tile_meta(int ntc, const int* __restrict__ tptr, const int* __restrict__ first,
-                                                   const int* __restrict__ last, int4* __restrict__ meta) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < ntc) meta[q] = make_int4(tptr[q], tptr[q + 1] - tptr[q], first[q], last[q]);
-}
-
 // per output tile column J: row-tile window aligned to blocks of 8 row tiles, and the DMMA count
-__global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int* __restrict__ imin8, int* __restrict__ nI8,
-                                                     unsigned long long* __restrict__ ndmma) {
+__global__ void __launch_bounds__(256) k_tile_bounds(CtView A, CtView B, int nJ, int* __restrict__ imin8, int* __restrict__ nI8,
+                                                     unsigned long long* __restrict__ ndmma, int diag_on, int dd,
+                                                     int ncols_diag, int nrows) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
   unsigned long long mine = 0;
-  for (int J = gw; J < B.ntc; J += nw) {
+  for (int J = gw; J < nJ; J += nw) {
+    const int4 cm = B.colmeta[J >> 3];
+    const int jj = J & 7;
     int mn = INT_MAX, mx = -1;
-    for (int t = B.tptr[J] + lane; t < B.tptr[J + 1]; t += 32) {
-      const int4 m = A.meta[B.tid[t]];
-      if (m.y > 0) { mn = min(mn, m.z); mx = max(mx, m.w); mine += (unsigned long long)m.y; }
+    for (int e = lane; e < cm.y; e += 32) {
+      const int4 en = B.ent[cm.x + e];
+      const unsigned long long m = ((unsigned long long)(unsigned)en.w << 32) | (unsigned)en.z;
+      unsigned byte = (unsigned)(m >> (jj * 8)) & 0xffu;
+      while (byte) {
+        const int kk = __ffs(byte) - 1;
+        byte &= byte - 1;
+        const int4 km = A.kmeta[en.x * 8 + kk];
+        if (km.y > 0) { mn = min(mn, km.z); mx = max(mx, km.w); mine += (unsigned long long)km.y; }
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
       mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if (diag_on && J * 8 < ncols_diag) {      // the window must hold the rows of the shifted diagonal entries
+      const int r0 = J * 8 + dd, r1 = min(J * 8 + 7, ncols_diag - 1) + dd;
+      if (r1 >= 0 && r0 < nrows) { mn = min(mn, max(r0, 0) >> 3); mx = max(mx, min(r1, nrows - 1) >> 3); }
     }
     if (lane == 0) {
       if (mx >= 0) { imin8[J] = (mn >> 3) << 3; nI8[J] = (((mx >> 3) + 1) << 3) - ((mn >> 3) << 3); }
@@ -179,62 +231,53 @@ __global__ void __launch_bounds__(256) k_tile_bounds(TileView A, TileView B, int
   if (lane == 0 && mine) atomicAdd(ndmma, mine);
 }
 
+// groups of 8 tile columns (64 output columns): union of their 64-row block ranges
+__global__ void __launch_bounds__(256) k_group_bounds(int nJ, int nG, const int* __restrict__ imin8, const int* __restrict__ nI8,
+                                                      int* __restrict__ gbmin, int* __restrict__ gnb) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nG) return;
+  int mn = INT_MAX, mx = -1;
+  for (int J = g * 8; J < min(nJ, g * 8 + 8); ++J)
+    if (nI8[J] > 0) { mn = min(mn, imin8[J] >> 3); mx = max(mx, ((imin8[J] + nI8[J]) >> 3) - 1); }
+  gbmin[g] = (mx >= 0) ? mn : 0;
+  gnb[g] = (mx >= 0) ? (mx - mn + 1) : 0;
+}
+
+// task t = (group g, 64-row block Ib)
+__global__ void __launch_bounds__(256) k_task_table(int nG, const int* __restrict__ gbmin, const int* __restrict__ gtask_off,
+                                                    int2* __restrict__ tasks) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= nG) return;
+  const int t0 = gtask_off[g], n = gtask_off[g + 1] - t0, b0 = gbmin[g];
+  for (int b = lane; b < n; b += 32) tasks[t0 + b] = make_int2(g, b0 + b);
+}
+
 __device__ __forceinline__ bool tile_rule(const RuleView& r, int inner_idx, int outer_idx) {
   if (r.tbl == nullptr) return false;
   return r.tbl[(inner_idx / r.rb) * r.nJ + (outer_idx / r.cb)] != 0;
 }
 
-// groups of 8 tile columns (64 output columns): union of their 64-row block ranges, and the
-// range of inner tile indices K their B tiles span
-__global__ void __launch_bounds__(256) k_group_bounds(int nJ, int nG, const int* __restrict__ imin8, const int* __restrict__ nI8,
-                                                      const int4* __restrict__ metaB, int* __restrict__ gbmin,
-                                                      int* __restrict__ gnb, int2* __restrict__ gk) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nG) return;
-  int mn = INT_MAX, mx = -1, kmn = INT_MAX, kmx = -1;
-  for (int J = g * 8; J < min(nJ, g * 8 + 8); ++J)
-    if (nI8[J] > 0) {
-      mn = min(mn, imin8[J] >> 3); mx = max(mx, ((imin8[J] + nI8[J]) >> 3) - 1);
-      const int4 m = metaB[J];
-      kmn = min(kmn, m.z); kmx = max(kmx, m.w);
-    }
-  gbmin[g] = (mx >= 0) ? mn : 0;
-  gnb[g] = (mx >= 0) ? (mx - mn + 1) : 0;
-  gk[g] = (kmx >= 0) ? make_int2(kmn, kmx - kmn + 1) : make_int2(0, 0);
+// how an accumulated product entry becomes an output entry: threshold rule, alpha, optional diagonal shift
+struct EmitSpec {
+  double alpha, thr, sigma;
+  int dd, ncols_diag;
+  RuleView rules;
+};
+template <bool RULES>
+__device__ __forceinline__ double final_value(const EmitSpec& e, double v, int row, int col, bool& keep) {
+  double sv = e.alpha * v;
+  keep = ((RULES && tile_rule(e.rules, row, col)) ? fabs(v) : fabs(sv)) > e.thr;
+  if (!keep) sv = 0.0;
+  if (e.sigma != 0.0 && row == col + e.dd && col < e.ncols_diag) { sv += e.sigma; keep = (sv != 0.0); }
+  return sv;
 }
 
-// task t = (group g, 64-row block): {g, first row tile I0, first live inner tile, live inner tile count | window mask << 24}
-// "live" = the range of inner tiles K whose A tile column meets the rows of the block (dead chunks at both ends of
-// the group's K range are never visited); window mask bit jj = block lies inside the row window of tile column 8g+jj.
-// One warp per group, lanes over its row blocks; the A.meta reads are warp-uniform.
-__global__ void __launch_bounds__(256) k_task_table(int nG, int nJ, const int* __restrict__ gbmin, const int* __restrict__ gtask_off,
-                                                    const int2* __restrict__ gk, const int4* __restrict__ metaA,
-                                                    const int* __restrict__ imin8, const int* __restrict__ nI8,
-                                                    int4* __restrict__ tasks) {
-  const int lane = threadIdx.x & 31;
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (g >= nG) return;
-  const int t0 = gtask_off[g], n = gtask_off[g + 1] - t0;
-  if (n == 0) return;
-  const int2 k2 = gk[g];
-  const int b0 = gbmin[g];
-  for (int bb = 0; bb < n; bb += 32) {
-    const int b = bb + lane;
-    const int I0 = (b0 + b) << 3;
-    int klo = INT_MAX, khi = -1;
-    for (int k = 0; k < k2.y; ++k) {
-      const int4 m = metaA[k2.x + k];
-      if (m.y > 0 && m.z <= I0 + 7 && m.w >= I0) { klo = min(klo, k); khi = k; }
-    }
-    unsigned win = 0;
-    for (int jj = 0; jj < 8; ++jj) {
-      const int J = g * 8 + jj;
-      if (J < nJ) { const int iw0 = imin8[J]; if (I0 >= iw0 && I0 < iw0 + nI8[J]) win |= 1u << jj; }
-    }
-    if (b < n)
-      tasks[t0 + b] = (khi >= 0) ? make_int4(g, I0, k2.x + klo, (khi - klo + 1) | (int)(win << 24))
-                                 : make_int4(g, I0, k2.x, 0 | (int)(win << 24));
-  }
+// out-of-line: keeps the (rare) rule-table / shifted-diagonal test out of the numeric kernel's hot code
+__device__ __noinline__ bool keep_general(const EmitSpec& e, double v, int row, int col) {
+  bool keep;
+  (void)final_value<true>(e, v, row, col, keep);
+  return keep;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -267,54 +310,67 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// pipeline shape: KC inner tiles (of 4 indices) per stage, NSTAGE stages; a stage holds the A slab
-// [KC][8 row tiles] and the B slab [8 tile columns][KC] (KC * 4 KB), 96 KB per CTA, two CTAs per SM
-constexpr int META_BYTES = 32;                               // maskA[8] maskB[8] flags g I0 pad
-template <int KC, int NSTAGE> struct PipeCfg {
-  static constexpr int STAGE_DOUBLES = 2 * KC * 8 * 32;
-  static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
-  static constexpr int SMEM = NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES + 2 * NSTAGE * 8;
-};
-constexpr int CW = 16;                                       // DMMA warps: 8 tile columns x 2 halves of the row block
+// pipeline shape: a stage = one A super-tile (<= 64 tiles, 16 KB) + one B super-tile (16 KB); 3 stages = 96 KB per
+// CTA, two CTAs per SM
+constexpr int NSTAGE = 3;
+constexpr int SLAB_DOUBLES = 64 * 32;                        // one super-tile, all tiles present
+constexpr int STAGE_DOUBLES = 2 * SLAB_DOUBLES;
+constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;               // 32 KB
+constexpr int META_BYTES = 32;                               // maskA (8 B), maskB (8 B), flags, g, Ib, pad
+constexpr int NUMERIC_SMEM = NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES + 2 * NSTAGE * 8;
+constexpr int CW = 8;                                        // DMMA warps: one per tile column of the group
 constexpr int NUMERIC_THREADS = (CW + 1) * 32;               // + 1 copy warp
 
-// tiles whose ids are the set bits of `mask` lie consecutively in memory from tile `src`; copy those also set in
-// `want` to their natural slots (slot = bit) with as few bulk copies as the id runs allow. Returns nothing: the
-// byte count was announced to the barrier beforehand (256 B per bit of mask & want).
-__device__ __forceinline__ void copy_runs(unsigned mask, unsigned want, long long src, const double* __restrict__ tval,
-                                          unsigned dst_slot0, unsigned bar) {
-  while (mask) {
-    const int b = __ffs(mask) - 1;
-    const int len = __ffs(~(mask >> b)) - 1;             // run of consecutive ids
-    const unsigned runbits = ((1u << len) - 1u) << b;
-    unsigned w = want & runbits;
-    while (w) {
-      const int wb = __ffs(w) - 1;
-      const int wl = __ffs(~(w >> wb)) - 1;
-      bulk_g2s(dst_slot0 + wb * 256, tval + (src + (wb - b)) * 32, wl * 256, bar);
-      w &= ~(((1u << wl) - 1u) << wb);
-    }
-    src += len;
-    mask &= ~runbits;
+__device__ __forceinline__ unsigned long long mask64(const int4& e) {
+  return ((unsigned long long)(unsigned)e.w << 32) | (unsigned)e.z;
+}
+// bit kk set iff byte kk of m is non-zero
+__device__ __forceinline__ unsigned nonzero_bytes(unsigned long long m) {
+  unsigned r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r |= (((unsigned)(m >> (8 * k)) & 0xffu) ? 1u : 0u) << k;
+  return r;
+}
+__device__ __forceinline__ unsigned or_bytes(unsigned long long m) {
+  unsigned long long t = m | (m >> 32);
+  t |= t >> 16;
+  t |= t >> 8;
+  return (unsigned)t & 0xffu;
+}
+
+// entry index of super-tile `id` in a chunk column (binary search unless the ids are one contiguous run), or -1
+__device__ __forceinline__ int ct_find(const CtView& A, const int4& ca, int id) {
+  if (ca.y <= 0 || id < ca.z || id > ca.w) return -1;
+  if (ca.w - ca.z + 1 == ca.y) return ca.x + (id - ca.z);
+  int l2 = 0, h2 = ca.y;
+  while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.ent[ca.x + mid].x < id) l2 = mid + 1; else h2 = mid; }
+  return (l2 < ca.y) ? ca.x + l2 : -1;
+}
+// the (A super-tile, B super-tile) pair of one inner chunk: masks and tile offsets when they share an inner tile
+__device__ __forceinline__ void ct_pair(const int4& ea, const int4& eb, int Ib, bool found, unsigned long long& mA,
+                                        unsigned long long& mB, int& offA, int& offB) {
+  mA = 0ull; mB = 0ull; offA = 0; offB = 0;
+  if (found && ea.x == Ib) {
+    const unsigned long long ma = mask64(ea), mb = mask64(eb);
+    if (nonzero_bytes(ma) & or_bytes(mb)) { mA = ma; mB = mb; offA = ea.y; offB = eb.y; }
   }
 }
 
 // Persistent CTAs; task = 64x64 output block (8 tile columns x 8 row tiles), handed out by an atomic counter.
-// Warp 8 (copy warp): for every chunk of KC inner tiles it works out which A tiles (rows of the block) and which
-// B tiles (columns of the group) exist, publishes the two 8x8 presence masks, and moves the tiles with 1-D bulk
-// copies (TMA) into a 3-stage shared-memory ring guarded by full/empty mbarriers. Warps 0-7: warp w owns tile
-// column 8g+w, i.e. a 64x8 strip with its 8 accumulator tiles in registers, and issues one DMMA.8x8x4 per
-// (present A tile, present B tile) pair from conflict-free 256-byte shared-memory fragments. The strip is
+// Warp 8 (copy warp): at the start of a task each lane looks up one inner chunk: the B super-tile (chunk, group)
+// and the A super-tile (row block, chunk). For every chunk where both exist and share an inner tile, one lane
+// publishes the two 64-bit presence masks and issues TWO 1-D bulk copies (TMA) into a 3-stage shared-memory ring
+// guarded by full/empty mbarriers. Warps 0-7: warp w owns tile column 8g + w, i.e. a 64x8 strip of the block with
+// its 8 accumulator tiles in registers, and issues one DMMA.8x8x4 per (present A tile, present B tile) pair from
+// conflict-free 256-byte shared-memory fragments; tiles are located by popcount rank in the masks. Absent tiles
+// are skipped with real branches (a predicated-off DMMA occupies the pipe for its full 16 cycles). The strip is
 // written to the dense staging window and the kept-entry counts of its 8 columns are accumulated on the fly
 // (threshold rule fused), so the emit pass is a single sweep.
-template <int KC, int NSTAGE>
 __global__ void __launch_bounds__(NUMERIC_THREADS, 2)
-k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int* __restrict__ nI8,
-               const long long* __restrict__ stg_off, const int4* __restrict__ tasks,
-               int ntasks, int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
-               int nrows, int ncols, double alpha, double thr, RuleView rules) {
-  constexpr int STAGE_DOUBLES = PipeCfg<KC, NSTAGE>::STAGE_DOUBLES;
-  constexpr int STAGE_BYTES = PipeCfg<KC, NSTAGE>::STAGE_BYTES;
+k_tile_numeric(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const int* __restrict__ nI8,
+               const long long* __restrict__ stg_off, const int2* __restrict__ tasks, int ntasks,
+               int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
+               unsigned char* __restrict__ fmA, unsigned char* __restrict__ fmB, int nrows, int ncols, EmitSpec es) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* slab = reinterpret_cast<double*>(smem);
   unsigned char* meta = smem + NSTAGE * STAGE_BYTES;
@@ -331,147 +387,176 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
   unsigned ph = 0;
   if (warp == CW) {
     // ------------------------------------------------------------------ copy warp
+    // The look-ups of a task are a chain of five dependent global loads (task -> B column meta -> B super-tile
+    // -> A column meta -> A super-tile). They are software-pipelined: while the stages of task n are pushed,
+    // one link of the chain of task n+1 is advanced per pushed stage, so the latency hides behind the ring.
     const int4 none = make_int4(0, 0, 0, -1);
-    int task = 0;
-    if (lane == 0) task = atomicAdd(task_counter, 1);
-    task = __shfl_sync(0xffffffffu, task, 0);
-    int4 tk = (task < ntasks) ? tasks[task] : make_int4(0, 0, 0, 0);
-    for (;;) {
-      const bool done = task >= ntasks;
-      const int g = tk.x, I0 = tk.y, kmin = tk.z, nk = tk.w & 0xffffff;
-      const unsigned win = (unsigned)tk.w >> 24;
-      // claim the next task now; its table entry is read after this task's chunks are under way
-      int task_n = 0;
-      if (!done && lane == 0) task_n = atomicAdd(task_counter, 1);
-      // B role (lanes 8..15): tile column J = 8g + lane - 8, skipped when the block is outside its row window
-      int4 mb4 = none;
-      if (!done && lane >= 8 && lane < 16 && ((win >> (lane - 8)) & 1u)) mb4 = B.meta[g * 8 + lane - 8];
-      int4 ma_next = (!done && lane < KC && lane < nk) ? A.meta[kmin + lane] : none;
-      long long pB = mb4.x;
-      const long long endB = (long long)mb4.x + mb4.y;
-      const bool contigB = (mb4.w - mb4.z + 1 == mb4.y);
-      if (!contigB) {                               // skip the tiles below the live range
-        while (pB < endB && B.tid[pB] < kmin) ++pB;
+    int task_raw = 0;                               // lane 0: task id returned by the atomic counter
+    int pstep = 0;
+    bool valid_n = false, have_n = false, found_n = false;
+    int tid_n = 0;
+    int2 tk_n = make_int2(0, 0);
+    int4 cmB_n = none, eb_n = none, ca_n = none, ea_n = none;
+    unsigned long long mA_n = 0ull, mB_n = 0ull;
+    int offA_n = 0, offB_n = 0;
+    auto advance = [&]() {
+      switch (pstep) {
+        case 0: {
+          const int t = __shfl_sync(0xffffffffu, task_raw, 0);
+          tid_n = t;
+          valid_n = t < ntasks;
+          tk_n = valid_n ? tasks[t] : make_int2(0, 0);
+          break;
+        }
+        case 1: cmB_n = valid_n ? B.colmeta[tk_n.x] : none; break;
+        case 2: have_n = valid_n && lane < cmB_n.y; eb_n = have_n ? B.ent[cmB_n.x + lane] : none; break;
+        case 3: ca_n = have_n ? A.colmeta[eb_n.x] : none; break;
+        case 4: {
+          const int idx = have_n ? ct_find(A, ca_n, tk_n.y) : -1;
+          found_n = idx >= 0;
+          ea_n = found_n ? A.ent[idx] : none;
+          break;
+        }
+        case 5: ct_pair(ea_n, eb_n, tk_n.y, found_n, mA_n, mB_n, offA_n, offB_n); break;
+        default: break;
       }
-      const int nch = done ? 1 : max(1, (nk + KC - 1) / KC);
-      int4 tk_n = make_int4(0, 0, 0, 0);
-      for (int c = 0; c < nch; ++c) {
-        const int K0 = kmin + c * KC, Kend = min(K0 + KC, kmin + nk);
-        const bool last = (c == nch - 1);
-        const int4 m = ma_next;
-        ma_next = (lane < KC && K0 + KC + lane < kmin + nk) ? A.meta[K0 + KC + lane] : none;
-        if (c == 0 && !done) {
-          task_n = __shfl_sync(0xffffffffu, task_n, 0);
-          tk_n = (task_n < ntasks) ? tasks[task_n] : make_int4(0, 0, 0, 0);
+      ++pstep;
+    };
+    if (lane == 0) task_raw = atomicAdd(task_counter, 1);
+    while (pstep < 6) advance();
+    for (;;) {
+      const bool done = !valid_n;
+      const int g = tk_n.x, Ib = tk_n.y, task = tid_n;
+      const int4 cmB = cmB_n;
+      unsigned long long mA = mA_n, mB = mB_n;
+      int offA = offA_n, offB = offB_n;
+      if (!done) {
+        if (lane == 0) task_raw = atomicAdd(task_counter, 1);
+        pstep = 0;
+      }
+      const int nb = done ? 1 : max(1, (cmB.y + 31) / 32);
+      for (int bb = 0; bb < nb; ++bb) {
+        if (bb > 0) {                               // more than 32 inner chunks in this group: synchronous look-up
+          const int e = bb * 32 + lane;
+          const bool have = e < cmB.y;
+          const int4 eb = have ? B.ent[cmB.x + e] : none;
+          const int4 ca = have ? A.colmeta[eb.x] : none;
+          const int idx = have ? ct_find(A, ca, Ib) : -1;
+          const int4 ea = (idx >= 0) ? A.ent[idx] : none;
+          ct_pair(ea, eb, Ib, idx >= 0, mA, mB, offA, offB);
         }
-        unsigned mask = 0;
-        long long src = 0;
-        if (lane < 8) {
-          if (m.y > 0 && m.z <= I0 + 7 && m.w >= I0) {
-            if (m.w - m.z + 1 == m.y) {
-              const int lo = max(m.z, I0), hi = min(m.w, I0 + 7);
-              mask = ((1u << (hi - lo + 1)) - 1u) << (lo - I0);
-              src = (long long)m.x + (lo - m.z);
-            } else {
-              int l2 = 0, h2 = m.y;
-              while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.tid[m.x + mid] < I0) l2 = mid + 1; else h2 = mid; }
-              src = (long long)m.x + l2;
-              for (int p = l2; p < m.y; ++p) {
-                const int id = A.tid[m.x + p];
-                if (id >= I0 + 8) break;
-                mask |= 1u << (id - I0);
-              }
-            }
+        unsigned todo = __ballot_sync(0xffffffffu, mA != 0ull);
+        const bool final_batch = (bb == nb - 1);
+        if (todo == 0u && final_batch) todo = 1u;             // a task always ends with a (possibly empty) last stage
+        while (todo) {
+          const int l = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const bool last = final_batch && todo == 0u;
+          const unsigned long long sA = __shfl_sync(0xffffffffu, mA, l), sB = __shfl_sync(0xffffffffu, mB, l);
+          const int oA = __shfl_sync(0xffffffffu, offA, l), oB = __shfl_sync(0xffffffffu, offB, l);
+          mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
+          if (lane == 0) {
+            unsigned char* mt = meta + st * META_BYTES;
+            *reinterpret_cast<unsigned long long*>(mt) = sA;
+            *reinterpret_cast<unsigned long long*>(mt + 8) = sB;
+            *reinterpret_cast<int4*>(mt + 16) = make_int4((last ? 1 : 0) | (done ? 2 : 0), g, Ib, task);
+            const unsigned bA = (unsigned)popc64(sA) * 256u, bB = (unsigned)popc64(sB) * 256u;
+            mbar_arrive_expect_tx(bar0 + 8 * st, bA + bB);
+            const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
+            if (bA) bulk_g2s(slab_s, A.tval + (size_t)oA * 32, bA, bar0 + 8 * st);
+            if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + (size_t)oB * 32, bB, bar0 + 8 * st);
           }
-        } else if (lane < 16 && mb4.y > 0) {
-          if (contigB) {
-            const int lo = max(mb4.z, K0), hi = min(mb4.w, Kend - 1);
-            if (lo <= hi) { mask = ((1u << (hi - lo + 1)) - 1u) << (lo - K0); src = (long long)mb4.x + (lo - mb4.z); }
-          } else {
-            src = pB;
-            while (pB < endB) {
-              const int id = B.tid[pB];
-              if (id >= Kend) break;
-              mask |= 1u << (id - K0);
-              ++pB;
-            }
-          }
+          __syncwarp();
+          if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+          if (!done) advance();
         }
-        // inner tiles that have both an A tile in the block and a B tile in the group
-        const unsigned kA = __ballot_sync(0xffffffffu, lane < 8 && mask != 0u) & 0xffu;
-        const unsigned kB = __reduce_or_sync(0xffffffffu, (lane >= 8 && lane < 16) ? mask : 0u);
-        const unsigned live = kA & kB;
-        if (live == 0u && !last) continue;
-        unsigned want = 0;
-        if (lane < 8) want = ((live >> lane) & 1u) ? mask : 0u;
-        else if (lane < 16) want = mask & live;
-        const unsigned bytes = __reduce_add_sync(0xffffffffu, (unsigned)__popc(want) * 256u);
-        mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
-        unsigned char* mt = meta + st * META_BYTES;
-        if (lane < 16) mt[lane] = (unsigned char)want;
-        if (lane == 16) {
-          int* mi = reinterpret_cast<int*>(mt + 16);
-          mi[0] = (last ? 1 : 0) | (done ? 2 : 0);
-          mi[1] = g;
-          mi[2] = I0;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(bar0 + 8 * st, bytes);
-        __syncwarp();
-        if (want) {
-          const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
-          if (lane < 8) copy_runs(mask, want, src, A.tval, slab_s + lane * (8 * 256), bar0 + 8 * st);
-          else copy_runs(mask, want, src, B.tval, slab_s + KC * 8 * 256 + (lane - 8) * (KC * 256), bar0 + 8 * st);
-        }
-        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
       }
       if (done) break;
-      task = task_n;
-      tk = tk_n;
+      while (pstep < 6) advance();
     }
     return;
   }
 
   // -------------------------------------------------------------------- DMMA warps
-  const int wj = warp & 7, half = warp >> 3;        // tile column of the group, upper/lower 4 row tiles of the block
+  const int wj = warp;                              // tile column of the group
   for (;;) {
-    double acc[4][2];
+    double acc[8][2];
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
-    int g = 0, I0 = 0;
+    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
+    int g = 0, Ib = 0, task = 0;
     unsigned fl = 0;
     do {
       mbar_wait(bar0 + 8 * st, ph);
       const unsigned char* mt = meta + st * META_BYTES;
-      const uint4 mm = *reinterpret_cast<const uint4*>(mt);               // maskA[0..7], maskB[0..7]
+      const ulonglong2 mm = *reinterpret_cast<const ulonglong2*>(mt);     // maskA, maskB
       const int4 mi = *reinterpret_cast<const int4*>(mt + 16);
-      fl = (unsigned)mi.x; g = mi.y; I0 = mi.z;
-      const unsigned mb = ((wj < 4 ? mm.z >> (8 * wj) : mm.w >> (8 * (wj - 4)))) & 0xffu;
-      // this warp's 4 row tiles: nibble `half` of every maskA byte
-      const unsigned mlo = (mm.x >> (4 * half)) & 0x0f0f0f0fu, mhi = (mm.y >> (4 * half)) & 0x0f0f0f0fu;
-      if (mb && (mlo | mhi)) {
-        const double* As = slab + (size_t)st * STAGE_DOUBLES + half * (4 * 32) + lane;
-        const double* Bs = slab + (size_t)st * STAGE_DOUBLES + KC * 8 * 32 + wj * (KC * 32) + lane;
+      fl = (unsigned)mi.x; g = mi.y; Ib = mi.z; task = mi.w;
+      const unsigned mb = (unsigned)(mm.y >> (8 * wj)) & 0xffu;           // my tile column: bits over kk
+      if (mb != 0u && mm.x != 0ull) {
+        // tiles are rank-packed: byte kk of `excl` = number of A tiles stored before inner tile kk
+        unsigned long long x = mm.x - ((mm.x >> 1) & 0x5555555555555555ull);
+        x = (x & 0x3333333333333333ull) + ((x >> 2) & 0x3333333333333333ull);
+        x = (x + (x >> 4)) & 0x0f0f0f0f0f0f0f0full;
+        const unsigned long long excl = (x * 0x0101010101010101ull) << 8;
+        const double* As = slab + (size_t)st * STAGE_DOUBLES + lane;
+        const double* Bs = As + SLAB_DOUBLES + popc64(mm.y & ((1ull << (8 * wj)) - 1ull)) * 32;
+        // one copy of the loop body (not unrolled over kk): the four code paths below times eight would not
+        // fit the instruction cache (measured: stall_no_instruction dominated)
+        unsigned live = mb & nonzero_bytes(mm.x);
+#pragma unroll 1
+        while (live) {
+          const int kk = __ffs(live) - 1;
+          live &= live - 1u;
+          const unsigned ma = (unsigned)(mm.x >> (8 * kk)) & 0xffu;
+          const double bv = Bs[__popc(mb & ((1u << kk) - 1u)) * 32];
+          const double* ap = As + ((unsigned)(excl >> (8 * kk)) & 0xffu) * 32;
+          double av[8];
+          if (ma == 0xffu) {
 #pragma unroll
-        for (int kk = 0; kk < KC; ++kk) {
-          const unsigned ma = ((kk < 4 ? mlo >> (8 * kk) : mhi >> (8 * (kk - 4)))) & 0xfu;
-          if (((mb >> kk) & 1u) == 0u || ma == 0u) continue;
-          const double bv = Bs[kk * 32];
-          const double* ap = As + kk * (8 * 32);
-          if (ma == 0xfu) {
-            double av[4];
+            for (int ii = 0; ii < 8; ++ii) av[ii] = ap[ii * 32];
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii) av[ii] = ap[ii * 32];
+            for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
+          } else if ((ma & (ma + 1u)) == 0u) {
+            // Absent tiles are skipped with branches, not predicates: a predicated-off DMMA still holds the FP64
+            // tensor pipe for 16 cycles (scripts/micro/dmma_shapes.cu).
+            // prefix run (row tiles 0..h0, the band edge leaving the block): one jump into a descending sequence
+            const int h0 = __popc(ma) - 1;
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
+            for (int ii = 0; ii < 7; ++ii)
+              if (ii <= h0) av[ii] = ap[ii * 32];
+#define NTB_D(i) dmma884(acc[i][0], acc[i][1], av[i], bv);
+            switch (h0) {
+              case 6: NTB_D(6)
+              case 5: NTB_D(5)
+              case 4: NTB_D(4)
+              case 3: NTB_D(3)
+              case 2: NTB_D(2)
+              case 1: NTB_D(1)
+              default: NTB_D(0)
+            }
+          } else if (((ma | (ma - 1u)) & 0xffu) == 0xffu) {
+            // suffix run (row tiles l0..7, the band edge entering the block): one jump into an ascending sequence
+            const int l0 = __ffs(ma) - 1;
+            const double* aq = ap - l0 * 32;
+#pragma unroll
+            for (int ii = 1; ii < 8; ++ii)
+              if (ii >= l0) av[ii] = aq[ii * 32];
+            switch (l0) {
+              case 1: NTB_D(1)
+              case 2: NTB_D(2)
+              case 3: NTB_D(3)
+              case 4: NTB_D(4)
+              case 5: NTB_D(5)
+              case 6: NTB_D(6)
+              default: NTB_D(7)
+            }
+#undef NTB_D
           } else {
-            // a predicated-off DMMA still occupies the FP64 tensor pipe for its full 16 cycles (measured,
-            // scripts/micro/dmma_shapes.cu), so absent tiles are skipped with real branches: enter the
-            // unrolled sequence at the first tile of each id run, leave it after the last.
-            double av[4];
+            // general pattern: load the present tiles (rank-packed), then enter the unrolled DMMA sequence at the
+            // first tile of each id run and leave it after the last
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii)
-              if ((ma >> ii) & 1u) av[ii] = ap[ii * 32];
+            for (int ii = 0; ii < 8; ++ii)
+              if ((ma >> ii) & 1u) av[ii] = ap[__popc(ma & ((1u << ii) - 1u)) * 32];
             unsigned m = ma;
 #define NTB_RUN_STEP(i) dmma884(acc[i][0], acc[i][1], av[i], bv); if (h0 == i) break;
             do {
@@ -483,7 +568,11 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
                 case 0: NTB_RUN_STEP(0)
                 case 1: NTB_RUN_STEP(1)
                 case 2: NTB_RUN_STEP(2)
-                default: dmma884(acc[3][0], acc[3][1], av[3], bv);
+                case 3: NTB_RUN_STEP(3)
+                case 4: NTB_RUN_STEP(4)
+                case 5: NTB_RUN_STEP(5)
+                case 6: NTB_RUN_STEP(6)
+                default: dmma884(acc[7][0], acc[7][1], av[7], bv);
               }
             } while (m);
 #undef NTB_RUN_STEP
@@ -496,39 +585,45 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
     } while ((fl & 1u) == 0u);
     if (fl & 2u) break;
     const int J = g * 8 + wj;
-    if (J >= B.ntc) continue;
+    if (J >= nJ) continue;
+    const int I0 = Ib << 3;
     const int iw0 = imin8[J], nI = nI8[J];
     if (I0 < iw0 || I0 >= iw0 + nI) continue;
-    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column
+    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column.
+    // Alongside the raw strip: kept-entry counts of the 8 columns and the presence bytes of the strip's tiles in
+    // the two tile forms of the RESULT (the next product reads them without ever rebuilding tiles from CSC).
     const int wlen = nI * 8;
     const int r = lane >> 2, cc = (lane & 3) * 2;
-    const int Ih = I0 + 4 * half;
-    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(Ih - iw0) * 8 + r;
+    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
     const int j0 = J * 8 + cc;
+    const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
+    const bool plain = es.rules.tbl == nullptr && es.sigma == 0.0;
     int c0 = 0, c1 = 0;
-    if (rules.tbl == nullptr) {                 // sparse rule everywhere: |alpha*v| > thr
-      const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
+    unsigned bR0 = 0, bR1 = 0, bL0 = 0, bL1 = 0;   // right-form bytes (rows 0-31 / 32-63), left-form bytes (cols 0-3 / 4-7)
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii) {
-        const double v0 = acc[ii][0], v1 = acc[ii][1];
-        o[ii * 8] = v0;
-        o[wlen + ii * 8] = v1;
-        const bool rin = (Ih + ii) * 8 + r < nrows;
-        c0 += (rin && in0 && fabs(alpha * v0) > thr) ? 1 : 0;
-        c1 += (rin && in1 && fabs(alpha * v1) > thr) ? 1 : 0;
-      }
-    } else {
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii) {
-        const double v0 = acc[ii][0], v1 = acc[ii][1];
-        o[ii * 8] = v0;
-        o[wlen + ii * 8] = v1;
-        const int row = (Ih + ii) * 8 + r;
-        if (row < nrows) {
-          if (j0 < ncols) c0 += ((tile_rule(rules, row, j0) ? fabs(v0) : fabs(alpha * v0)) > thr) ? 1 : 0;
-          if (j0 + 1 < ncols) c1 += ((tile_rule(rules, row, j0 + 1) ? fabs(v1) : fabs(alpha * v1)) > thr) ? 1 : 0;
+    for (int ii = 0; ii < 8; ++ii) {
+      const double v0 = acc[ii][0], v1 = acc[ii][1];
+      o[ii * 8] = v0;
+      o[wlen + ii * 8] = v1;
+      const int row = (I0 + ii) * 8 + r;
+      bool k0 = false, k1 = false;
+      if (row < nrows) {
+        if (plain) {                            // sparse rule everywhere, no shift: |alpha*v| > thr
+          k0 = in0 && fabs(es.alpha * v0) > es.thr;
+          k1 = in1 && fabs(es.alpha * v1) > es.thr;
+        } else {
+          if (in0) k0 = keep_general(es, v0, row, j0);
+          if (in1) k1 = keep_general(es, v1, row, j0 + 1);
         }
       }
+      c0 += k0 ? 1 : 0;
+      c1 += k1 ? 1 : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, k0 || k1);
+      const unsigned lo = (bal & 0x0000ffffu) ? 1u : 0u, hi = (bal & 0xffff0000u) ? 1u : 0u;
+      if (ii < 4) bR0 |= (lo << (2 * ii)) | (hi << (2 * ii + 1));
+      else bR1 |= (lo << (2 * (ii - 4))) | (hi << (2 * (ii - 4) + 1));
+      bL0 |= ((bal & 0x33333333u) ? 1u : 0u) << ii;
+      bL1 |= ((bal & 0xccccccccu) ? 1u : 0u) << ii;
     }
 #pragma unroll
     for (int d = 4; d < 32; d <<= 1) {
@@ -539,14 +634,21 @@ k_tile_numeric(TileView A, TileView B, const int* __restrict__ imin8, const int*
       if (c0) atomicAdd(&cnt[j0], c0);
       if (c1) atomicAdd(&cnt[j0 + 1], c1);
     }
+    if (lane == 0) {
+      fmB[((size_t)task * 2 + 0) * 8 + wj] = (unsigned char)bR0;
+      fmB[((size_t)task * 2 + 1) * 8 + wj] = (unsigned char)bR1;
+      unsigned char* fa = fmA + ((size_t)task * 2 + (wj >> 2)) * 8 + 2 * (wj & 3);
+      fa[0] = (unsigned char)bL0;
+      fa[1] = (unsigned char)bL1;
+    }
   }
 }
 
 // ordered emit of the kept entries of every output column into CSC (counts came from the numeric kernel)
 __global__ void __launch_bounds__(256)
 k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __restrict__ nI8,
-            const long long* __restrict__ stg_off, const double* __restrict__ stg, double alpha, double thr,
-            RuleView rules, const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ val) {
+            const long long* __restrict__ stg_off, const double* __restrict__ stg, EmitSpec es,
+            const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -561,11 +663,7 @@ k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __re
       const int t = t0 + lane;
       bool keep = false;
       double sv = 0.0;
-      if (t < wlen && base + t < nrows) {
-        const double v = src[t];
-        sv = alpha * v;
-        keep = (tile_rule(rules, base + t, j) ? fabs(v) : fabs(sv)) > thr;
-      }
+      if (t < wlen && base + t < nrows) sv = final_value<true>(es, src[t], base + t, j, keep);
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if (keep) {
         const int pos = dst + count + __popc(m & ((1u << lane) - 1));
@@ -577,32 +675,222 @@ k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __re
   }
 }
 
+// ---- tile forms of the result, straight from the staging strips --------------------------------------------
+// Every task (group g, row block Ib) owns two super-tiles of each form: left form (Ib, chunk column 2g+c), right
+// form (inner chunk 2Ib+h, group g); their presence masks were written by the numeric kernel (fmA / fmB).
+// Slots are enumerated in chunk-column order: right form slot = 2*task + h; left form slot = 2*t0(g) + c*n(g) + b.
+constexpr int FI_T = 1024, FI_ITEMS = 8;
+
+__device__ __forceinline__ void form_slot(bool left, int s, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
+                                          const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
+                                          unsigned long long& mask, int& id) {
+  const int t = s >> 1;
+  const int2 tk = tasks[t];
+  if (!left) { mask = fmB[s]; id = 2 * tk.y + (s & 1); return; }
+  const int t0 = gtask_off[tk.x], nn = gtask_off[tk.x + 1] - t0;
+  const int local = s - 2 * t0, c = local / nn, b = local - c * nn;
+  mask = fmA[(size_t)(t0 + b) * 2 + c];
+  id = tasks[t0 + b].y;
+}
+
+// blockIdx.x: 0 = left form, 1 = right form. One CTA scans all slots (a few 10^4) and writes entries + column meta.
+__global__ void __launch_bounds__(FI_T)
+k_forms_index(int ntasks, int nG, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
+              const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
+              int4* __restrict__ entL, int4* __restrict__ entR, int4* __restrict__ colmetaL, int4* __restrict__ colmetaR,
+              int* __restrict__ seidxL, int* __restrict__ seidxR, int* __restrict__ stoffL, int* __restrict__ stoffR,
+              int* __restrict__ totals) {
+  const bool left = blockIdx.x == 0;
+  int4* ent = left ? entL : entR;
+  int4* colmeta = left ? colmetaL : colmetaR;
+  int* seidx = left ? seidxL : seidxR;
+  int* stoff = left ? stoffL : stoffR;
+  const int n = 2 * ntasks;
+  __shared__ int wsum[2][32];
+  __shared__ int carry[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
+  __syncthreads();
+  for (int base = 0; base < n; base += FI_T * FI_ITEMS) {
+    const int s0 = base + threadIdx.x * FI_ITEMS;
+    unsigned long long m[FI_ITEMS];
+    int id[FI_ITEMS];
+    int f = 0, pc = 0;
+#pragma unroll
+    for (int k = 0; k < FI_ITEMS; ++k) {
+      m[k] = 0ull; id[k] = 0;
+      if (s0 + k < n) form_slot(left, s0 + k, tasks, gtask_off, fmA, fmB, m[k], id[k]);
+      f += (m[k] != 0ull); pc += popc64(m[k]);
+    }
+    int fi = f, pi = pc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, fi, d), b = __shfl_up_sync(0xffffffffu, pi, d);
+      if (lane >= d) { fi += a; pi += b; }
+    }
+    if (lane == 31) { wsum[0][warp] = fi; wsum[1][warp] = pi; }
+    __syncthreads();
+    if (warp == 0) {
+      const int a = wsum[0][lane], b = wsum[1][lane];
+      int ai = a, bi = b;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, ai, d), y = __shfl_up_sync(0xffffffffu, bi, d);
+        if (lane >= d) { ai += x; bi += y; }
+      }
+      wsum[0][lane] = ai - a; wsum[1][lane] = bi - b;      // exclusive warp offsets
+    }
+    __syncthreads();
+    int e = carry[0] + wsum[0][warp] + fi - f, t = carry[1] + wsum[1][warp] + pi - pc;
+#pragma unroll
+    for (int k = 0; k < FI_ITEMS; ++k) {
+      if (s0 + k < n) {
+        seidx[s0 + k] = e; stoff[s0 + k] = t;
+        if (m[k] != 0ull) {
+          ent[e] = make_int4(id[k], t, (int)(unsigned)(m[k] & 0xffffffffull), (int)(unsigned)(m[k] >> 32));
+          ++e; t += popc64(m[k]);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == FI_T - 1) { carry[0] = e; carry[1] = t; }   // last thread ends at the chunk totals
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { seidx[n] = carry[0]; totals[left ? 0 : 2] = carry[0]; totals[left ? 1 : 3] = carry[1]; }
+  __syncthreads();
+  // column meta
+  const int ncc = left ? 2 * nG : nG;
+  for (int q = threadIdx.x; q < ncc; q += FI_T) {
+    const int g = left ? (q >> 1) : q;
+    const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
+    const int sa = left ? 2 * t0 + (q & 1) * nn : 2 * t0, sb = sa + (left ? nn : 2 * nn);
+    const int e0 = seidx[sa], e1 = seidx[sb];
+    colmeta[q] = (e1 > e0) ? make_int4(e0, e1 - e0, ent[e0].x, ent[e1 - 1].x) : make_int4(0, 0, 0, -1);
+  }
+}
+
+// left form: per inner tile K of the result (4 columns): tile count, first and last row tile
+__global__ void __launch_bounds__(256)
+k_forms_kmeta(int nk, int nG, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
+              const unsigned long long* __restrict__ fmA, int4* __restrict__ kmeta) {
+  const int K = blockIdx.x * blockDim.x + threadIdx.x;
+  if (K >= nk) return;
+  const int g = K >> 4, c = (K >> 3) & 1, kk = K & 7;
+  int cnt = 0, fk = INT_MAX, lk = -1;
+  if (g < nG) {
+    const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
+    for (int b = 0; b < nn; ++b) {
+      const unsigned byte = (unsigned)(fmA[(size_t)(t0 + b) * 2 + c] >> (8 * kk)) & 0xffu;
+      if (byte) {
+        const int base = tasks[t0 + b].y * 8;
+        cnt += __popc(byte);
+        fk = min(fk, base + __ffs(byte) - 1);
+        lk = max(lk, base + 31 - __clz(byte));
+      }
+    }
+  }
+  kmeta[K] = (cnt > 0) ? make_int4(0, cnt, fk, lk) : make_int4(0, 0, 0, -1);
+}
+
+// one CTA per task, warp w <-> tile column 8g+w: thresholded, scaled (and shifted) values into both tile forms
+__global__ void __launch_bounds__(256)
+k_forms_fill(int nJ, int nrows, int ncols, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
+             const int* __restrict__ imin8, const int* __restrict__ nI8, const long long* __restrict__ stg_off,
+             const double* __restrict__ stg, EmitSpec es, const unsigned long long* __restrict__ fmA,
+             const unsigned long long* __restrict__ fmB, const int* __restrict__ stoffL, const int* __restrict__ stoffR,
+             double* __restrict__ tvalL, double* __restrict__ tvalR) {
+  const int task = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int2 tk = tasks[task];
+  const int g = tk.x, I0 = tk.y << 3, J = g * 8 + w;
+  if (J >= nJ) return;
+  const int iw0 = imin8[J], nI = nI8[J];
+  if (I0 < iw0 || I0 >= iw0 + nI) return;
+  const int wlen = nI * 8;
+  const double* src = stg + stg_off[J] * 64 + (size_t)(I0 - iw0) * 8;
+  // right form: tiles (h, jj = w, kk): rows 32h + 4kk + lane%4, column lane/4
+  {
+    const int c = lane >> 2, r = lane & 3, col = J * 8 + c;
+    for (int h = 0; h < 2; ++h) {
+      const unsigned long long m = fmB[(size_t)task * 2 + h];
+      unsigned byte = (unsigned)(m >> (8 * w)) & 0xffu;
+      long long t = (long long)stoffR[task * 2 + h] + popc64(m & ((1ull << (8 * w)) - 1ull));
+      while (byte) {
+        const int kk = __ffs(byte) - 1;
+        byte &= byte - 1;
+        const int lr = 32 * h + 4 * kk + r, row = I0 * 8 + lr;
+        bool keep = false;
+        double v = 0.0;
+        if (row < nrows && col < ncols) v = final_value<true>(es, src[(size_t)c * wlen + lr], row, col, keep);
+        tvalR[t * 32 + lane] = keep ? v : 0.0;
+        ++t;
+      }
+    }
+  }
+  // left form: chunk column c = w/4, inner tiles kk = 2(w%4) + ch: rows 8ii + lane/4, column 4ch + lane%4
+  {
+    const int cch = w >> 2, r = lane >> 2, c4 = lane & 3;
+    const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
+    const unsigned long long m = fmA[(size_t)task * 2 + cch];
+    const int slot = 2 * t0 + cch * nn + (task - t0);
+    for (int ch = 0; ch < 2; ++ch) {
+      const int kk = 2 * (w & 3) + ch;
+      unsigned byte = (unsigned)(m >> (8 * kk)) & 0xffu;
+      long long t = (long long)stoffL[slot] + popc64(m & ((1ull << (8 * kk)) - 1ull));
+      const int lc = 4 * ch + c4, col = J * 8 + lc;
+      while (byte) {
+        const int ii = __ffs(byte) - 1;
+        byte &= byte - 1;
+        const int lr = 8 * ii + r, row = I0 * 8 + lr;
+        bool keep = false;
+        double v = 0.0;
+        if (row < nrows && col < ncols) v = final_value<true>(es, src[(size_t)lc * wlen + lr], row, col, keep);
+        tvalL[t * 32 + lane] = keep ? v : 0.0;
+        ++t;
+      }
+    }
+  }
+}
+
+// the cached (or freshly built) tile form of an operand; nullptr when its pattern cannot be tiled
+static const ChunkTiles* operand_form(const LocalCsc<double>& M, bool left) {
+  if (!M.forms) M.forms = std::make_shared<TileForms>();
+  TileForms& f = *M.forms;
+  int& has = left ? f.has_left : f.has_right;
+  ChunkTiles& T = left ? f.left : f.right;
+  if (has == 0) {
+    const bool ok = left ? build_chunk_tiles<true>(M.view(), T) : build_chunk_tiles<false>(M.view(), T);
+    has = ok ? 1 : -1;
+    rt().tile_builds++;
+  }
+  return has == 1 ? &T : nullptr;
+}
+
 // returns false when the operands are not locally dense enough (caller falls back to the
 // scalar window kernels). useful_products = sum over B entries of the A column lengths.
-bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alpha, double thr, const RuleView& rules,
-                 LocalCsc<double>& Z, double useful_products, long long nnzX, long long nnzY) {
-  const int ncols = X.cols, nrows = Y.rows;
-  if (ncols == 0 || nnzX == 0 || nnzY == 0 || !(thr >= 0.0)) return false;
-  TileCsc A, B;
-  if (!build_tiles<8, 4>(Y, A)) return false;
-  if ((double)nnzY < 0.20 * 32.0 * (double)A.ntiles) return false;   // tiles mostly padding
-  if (!build_tiles<4, 8>(X, B)) return false;
-  if ((double)nnzX < 0.20 * 32.0 * (double)B.ntiles) return false;
-  const int nJ = B.ntc, nG = div_up(nJ, 8);
-  DevBuf<int4> metaA((size_t)A.ntc), metaB((size_t)nJ);
-  NTB_LAUNCH(k_tile_meta, div_up(A.ntc, 256), 256, 0, A.ntc, A.tptr.get(), A.first.get(), A.last.get(), metaA.get());
-  NTB_LAUNCH(k_tile_meta, div_up(nJ, 256), 256, 0, nJ, B.tptr.get(), B.first.get(), B.last.get(), metaB.get());
-  const TileView Av{A.tptr.get(), A.tid.get(), metaA.get(), A.tval.get(), A.ntc};
-  const TileView Bv{B.tptr.get(), B.tid.get(), metaB.get(), B.tval.get(), B.ntc};
+bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double alpha, double thr, const RuleView& rules,
+                 LocalCsc<double>& Z, double useful_products, const DiagShift* shift) {
+  const int ncols = Xl.cols, nrows = Yl.rows;
+  if (ncols == 0 || Xl.nnz == 0 || Yl.nnz == 0 || !(thr >= 0.0)) return false;
+  const ChunkTiles* A = operand_form(Yl, true);
+  if (!A || (double)Yl.nnz < 0.20 * 32.0 * (double)A->ntiles) return false;   // tiles mostly padding
+  const ChunkTiles* B = operand_form(Xl, false);
+  if (!B || (double)Xl.nnz < 0.20 * 32.0 * (double)B->ntiles) return false;
+  const int nJ = div_up(ncols, 8), nG = B->ncc;
+  const CtView Av{A->colmeta.get(), A->ent.get(), A->tval.get(), A->kmeta.get(), A->ncc};
+  const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc};
+  EmitSpec es;
+  es.alpha = alpha; es.thr = thr; es.rules = rules;
+  es.sigma = shift ? shift->sigma : 0.0;
+  es.dd = shift ? shift->dd : 0;
+  es.ncols_diag = shift ? shift->ncols_diag : 0;
   DevBuf<int> imin8((size_t)nJ), nI8((size_t)nJ), gbmin((size_t)nG), gnb((size_t)nG), gtask_off((size_t)nG + 1);
-  DevBuf<int2> gk((size_t)nG);
   DevBuf<long long> stg_off((size_t)nJ + 1);
   DevBuf<unsigned long long> ndmma(1);
   ndmma.zero();
-  NTB_LAUNCH(k_tile_bounds, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, imin8.get(),
-             nI8.get(), ndmma.get());
-  NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), metaB.get(), gbmin.get(),
-             gnb.get(), gk.get());
+  NTB_LAUNCH(k_tile_bounds, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, nJ, imin8.get(),
+             nI8.get(), ndmma.get(), es.sigma != 0.0 ? 1 : 0, es.dd, es.ncols_diag, nrows);
+  NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), gbmin.get(), gnb.get());
   exclusive_scan(nI8.get(), stg_off.get(), nJ);        // staging in units of 64 doubles (8 cols x 8 rows per row tile)
   exclusive_scan(gnb.get(), gtask_off.get(), nG);
   long long h_stg = 0;
@@ -616,13 +904,15 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
   if ((double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
 
   DevBuf<double> stg((size_t)h_stg * 64);
-  DevBuf<int4> tasks((size_t)max(h_tasks, 1));
+  DevBuf<int2> tasks((size_t)max(h_tasks, 1));
   DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
+  DevBuf<unsigned long long> fmA((size_t)max(h_tasks, 1) * 2), fmB((size_t)max(h_tasks, 1) * 2);
   cnt.zero();
   task_counter.zero();
+  fmA.zero();
+  fmB.zero();
   if (h_tasks > 0)
-    NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, nJ, gbmin.get(), gtask_off.get(), gk.get(), metaA.get(),
-               imin8.get(), nI8.get(), tasks.get());
+    NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, gbmin.get(), gtask_off.get(), tasks.get());
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (rt().profile) {
     CUDA_CHECK(cudaEventCreate(&ev0));
@@ -630,36 +920,62 @@ bool spgemm_tile(const CscView<double>& X, const CscView<double>& Y, double alph
     CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
   }
   if (h_tasks > 0) {
-    static int shape = -1;
-    if (shape < 0) {
-      const char* e = std::getenv("NTB_TILE_PIPE");      // developer knob: 0 = 8x3, 1 = 4x6, 2 = 2x12
-      shape = e ? std::atoi(e) : 0;
-      CUDA_CHECK(cudaFuncSetAttribute((k_tile_numeric<8, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<8, 3>::SMEM));
-      CUDA_CHECK(cudaFuncSetAttribute((k_tile_numeric<4, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<4, 6>::SMEM));
-      CUDA_CHECK(cudaFuncSetAttribute((k_tile_numeric<2, 12>), cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<2, 12>::SMEM));
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_tile_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, NUMERIC_SMEM));
+      attr_set = true;
     }
-    const int grid = min(h_tasks, kNumSMs * 2);
-#define NTB_NUMERIC_ARGS Av, Bv, imin8.get(), nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), \
-                         cnt.get(), nrows, ncols, alpha, thr, rules
-    if (shape == 0) NTB_LAUNCH((k_tile_numeric<8, 3>), grid, NUMERIC_THREADS, (PipeCfg<8, 3>::SMEM), NTB_NUMERIC_ARGS);
-    else if (shape == 2) NTB_LAUNCH((k_tile_numeric<2, 12>), grid, NUMERIC_THREADS, (PipeCfg<2, 12>::SMEM), NTB_NUMERIC_ARGS);
-    else NTB_LAUNCH((k_tile_numeric<4, 6>), grid, NUMERIC_THREADS, (PipeCfg<4, 6>::SMEM), NTB_NUMERIC_ARGS);
-#undef NTB_NUMERIC_ARGS
+    NTB_LAUNCH(k_tile_numeric, min(h_tasks, kNumSMs * 2), NUMERIC_THREADS, NUMERIC_SMEM, Av, Bv, nJ, imin8.get(),
+               nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
+               reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
   }
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
     rt().prof_events.emplace_back(ev0, ev1);
   }
+  // ---- CSC of the result
   const int egrid = max(1, min(div_up((long long)ncols * 32, 256), kNumSMs * 16));
   Z.rows = nrows; Z.cols = ncols;
   Z.outer.alloc((size_t)ncols + 1);
   exclusive_scan(cnt.get(), Z.outer.get(), ncols);
-  int h_nnz = 0;
-  d2h(&h_nnz, Z.outer.get() + ncols, 1);
+  // ---- index of the result's tile forms (same read-back as the entry count)
+  auto forms = std::make_shared<TileForms>();
+  ChunkTiles& L = forms->left;
+  ChunkTiles& R = forms->right;
+  DevBuf<int> seidxL, seidxR, stoffL, stoffR, totals(4);
+  const int nk = div_up(ncols, 4);
+  if (h_tasks > 0) {
+    const size_t ns = (size_t)h_tasks * 2;
+    L.ent.alloc(ns); R.ent.alloc(ns);
+    L.colmeta.alloc((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
+    L.kmeta.alloc((size_t)nk);
+    seidxL.alloc(ns + 1); seidxR.alloc(ns + 1); stoffL.alloc(ns); stoffR.alloc(ns);
+    NTB_LAUNCH(k_forms_index, 2, FI_T, 0, h_tasks, nG, tasks.get(), gtask_off.get(), fmA.get(), fmB.get(), L.ent.get(),
+               R.ent.get(), L.colmeta.get(), R.colmeta.get(), seidxL.get(), seidxR.get(), stoffL.get(), stoffR.get(),
+               totals.get());
+    NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), fmA.get(), L.kmeta.get());
+  } else {
+    totals.zero();
+  }
+  int h_nnz = 0, h_tot[4] = {0, 0, 0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(&h_nnz, Z.outer.get() + ncols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  CUDA_CHECK(cudaMemcpyAsync(h_tot, totals.get(), sizeof(h_tot), cudaMemcpyDeviceToHost, rt().stream));
+  stream_sync();
   Z.alloc_entries(h_nnz);
   if (h_nnz > 0)
-    NTB_LAUNCH(k_tile_emit, egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(),
-               alpha, thr, rules, Z.outer.get(), Z.inner.get(), Z.val.get());
+    NTB_LAUNCH(k_tile_emit, egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(), es,
+               Z.outer.get(), Z.inner.get(), Z.val.get());
+  if (h_tasks > 0 && h_nnz > 0) {
+    L.ncc = div_up(ncols, 32); L.nsuper = h_tot[0]; L.ntiles = h_tot[1];
+    R.ncc = nG; R.nsuper = h_tot[2]; R.ntiles = h_tot[3];
+    L.tval.alloc((size_t)L.ntiles * 32);
+    R.tval.alloc((size_t)R.ntiles * 32);
+    NTB_LAUNCH(k_forms_fill, h_tasks, 256, 0, nJ, nrows, ncols, tasks.get(), gtask_off.get(), imin8.get(), nI8.get(),
+               stg_off.get(), stg.get(), es, fmA.get(), fmB.get(), stoffL.get(), stoffR.get(), L.tval.get(), R.tval.get());
+    forms->has_left = 1;
+    forms->has_right = 1;
+    Z.forms = forms;
+  }
   rt().tile_products++;
   rt().dmma_issued += (double)h_ndmma;
   return true;

@@ -163,3 +163,91 @@ def test_scattered_product_stays_on_scalar_path(nt):
     C.Gemm(A, A)
     assert nt.tile_counters()["tile_products"] == 0
     compare_sparse(C.to_scipy(), a @ a)
+
+
+# ---- tile forms carried by the operands (emitted with a product's result, shared by copies) ----------------------
+def test_tile_forms_chain_matches_oracle(nt, oracle):
+    """C = A*A, D = C*A, E = A*C, F = C*C: the products after the first read the tile forms emitted with C
+    instead of rebuilding them from CSC; results must not depend on where the forms came from."""
+    n, thr = 1500, 1e-7
+    a = banded(n, half_bandwidth=40)
+    A, C, D, E, F = to_gpu(nt, a), nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    nt.reset_counters()
+    C.Gemm(A, A, None, threshold=thr)
+    assert nt.tile_counters()["tile_products"] == 1
+    builds_first = nt.tile_builds()
+    assert builds_first == 2                      # left + right form of A
+    D.Gemm(C, A, None, threshold=thr)
+    E.Gemm(A, C, None, threshold=thr)
+    F.Gemm(C, C, None, alpha=-0.5, threshold=thr)
+    assert nt.tile_builds() == builds_first       # nothing was rebuilt from CSC
+    oa = oracle.PSMatrix.from_scipy(a)
+    oc = oracle.multiply(oa, oa, thr=thr)
+    compare_sparse(C.to_scipy(), oc.to_scipy(), thr)
+    # feed the oracle the GPU's C so that only the product under test differs
+    ocg = oracle.PSMatrix.from_scipy(C.to_scipy())
+    compare_sparse(D.to_scipy(), oracle.multiply(ocg, oa, thr=thr).to_scipy(), thr)
+    compare_sparse(E.to_scipy(), oracle.multiply(oa, ocg, thr=thr).to_scipy(), thr)
+    compare_sparse(F.to_scipy(), oracle.multiply(ocg, ocg, alpha=-0.5, thr=thr).to_scipy(), thr)
+    # a copy shares the forms; a changed matrix drops them
+    G = nt.Matrix_ps(C)
+    H = nt.Matrix_ps(n)
+    H.Gemm(G, A, None, threshold=thr)
+    assert nt.tile_builds() == builds_first
+    compare_sparse(H.to_scipy(), D.to_scipy(), thr)
+    G.Scale(2.0)                                  # G shares C's forms: they must not be scaled under C's feet
+    H.Gemm(G, A, None, threshold=thr)
+    assert nt.tile_builds() == builds_first + 1
+    compare_sparse(H.to_scipy(), oracle.multiply(oracle.PSMatrix.from_scipy(G.to_scipy()), oa, thr=thr).to_scipy(), thr)
+    H.Gemm(C, A, None, threshold=thr)             # C is unchanged
+    compare_sparse(H.to_scipy(), D.to_scipy(), thr)
+    F.Scale(-3.0)                                 # sole owner: forms are scaled in place
+    H.Gemm(F, A, None, threshold=thr)
+    assert nt.tile_builds() == builds_first + 1
+    compare_sparse(H.to_scipy(), oracle.multiply(oracle.PSMatrix.from_scipy(F.to_scipy()), oa, thr=thr).to_scipy(), thr)
+
+
+@pytest.mark.parametrize("n,hb,thr,alpha,sigma", [(1500, 40, 1e-7, -1.3, 3.0), (777, 30, 0.0, 1.0, -1.0),
+                                                   (2048, 12, 1e-3, 0.5, 2.5)])
+def test_fused_identity_shift_is_bit_exact(nt, n, hb, thr, alpha, sigma):
+    """MatrixMultiplyShift == MatrixMultiply followed by IncrementMatrix(Identity, C, sigma): same pattern, same bits."""
+    a = banded(n, half_bandwidth=hb)
+    A, I = to_gpu(nt, a), nt.Matrix_ps(n)
+    I.FillIdentity()
+    ref, fused, twice = nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    ref.Gemm(A, A, None, alpha=alpha, threshold=thr)
+    ref.Increment(I, sigma)
+    nt.set_fused_shift(True)
+    fused.GemmShift(A, A, I, sigma, None, alpha=alpha, threshold=thr)
+    r, f = ref.to_scipy().tocsc(), fused.to_scipy().tocsc()
+    r.sort_indices(); f.sort_indices()
+    assert np.array_equal(r.indptr, f.indptr) and np.array_equal(r.indices, f.indices)
+    assert np.array_equal(r.data, f.data)
+    # the emitted tile forms carry the shift: use the result as an operand
+    nt.reset_counters()
+    twice.Gemm(fused, fused, None, threshold=thr)
+    assert nt.tile_builds() == 0
+    chk = nt.Matrix_ps(n)
+    nt.set_fused_shift(False)
+    chk.Gemm(ref, ref, None, threshold=thr)
+    nt.set_fused_shift(True)
+    compare_sparse(twice.to_scipy(), chk.to_scipy(), thr)
+
+
+def test_fused_shift_empty_product_columns(nt):
+    """diagonal entries must appear even where the product has no entry at all (window extension)"""
+    n = 600
+    a = banded(n, half_bandwidth=20).tolil()
+    a[:, 100:164] = 0.0          # 64 empty columns -> a whole group of output columns is empty
+    a[100:164, :] = 0.0
+    a = sp.csc_matrix(a); a.eliminate_zeros()
+    A, I = to_gpu(nt, a), nt.Matrix_ps(n)
+    I.FillIdentity()
+    ref, fused = nt.Matrix_ps(n), nt.Matrix_ps(n)
+    ref.Gemm(A, A, None, threshold=1e-9)
+    ref.Increment(I, 3.0)
+    fused.GemmShift(A, A, I, 3.0, None, threshold=1e-9)
+    r, f = ref.to_scipy().tocsc(), fused.to_scipy().tocsc()
+    r.sort_indices(); f.sort_indices()
+    assert np.array_equal(r.indptr, f.indptr) and np.array_equal(r.indices, f.indices)
+    assert np.array_equal(r.data, f.data)
