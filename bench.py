@@ -32,6 +32,8 @@ METRIC = "spgemm_useful_gflops_per_sign_iteration"
 UNIT = "GFLOP/s"
 GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 ALPHA_MAX = 1.69770248526
+FP64_PEAK_TFLOPS = 37.2          # DMMA.8x8x4 issue peak measured on this pool's B200 (scripts/micro/dmma_shapes.cu)
+TRAFFIC_PER_LAUNCH = None        # dram bytes of one numeric launch from the ncu --set full capture (profiles/), or None
 
 
 def parse():
@@ -222,21 +224,21 @@ def main():
     X = nt.Matrix_ps(M)
     X.Scale(1.0 / abs(e_max))
     pool = nt.PMatrixMemoryPool(X)
-    T1, T2, D = nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    T1, T2 = nt.Matrix_ps(n), nt.Matrix_ps(n)
+
+    W = nt.Matrix_ps(n)
 
     def step(Xin, ak):
-        """loop body of SignSolversModule.F90:207-240 through the C ABI"""
-        T1.Gemm(Xin, Xin, pool, alpha=-ak * ak, threshold=thr)
-        T1.Increment(I, 3.0)
-        T2.Gemm(Xin, T1, pool, alpha=0.5 * ak, threshold=thr)
-        lib = nt.lib()
-        lib.CopyMatrix_ps_wrp(Xin.ih, D.ih)
-        D.Increment(T2, -1.0)
-        return D.Norm()
+        """CopyMatrix(X_k -> W), then the loop body of SignFunction (SignSolversModule.F90:207-240) exactly as the
+        SignFunction_wrp driver of this library runs it (csrc/solvers.cu: sign_iteration) on W, through the C ABI:
+        two thresholded multiplies (the first with the 3I shift of the following IncrementMatrix fused into its
+        emit pass), the convergence norm ||X_{k+1} - X_k||, CopyMatrix. W ends as X_{k+1}; X_k is left untouched so
+        that every step does identical work."""
+        nt.lib().CopyMatrix_ps_wrp(Xin.ih, W.ih)
+        return nt.sign_iteration(W, I, T1, T2, ak, thr, pool)
 
     for k in range(args.iterate - 1):         # advance to the iterate the step is quoted on
-        step(X, alphas[k])
-        nt.lib().CopyMatrix_ps_wrp(T2.ih, X.ih)
+        nt.sign_iteration(X, I, T1, T2, alphas[k], thr, pool)
     ak = alphas[args.iterate - 1]
 
     for _ in range(max(args.warmup, 3)):
@@ -290,7 +292,7 @@ def main():
         for _ in range(e2e_steps):
             Xh.fill_from_arrays(*pin)                     # H2D of this step's input
             nv = step(Xh, ak)
-            out = T2.get_arrays()                         # D2H of the step's result (+ the norm scalar)
+            out = W.get_arrays()                          # D2H of the step's result X_{k+1} (+ the norm scalar)
             d2h = sum(a.nbytes for a in out) + 8
         barrier()
         dt = time.perf_counter() - t0
@@ -317,12 +319,16 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (prof["numeric_ms"] * 1e-3) / 1e9 if prof["numeric_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_numeric_warp (numeric SpGEMM, per product)",
+                "traffic": TRAFFIC_PER_LAUNCH, "kernel": "k_tile_numeric (numeric SpGEMM, one launch per product)",
                 "launches_timed": prof["products"], "peak_source": peak_src,
                 "numeric_share_of_step": prof["numeric_ms"] / (ms_total if world == 1 else float(t[0])),
                 "fp64_tflops_useful": cnt["flops"] / (prof["numeric_ms"] * 1e-3) / 1e12 if prof["numeric_ms"] > 0 else 0.0,
+                "fp64_tensor_peak_tflops": FP64_PEAK_TFLOPS,
+                "fp64_frac": (cnt["flops"] / (prof["numeric_ms"] * 1e-3) / 1e12 / FP64_PEAK_TFLOPS) if prof["numeric_ms"] > 0 else 0.0,
+                "tile_form_builds_in_timed_region": nt.tile_builds(),
                 "note": "arithmetic intensity of this product (~10 flop/B) is above the FP64 machine balance "
-                        "(35.5 TF/s cuBLAS DGEMM measured / HBM peak): see DESIGN.md"}
+                        "(37.2 TF/s DMMA measured, scripts/micro / HBM peak): the kernel is bound by the FP64 tensor "
+                        "pipe, fp64_frac is its share of that peak; see DESIGN.md"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -337,8 +343,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"newton-schulz sign iteration (2 multiplies + 2 adds + norm), banded N={n} "
-                               f"half-bandwidth 82, thr={thr:g}, iterate X_{args.iterate}",
+        "config": {"workload": f"newton-schulz sign iteration (SignFunction driver loop body: 2 multiplies, identity "
+                               f"shift, convergence norm, copy), banded N={n} half-bandwidth 82, thr={thr:g}, "
+                               f"iterate X_{args.iterate}",
                    "grid": f"{R}x{C}x{S}", "l2": "inputs exceed L2 (operands > 500 MB vs 126 MB L2)",
                    "sec_per_iteration": ms_per_step * 1e-3},
         "clocks": clocks, "e2e": e2e, "gpu_launches": cnt["launches"], "roofline": roofline,

@@ -423,6 +423,38 @@ template <typename T> void csc_col_abs_sums(const CscView<T>& M, double* d_colsu
   NTB_LAUNCH((k_col_abs<T>), warp_grid(M.cols), 256, 0, M, d_colsum);
 }
 
+// column sums of |alpha*A + B| without forming the sum (the drivers' "IncrementMatrix then MatrixNorm" on a matrix
+// that is overwritten right after, e.g. SignSolversModule.F90:230-232): entries dropped by the add are exact zeros
+// and contribute nothing, so the value is the reference's up to summation order
+template <typename T>
+__global__ void __launch_bounds__(256) k_diff_col_abs(CscView<T> A, CscView<T> B, double alpha, double* __restrict__ colsum) {
+  WARP_COL_LOOP(A.cols) {
+    const int a0 = A.outer[j], na = A.outer[j + 1] - a0;
+    const int b0 = B.outer[j], nb = B.outer[j + 1] - b0;
+    const int* ai = A.inner + a0;
+    const int* bi = B.inner + b0;
+    double s = 0.0;
+    for (int t = lane; t < na; t += 32) {
+      const int ia = ai[t];
+      const int pb = lower_bound_dev(bi, nb, ia);
+      T v = s_scale(alpha, A.val[a0 + t]);
+      if (pb < nb && bi[pb] == ia) v = s_add(v, B.val[b0 + pb]);
+      s += s_abs(v);
+    }
+    for (int t = lane; t < nb; t += 32) {
+      const int ib = bi[t];
+      const int pa = lower_bound_dev(ai, na, ib);
+      if (!(pa < na && ai[pa] == ib)) s += s_abs(B.val[b0 + t]);
+    }
+    s = warp_sum(s);
+    if (lane == 0) colsum[j] = s;
+  }
+}
+template <typename T> void csc_diff_col_abs_sums(const CscView<T>& A, const CscView<T>& B, double alpha, double* d_colsum) {
+  NTB_CHECK(A.cols == B.cols && A.rows == B.rows, "diff norm: shape mismatch");
+  NTB_LAUNCH((k_diff_col_abs<T>), warp_grid(A.cols), 256, 0, A, B, alpha, d_colsum);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_gersh(CscView<T> M, int start_row, int start_col, double* __restrict__ dmin,
                                                double* __restrict__ dmax) {
@@ -596,6 +628,7 @@ template <typename T> void csc_transpose(const CscView<T>& M, LocalCsc<T>& out) 
   template void csc_stack_rows<T>(const CscView<T>*, const int*, int, int, LocalCsc<T>&);                      \
   template void csc_trace<T>(const CscView<T>&, int, int, double*);                                            \
   template void csc_col_abs_sums<T>(const CscView<T>&, double*);                                               \
+  template void csc_diff_col_abs_sums<T>(const CscView<T>&, const CscView<T>&, double, double*);               \
   template void csc_gershgorin_cols<T>(const CscView<T>&, int, int, double*, double*);                         \
   template void csc_dot<T>(const CscView<T>&, const CscView<T>&, double*);                                     \
   template void csc_identity_check<T>(const CscView<T>&, int, int, double*);                                   \

@@ -32,6 +32,7 @@ template <typename T> void csc_stack_rows(const CscView<T>* parts, const int* ro
 template <typename T> void csc_trace(const CscView<T>& M, int start_row, int start_col, double* d_out);
 // d_colsum[j] = sum_i |M(i,j)|
 template <typename T> void csc_col_abs_sums(const CscView<T>& M, double* d_colsum);
+template <typename T> void csc_diff_col_abs_sums(const CscView<T>& A, const CscView<T>& B, double alpha, double* d_colsum);
 // d_min[j] / d_max[j] Gershgorin column contributions (solver_includes/GershgorinBounds.f90)
 template <typename T> void csc_gershgorin_cols(const CscView<T>& M, int start_row, int start_col, double* d_min, double* d_max);
 // d_out[0..1] = sum conj(a_ij) * b_ij  (re, im)

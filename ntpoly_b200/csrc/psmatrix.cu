@@ -500,6 +500,26 @@ double mat_norm(const Matrix& M) {
   return h;
 }
 
+// MatrixNorm(alpha*A + B) without forming the sum (see k_diff_col_abs); operands of equal type and layout
+double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha) {
+  NTB_CHECK(A.constructed && B.constructed && A.logical_dim == B.logical_dim && A.grid == B.grid, "diff norm: operands differ in layout");
+  if (A.is_complex != B.is_complex) {           // mixed types: the two reference calls on a scratch copy
+    Matrix t;
+    mat_copy(B, t);
+    mat_increment(A, t, alpha, 0.0);
+    return mat_norm(t);
+  }
+  DevBuf<double> colsum((size_t)B.local_cols), d(1);
+  if (A.is_complex) csc_diff_col_abs_sums<cplx>(A.c.view(), B.c.view(), alpha, colsum.get());
+  else csc_diff_col_abs_sums<double>(A.r.view(), B.r.view(), alpha, colsum.get());
+  comm_allreduce_f64(B.grid->column, colsum.get(), (size_t)B.local_cols, RedOp::Sum);
+  reduce_max(colsum.get(), B.local_cols, d.get());
+  comm_allreduce_f64(B.grid->row, d.get(), 1, RedOp::Max);
+  double h;
+  d2h(&h, d.get(), 1);
+  return h;
+}
+
 double mat_sigma(const Matrix& M) {
   const double n = mat_norm(M);
   return 1.0 / (n * n);

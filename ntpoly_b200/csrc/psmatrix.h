@@ -95,6 +95,7 @@ void mat_scale(Matrix& M, double c);
 void mat_scale_c(Matrix& M, cplx c);
 double mat_trace(const Matrix& M);
 double mat_norm(const Matrix& M);
+double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha);   // MatrixNorm(alpha*A + B), sum not formed
 double mat_sigma(const Matrix& M);
 void mat_dot(const Matrix& A, const Matrix& B, double* re, double* im);
 void mat_pairwise(const Matrix& A, const Matrix& B, Matrix& C);

@@ -423,8 +423,8 @@ double sign_iteration(Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& T2,
     mat_multiply_shift(X, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool);   // T1 = 3I - a^2 X^2
   }
   mat_multiply(X, T1, T2, 0.5 * alpha_k, 0.0, threshold, pool);
-  mat_increment(T2, X, -1.0, 0.0);
-  const double norm_value = mat_norm(X);
+  // reference: IncrementMatrix(T2, X, -1); norm = MatrixNorm(X); CopyMatrix(T2, X) — X - T2 is never needed itself
+  const double norm_value = mat_diff_norm(T2, X, -1.0);
   mat_copy(T2, X);
   return norm_value;
 }
@@ -497,10 +497,7 @@ void solve_invert(const Matrix& In, Matrix& Out, const SolverParameters& p) {
   int II = 1;
   for (II = 1; II <= p.max_iterations; ++II) {
     mat_multiply(X, Bal, T1, 1.0, 0.0, p.threshold, &pool);
-    mat_copy(Identity, T2);
-    mat_increment(T1, T2, -1.0, 0.0);
-    const double norm_value = mat_norm(T2);
-    mat_destruct(T2);
+    const double norm_value = mat_diff_norm(T1, Identity, -1.0);      // ||I - X*A|| (reference: Copy, Increment, Norm)
     mat_multiply(T1, X, T2, -1.0, 0.0, p.threshold, &pool);
     mat_scale(X, 2.0);
     mat_increment(T2, X, 1.0, p.threshold);
@@ -537,9 +534,7 @@ static void ns_isr_order2(const Matrix& In, Matrix& Out, const SolverParameters&
     mat_gershgorin(X, &e_min, &e_max);
     const double lambda = 1.0 / std::max(std::fabs(e_min), std::fabs(e_max));
     mat_scale(X, lambda);
-    mat_copy(Identity, T);
-    mat_increment(X, T, -1.0, 0.0);
-    const double norm_value = mat_norm(T);
+    const double norm_value = mat_diff_norm(X, Identity, -1.0);       // ||I - X|| (reference: Copy, Increment, Norm)
     mat_copy(Identity, Tk);
     mat_scale(Tk, 3.0);
     mat_increment(X, Tk, -1.0, 0.0);

@@ -273,6 +273,20 @@ __global__ void __launch_bounds__(256) k_compact(int ncols, const long long* __r
   }
 }
 
+// useful products of the local product: sum over the entries (k,j) of X of len(Y(:,k))  (F = 2 * this)
+template <typename T>
+__global__ void __launch_bounds__(256) k_useful_products(CscView<T> X, CscView<T> Y, long long nnzX,
+                                                         unsigned long long* __restrict__ total) {
+  unsigned long long s = 0;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnzX; p += (long long)gridDim.x * blockDim.x) {
+    const int k = X.inner[p];
+    s += (unsigned long long)(Y.outer[k + 1] - Y.outer[k]);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+
 // ---------------------------------------------------------------------------
 template <typename T>
 void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double thr, const RuleView& rules,
@@ -295,6 +309,34 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   for (int b = 1; b <= 4; ++b) cfg.wmax[b] = per_warp_elems[b];
   cfg.wmax[5] = (int)(SMEM_BUDGET / sizeof(T));
   cfg.wmax[6] = INT_MAX;
+
+  auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
+  auto account_bytes = [&](long long nnz_out) {
+    double b = csc_bytes(Xl.nnz, X.cols) + csc_bytes(nnz_out, ncols);
+    if (Y.val != X.val) b += csc_bytes(Yl.nnz, Y.cols);   // A counted once when A == B (SURVEY 8d)
+    rt().alg_bytes += b;
+  };
+
+  // ---- tile path first: it needs only the useful-product count, not the per-column windows
+  if constexpr (!scalar_traits<T>::is_complex) {
+    if (tile_path_enabled() && Xl.nnz > 0 && Yl.nnz > 0) {
+      DevBuf<unsigned long long> fl(1);
+      fl.zero();
+      NTB_LAUNCH((k_useful_products<T>), min(div_up(Xl.nnz, 256 * 8), kNumSMs * 16), 256, 0, X, Y, Xl.nnz, fl.get());
+      unsigned long long h_fl = 0;
+      d2h(&h_fl, fl.get(), 1);
+      // worth it only when columns are long enough to fill tiles
+      if ((double)h_fl >= 16.0 * (double)ncols && spgemm_tile(Xl, Yl, alpha, thr, rules, Z, (double)h_fl, shift)) {
+        if (stats) {
+          stats->shift_applied = shift && shift->sigma != 0.0;
+          stats->flops = 2.0 * (double)h_fl;
+          stats->tmp_entries = 0;
+        }
+        account_bytes(Z.nnz);
+        return;
+      }
+    }
+  }
 
   DevBuf<int> lo(ncols), wid(ncols), cap(ncols), binid(ncols), cnt(ncols);
   DevBuf<int> lists((size_t)NBINS * ncols);
@@ -322,28 +364,13 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   stream_sync();
 
   auto account = [&](long long nnz_out) {
-    auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
-    double b = csc_bytes(Xl.nnz, X.cols) + csc_bytes(nnz_out, ncols);
-    if (Y.val != X.val) b += csc_bytes(Yl.nnz, Y.cols);   // A counted once when A == B (SURVEY 8d)
-    rt().alg_bytes += b;
+    account_bytes(nnz_out);
     if (stats) {
       stats->flops = 2.0 * (double)h_flops * (scalar_traits<T>::is_complex ? 4.0 : 1.0);
       stats->tmp_entries = h_tmp_total;
       for (int b2 = 0; b2 < NBINS; ++b2) stats->bins[b2] = h_bins[b2];
     }
   };
-
-  if constexpr (!scalar_traits<T>::is_complex) {
-    if (tile_path_enabled() && h_flops > 0) {
-      // worth it only when columns are long enough to fill tiles
-      if ((double)h_flops >= 16.0 * (double)ncols &&
-          spgemm_tile(Xl, Yl, alpha, thr, rules, Z, (double)h_flops, shift)) {
-        if (stats && shift && shift->sigma != 0.0) stats->shift_applied = true;
-        account(Z.nnz);
-        return;
-      }
-    }
-  }
 
   DevBuf<int> tmp_idx((size_t)h_tmp_total);
   DevBuf<T> tmp_val((size_t)h_tmp_total);

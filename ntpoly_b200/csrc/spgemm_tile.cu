@@ -681,28 +681,40 @@ k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __re
 // Slots are enumerated in chunk-column order: right form slot = 2*task + h; left form slot = 2*t0(g) + c*n(g) + b.
 constexpr int FI_T = 1024, FI_ITEMS = 8;
 
+// slot s of a form -> its task-owned mask, super-tile id and the slot range [sa, sb) of its chunk column
 __device__ __forceinline__ void form_slot(bool left, int s, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
                                           const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
-                                          unsigned long long& mask, int& id) {
+                                          unsigned long long& mask, int& id, int& q, int& sa, int& sb) {
   const int t = s >> 1;
   const int2 tk = tasks[t];
-  if (!left) { mask = fmB[s]; id = 2 * tk.y + (s & 1); return; }
   const int t0 = gtask_off[tk.x], nn = gtask_off[tk.x + 1] - t0;
+  if (!left) { mask = fmB[s]; id = 2 * tk.y + (s & 1); q = tk.x; sa = 2 * t0; sb = sa + 2 * nn; return; }
   const int local = s - 2 * t0, c = local / nn, b = local - c * nn;
   mask = fmA[(size_t)(t0 + b) * 2 + c];
   id = tasks[t0 + b].y;
+  q = 2 * tk.x + c; sa = 2 * t0 + c * nn; sb = sa + nn;
 }
 
-// blockIdx.x: 0 = left form, 1 = right form. One CTA scans all slots (a few 10^4) and writes entries + column meta.
-__global__ void __launch_bounds__(FI_T)
-k_forms_index(int ntasks, int nG, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
+// (1) masks in slot order, both forms (blockIdx.y: 0 = left, 1 = right)
+__global__ void __launch_bounds__(256)
+k_forms_slots(int ntasks, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
               const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
-              int4* __restrict__ entL, int4* __restrict__ entR, int4* __restrict__ colmetaL, int4* __restrict__ colmetaR,
-              int* __restrict__ seidxL, int* __restrict__ seidxR, int* __restrict__ stoffL, int* __restrict__ stoffR,
-              int* __restrict__ totals) {
+              unsigned long long* __restrict__ smaskL, unsigned long long* __restrict__ smaskR) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= 2 * ntasks) return;
+  const bool left = blockIdx.y == 0;
+  unsigned long long m; int id, q, sa, sb;
+  form_slot(left, s, tasks, gtask_off, fmA, fmB, m, id, q, sa, sb);
+  (left ? smaskL : smaskR)[s] = m;
+}
+
+// (2) one CTA per form: exclusive scans of (non-empty, tile count) over the slots
+__global__ void __launch_bounds__(FI_T)
+k_forms_scan(int ntasks, const unsigned long long* __restrict__ smaskL, const unsigned long long* __restrict__ smaskR,
+             int* __restrict__ seidxL, int* __restrict__ seidxR, int* __restrict__ stoffL, int* __restrict__ stoffR,
+             int* __restrict__ totals) {
   const bool left = blockIdx.x == 0;
-  int4* ent = left ? entL : entR;
-  int4* colmeta = left ? colmetaL : colmetaR;
+  const unsigned long long* smask = left ? smaskL : smaskR;
   int* seidx = left ? seidxL : seidxR;
   int* stoff = left ? stoffL : stoffR;
   const int n = 2 * ntasks;
@@ -714,12 +726,10 @@ k_forms_index(int ntasks, int nG, const int2* __restrict__ tasks, const int* __r
   for (int base = 0; base < n; base += FI_T * FI_ITEMS) {
     const int s0 = base + threadIdx.x * FI_ITEMS;
     unsigned long long m[FI_ITEMS];
-    int id[FI_ITEMS];
     int f = 0, pc = 0;
 #pragma unroll
     for (int k = 0; k < FI_ITEMS; ++k) {
-      m[k] = 0ull; id[k] = 0;
-      if (s0 + k < n) form_slot(left, s0 + k, tasks, gtask_off, fmA, fmB, m[k], id[k]);
+      m[k] = (s0 + k < n) ? smask[s0 + k] : 0ull;
       f += (m[k] != 0ull); pc += popc64(m[k]);
     }
     int fi = f, pi = pc;
@@ -746,27 +756,48 @@ k_forms_index(int ntasks, int nG, const int2* __restrict__ tasks, const int* __r
     for (int k = 0; k < FI_ITEMS; ++k) {
       if (s0 + k < n) {
         seidx[s0 + k] = e; stoff[s0 + k] = t;
-        if (m[k] != 0ull) {
-          ent[e] = make_int4(id[k], t, (int)(unsigned)(m[k] & 0xffffffffull), (int)(unsigned)(m[k] >> 32));
-          ++e; t += popc64(m[k]);
-        }
+        if (m[k] != 0ull) { ++e; t += popc64(m[k]); }
       }
     }
     __syncthreads();
-    if (threadIdx.x == FI_T - 1) { carry[0] = e; carry[1] = t; }   // last thread ends at the chunk totals
+    if (threadIdx.x == FI_T - 1) { carry[0] = e; carry[1] = t; }   // the last thread ends at the running totals
     __syncthreads();
   }
   if (threadIdx.x == 0) { seidx[n] = carry[0]; totals[left ? 0 : 2] = carry[0]; totals[left ? 1 : 3] = carry[1]; }
-  __syncthreads();
-  // column meta
-  const int ncc = left ? 2 * nG : nG;
-  for (int q = threadIdx.x; q < ncc; q += FI_T) {
-    const int g = left ? (q >> 1) : q;
-    const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
-    const int sa = left ? 2 * t0 + (q & 1) * nn : 2 * t0, sb = sa + (left ? nn : 2 * nn);
-    const int e0 = seidx[sa], e1 = seidx[sb];
-    colmeta[q] = (e1 > e0) ? make_int4(e0, e1 - e0, ent[e0].x, ent[e1 - 1].x) : make_int4(0, 0, 0, -1);
+}
+
+// (3) entries and chunk-column meta (blockIdx.y: 0 = left, 1 = right); threads beyond the slots mark empty columns
+__global__ void __launch_bounds__(256)
+k_forms_write(int ntasks, int nG, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
+              const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
+              const int* __restrict__ seidxL, const int* __restrict__ seidxR, const int* __restrict__ stoffL,
+              const int* __restrict__ stoffR, int4* __restrict__ entL, int4* __restrict__ entR,
+              int4* __restrict__ colmetaL, int4* __restrict__ colmetaR) {
+  const bool left = blockIdx.y == 0;
+  const int* seidx = left ? seidxL : seidxR;
+  const int* stoff = left ? stoffL : stoffR;
+  int4* ent = left ? entL : entR;
+  int* cm = reinterpret_cast<int*>(left ? colmetaL : colmetaR);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 2 * ntasks;
+  if (i < n) {
+    unsigned long long m; int id, q, sa, sb;
+    form_slot(left, i, tasks, gtask_off, fmA, fmB, m, id, q, sa, sb);
+    if (m != 0ull) {
+      const int e = seidx[i], e0 = seidx[sa], e1 = seidx[sb];
+      ent[e] = make_int4(id, stoff[i], (int)(unsigned)(m & 0xffffffffull), (int)(unsigned)(m >> 32));
+      if (e == e0) { cm[4 * q + 0] = e0; cm[4 * q + 1] = e1 - e0; cm[4 * q + 2] = id; }
+      if (e + 1 == e1) cm[4 * q + 3] = id;
+    }
+    return;
   }
+  const int q = i - n;                       // one extra thread per chunk column: empty columns
+  const int ncc = left ? 2 * nG : nG;
+  if (q >= ncc) return;
+  const int g = left ? (q >> 1) : q;
+  const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
+  const int sa = left ? 2 * t0 + (q & 1) * nn : 2 * t0, sb = sa + (left ? nn : 2 * nn);
+  if (seidx[sa] == seidx[sb]) reinterpret_cast<int4*>(cm)[q] = make_int4(0, 0, 0, -1);
 }
 
 // left form: per inner tile K of the result (4 columns): tile count, first and last row tile
@@ -950,9 +981,14 @@ bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double 
     L.colmeta.alloc((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
     L.kmeta.alloc((size_t)nk);
     seidxL.alloc(ns + 1); seidxR.alloc(ns + 1); stoffL.alloc(ns); stoffR.alloc(ns);
-    NTB_LAUNCH(k_forms_index, 2, FI_T, 0, h_tasks, nG, tasks.get(), gtask_off.get(), fmA.get(), fmB.get(), L.ent.get(),
-               R.ent.get(), L.colmeta.get(), R.colmeta.get(), seidxL.get(), seidxR.get(), stoffL.get(), stoffR.get(),
-               totals.get());
+    DevBuf<unsigned long long> smaskL(ns), smaskR(ns);
+    NTB_LAUNCH(k_forms_slots, dim3(div_up((long long)ns, 256), 2), 256, 0, h_tasks, tasks.get(), gtask_off.get(), fmA.get(),
+               fmB.get(), smaskL.get(), smaskR.get());
+    NTB_LAUNCH(k_forms_scan, 2, FI_T, 0, h_tasks, smaskL.get(), smaskR.get(), seidxL.get(), seidxR.get(), stoffL.get(),
+               stoffR.get(), totals.get());
+    NTB_LAUNCH(k_forms_write, dim3(div_up((long long)ns + 2 * nG, 256), 2), 256, 0, h_tasks, nG, tasks.get(), gtask_off.get(),
+               fmA.get(), fmB.get(), seidxL.get(), seidxR.get(), stoffL.get(), stoffR.get(), L.ent.get(), R.ent.get(),
+               L.colmeta.get(), R.colmeta.get());
     NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), fmA.get(), L.kmeta.get());
   } else {
     totals.zero();

@@ -14,7 +14,13 @@ T1, T2, D = nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n)
 def timed(name, fn):
     nt.synchronize(); t0 = time.perf_counter(); r = fn(); nt.synchronize()
     print(f"  {name:28s} {(time.perf_counter()-t0)*1e3:9.3f} ms", flush=True); return r
-for it in range(5):
+pool = None
+for it in range(3):
+    nt.synchronize(); t0 = time.perf_counter()
+    nv = nt.sign_iteration(X, I, T1, T2, 1.2, thr)
+    nt.synchronize()
+    print(f"driver sign_iteration {it}: {(time.perf_counter()-t0)*1e3:.3f} ms norm={nv:.4e} nnz(X)={X.GetSize()} builds={nt.tile_builds()}", flush=True)
+for it in range(3):
     print("iteration", it, "nnz(X)", X.GetSize(), flush=True)
     ak = 1.2
     timed("gemm X*X", lambda: T1.Gemm(X, X, None, alpha=-ak*ak, threshold=thr))
