@@ -526,10 +526,16 @@ class Matrix_ps:
                                           vals.view(np.float64).ctypes.data_as(POINTER(c_double)),
                                           c_int(1 if cplx else 0))
 
-    def get_arrays(self):
+    def get_arrays(self, out=None):
+        """local block as global 1-based triplets; `out` = (rows, cols, vals) buffers to fill (e.g. pinned memory,
+        at least GetMatrixLocalSize entries each) instead of fresh arrays"""
         n = lib().ntb_GetMatrixLocalSize_ps(self.ih)
-        rows, cols = np.zeros(n, np.int32), np.zeros(n, np.int32)
-        vals = np.zeros(n, np.complex128 if self.IsComplex() else np.float64)
+        if out is not None:
+            rows, cols, vals = (a[:n] for a in out)
+            assert rows.dtype == np.int32 and cols.dtype == np.int32
+        else:
+            rows, cols = np.empty(n, np.int32), np.empty(n, np.int32)
+            vals = np.empty(n, np.complex128 if self.IsComplex() else np.float64)
         if n:
             lib().ntb_GetMatrixArrays_ps(self.ih, _ip(rows), _ip(cols),
                                          vals.view(np.float64).ctypes.data_as(POINTER(c_double)))

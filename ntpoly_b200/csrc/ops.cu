@@ -381,9 +381,45 @@ __global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ in, 
     if (threadIdx.x == 0) out[0] = acc;
   }
 }
-void reduce_sum(const double* d_in, int n, double* d_out) { NTB_LAUNCH((k_reduce<0>), 1, 1024, 0, d_in, n, d_out); }
-void reduce_max(const double* d_in, int n, double* d_out) { NTB_LAUNCH((k_reduce<1>), 1, 1024, 0, d_in, n, d_out); }
-void reduce_min(const double* d_in, int n, double* d_out) { NTB_LAUNCH((k_reduce<2>), 1, 1024, 0, d_in, n, d_out); }
+template <int OP>
+__global__ void __launch_bounds__(1024) k_reduce_chunks(const double* __restrict__ in, int n, double* __restrict__ part) {
+  __shared__ double sw[32];
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per, hi = min(n, lo + per);
+  double acc = (OP == 0) ? 0.0 : (OP == 1 ? -INFINITY : INFINITY);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double v = in[i];
+    acc = (OP == 0) ? acc + v : (OP == 1 ? fmax(acc, v) : fmin(acc, v));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, acc, d);
+    acc = (OP == 0) ? acc + o : (OP == 1 ? fmax(acc, o) : fmin(acc, o));
+  }
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = sw[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, acc, d);
+      acc = (OP == 0) ? acc + o : (OP == 1 ? fmax(acc, o) : fmin(acc, o));
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+  }
+}
+// two deterministic stages: up to 148 blocks reduce contiguous chunks, one block reduces the partials
+template <int OP> static void reduce_impl(const double* d_in, int n, double* d_out) {
+  const int chunk = 8192;
+  const int nb = min(div_up(max(n, 1), chunk), kNumSMs);
+  if (nb <= 1) { NTB_LAUNCH((k_reduce<OP>), 1, 1024, 0, d_in, n, d_out); return; }
+  DevBuf<double> part((size_t)nb);
+  NTB_LAUNCH((k_reduce_chunks<OP>), nb, 1024, 0, d_in, n, part.get());
+  NTB_LAUNCH((k_reduce<OP>), 1, 1024, 0, (const double*)part.get(), nb, d_out);
+}
+void reduce_sum(const double* d_in, int n, double* d_out) { reduce_impl<0>(d_in, n, d_out); }
+void reduce_max(const double* d_in, int n, double* d_out) { reduce_impl<1>(d_in, n, d_out); }
+void reduce_min(const double* d_in, int n, double* d_out) { reduce_impl<2>(d_in, n, d_out); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -434,17 +470,36 @@ __global__ void __launch_bounds__(256) k_diff_col_abs(CscView<T> A, CscView<T> B
     const int* ai = A.inner + a0;
     const int* bi = B.inner + b0;
     double s = 0.0;
-    for (int t = lane; t < na; t += 32) {
-      const int ia = ai[t];
-      const int pb = lower_bound_dev(bi, nb, ia);
-      T v = s_scale(alpha, A.val[a0 + t]);
-      if (pb < nb && bi[pb] == ia) v = s_add(v, B.val[b0 + pb]);
-      s += s_abs(v);
+    // the two patterns are usually almost equal (successive iterates): try the position suggested by the
+    // previous chunk's offset before falling back to the binary search
+    int delta = 0;
+    for (int t0 = 0; t0 < na; t0 += 32) {
+      const int t = t0 + lane;
+      int pb = 0;
+      if (t < na) {
+        const int ia = ai[t];
+        const int g = t + delta;
+        if (g >= 0 && g < nb && bi[g] == ia) pb = g;
+        else pb = lower_bound_dev(bi, nb, ia);
+        T v = s_scale(alpha, A.val[a0 + t]);
+        if (pb < nb && bi[pb] == ia) v = s_add(v, B.val[b0 + pb]);
+        s += s_abs(v);
+      }
+      delta = __shfl_sync(0xffffffffu, pb - t, min(31, na - 1 - t0));
     }
-    for (int t = lane; t < nb; t += 32) {
-      const int ib = bi[t];
-      const int pa = lower_bound_dev(ai, na, ib);
-      if (!(pa < na && ai[pa] == ib)) s += s_abs(B.val[b0 + t]);
+    delta = 0;
+    for (int t0 = 0; t0 < nb; t0 += 32) {
+      const int t = t0 + lane;
+      int pa = 0;
+      if (t < nb) {
+        const int ib = bi[t];
+        const int g = t + delta;
+        bool matched;
+        if (g >= 0 && g < na && ai[g] == ib) { pa = g; matched = true; }
+        else { pa = lower_bound_dev(ai, na, ib); matched = pa < na && ai[pa] == ib; }
+        if (!matched) s += s_abs(B.val[b0 + t]);
+      }
+      delta = __shfl_sync(0xffffffffu, pa - t, min(31, nb - 1 - t0));
     }
     s = warp_sum(s);
     if (lane == 0) colsum[j] = s;

@@ -309,15 +309,23 @@ static long long allgather_triplets(CommHandle* comm, DevBuf<int>& row, DevBuf<i
   return off[np];
 }
 
+__global__ void __launch_bounds__(256) k_add_const2(int* __restrict__ a, int* __restrict__ b, long long n, int da, int db) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    a[i] += da;
+    b[i] += db;
+  }
+}
+
 template <typename T>
 static void fill_from_triplets_t(Matrix& M, const int* rows, const int* cols, const T* vals, long long n,
                                  bool preduplicated, bool prepartitioned) {
-  // host: 1-based global -> 0-based global
-  std::vector<int> r0((size_t)n), c0((size_t)n);
-  for (long long i = 0; i < n; ++i) { r0[i] = rows[i] - 1; c0[i] = cols[i] - 1; }
+  // the caller's arrays go to the device as they are; 1-based global -> 0-based global happens there
   DevBuf<int> d_row((size_t)n), d_col((size_t)n);
   DevBuf<T> d_val((size_t)n);
-  if (n) { h2d(d_row.get(), r0.data(), (size_t)n); h2d(d_col.get(), c0.data(), (size_t)n); h2d(d_val.get(), vals, (size_t)n); }
+  if (n) {
+    h2d(d_row.get(), rows, (size_t)n); h2d(d_col.get(), cols, (size_t)n); h2d(d_val.get(), vals, (size_t)n);
+    NTB_LAUNCH(k_add_const2, std::min(div_up(n, 256), kNumSMs * 16), 256, 0, d_row.get(), d_col.get(), n, -1, -1);
+  }
   stream_sync();
   long long total = n;
   if (!prepartitioned) total = allgather_triplets<T>(M.grid->within_slice, d_row, d_col, d_val, n);
@@ -346,6 +354,9 @@ long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r
   DevBuf<int> d_row((size_t)nnz), d_col((size_t)nnz);
   if (M.is_complex) csc_to_device_triplets<cplx>(M.c.view(), nnz, d_row.get(), d_col.get());
   else csc_to_device_triplets<double>(M.r.view(), nnz, d_row.get(), d_col.get());
+  // local 0-based -> global 1-based on the device
+  NTB_LAUNCH(k_add_const2, std::min(div_up(nnz, 256), kNumSMs * 16), 256, 0, d_row.get(), d_col.get(), nnz, M.start_row + 1,
+             M.start_col + 1);
   CUDA_CHECK(cudaMemcpyAsync(rows, d_row.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   CUDA_CHECK(cudaMemcpyAsync(cols, d_col.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   if (M.is_complex) {
@@ -356,7 +367,6 @@ long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r
     CUDA_CHECK(cudaMemcpyAsync(vals_r, M.r.val.get(), nnz * sizeof(double), cudaMemcpyDeviceToHost, rt().stream));
   }
   stream_sync();
-  for (long long i = 0; i < nnz; ++i) { rows[i] += M.start_row + 1; cols[i] += M.start_col + 1; }
   return nnz;
 }
 
