@@ -6,7 +6,7 @@ one Newton-Schulz sign-function iteration (reference SignSolversModule.F90:207-2
 thresholded distributed multiplies, two sparse adds, one 1-norm) on the synthetic banded matrix
 N=262144 (half-bandwidth 82, 165 nnz/row) shifted to straddle zero, threshold 1e-6, applied to
 the fixed iterate X_3 so that every step does identical work.  N GPUs share the SAME matrix on
-NTPoly's process grid (2x1x1, 2x2x1, 2x2x2): strong scaling.
+NTPoly's process grid (1x2x1, 1x4x1, 1x8x1: column split): strong scaling.
 
   python bench.py --gpus 1 --steps 10 --warmup 3
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "spgemm_useful_gflops_per_sign_iteration"
 UNIT = "GFLOP/s"
-GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+GRIDS = {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 4, 1), 8: (1, 8, 1)}   # column split: tile halo exchange, no panel gather
 ALPHA_MAX = 1.69770248526
 FP64_PEAK_TFLOPS = 37.2          # DMMA.8x8x4 issue peak measured on this pool's B200 (scripts/micro/dmma_shapes.cu)
 TRAFFIC_PER_LAUNCH = None        # dram bytes of one numeric launch from the ncu --set full capture (profiles/), or None

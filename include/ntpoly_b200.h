@@ -219,6 +219,10 @@ void ntb_set_tile_path(int on);
 void ntb_set_fused_shift(int on);
 /* CSC -> tile-form conversions since the last reset (0 per product once operands carry their tile forms) */
 double ntb_tile_builds(void);
+/* distributed products whose left operand was fetched as a tile halo (1 x C x 1 grids): {count, tile bytes} */
+void ntb_get_halo_counters(double *out2);
+/* 1 (default): column-split grids use the tile halo exchange; 0: always the reference-style CSC panel gather */
+void ntb_set_halo_path(int on);
 /* C = alpha*A*B (thresholded), then IncrementMatrix(Identity, C, sigma) with threshold 0 — the call pair of
  * SignSolversModule.F90:226-229 / SquareRootSolversModule.F90 as one entry point. */
 void ntb_MatrixMultiplyShift_ps(const int *ih_matA, const int *ih_matB, int *ih_matC, const double *alpha,

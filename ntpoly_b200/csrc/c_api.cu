@@ -379,7 +379,7 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().halo_bytes = 0.0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
 // C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when
@@ -403,6 +403,8 @@ double ntb_SignIteration(int* ih_x, const int* ih_identity, int* ih_t1, int* ih_
 }
 void ntb_get_tile_counters(double* out2) { out2[0] = (double)rt().tile_products; out2[1] = rt().dmma_issued; }
 double ntb_tile_builds(void) { return (double)rt().tile_builds; }
+void ntb_get_halo_counters(double* out2) { out2[0] = (double)rt().halo_products; out2[1] = rt().halo_bytes; }
+void ntb_set_halo_path(int on) { ntb::set_halo_path(on); }
 double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }
 void ntb_profile_enable(int on) { ensure_init(); rt().profile = on != 0; }
 void ntb_profile_read(double* out2) {

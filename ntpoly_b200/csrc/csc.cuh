@@ -17,6 +17,7 @@ struct ChunkTiles {
   DevBuf<int4> ent;                          // [nsuper] {id, first tile, mask lo, mask hi}; id = row block (left) / inner chunk (right)
   DevBuf<double> tval;                       // [ntiles*32] fragment-ordered values
   DevBuf<int4> kmeta;                        // left form only: per inner tile K {0, tile count, first row tile, last row tile}
+  DevBuf<int> coltile;                       // left form only: [ncc+1] first tile of every chunk column (halo exchange)
 };
 // Both forms of one matrix, built on first use as a product operand or emitted together with a product's result.
 // Immutable once built, so copies of a matrix share them; any change of the entries drops them.
@@ -103,10 +104,31 @@ struct DiagShift {
 template <typename T>
 void spgemm(const LocalCsc<T>& X, const LocalCsc<T>& Y, double alpha, double thr,
             const RuleView& rules, LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift = nullptr);
+// ---- pieces of the tile path used by the distributed layer (spgemm_tile.cu)
+// cached or freshly built tile form of a real block (nullptr: the pattern cannot be tiled)
+const ChunkTiles* tile_operand_form(const LocalCsc<double>& M, bool left);
+// product from tile forms alone: A = left form of the (possibly gathered) left operand, B = right form of the local
+// right operand. force: never decline (the caller has already committed collectively to this path).
+bool spgemm_tile_core(const ChunkTiles& A, const ChunkTiles& B, int ncols, int nrows, double alpha, double thr,
+                      const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
+                      bool force);
+// assemble the left form of a row of column blocks from per-rank pieces (see psmatrix.cu: halo gather)
+struct LeftPiece {          // one rank's contribution, all offsets in units of that rank / of the gathered arrays
+  int ent_base;             // first entry of this rank in the gathered entry array
+  int ncols_chunk;          // chunk columns per rank
+  int a, b;                 // chunk columns [a, b) of this rank were received
+  int tile_lo;              // first tile (rank-local numbering) that was received
+  int recv_base;            // where that tile sits in the gathered value array
+  int nent;                 // entries of this rank
+};
+void tile_fixup_gathered_left(ChunkTiles& G, const LeftPiece* pieces, int npieces);
+// sum over the entries (k,j) of X of ylen[k]  (useful products when the left operand exists only as a tile form)
+double useful_products_from_lengths(const LocalCsc<double>& X, const int* d_ylen);
 // true when spgemm can apply a DiagShift to this product (real operands on the tile path decide at run time:
 // the caller must check GemmStats::shift_applied)
 
 // 1: locally dense real products may run on the DMMA tile path (default), 0: scalar kernels only
 void set_tile_path(int on);
+bool tile_path_on();
 
 }  // namespace ntb

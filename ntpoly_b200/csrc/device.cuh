@@ -18,6 +18,8 @@ struct Runtime {
   unsigned long long dense_rule_blocks = 0;
   unsigned long long tile_products = 0;  // local products that ran on the DMMA tile path
   unsigned long long tile_builds = 0;    // CSC -> tile-form conversions (0 per product once operands carry their forms)
+  unsigned long long halo_products = 0;  // distributed products that fetched the left operand as a tile halo
+  double halo_bytes = 0.0;               // tile bytes of those halos (own part included)
   double dmma_issued = 0.0;              // DMMA.8x8x4 instructions (x256 FMAs) issued by the tile path
   double alg_bytes = 0.0;          // compulsory bytes of the local products: bytes(A)+bytes(B)+bytes(C_kept)
   // optional device timing of the dominant (numeric SpGEMM) kernels, for bench.py's roofline

@@ -604,20 +604,30 @@ void mat_symmetrize(Matrix& M) {                       // PSMatrixAlgebraModule.
 // ---------------------------------------------------------------------------
 // the distributed multiply (distributed_algebra_includes/MatrixMultiply.f90)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rowblock_nnz(const int* __restrict__ inner, long long nnz, int rb,
+// entries per row block of a CSC panel. Consecutive entries of a column fall into the same block almost always, so
+// each thread counts runs locally and flushes a run with one shared-memory atomic; one global atomic per block and bin.
+constexpr int RB_BINS = 1024;
+__global__ void __launch_bounds__(256) k_rowblock_nnz(const int* __restrict__ inner, long long nnz, int rb, int nbins,
                                                       unsigned long long* __restrict__ counts) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&counts[inner[i] / rb], 1ull);
+  __shared__ unsigned int sh[RB_BINS];
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  // contiguous chunk per thread so that runs are long
+  const long long per = (nnz + (long long)gridDim.x * blockDim.x - 1) / ((long long)gridDim.x * blockDim.x);
+  const long long lo = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * per, hi = min(nnz, lo + per);
+  int cur = -1;
+  unsigned int run = 0;
+  for (long long i = lo; i < hi; ++i) {
+    const int b = inner[i] / rb;
+    if (b != cur) { if (run) atomicAdd(&sh[cur], run); cur = b; run = 0; }
+    ++run;
+  }
+  if (run) atomicAdd(&sh[cur], run);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+    if (sh[i]) atomicAdd(&counts[i], (unsigned long long)sh[i]);
 }
 
-static int g_fused_shift = -1;
-void set_fused_shift(int on) { g_fused_shift = on ? 1 : 0; }
-static bool fused_shift_enabled() {
-  if (g_fused_shift < 0) { const char* e = std::getenv("NTB_FUSED_SHIFT"); g_fused_shift = (e && e[0] == '0') ? 0 : 1; }
-  return g_fused_shift == 1;
-}
-
-// returns true when the optional diagonal shift `sigma` (C = alpha*A*B + sigma*I, see DiagShift) was fused
 template <typename T>
 static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
                        double sigma = 0.0) {
@@ -628,79 +638,112 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
   const LocalCsc<T>& Bl = loc<T>(B);
   const int rb = A.row_block(), cb = A.col_block();
 
-  // ---- A task: my slice's column blocks, gathered along the process row (:94-145)
-  LocalCsc<T> Asel, Ypanel;
-  const LocalCsc<T>* Ysrc = &Al;
-  if (S > 1) { csc_select_col_blocks<T>(Al.view(), cb, S, g.my_slice, Asel); Ysrc = &Asel; }
-  if (comm_size(g.row) > 1) { gather_concat_cols<T>(*Ysrc, g.row, Ypanel); Ysrc = &Ypanel; }
-  // ---- B task: my slice's row blocks, gathered along the process column (:154-193)
-  LocalCsc<T> Bsel, Xpanel;
-  const LocalCsc<T>* Xsrc = &Bl;
-  if (S > 1) { csc_select_row_blocks<T>(Bl.view(), rb, S, g.my_slice, Bsel); Xsrc = &Bsel; }
-  if (comm_size(g.column) > 1) {
-    std::vector<LocalCsc<T>> parts;
-    std::vector<CscView<T>> views;
-    gather_parts<T>(*Xsrc, g.column, parts, views);
-    std::vector<int> roff(views.size());
-    for (size_t q = 0; q < views.size(); ++q) roff[q] = (int)q * Xsrc->rows;
-    csc_stack_rows<T>(views.data(), roff.data(), (int)views.size(), Xsrc->rows * (int)views.size(), Xpanel);
-    Xsrc = &Xpanel;
-  }
-  const CscView<T> Y = Ysrc->view();   // A panel: rows = my rows, cols = inner index
-  const CscView<T> X = Xsrc->view();   // B panel: rows = inner index, cols = my columns
-  NTB_CHECK(Y.cols == X.rows, "multiply: gathered panels disagree on the inner dimension");
-
-  // ---- per local block pair: dense or sparse threshold rule (GemmMatrix.f90:49-61)
   const int nI = g.nbr, nJ = g.nbc;
-  std::vector<unsigned char> rule((size_t)nI * nJ, 0);
-  {
-    std::vector<double> fa(nI), fb(nJ);
-    const double inner_dim = (double)X.rows;
-    if (nI == 1) fa[0] = (double)Ysrc->nnz / ((double)rb * inner_dim);
-    else {
-      DevBuf<unsigned long long> cnt((size_t)nI);
-      cnt.zero();
-      if (Ysrc->nnz) NTB_LAUNCH(k_rowblock_nnz, std::min(div_up(Ysrc->nnz, 256), kNumSMs * 8), 256, 0, Y.inner, Ysrc->nnz, rb, cnt.get());
-      std::vector<unsigned long long> h(nI);
-      d2h(h.data(), cnt.get(), (size_t)nI);
-      for (int i = 0; i < nI; ++i) fa[i] = (double)h[i] / ((double)rb * inner_dim);
-    }
-    if (nJ == 1) fb[0] = (double)Xsrc->nnz / ((double)cb * inner_dim);
-    else {
-      std::vector<int> marks(nJ + 1);
-      for (int j = 0; j <= nJ; ++j) CUDA_CHECK(cudaMemcpyAsync(&marks[j], X.outer + (size_t)j * cb, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-      stream_sync();
-      for (int j = 0; j < nJ; ++j) fb[j] = (double)(marks[j + 1] - marks[j]) / ((double)cb * inner_dim);
-    }
-    for (int i = 0; i < nI; ++i)
-      for (int j = 0; j < nJ; ++j) {
-        rule[(size_t)i * nJ + j] = (std::min(fa[i], fb[j]) > 0.1) ? 1 : 0;
-        if (rule[(size_t)i * nJ + j]) rt().dense_rule_blocks++;
-      }
-  }
-  DevBuf<unsigned char> d_rule;
-  RuleView rv;
-  if (std::any_of(rule.begin(), rule.end(), [](unsigned char c) { return c != 0; })) {
-    d_rule.alloc(rule.size());
-    h2d(d_rule.get(), rule.data(), rule.size());
-    rv.tbl = d_rule.get(); rv.rb = rb; rv.cb = cb; rv.nJ = nJ;
-  }
-
-  // ---- local product
-  Matrix AB;
-  mat_construct_empty(AB, A.actual_dim, A.grid, scalar_traits<T>::is_complex);
-  GemmStats st;
-  DiagShift ds;
   const bool want_shift = sigma != 0.0 && S == 1 && std::fabs(beta) < 2.2250738585072014e-308;
+  DiagShift ds;
   if (want_shift) {
     ds.sigma = sigma;
     ds.dd = A.start_col - A.start_row;        // same block coordinates for A, B and the product
     ds.ncols_diag = std::max(0, std::min(A.local_cols, A.actual_dim - A.start_col));
   }
-  spgemm<T>(*Xsrc, *Ysrc, alpha, wthr, rv, loc<T>(AB), &st, want_shift ? &ds : nullptr);
+  // per local block pair: dense or sparse threshold rule (GemmMatrix.f90:49-61) from the panel fills
+  DevBuf<unsigned char> d_rule;
+  RuleView rv;
+  auto set_rules = [&](const std::vector<double>& fa, const std::vector<double>& fb) {
+    std::vector<unsigned char> rule((size_t)nI * nJ, 0);
+    bool any = false;
+    for (int i = 0; i < nI; ++i)
+      for (int j = 0; j < nJ; ++j) {
+        rule[(size_t)i * nJ + j] = (std::min(fa[i], fb[j]) > 0.1) ? 1 : 0;
+        if (rule[(size_t)i * nJ + j]) { rt().dense_rule_blocks++; any = true; }
+      }
+    if (any) {
+      d_rule.alloc(rule.size());
+      h2d(d_rule.get(), rule.data(), rule.size());
+      stream_sync();                           // rule (host vector) is the h2d source
+      rv.tbl = d_rule.get(); rv.rb = rb; rv.cb = cb; rv.nJ = nJ;
+    }
+  };
+  auto rowblock_counts = [&](const LocalCsc<T>& Ypan, std::vector<double>& cnt_out) {
+    cnt_out.assign(nI, 0.0);
+    if (nI == 1) { cnt_out[0] = (double)Ypan.nnz; return; }
+    DevBuf<unsigned long long> cnt((size_t)nI);
+    cnt.zero();
+    NTB_CHECK(nI <= RB_BINS, "more than 1024 row blocks per rank");
+    if (Ypan.nnz) NTB_LAUNCH(k_rowblock_nnz, std::min(div_up(Ypan.nnz, 256 * 64), kNumSMs * 8), 256, 0, Ypan.inner.get(), Ypan.nnz, rb, nI, cnt.get());
+    std::vector<unsigned long long> h(nI);
+    d2h(h.data(), cnt.get(), (size_t)nI);
+    for (int i = 0; i < nI; ++i) cnt_out[i] = (double)h[i];
+  };
+  auto colblock_fills = [&](const LocalCsc<T>& Xpan, double inner_dim, std::vector<double>& fb) {
+    fb.assign(nJ, 0.0);
+    if (nJ == 1) { fb[0] = (double)Xpan.nnz / ((double)cb * inner_dim); return; }
+    std::vector<int> marks(nJ + 1);
+    for (int j = 0; j <= nJ; ++j) CUDA_CHECK(cudaMemcpyAsync(&marks[j], Xpan.outer.get() + (size_t)j * cb, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+    stream_sync();
+    for (int j = 0; j < nJ; ++j) fb[j] = (double)(marks[j + 1] - marks[j]) / ((double)cb * inner_dim);
+  };
+
+  Matrix AB;
+  mat_construct_empty(AB, A.actual_dim, A.grid, scalar_traits<T>::is_complex);
+  GemmStats st;
+  bool product_done = false;
+
+  // ---- column-split grids: tile forms + halo exchange, no CSC gather (real matrices)
+  if constexpr (!scalar_traits<T>::is_complex) {
+    if (g.R == 1 && S == 1 && g.C > 1 && tile_path_on() && A.local_cols % 64 == 0 && halo_enabled()) {
+      // panel fills for the rule table: A's row panel is the union of the ranks' blocks, B's column panel is local
+      std::vector<double> cnt, fb;
+      rowblock_counts(Al, cnt);
+      {
+        DevBuf<double> d((size_t)nI);
+        h2d(d.get(), cnt.data(), (size_t)nI);
+        comm_allreduce_f64(g.row, d.get(), (size_t)nI, RedOp::Sum);
+        d2h(cnt.data(), d.get(), (size_t)nI);
+      }
+      const double inner_dim = (double)Bl.rows;
+      std::vector<double> fa(nI);
+      for (int i = 0; i < nI; ++i) fa[i] = cnt[i] / ((double)rb * inner_dim);
+      colblock_fills(Bl, inner_dim, fb);
+      set_rules(fa, fb);
+      product_done = halo_tile_product(A, B, alpha, wthr, rv, want_shift ? &ds : nullptr, loc<double>(AB), st);
+      if (!product_done) { rv = RuleView(); }
+    }
+  }
+
+  if (!product_done) {
+    // ---- A task: my slice's column blocks, gathered along the process row (:94-145)
+    LocalCsc<T> Asel, Ypanel;
+    const LocalCsc<T>* Ysrc = &Al;
+    if (S > 1) { csc_select_col_blocks<T>(Al.view(), cb, S, g.my_slice, Asel); Ysrc = &Asel; }
+    if (comm_size(g.row) > 1) { gather_concat_cols<T>(*Ysrc, g.row, Ypanel); Ysrc = &Ypanel; }
+    // ---- B task: my slice's row blocks, gathered along the process column (:154-193)
+    LocalCsc<T> Bsel, Xpanel;
+    const LocalCsc<T>* Xsrc = &Bl;
+    if (S > 1) { csc_select_row_blocks<T>(Bl.view(), rb, S, g.my_slice, Bsel); Xsrc = &Bsel; }
+    if (comm_size(g.column) > 1) {
+      std::vector<LocalCsc<T>> parts;
+      std::vector<CscView<T>> views;
+      gather_parts<T>(*Xsrc, g.column, parts, views);
+      std::vector<int> roff(views.size());
+      for (size_t q = 0; q < views.size(); ++q) roff[q] = (int)q * Xsrc->rows;
+      csc_stack_rows<T>(views.data(), roff.data(), (int)views.size(), Xsrc->rows * (int)views.size(), Xpanel);
+      Xsrc = &Xpanel;
+    }
+    NTB_CHECK(Ysrc->cols == Xsrc->rows, "multiply: gathered panels disagree on the inner dimension");
+    {
+      const double inner_dim = (double)Xsrc->rows;
+      std::vector<double> cnt, fa(nI), fb;
+      rowblock_counts(*Ysrc, cnt);
+      for (int i = 0; i < nI; ++i) fa[i] = cnt[i] / ((double)rb * inner_dim);
+      colblock_fills(*Xsrc, inner_dim, fb);
+      set_rules(fa, fb);
+    }
+    // ---- local product
+    spgemm<T>(*Xsrc, *Ysrc, alpha, wthr, rv, loc<T>(AB), &st, want_shift ? &ds : nullptr);
+  }
   rt().flops_useful += st.flops;
   rt().multiplies++;
-  stream_sync();  // rule (host vector) was an h2d source
 
   // ---- between-slice sum (:234-261)
   if (S > 1) reduce_and_sum<T>(loc<T>(AB), g.between_slice, threshold, rb);

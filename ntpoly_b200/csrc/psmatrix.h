@@ -90,6 +90,7 @@ void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, dou
 void mat_multiply_shift(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double threshold, double sigma,
                         const Matrix& Identity, MemoryPool* pool);
 void set_fused_shift(int on);
+void set_halo_path(int on);
 void mat_increment(const Matrix& A, Matrix& B, double alpha, double threshold);
 void mat_scale(Matrix& M, double c);
 void mat_scale_c(Matrix& M, cplx c);

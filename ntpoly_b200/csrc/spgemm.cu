@@ -34,6 +34,8 @@ static bool tile_path_enabled() {
   return g_tile_mode == 1;
 }
 
+bool tile_path_on() { return tile_path_enabled(); }
+
 constexpr int NBINS = 7;       // 0: empty column, 1..4 warp windows, 5 CTA window, 6 global slab
 constexpr int WARPS = 8;       // warps per CTA in the warp-window kernels
 constexpr int CTA_T = 256;     // threads per CTA in the CTA-window kernels
@@ -285,6 +287,25 @@ __global__ void __launch_bounds__(256) k_useful_products(CscView<T> X, CscView<T
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+
+__global__ void __launch_bounds__(256) k_useful_products_len(const int* __restrict__ xinner, const int* __restrict__ ylen,
+                                                             long long nnzX, unsigned long long* __restrict__ total) {
+  unsigned long long s = 0;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnzX; p += (long long)gridDim.x * blockDim.x)
+    s += (unsigned long long)ylen[xinner[p]];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+double useful_products_from_lengths(const LocalCsc<double>& X, const int* d_ylen) {
+  if (X.nnz == 0) return 0.0;
+  DevBuf<unsigned long long> fl(1);
+  fl.zero();
+  NTB_LAUNCH(k_useful_products_len, min(div_up(X.nnz, 256 * 8), kNumSMs * 16), 256, 0, X.inner.get(), d_ylen, X.nnz, fl.get());
+  unsigned long long h = 0;
+  d2h(&h, fl.get(), 1);
+  return (double)h;
 }
 
 // ---------------------------------------------------------------------------

@@ -186,6 +186,7 @@ static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
   T.tval.zero();
   NTB_LAUNCH((k_ct_build<ISA, true>), grid, TW * 32, 0, M, ncc, (int*)nullptr, (int*)nullptr, T.colmeta.get(),
              (int4*)nullptr, nk, (int*)nullptr, sptr.get(), tptr.get(), T.ent.get(), T.tval.get());
+  if (ISA) T.coltile = std::move(tptr);
   return true;
 }
 
@@ -772,7 +773,8 @@ k_forms_write(int ntasks, int nG, const int2* __restrict__ tasks, const int* __r
               const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
               const int* __restrict__ seidxL, const int* __restrict__ seidxR, const int* __restrict__ stoffL,
               const int* __restrict__ stoffR, int4* __restrict__ entL, int4* __restrict__ entR,
-              int4* __restrict__ colmetaL, int4* __restrict__ colmetaR) {
+              int4* __restrict__ colmetaL, int4* __restrict__ colmetaR, int* __restrict__ coltileL,
+              const int* __restrict__ totals) {
   const bool left = blockIdx.y == 0;
   const int* seidx = left ? seidxL : seidxR;
   const int* stoff = left ? stoffL : stoffR;
@@ -798,6 +800,10 @@ k_forms_write(int ntasks, int nG, const int2* __restrict__ tasks, const int* __r
   const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
   const int sa = left ? 2 * t0 + (q & 1) * nn : 2 * t0, sb = sa + (left ? nn : 2 * nn);
   if (seidx[sa] == seidx[sb]) reinterpret_cast<int4*>(cm)[q] = make_int4(0, 0, 0, -1);
+  if (left) {
+    coltileL[q] = (sa < n) ? stoff[sa] : totals[1];
+    if (q == ncc - 1) coltileL[ncc] = totals[1];
+  }
 }
 
 // left form: per inner tile K of the result (4 columns): tile count, first and last row tile
@@ -884,7 +890,7 @@ k_forms_fill(int nJ, int nrows, int ncols, const int2* __restrict__ tasks, const
 }
 
 // the cached (or freshly built) tile form of an operand; nullptr when its pattern cannot be tiled
-static const ChunkTiles* operand_form(const LocalCsc<double>& M, bool left) {
+const ChunkTiles* tile_operand_form(const LocalCsc<double>& M, bool left) {
   if (!M.forms) M.forms = std::make_shared<TileForms>();
   TileForms& f = *M.forms;
   int& has = left ? f.has_left : f.has_right;
@@ -897,16 +903,45 @@ static const ChunkTiles* operand_form(const LocalCsc<double>& M, bool left) {
   return has == 1 ? &T : nullptr;
 }
 
+// ---- gathered left form (halo exchange along a process row): rebase one rank's piece ---------------------------
+__global__ void __launch_bounds__(256) k_fixup_left(LeftPiece pc, int rank, int4* __restrict__ colmeta, int4* __restrict__ ent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pc.ncols_chunk) {                     // chunk columns of this rank, global index rank*ncols_chunk + i
+    int4 cm = colmeta[(size_t)rank * pc.ncols_chunk + i];
+    if (i >= pc.a && i < pc.b && cm.y > 0) cm.x += pc.ent_base;
+    else cm = make_int4(0, 0, 0, -1);           // not received: must never be referenced
+    colmeta[(size_t)rank * pc.ncols_chunk + i] = cm;
+  }
+  if (i < pc.nent) {
+    int4 e = ent[(size_t)pc.ent_base + i];
+    e.y = e.y - pc.tile_lo + pc.recv_base;
+    ent[(size_t)pc.ent_base + i] = e;
+  }
+}
+void tile_fixup_gathered_left(ChunkTiles& G, const LeftPiece* pieces, int npieces) {
+  for (int p = 0; p < npieces; ++p) {
+    const int n = max(pieces[p].ncols_chunk, pieces[p].nent);
+    if (n > 0) NTB_LAUNCH(k_fixup_left, div_up(n, 256), 256, 0, pieces[p], p, G.colmeta.get(), G.ent.get());
+  }
+}
+
 // returns false when the operands are not locally dense enough (caller falls back to the
 // scalar window kernels). useful_products = sum over B entries of the A column lengths.
 bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double alpha, double thr, const RuleView& rules,
                  LocalCsc<double>& Z, double useful_products, const DiagShift* shift) {
-  const int ncols = Xl.cols, nrows = Yl.rows;
-  if (ncols == 0 || Xl.nnz == 0 || Yl.nnz == 0 || !(thr >= 0.0)) return false;
-  const ChunkTiles* A = operand_form(Yl, true);
+  if (Xl.cols == 0 || Xl.nnz == 0 || Yl.nnz == 0 || !(thr >= 0.0)) return false;
+  const ChunkTiles* A = tile_operand_form(Yl, true);
   if (!A || (double)Yl.nnz < 0.20 * 32.0 * (double)A->ntiles) return false;   // tiles mostly padding
-  const ChunkTiles* B = operand_form(Xl, false);
+  const ChunkTiles* B = tile_operand_form(Xl, false);
   if (!B || (double)Xl.nnz < 0.20 * 32.0 * (double)B->ntiles) return false;
+  return spgemm_tile_core(*A, *B, Xl.cols, Yl.rows, alpha, thr, rules, Z, useful_products, shift, false);
+}
+
+bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncols, int nrows, double alpha, double thr,
+                      const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
+                      bool force) {
+  const ChunkTiles* A = &Aform;
+  const ChunkTiles* B = &Bform;
   const int nJ = div_up(ncols, 8), nG = B->ncc;
   const CtView Av{A->colmeta.get(), A->ent.get(), A->tval.get(), A->kmeta.get(), A->ncc};
   const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc};
@@ -932,7 +967,7 @@ bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double 
   CUDA_CHECK(cudaMemcpyAsync(&h_tasks, gtask_off.get() + nG, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
   // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
-  if ((double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
+  if (!force && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
 
   DevBuf<double> stg((size_t)h_stg * 64);
   DevBuf<int2> tasks((size_t)max(h_tasks, 1));
@@ -980,6 +1015,7 @@ bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double 
     L.ent.alloc(ns); R.ent.alloc(ns);
     L.colmeta.alloc((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
     L.kmeta.alloc((size_t)nk);
+    L.coltile.alloc((size_t)nG * 2 + 1);
     seidxL.alloc(ns + 1); seidxR.alloc(ns + 1); stoffL.alloc(ns); stoffR.alloc(ns);
     DevBuf<unsigned long long> smaskL(ns), smaskR(ns);
     NTB_LAUNCH(k_forms_slots, dim3(div_up((long long)ns, 256), 2), 256, 0, h_tasks, tasks.get(), gtask_off.get(), fmA.get(),
@@ -988,7 +1024,7 @@ bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double 
                stoffR.get(), totals.get());
     NTB_LAUNCH(k_forms_write, dim3(div_up((long long)ns + 2 * nG, 256), 2), 256, 0, h_tasks, nG, tasks.get(), gtask_off.get(),
                fmA.get(), fmB.get(), seidxL.get(), seidxR.get(), stoffL.get(), stoffR.get(), L.ent.get(), R.ent.get(),
-               L.colmeta.get(), R.colmeta.get());
+               L.colmeta.get(), R.colmeta.get(), L.coltile.get(), totals.get());
     NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), fmA.get(), L.kmeta.get());
   } else {
     totals.zero();

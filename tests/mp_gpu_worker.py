@@ -32,8 +32,8 @@ def main():
     from oracle import oracle as O
     from util import compare_sparse, banded
     nt.init_world_from_torch()
-    grids = {2: [(2, 1, 1), (1, 2, 1), (1, 1, 2)], 4: [(2, 2, 1), (1, 2, 2), (4, 1, 1)],
-             8: [(2, 2, 2), (4, 2, 1), (1, 2, 4)]}[world]
+    grids = {2: [(2, 1, 1), (1, 2, 1), (1, 1, 2)], 4: [(2, 2, 1), (1, 2, 2), (4, 1, 1), (1, 4, 1)],
+             8: [(2, 2, 2), (4, 2, 1), (1, 2, 4), (1, 8, 1)]}[world]
     for (R, C, S) in grids:
         nt.ConstructGlobalProcessGrid(R, C, S)
         g = O.Grid(R, C, S)
@@ -72,8 +72,43 @@ def main():
         A, Cm = nt.Matrix_ps(n), nt.Matrix_ps(n)
         A.fill_from_arrays(a.row[rank::world] + 1, a.col[rank::world] + 1, a.data[rank::world])
         OA = O.PSMatrix.from_scipy(a, g)
+        nt.reset_counters()
         Cm.Gemm(A, A, None, threshold=1e-9)
         compare_sparse(local_block(Cm), oracle_block(O, O.multiply(OA, OA, thr=1e-9), rank), 1e-9)
+        column_split = (R == 1 and S == 1 and C > 1)
+        # column-split grids fetch the left operand as a tile halo; the other grids gather CSC panels
+        assert nt.halo_counters()["products"] == (1 if column_split else 0), nt.halo_counters()
+        # a product of products reads the tile forms emitted with Cm; check it against the oracle fed with the GPU's Cm
+        parts = [None] * world
+        dist.all_gather_object(parts, local_block(Cm))
+        # slices hold replicas: assemble the global matrix from slice 0 only
+        OC = O.PSMatrix.from_scipy(sum(pb for r_, pb in enumerate(parts) if g.coords(r_)[0] == 0).tocoo(), g)
+        D = nt.Matrix_ps(n)
+        D.Gemm(Cm, A, None, alpha=-0.5, threshold=1e-9)
+        compare_sparse(local_block(D), oracle_block(O, O.multiply(OC, OA, alpha=-0.5, thr=1e-9), rank), 1e-9)
+        D.Gemm(A, Cm, None, threshold=1e-9)
+        compare_sparse(local_block(D), oracle_block(O, O.multiply(OA, OC, thr=1e-9), rank), 1e-9)
+        if column_split:
+            assert nt.halo_counters()["products"] == 3 and nt.tile_builds() == 2
+        # fused identity shift across the grid == the two reference calls, bit for bit
+        I = nt.Matrix_ps(n); I.FillIdentity()
+        F, G2 = nt.Matrix_ps(n), nt.Matrix_ps(n)
+        F.GemmShift(A, A, I, 3.0, None, alpha=-1.1, threshold=1e-9)
+        G2.Gemm(A, A, None, alpha=-1.1, threshold=1e-9)
+        G2.Increment(I, 3.0)
+        fb, gb = local_block(F), local_block(G2)
+        fb.sort_indices(); gb.sort_indices()
+        assert np.array_equal(fb.indptr, gb.indptr) and np.array_equal(fb.indices, gb.indices) and np.array_equal(fb.data, gb.data)
+        # sign function: iteration count and result against the oracle
+        sgn = (banded(1024, half_bandwidth=10, scale=0.2) - 0.05 * sp.identity(1024)).tocoo()
+        Sg, So = nt.Matrix_ps(1024), nt.Matrix_ps(1024)
+        Sg.fill_from_arrays(sgn.row[rank::world] + 1, sgn.col[rank::world] + 1, sgn.data[rank::world])
+        sps = nt.SolverParameters(); sps.SetConvergeDiff(1e-6); sps.SetThreshold(1e-8)
+        nt.SignSolvers.ComputeSign(Sg, So, sps)
+        OS = O.PSMatrix.from_scipy(sgn, g)
+        Sref, sinfo = O.sign_function(OS, O.SolverParameters(converge_diff=1e-6, threshold=1e-8))
+        assert nt.last_solve()["loop_counter"] == sinfo.iterations, (nt.last_solve(), sinfo.iterations)
+        compare_sparse(local_block(So), oracle_block(O, Sref, rank), 1e-8, tol=1e-7)
         h = (banded(512, half_bandwidth=6, scale=0.2)).tocoo()
         H, ISQ, K = nt.Matrix_ps(512), nt.Matrix_ps(512), nt.Matrix_ps(512)
         H.fill_from_arrays(h.row[rank::world] + 1, h.col[rank::world] + 1, h.data[rank::world])
