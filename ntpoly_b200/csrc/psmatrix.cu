@@ -628,6 +628,170 @@ __global__ void __launch_bounds__(256) k_rowblock_nnz(const int* __restrict__ in
     if (sh[i]) atomicAdd(&counts[i], (unsigned long long)sh[i]);
 }
 
+
+// ---------------------------------------------------------------------------
+// Tile-form product on a 1 x C x 1 grid (column split): every rank owns all rows of its columns, so
+//   * the right operand B needs no gather at all (process column of size 1): its cached right form is used as is;
+//   * the left operand A is needed only for the inner indices that occur as ROWS of the local B block. The left form
+//     is stored per chunk column (32 matrix columns) with its tiles contiguous, so "gathering A" is: all-gather the
+//     small index arrays, then fetch from each peer ONE contiguous run of tiles — the halo — with ncclSend/ncclRecv.
+//     For banded/short-range matrices the halo is a few chunk columns instead of the reference's whole row panel
+//     (comm_includes/ReduceAndComposeMatrix*.f90), and nothing is ever converted back to CSC or re-tiled.
+// All decisions are taken from all-gathered records, so every rank takes the same branch.
+__global__ void __launch_bounds__(256) k_right_form_range(const int4* __restrict__ colmeta, int ncc, int* __restrict__ out2) {
+  int lo = INT_MAX, hi = -1;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ncc; q += gridDim.x * blockDim.x) {
+    const int4 m = colmeta[q];
+    if (m.y > 0) { lo = min(lo, m.z); hi = max(hi, m.w); }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&out2[0], lo); atomicMax(&out2[1], hi); }
+}
+__global__ void __launch_bounds__(256) k_col_len(const int* __restrict__ outer, int cols, int* __restrict__ len) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cols) len[j] = outer[j + 1] - outer[j];
+}
+
+struct HaloRecord { long long ok, nsuper, ntiles, nnzA, qlo, qhi, nnzB, ntilesB; };
+
+// returns false (on every rank alike) when this product does not qualify; then the caller takes the CSC gather path
+static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, double wthr, const RuleView& rv,
+                              const DiagShift* ds, LocalCsc<double>& out, GemmStats& st) {
+  ProcessGrid& g = *A.grid;
+  if (!(g.R == 1 && g.S == 1 && g.C > 1) || !tile_path_on() || A.local_cols % 64 != 0 || !(wthr >= 0.0)) return false;
+  const int C = g.C, me = comm_rank(g.row);
+  const LocalCsc<double>& Al = A.r;
+  const LocalCsc<double>& Bl = B.r;
+  const int lcols = A.local_cols, nccl = lcols / 32, nkl = lcols / 4;
+  const ChunkTiles* Lf = tile_operand_form(Al, true);
+  const ChunkTiles* Rf = tile_operand_form(Bl, false);
+  // ---- records: who can play, sizes, and which global chunk columns of A each rank needs
+  HaloRecord mine{};
+  mine.ok = (Lf && Rf) ? 1 : 0;
+  mine.qlo = INT_MAX; mine.qhi = -1;
+  if (mine.ok) {
+    mine.nsuper = Lf->nsuper; mine.ntiles = Lf->ntiles; mine.nnzA = Al.nnz; mine.nnzB = Bl.nnz; mine.ntilesB = Rf->ntiles;
+    DevBuf<int> d2(2);
+    const int init[2] = {INT_MAX, -1};
+    h2d(d2.get(), init, 2);
+    if (Rf->ncc > 0) NTB_LAUNCH(k_right_form_range, std::min(div_up(Rf->ncc, 256), kNumSMs), 256, 0, Rf->colmeta.get(), Rf->ncc, d2.get());
+    int h2[2];
+    d2h(h2, d2.get(), 2);
+    mine.qlo = h2[0]; mine.qhi = h2[1];
+  }
+  std::vector<HaloRecord> rec(C);
+  {
+    DevBuf<HaloRecord> d_mine(1), d_all((size_t)C);
+    h2d(d_mine.get(), &mine, 1);
+    comm_allgather_bytes(g.row, d_mine.get(), d_all.get(), sizeof(HaloRecord));
+    d2h(rec.data(), d_all.get(), (size_t)C);
+  }
+  long long nnzA = 0, ntilesA = 0, nnzB = 0, ntilesB = 0;
+  for (int p = 0; p < C; ++p) {
+    if (!rec[p].ok) return false;
+    nnzA += rec[p].nnzA; ntilesA += rec[p].ntiles; nnzB += rec[p].nnzB; ntilesB += rec[p].ntilesB;
+  }
+  if (nnzA == 0 || nnzB == 0) return false;
+  if ((double)nnzA < 0.20 * 32.0 * (double)ntilesA || (double)nnzB < 0.20 * 32.0 * (double)ntilesB) return false;
+
+  // ---- small index arrays of every rank
+  ChunkTiles G;
+  G.ncc = C * nccl;
+  G.colmeta.alloc((size_t)C * nccl);
+  G.kmeta.alloc((size_t)C * nkl);
+  DevBuf<int> coltile_g((size_t)C * (nccl + 1)), ylen((size_t)lcols), ylen_g((size_t)C * lcols);
+  NTB_LAUNCH(k_col_len, div_up(lcols, 256), 256, 0, Al.outer.get(), lcols, ylen.get());
+  std::vector<int> ent_base(C + 1, 0);
+  for (int p = 0; p < C; ++p) ent_base[p + 1] = ent_base[p] + (int)rec[p].nsuper;
+  G.nsuper = ent_base[C];
+  G.ent.alloc((size_t)std::max(G.nsuper, 1));
+  comm_group_start();
+  comm_allgather_bytes(g.row, Lf->colmeta.get(), G.colmeta.get(), (size_t)nccl * sizeof(int4));
+  comm_allgather_bytes(g.row, Lf->kmeta.get(), G.kmeta.get(), (size_t)nkl * sizeof(int4));
+  comm_allgather_bytes(g.row, Lf->coltile.get(), coltile_g.get(), ((size_t)nccl + 1) * sizeof(int));
+  comm_allgather_bytes(g.row, ylen.get(), ylen_g.get(), (size_t)lcols * sizeof(int));
+  for (int p = 0; p < C; ++p)
+    if (rec[p].nsuper > 0)
+      comm_broadcast_bytes(g.row, Lf->ent.get(), G.ent.get() + ent_base[p], (size_t)rec[p].nsuper * sizeof(int4), p);
+  comm_group_end();
+  std::vector<int> ct((size_t)C * (nccl + 1));
+  d2h(ct.data(), coltile_g.get(), ct.size());
+
+  // ---- the halo: tiles of chunk columns [a,b) of rank p, one contiguous run
+  auto run_of = [&](int need_lo, int need_hi, int p, int& a, int& b, int& tl, int& th) {
+    a = std::max(need_lo - p * nccl, 0);
+    b = std::min(need_hi + 1 - p * nccl, nccl);
+    if (a >= b) { a = b = 0; tl = th = 0; return; }
+    tl = ct[(size_t)p * (nccl + 1) + a];
+    th = ct[(size_t)p * (nccl + 1) + b];
+  };
+  std::vector<LeftPiece> pieces(C);
+  long long total_tiles = 0;
+  for (int p = 0; p < C; ++p) {
+    int a, b, tl, th;
+    run_of((int)mine.qlo, (int)mine.qhi, p, a, b, tl, th);
+    pieces[p] = LeftPiece{ent_base[p], nccl, a, b, tl, (int)total_tiles, (int)rec[p].nsuper};
+    total_tiles += th - tl;
+  }
+  NTB_CHECK(total_tiles < (1ll << 26), "halo of the left operand exceeds 2^26 tiles");
+  G.ntiles = total_tiles;
+  G.tval.alloc((size_t)std::max(total_tiles, 1ll) * 32);
+  comm_group_start();
+  for (int p = 0; p < C; ++p) {
+    int a, b, tl, th;
+    run_of((int)mine.qlo, (int)mine.qhi, p, a, b, tl, th);                        // what I take from p
+    const size_t rbytes = (size_t)(th - tl) * 256;
+    if (p == me) {
+      if (rbytes) CUDA_CHECK(cudaMemcpyAsync(G.tval.get() + (size_t)pieces[p].recv_base * 32, Lf->tval.get() + (size_t)tl * 32,
+                                             rbytes, cudaMemcpyDeviceToDevice, rt().stream));
+      continue;
+    }
+    if (rbytes) comm_recv_bytes(g.row, G.tval.get() + (size_t)pieces[p].recv_base * 32, rbytes, p);
+    run_of((int)rec[p].qlo, (int)rec[p].qhi, me, a, b, tl, th);                   // what p takes from me
+    const size_t sbytes = (size_t)(th - tl) * 256;
+    if (sbytes) comm_send_bytes(g.row, Lf->tval.get() + (size_t)tl * 32, sbytes, p);
+  }
+  comm_group_end();
+  tile_fixup_gathered_left(G, pieces.data(), C);
+
+  // ---- product from the forms
+  const double useful = useful_products_from_lengths(Bl, ylen_g.get());
+  const bool done = spgemm_tile_core(G, *Rf, B.local_cols, A.local_rows, alpha, wthr, rv, out, useful, ds, true);
+  NTB_CHECK(done, "forced tile product declined");
+  st.flops = 2.0 * useful;
+  st.shift_applied = ds && ds->sigma != 0.0;
+  // compulsory bytes: B block, kept C block, and the share of A that was actually needed (by tile count)
+  double a_bytes = 0.0;
+  for (int p = 0; p < C; ++p) {
+    int a, b, tl, th;
+    run_of((int)mine.qlo, (int)mine.qhi, p, a, b, tl, th);
+    if (rec[p].ntiles > 0) a_bytes += (double)rec[p].nnzA * 12.0 * (double)(th - tl) / (double)rec[p].ntiles;
+  }
+  rt().alg_bytes += a_bytes + (double)Bl.bytes() + (double)out.bytes();
+  rt().halo_products++;
+  rt().halo_bytes += (double)total_tiles * 256.0;
+  stream_sync();
+  return true;
+}
+
+static int g_halo = -1;
+void set_halo_path(int on) { g_halo = on ? 1 : 0; }
+static bool halo_enabled() {
+  if (g_halo < 0) { const char* e = std::getenv("NTB_HALO"); g_halo = (e && e[0] == '0') ? 0 : 1; }
+  return g_halo == 1;
+}
+static int g_fused_shift = -1;
+void set_fused_shift(int on) { g_fused_shift = on ? 1 : 0; }
+static bool fused_shift_enabled() {
+  if (g_fused_shift < 0) { const char* e = std::getenv("NTB_FUSED_SHIFT"); g_fused_shift = (e && e[0] == '0') ? 0 : 1; }
+  return g_fused_shift == 1;
+}
+
+// returns true when the optional diagonal shift `sigma` (C = alpha*A*B + sigma*I, see DiagShift) was fused
 template <typename T>
 static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
                        double sigma = 0.0) {
