@@ -56,7 +56,12 @@ struct Arena {
 size_t round_size(size_t bytes) {
   if (bytes < 512) return 512;
   if (bytes < (1u << 20)) return (bytes + 511) & ~size_t(511);
-  return (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);   // 2 MiB granules for large blocks
+  // large blocks: 1/8-octave bins (at least 2 MiB granules) so that the slightly different sizes of successive
+  // iterates map to the same capacity and hit the cache instead of cudaMalloc
+  size_t gran = size_t(2) << 20;
+  int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+  if (lg - 3 > 21) gran = size_t(1) << (lg - 3);
+  return (bytes + gran - 1) & ~(gran - 1);
 }
 }  // namespace
 

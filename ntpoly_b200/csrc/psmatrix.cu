@@ -1,4 +1,5 @@
 #include "psmatrix.h"
+#include <chrono>
 #include "ops.cuh"
 #include <algorithm>
 #include <cmath>
@@ -663,6 +664,11 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
                               const DiagShift* ds, LocalCsc<double>& out, GemmStats& st) {
   ProcessGrid& g = *A.grid;
   if (!(g.R == 1 && g.S == 1 && g.C > 1) || !tile_path_on() || A.local_cols % 64 != 0 || !(wthr >= 0.0)) return false;
+  static const bool timing = std::getenv("NTB_HALO_TIMING") != nullptr;      // developer probe: wall time per phase
+  auto now = [&]() { if (timing) stream_sync(); return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   const int C = g.C, me = comm_rank(g.row);
   const LocalCsc<double>& Al = A.r;
   const LocalCsc<double>& Bl = B.r;
@@ -690,6 +696,7 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
     comm_allgather_bytes(g.row, d_mine.get(), d_all.get(), sizeof(HaloRecord));
     d2h(rec.data(), d_all.get(), (size_t)C);
   }
+  const auto t1 = now();
   long long nnzA = 0, ntilesA = 0, nnzB = 0, ntilesB = 0;
   for (int p = 0; p < C; ++p) {
     if (!rec[p].ok) return false;
@@ -720,6 +727,7 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   comm_group_end();
   std::vector<int> ct((size_t)C * (nccl + 1));
   d2h(ct.data(), coltile_g.get(), ct.size());
+  const auto t2 = now();
 
   // ---- the halo: tiles of chunk columns [a,b) of rank p, one contiguous run
   auto run_of = [&](int need_lo, int need_hi, int p, int& a, int& b, int& tl, int& th) {
@@ -757,10 +765,16 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   }
   comm_group_end();
   tile_fixup_gathered_left(G, pieces.data(), C);
+  const auto t3 = now();
 
   // ---- product from the forms
   const double useful = useful_products_from_lengths(Bl, ylen_g.get());
+  const auto t4 = now();
   const bool done = spgemm_tile_core(G, *Rf, B.local_cols, A.local_rows, alpha, wthr, rv, out, useful, ds, true);
+  const auto t5 = now();
+  if (timing && me == 0)
+    std::fprintf(stderr, "[halo] records %.3f  index gather %.3f  tiles %.3f (%.1f MB)  flops %.3f  product %.3f ms\n",
+                 ms(t0, t1), ms(t1, t2), ms(t2, t3), (double)total_tiles * 256.0 / 1e6, ms(t3, t4), ms(t4, t5));
   NTB_CHECK(done, "forced tile product declined");
   st.flops = 2.0 * useful;
   st.shift_applied = ds && ds->sigma != 0.0;

@@ -25,6 +25,7 @@
 // by tile padding never survive the strict |v| > thr test, so results equal the scalar
 // path up to summation order.
 #include "csc.cuh"
+#include <chrono>
 
 namespace ntb {
 
@@ -598,7 +599,9 @@ k_tile_numeric(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const 
     double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
     const int j0 = J * 8 + cc;
     const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
-    const bool plain = es.rules.tbl == nullptr && es.sigma == 0.0;
+    // the shifted diagonal touches only the strips that cross it: everything else takes the plain test
+    const bool on_diag = es.sigma != 0.0 && (I0 * 8 <= J * 8 + 7 + es.dd) && (I0 * 8 + 63 >= J * 8 + es.dd);
+    const bool plain = es.rules.tbl == nullptr && !on_diag;
     int c0 = 0, c1 = 0;
     unsigned bR0 = 0, bR1 = 0, bL0 = 0, bL1 = 0;   // right-form bytes (rows 0-31 / 32-63), left-form bytes (cols 0-3 / 4-7)
 #pragma unroll
@@ -942,6 +945,11 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
                       bool force) {
   const ChunkTiles* A = &Aform;
   const ChunkTiles* B = &Bform;
+  static const bool timing = std::getenv("NTB_TILE_TIMING") != nullptr;      // developer probe: wall time per phase
+  auto now = [&]() { if (timing) stream_sync(); return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   const int nJ = div_up(ncols, 8), nG = B->ncc;
   const CtView Av{A->colmeta.get(), A->ent.get(), A->tval.get(), A->kmeta.get(), A->ncc};
   const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc};
@@ -969,6 +977,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
   if (!force && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
 
+  const auto t1 = now();
   DevBuf<double> stg((size_t)h_stg * 64);
   DevBuf<int2> tasks((size_t)max(h_tasks, 1));
   DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
@@ -979,6 +988,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   fmB.zero();
   if (h_tasks > 0)
     NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, gbmin.get(), gtask_off.get(), tasks.get());
+  const auto t2 = now();
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (rt().profile) {
     CUDA_CHECK(cudaEventCreate(&ev0));
@@ -999,6 +1009,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
     rt().prof_events.emplace_back(ev0, ev1);
   }
+  const auto t3 = now();
   // ---- CSC of the result
   const int egrid = max(1, min(div_up((long long)ncols * 32, 256), kNumSMs * 16));
   Z.rows = nrows; Z.cols = ncols;
@@ -1033,10 +1044,12 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   CUDA_CHECK(cudaMemcpyAsync(&h_nnz, Z.outer.get() + ncols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   CUDA_CHECK(cudaMemcpyAsync(h_tot, totals.get(), sizeof(h_tot), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
+  const auto t4 = now();
   Z.alloc_entries(h_nnz);
   if (h_nnz > 0)
     NTB_LAUNCH(k_tile_emit, egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(), es,
                Z.outer.get(), Z.inner.get(), Z.val.get());
+  const auto t5 = now();
   if (h_tasks > 0 && h_nnz > 0) {
     L.ncc = div_up(ncols, 32); L.nsuper = h_tot[0]; L.ntiles = h_tot[1];
     R.ncc = nG; R.nsuper = h_tot[2]; R.ntiles = h_tot[3];
@@ -1048,6 +1061,10 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
     forms->has_right = 1;
     Z.forms = forms;
   }
+  const auto t6 = now();
+  if (timing)
+    std::fprintf(stderr, "[tile] bounds %.3f  alloc+tasks %.3f  numeric %.3f  index %.3f  emit %.3f  fill %.3f ms  (tasks %d, stg %.0f MB, nnz %d)\n",
+                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), ms(t5, t6), h_tasks, (double)h_stg * 512.0 / 1e6, h_nnz);
   rt().tile_products++;
   rt().dmma_issued += (double)h_ndmma;
   return true;

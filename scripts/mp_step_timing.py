@@ -26,9 +26,14 @@ for it in range(4):
     timed("sign_iteration", lambda: nt.sign_iteration(X, I, T1, T2, 1.2, thr))
     if rank == 0: print("   halo", nt.halo_counters(), "builds", nt.tile_builds(), "nnz local", X.get_arrays()[0].size, flush=True)
 ak = 1.2
+nt.profile_enable(True)
 for it in range(2):
+    nt.reset_counters(); nt.profile_read()
     timed("gemm-shift X*X", lambda: T1.GemmShift(X, X, I, 3.0, None, alpha=-ak*ak, threshold=thr))
+    if rank == 0: print("     numeric", nt.profile_read(), nt.tile_counters(), "nnz out", T1.get_arrays()[0].size, flush=True)
+    nt.reset_counters()
     timed("gemm X*T1", lambda: T2.Gemm(X, T1, None, alpha=0.5*ak, threshold=thr))
+    if rank == 0: print("     numeric", nt.profile_read(), nt.tile_counters(), "nnz out", T2.get_arrays()[0].size, flush=True)
     timed("copy", lambda: nt.lib().CopyMatrix_ps_wrp(X.ih, W.ih))
     timed("norm", lambda: X.Norm())
 dist.destroy_process_group()
