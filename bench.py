@@ -33,13 +33,13 @@ UNIT = "GFLOP/s"
 GRIDS = {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 4, 1), 8: (1, 8, 1)}   # column split: tile halo exchange, no panel gather
 ALPHA_MAX = 1.69770248526
 FP64_PEAK_TFLOPS = 37.2          # DMMA.8x8x4 issue peak measured on this pool's B200 (scripts/micro/dmma_shapes.cu)
-TRAFFIC_PER_LAUNCH = None        # dram bytes of one numeric launch from the ncu --set full capture (profiles/), or None
+TRAFFIC_PER_LAUNCH = 1.69e9       # dram read+write bytes of one numeric launch, ncu --set full (profiles/r01_prof_tile_numeric_bench.keys.txt)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=262144)
@@ -79,7 +79,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
