@@ -36,6 +36,11 @@ FP64_PEAK_TFLOPS = 37.2          # DMMA.8x8x4 issue peak measured on this pool's
 TRAFFIC_PER_LAUNCH = 1.69e9       # dram read+write bytes of one numeric launch, ncu --set full (profiles/r01_prof_tile_numeric_bench.keys.txt)
 
 
+def workload_name(n, thr, iterate):
+    return (f"newton-schulz sign iteration (SignFunction driver loop body: 2 multiplies, identity shift, convergence "
+            f"norm, copy), banded N={n} half-bandwidth 82, thr={thr:g}, iterate X_{iterate}")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,7 +170,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["gflops"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"newton-schulz sign iteration, banded N={args.n}, thr={args.threshold:g}, iterate X_{args.iterate}",
+        "config": {"workload": workload_name(args.n, args.threshold, args.iterate),
                    "sampled_n": n},
         "cpu_baseline": {"value": r["gflops"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["gflops"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -348,9 +353,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"newton-schulz sign iteration (SignFunction driver loop body: 2 multiplies, identity "
-                               f"shift, convergence norm, copy), banded N={n} half-bandwidth 82, thr={thr:g}, "
-                               f"iterate X_{args.iterate}",
+        "config": {"workload": workload_name(n, thr, args.iterate),
                    "grid": f"{R}x{C}x{S}", "l2": "inputs exceed L2 (operands > 500 MB vs 126 MB L2)",
                    "sec_per_iteration": ms_per_step * 1e-3},
         "clocks": clocks, "e2e": e2e, "gpu_launches": cnt["launches"], "roofline": roofline,

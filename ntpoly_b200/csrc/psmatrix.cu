@@ -1,5 +1,6 @@
 #include "psmatrix.h"
 #include <chrono>
+#include <functional>
 #include "ops.cuh"
 #include <algorithm>
 #include <cmath>
@@ -658,10 +659,14 @@ __global__ void __launch_bounds__(256) k_col_len(const int* __restrict__ outer, 
 }
 
 struct HaloRecord { long long ok, nsuper, ntiles, nnzA, qlo, qhi, nnzB, ntilesB; };
+__global__ void k_range_into_record(const int* __restrict__ r2, long long* __restrict__ qlo, long long* __restrict__ qhi) {
+  if (threadIdx.x == 0) { *qlo = r2[0]; *qhi = r2[1]; }
+}
 
 // returns false (on every rank alike) when this product does not qualify; then the caller takes the CSC gather path
 static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, double wthr, const RuleView& rv,
-                              const DiagShift* ds, LocalCsc<double>& out, GemmStats& st) {
+                              const std::function<void()>& full_rules, const DiagShift* ds, LocalCsc<double>& out,
+                              GemmStats& st) {
   ProcessGrid& g = *A.grid;
   if (!(g.R == 1 && g.S == 1 && g.C > 1) || !tile_path_on() || A.local_cols % 64 != 0 || !(wthr >= 0.0)) return false;
   static const bool timing = std::getenv("NTB_HALO_TIMING") != nullptr;      // developer probe: wall time per phase
@@ -675,26 +680,26 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   const int lcols = A.local_cols, nccl = lcols / 32, nkl = lcols / 4;
   const ChunkTiles* Lf = tile_operand_form(Al, true);
   const ChunkTiles* Rf = tile_operand_form(Bl, false);
-  // ---- records: who can play, sizes, and which global chunk columns of A each rank needs
+  // ---- records: who can play, sizes, and which global chunk columns of A each rank needs (the needed range is
+  // written into the device copy of the record by a kernel: one all-gather, one read-back)
   HaloRecord mine{};
   mine.ok = (Lf && Rf) ? 1 : 0;
   mine.qlo = INT_MAX; mine.qhi = -1;
-  if (mine.ok) {
-    mine.nsuper = Lf->nsuper; mine.ntiles = Lf->ntiles; mine.nnzA = Al.nnz; mine.nnzB = Bl.nnz; mine.ntilesB = Rf->ntiles;
-    DevBuf<int> d2(2);
-    const int init[2] = {INT_MAX, -1};
-    h2d(d2.get(), init, 2);
-    if (Rf->ncc > 0) NTB_LAUNCH(k_right_form_range, std::min(div_up(Rf->ncc, 256), kNumSMs), 256, 0, Rf->colmeta.get(), Rf->ncc, d2.get());
-    int h2[2];
-    d2h(h2, d2.get(), 2);
-    mine.qlo = h2[0]; mine.qhi = h2[1];
-  }
+  if (mine.ok) { mine.nsuper = Lf->nsuper; mine.ntiles = Lf->ntiles; mine.nnzA = Al.nnz; mine.nnzB = Bl.nnz; mine.ntilesB = Rf->ntiles; }
   std::vector<HaloRecord> rec(C);
   {
     DevBuf<HaloRecord> d_mine(1), d_all((size_t)C);
+    DevBuf<int> d2(2);
+    const int init[2] = {INT_MAX, -1};
     h2d(d_mine.get(), &mine, 1);
+    h2d(d2.get(), init, 2);
+    if (mine.ok && Rf->ncc > 0) {
+      NTB_LAUNCH(k_right_form_range, std::min(div_up(Rf->ncc, 256), kNumSMs), 256, 0, Rf->colmeta.get(), Rf->ncc, d2.get());
+      NTB_LAUNCH(k_range_into_record, 1, 32, 0, d2.get(), &d_mine.get()->qlo, &d_mine.get()->qhi);
+    }
     comm_allgather_bytes(g.row, d_mine.get(), d_all.get(), sizeof(HaloRecord));
     d2h(rec.data(), d_all.get(), (size_t)C);
+    mine = rec[me];
   }
   const auto t1 = now();
   long long nnzA = 0, ntilesA = 0, nnzB = 0, ntilesB = 0;
@@ -704,6 +709,9 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   }
   if (nnzA == 0 || nnzB == 0) return false;
   if ((double)nnzA < 0.20 * 32.0 * (double)ntilesA || (double)nnzB < 0.20 * 32.0 * (double)ntilesB) return false;
+  // A row block of A's panel cannot be more than 10 % full when the whole panel holds fewer entries than 10 % of
+  // ONE row block: only past that bound is the per-block histogram (and its all-reduce) needed for the rule table
+  if ((double)nnzA > 0.1 * (double)A.row_block() * (double)Bl.rows) full_rules();
 
   // ---- small index arrays of every rank
   ChunkTiles G;
@@ -788,7 +796,6 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   rt().alg_bytes += a_bytes + (double)Bl.bytes() + (double)out.bytes();
   rt().halo_products++;
   rt().halo_bytes += (double)total_tiles * 256.0;
-  stream_sync();
   return true;
 }
 
@@ -871,20 +878,22 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
   if constexpr (!scalar_traits<T>::is_complex) {
     if (g.R == 1 && S == 1 && g.C > 1 && tile_path_on() && A.local_cols % 64 == 0 && halo_enabled()) {
       // panel fills for the rule table: A's row panel is the union of the ranks' blocks, B's column panel is local
-      std::vector<double> cnt, fb;
-      rowblock_counts(Al, cnt);
-      {
-        DevBuf<double> d((size_t)nI);
-        h2d(d.get(), cnt.data(), (size_t)nI);
-        comm_allreduce_f64(g.row, d.get(), (size_t)nI, RedOp::Sum);
-        d2h(cnt.data(), d.get(), (size_t)nI);
-      }
-      const double inner_dim = (double)Bl.rows;
-      std::vector<double> fa(nI);
-      for (int i = 0; i < nI; ++i) fa[i] = cnt[i] / ((double)rb * inner_dim);
-      colblock_fills(Bl, inner_dim, fb);
-      set_rules(fa, fb);
-      product_done = halo_tile_product(A, B, alpha, wthr, rv, want_shift ? &ds : nullptr, loc<double>(AB), st);
+      auto full_rules = [&]() {
+        const double inner_dim = (double)Bl.rows;
+        std::vector<double> cnt, fb;
+        rowblock_counts(Al, cnt);
+        {
+          DevBuf<double> d((size_t)nI);
+          h2d(d.get(), cnt.data(), (size_t)nI);
+          comm_allreduce_f64(g.row, d.get(), (size_t)nI, RedOp::Sum);
+          d2h(cnt.data(), d.get(), (size_t)nI);
+        }
+        std::vector<double> fa(nI);
+        for (int i = 0; i < nI; ++i) fa[i] = cnt[i] / ((double)rb * inner_dim);
+        colblock_fills(Bl, inner_dim, fb);
+        set_rules(fa, fb);
+      };
+      product_done = halo_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st);
       if (!product_done) { rv = RuleView(); }
     }
   }

@@ -165,3 +165,46 @@ def test_trs2_banded_medium(nt, oracle):
     assert e == pytest.approx(info.energy, rel=1e-8)
     assert K.Trace() == pytest.approx(n // 2, abs=1e-3)
     compare_sparse(K.to_scipy(), Kref.to_scipy(), thr, tol=1e-7)
+
+
+@pytest.mark.parametrize("solver", ["TRS4", "PM"])
+def test_trs4_pm_banded_medium(nt, oracle, solver):
+    """TRS4 (config c3's driver) and PM on a banded Hamiltonian: iteration count, energy, chemical potential, density"""
+    n = 1024
+    h = banded(n, half_bandwidth=12, scale=0.2)
+    thr = 1e-7
+    H, ISQ, K = to_gpu(nt, h), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    ISQ.FillIdentity()
+    p = params(nt, 1e-6, thr)
+    e, mu = getattr(nt.DensityMatrixSolvers, solver)(H, ISQ, n // 2, K, p)
+    rec = nt.last_solve()
+    OH = oracle.PSMatrix.from_scipy(h)
+    fn = oracle.trs4 if solver == "TRS4" else oracle.pm
+    Kref, info = fn(OH, oracle.identity(OH), n // 2, oracle.SolverParameters(converge_diff=1e-6, threshold=thr))
+    assert rec["loop_counter"] == info.iterations
+    assert e == pytest.approx(info.energy, rel=1e-8)
+    assert K.Trace() == pytest.approx(n // 2, abs=1e-3)
+    compare_sparse(K.to_scipy(), Kref.to_scipy(), thr, tol=1e-7)
+
+
+def test_trs4_block_sparse_tile_path(nt, oracle):
+    """config c3 in small: block-sparse Hamiltonian (32x32 blocks) through TRS4 on the tile path, with the tile
+    forms of every iterate emitted by the products"""
+    from ntpoly_b200.workloads import block_sparse
+    n = 2048
+    # gapped (alternating on-site energies) so that the density matrix stays block-sparse
+    h = block_sparse(n, block=32, neighbours=4, band_blocks=3, seed=1234) * 0.3
+    h = sp.csc_matrix(h + sp.diags(np.where(np.arange(n) % 2 == 0, 0.5, -0.5)))
+    thr = 1e-6
+    H, ISQ, K = to_gpu(nt, h), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    ISQ.FillIdentity()
+    p = params(nt, 1e-6, thr)
+    nt.reset_counters()
+    e, mu = nt.DensityMatrixSolvers.TRS4(H, ISQ, n // 2, K, p)
+    rec = nt.last_solve()
+    assert nt.tile_counters()["tile_products"] > 0
+    OH = oracle.PSMatrix.from_scipy(h)
+    Kref, info = oracle.trs4(OH, oracle.identity(OH), n // 2, oracle.SolverParameters(converge_diff=1e-6, threshold=thr))
+    assert rec["loop_counter"] == info.iterations
+    assert e == pytest.approx(info.energy, rel=1e-8)
+    compare_sparse(K.to_scipy(), Kref.to_scipy(), thr, tol=1e-7)
