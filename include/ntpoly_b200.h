@@ -229,9 +229,21 @@ void ntb_MatrixMultiplyShift_ps(const int *ih_matA, const int *ih_matB, int *ih_
                                 const double *threshold, const double *sigma, const int *ih_identity,
                                 int *ih_memory_pool);
 /* One pass of the loop body of SignFunction (SignSolversModule.F90:213-234), exactly as the SignFunction_wrp driver
- * runs it: X advances in place, T1/T2 are work matrices, the return value is ||X_new - X_old||. */
+ * runs it: X advances in place, T1/T2 are work matrices (their contents afterwards are unspecified scratch: T2 holds
+ * the previous iterate), the return value is ||X_new - X_old||. */
 double ntb_SignIteration(int *ih_X, const int *ih_identity, int *ih_T1, int *ih_T2, const double *alpha_k,
                          const double *threshold, int *ih_memory_pool);
+/* The same loop body out of place: X_next receives the next iterate and X is left untouched; the return value is
+ * ||X_next - X||. SignFunction_wrp runs this and then exchanges the contents of X and X_next. */
+double ntb_SignStep(const int *ih_X, const int *ih_identity, int *ih_T1, int *ih_Xnext, const double *alpha_k,
+                    const double *threshold, int *ih_memory_pool);
+/* Instrumentation, 0 by default: when 1 every multiply also counts its useful products
+ * F = sum over the entries (k,j) of B of nnz(A(:,k)) (counters [2], ntb_last_solve [4]); one extra sweep over B and
+ * one read-back per product. When 0 the counts are only taken where the path choice needs them. */
+void ntb_set_flop_counting(int on);
+/* out2 = {tile products emitted as outer index + right tile form only (their CSC entries deferred),
+ *         deferred products whose entries had to be materialized later} */
+void ntb_get_deferred_counters(double *out2);
 /* device timing of the numeric SpGEMM kernels (CUDA events on the library stream):
  * enable, run, then read out2 = {total ms, number of timed products}; reading clears the record */
 void ntb_profile_enable(int on);

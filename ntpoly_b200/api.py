@@ -62,7 +62,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_set_fused_shift ntb_get_halo_counters ntb_set_halo_path ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_set_fused_shift ntb_get_halo_counters ntb_set_halo_path ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -78,6 +78,7 @@ def lib():
         L.MatrixNorm_ps_wrp.restype = c_double
         L.ntb_tile_builds.restype = c_double
         L.ntb_SignIteration.restype = c_double
+        L.ntb_SignStep.restype = c_double
         L.MeasureAsymmetry_ps_wrp.restype = c_double
         L.GetGlobalIsRoot_wrp.restype = c_bool
         L.ntb_GetMatrixLocalSize_ps.restype = c_longlong
@@ -704,6 +705,23 @@ def sign_iteration(X, identity, T1, T2, alpha_k, threshold, memory_pool=None):
     """one pass of the SignFunction driver's loop body; X advances in place, returns ||X_new - X_old||"""
     return float(lib().ntb_SignIteration(X.ih, identity.ih, T1.ih, T2.ih, _d(alpha_k), _d(threshold),
                                          memory_pool.ih if memory_pool is not None else None))
+
+
+def sign_step(X, identity, T1, Xnext, alpha_k, threshold, memory_pool=None):
+    """the same loop body out of place: Xnext <- next iterate, X untouched; returns ||Xnext - X||"""
+    return float(lib().ntb_SignStep(X.ih, identity.ih, T1.ih, Xnext.ih, _d(alpha_k), _d(threshold),
+                                    memory_pool.ih if memory_pool is not None else None))
+
+
+def set_flop_counting(on=True):
+    """instrumentation (off by default): count the useful products of every multiply"""
+    lib().ntb_set_flop_counting(c_int(1 if on else 0))
+
+
+def deferred_counters():
+    out = (c_double * 2)()
+    lib().ntb_get_deferred_counters(out)
+    return {"products": int(out[0]), "materialized": int(out[1])}
 
 
 def algorithmic_bytes():

@@ -379,7 +379,7 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().halo_bytes = 0.0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
 // C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when
@@ -401,6 +401,18 @@ double ntb_SignIteration(int* ih_x, const int* ih_identity, int* ih_t1, int* ih_
   return sign_iteration(*get<Matrix>(ih_x), *get<Matrix>(ih_identity), *get<Matrix>(ih_t1), *get<Matrix>(ih_t2), unused,
                         *alpha_k, *threshold, false, pool);
 }
+// the same loop body out of place: X_next receives the next iterate, X is left untouched (the driver's in-place form
+// is this call followed by an exchange of the two handles' contents)
+double ntb_SignStep(const int* ih_x, const int* ih_identity, int* ih_t1, int* ih_xnext, const double* alpha_k,
+                    const double* threshold, int* ih_pool) {
+  MemoryPool* pool = nullptr;
+  if (ih_pool) { std::memcpy(&pool, ih_pool, sizeof(pool)); }
+  Matrix unused;
+  return sign_step(*get<Matrix>(ih_x), *get<Matrix>(ih_identity), *get<Matrix>(ih_t1), *get<Matrix>(ih_xnext), unused,
+                   *alpha_k, *threshold, false, pool);
+}
+void ntb_set_flop_counting(int on) { ensure_init(); rt().count_flops = on != 0; }
+void ntb_get_deferred_counters(double* out2) { out2[0] = (double)rt().deferred_products; out2[1] = (double)rt().deferred_materialized; }
 void ntb_get_tile_counters(double* out2) { out2[0] = (double)rt().tile_products; out2[1] = rt().dmma_issued; }
 double ntb_tile_builds(void) { return (double)rt().tile_builds; }
 void ntb_get_halo_counters(double* out2) { out2[0] = (double)rt().halo_products; out2[1] = rt().halo_bytes; }

@@ -4,6 +4,7 @@
 #pragma once
 #include "device.cuh"
 #include <memory>
+#include <type_traits>
 
 namespace ntb {
 
@@ -26,17 +27,31 @@ struct TileForms {
   int has_left = 0, has_right = 0;           // 0 not built, 1 built, -1 cannot be built (pattern reach overflow)
 };
 
+template <typename T> struct LocalCsc;
+// fills inner/val of a block whose entries were deferred (spgemm_tile.cu)
+void tile_materialize_entries(const LocalCsc<double>& M);
+
 template <typename T> struct LocalCsc {
   int rows = 0;
   int cols = 0;
   long long nnz = 0;
   DevBuf<int> outer;  // [cols+1]
-  DevBuf<int> inner;  // [nnz]
-  DevBuf<T> val;      // [nnz]
+  mutable DevBuf<int> inner;  // [nnz]
+  mutable DevBuf<T> val;      // [nnz]
   mutable std::shared_ptr<TileForms> forms;   // cached tile forms of these very entries (real blocks only)
+  // A product whose only consumer is another tile product (the drivers' intermediates, e.g. 3I - a^2 X^2 of the
+  // sign iteration) is emitted as outer index + right tile form only: inner/val are DEFERRED and filled from the
+  // form the first time anything asks for the entries (view(), ensure_entries()). nnz and outer are always valid.
+  mutable bool deferred = false;
 
+  void ensure_entries() const {
+    if (!deferred) return;
+    if constexpr (std::is_same<T, double>::value) tile_materialize_entries(*this);
+    deferred = false;
+  }
   void init_empty(int r, int c) {
     forms.reset();
+    deferred = false;
     rows = r; cols = c; nnz = 0;
     outer.alloc((size_t)c + 1);
     outer.zero();
@@ -45,25 +60,28 @@ template <typename T> struct LocalCsc {
   }
   void alloc_entries(long long count) {
     forms.reset();
+    deferred = false;
     nnz = count;
     inner.alloc((size_t)count);
     val.alloc((size_t)count);
   }
-  CscView<T> view() const { return CscView<T>{rows, cols, outer.get(), inner.get(), val.get()}; }
+  CscView<T> view() const { ensure_entries(); return CscView<T>{rows, cols, outer.get(), inner.get(), val.get()}; }
   void copy_from(const LocalCsc<T>& o) {
     rows = o.rows; cols = o.cols; nnz = o.nnz;
     outer.alloc((size_t)cols + 1);
     d2d(outer.get(), o.outer.get(), (size_t)cols + 1);
+    forms = o.forms;
+    deferred = o.deferred;                     // a deferred block is copied as such (the forms are shared)
+    if (deferred) { inner.alloc(0); val.alloc(0); return; }
     inner.alloc((size_t)nnz);
     val.alloc((size_t)nnz);
     d2d(inner.get(), o.inner.get(), (size_t)nnz);
     d2d(val.get(), o.val.get(), (size_t)nnz);
-    forms = o.forms;
   }
   void swap(LocalCsc<T>& o) {
     std::swap(rows, o.rows); std::swap(cols, o.cols); std::swap(nnz, o.nnz);
     std::swap(outer, o.outer); std::swap(inner, o.inner); std::swap(val, o.val);
-    std::swap(forms, o.forms);
+    std::swap(forms, o.forms); std::swap(deferred, o.deferred);
   }
   size_t bytes() const {  // algorithmic bytes of this block
     return (size_t)nnz * (sizeof(T) + 4) + ((size_t)cols + 1) * 4;
@@ -101,9 +119,13 @@ struct DiagShift {
   int dd = 0;            // local row of the diagonal entry of local column 0
   int ncols_diag = 0;    // local columns whose global index is below the actual (unpadded) dimension
 };
+// What the caller needs of a product (tile path only; every other path delivers plain CSC): the CSC entries and/or
+// the tile forms of the result. Without WANT_CSC the entries are deferred (LocalCsc::deferred) and WANT_RIGHT is implied.
+constexpr unsigned WANT_CSC = 1u, WANT_LEFT = 2u, WANT_RIGHT = 4u, WANT_ALL = 7u;
 template <typename T>
 void spgemm(const LocalCsc<T>& X, const LocalCsc<T>& Y, double alpha, double thr,
-            const RuleView& rules, LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift = nullptr);
+            const RuleView& rules, LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift = nullptr,
+            unsigned want = WANT_ALL);
 // ---- pieces of the tile path used by the distributed layer (spgemm_tile.cu)
 // cached or freshly built tile form of a real block (nullptr: the pattern cannot be tiled)
 const ChunkTiles* tile_operand_form(const LocalCsc<double>& M, bool left);
@@ -111,7 +133,7 @@ const ChunkTiles* tile_operand_form(const LocalCsc<double>& M, bool left);
 // right operand. force: never decline (the caller has already committed collectively to this path).
 bool spgemm_tile_core(const ChunkTiles& A, const ChunkTiles& B, int ncols, int nrows, double alpha, double thr,
                       const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
-                      bool force);
+                      bool force, unsigned want = WANT_ALL);
 // assemble the left form of a row of column blocks from per-rank pieces (see psmatrix.cu: halo gather)
 struct LeftPiece {          // one rank's contribution, all offsets in units of that rank / of the gathered arrays
   int ent_base;             // first entry of this rank in the gathered entry array

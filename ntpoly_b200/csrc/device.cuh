@@ -21,6 +21,9 @@ struct Runtime {
   unsigned long long halo_products = 0;  // distributed products that fetched the left operand as a tile halo
   double halo_bytes = 0.0;               // tile bytes of those halos (own part included)
   double dmma_issued = 0.0;              // DMMA.8x8x4 instructions (x256 FMAs) issued by the tile path
+  unsigned long long deferred_products = 0;      // tile products emitted without CSC entries (outer + right form only)
+  unsigned long long deferred_materialized = 0; // ... whose entries had to be produced later after all
+  bool count_flops = false;        // instrumentation: count the useful products of every multiply (one extra sweep + read-back)
   double alg_bytes = 0.0;          // compulsory bytes of the local products: bytes(A)+bytes(B)+bytes(C_kept)
   // optional device timing of the dominant (numeric SpGEMM) kernels, for bench.py's roofline
   bool profile = false;

@@ -165,6 +165,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_scale(T* __restri
 }
 template <typename T> void csc_scale(LocalCsc<T>& M, T c) {
   if (M.nnz == 0) return;
+  M.ensure_entries();
   NTB_LAUNCH((k_scale<T>), min(div_up(M.nnz, 256), kNumSMs * 16), 256, 0, M.val.get(), M.nnz, c);
   // cached tile forms: scaled in place when this matrix is their only owner, dropped otherwise
   if constexpr (!scalar_traits<T>::is_complex) {
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(256) k_c2r(const cplx* __restrict__ in, double
     out[i] = in[i].x;
 }
 void csc_to_complex(const LocalCsc<double>& in, LocalCsc<cplx>& out) {
+  in.ensure_entries();
   out.rows = in.rows; out.cols = in.cols;
   out.outer.alloc((size_t)in.cols + 1);
   d2d(out.outer.get(), in.outer.get(), (size_t)in.cols + 1);

@@ -209,6 +209,7 @@ template <typename T>
 static void gather_concat_cols(const LocalCsc<T>& local, CommHandle* comm, LocalCsc<T>& out) {
   const int n = comm_size(comm);
   NTB_CHECK(n > 1, "gather_concat_cols on a single rank");
+  local.ensure_entries();
   std::vector<long long> nnz = exchange_counts(comm, local.nnz);
   std::vector<long long> off(n + 1, 0);
   for (int q = 0; q < n; ++q) off[q + 1] = off[q] + nnz[q];
@@ -666,7 +667,7 @@ __global__ void k_range_into_record(const int* __restrict__ r2, long long* __res
 // returns false (on every rank alike) when this product does not qualify; then the caller takes the CSC gather path
 static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, double wthr, const RuleView& rv,
                               const std::function<void()>& full_rules, const DiagShift* ds, LocalCsc<double>& out,
-                              GemmStats& st) {
+                              GemmStats& st, unsigned want) {
   ProcessGrid& g = *A.grid;
   if (!(g.R == 1 && g.S == 1 && g.C > 1) || !tile_path_on() || A.local_cols % 64 != 0 || !(wthr >= 0.0)) return false;
   static const bool timing = std::getenv("NTB_HALO_TIMING") != nullptr;      // developer probe: wall time per phase
@@ -718,8 +719,12 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   G.ncc = C * nccl;
   G.colmeta.alloc((size_t)C * nccl);
   G.kmeta.alloc((size_t)C * nkl);
-  DevBuf<int> coltile_g((size_t)C * (nccl + 1)), ylen((size_t)lcols), ylen_g((size_t)C * lcols);
-  NTB_LAUNCH(k_col_len, div_up(lcols, 256), 256, 0, Al.outer.get(), lcols, ylen.get());
+  const bool count = rt().count_flops;        // a process-wide setting: every rank takes the same branch
+  DevBuf<int> coltile_g((size_t)C * (nccl + 1)), ylen, ylen_g;
+  if (count) {
+    ylen.alloc((size_t)lcols); ylen_g.alloc((size_t)C * lcols);
+    NTB_LAUNCH(k_col_len, div_up(lcols, 256), 256, 0, Al.outer.get(), lcols, ylen.get());
+  }
   std::vector<int> ent_base(C + 1, 0);
   for (int p = 0; p < C; ++p) ent_base[p + 1] = ent_base[p] + (int)rec[p].nsuper;
   G.nsuper = ent_base[C];
@@ -728,7 +733,7 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   comm_allgather_bytes(g.row, Lf->colmeta.get(), G.colmeta.get(), (size_t)nccl * sizeof(int4));
   comm_allgather_bytes(g.row, Lf->kmeta.get(), G.kmeta.get(), (size_t)nkl * sizeof(int4));
   comm_allgather_bytes(g.row, Lf->coltile.get(), coltile_g.get(), ((size_t)nccl + 1) * sizeof(int));
-  comm_allgather_bytes(g.row, ylen.get(), ylen_g.get(), (size_t)lcols * sizeof(int));
+  if (count) comm_allgather_bytes(g.row, ylen.get(), ylen_g.get(), (size_t)lcols * sizeof(int));
   for (int p = 0; p < C; ++p)
     if (rec[p].nsuper > 0)
       comm_broadcast_bytes(g.row, Lf->ent.get(), G.ent.get() + ent_base[p], (size_t)rec[p].nsuper * sizeof(int4), p);
@@ -776,15 +781,16 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   const auto t3 = now();
 
   // ---- product from the forms
-  const double useful = useful_products_from_lengths(Bl, ylen_g.get());
+  double useful = -1.0;
+  if (count) { Bl.ensure_entries(); useful = useful_products_from_lengths(Bl, ylen_g.get()); }
   const auto t4 = now();
-  const bool done = spgemm_tile_core(G, *Rf, B.local_cols, A.local_rows, alpha, wthr, rv, out, useful, ds, true);
+  const bool done = spgemm_tile_core(G, *Rf, B.local_cols, A.local_rows, alpha, wthr, rv, out, useful, ds, true, want);
   const auto t5 = now();
   if (timing && me == 0)
     std::fprintf(stderr, "[halo] records %.3f  index gather %.3f  tiles %.3f (%.1f MB)  flops %.3f  product %.3f ms\n",
                  ms(t0, t1), ms(t1, t2), ms(t2, t3), (double)total_tiles * 256.0 / 1e6, ms(t3, t4), ms(t4, t5));
   NTB_CHECK(done, "forced tile product declined");
-  st.flops = 2.0 * useful;
+  st.flops = count ? 2.0 * useful : 0.0;
   st.shift_applied = ds && ds->sigma != 0.0;
   // compulsory bytes: B block, kept C block, and the share of A that was actually needed (by tile count)
   double a_bytes = 0.0;
@@ -815,7 +821,7 @@ static bool fused_shift_enabled() {
 // returns true when the optional diagonal shift `sigma` (C = alpha*A*B + sigma*I, see DiagShift) was fused
 template <typename T>
 static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
-                       double sigma = 0.0) {
+                       double sigma = 0.0, unsigned want = WANT_ALL) {
   ProcessGrid& g = *A.grid;
   const int S = g.S;
   const double wthr = (S > 1) ? threshold / (S * 1000) : threshold;      // MatrixMultiply.f90:25-29
@@ -852,6 +858,7 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
   auto rowblock_counts = [&](const LocalCsc<T>& Ypan, std::vector<double>& cnt_out) {
     cnt_out.assign(nI, 0.0);
     if (nI == 1) { cnt_out[0] = (double)Ypan.nnz; return; }
+    Ypan.ensure_entries();
     DevBuf<unsigned long long> cnt((size_t)nI);
     cnt.zero();
     NTB_CHECK(nI <= RB_BINS, "more than 1024 row blocks per rank");
@@ -893,12 +900,15 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
         colblock_fills(Bl, inner_dim, fb);
         set_rules(fa, fb);
       };
-      product_done = halo_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st);
+      product_done = halo_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st,
+                                       want);
       if (!product_done) { rv = RuleView(); }
     }
   }
 
   if (!product_done) {
+    // every path below except the single-rank tile product reads the CSC entries of both operands
+    if (S > 1 || comm_size(g.row) > 1 || comm_size(g.column) > 1 || nI > 1) { Al.ensure_entries(); Bl.ensure_entries(); }
     // ---- A task: my slice's column blocks, gathered along the process row (:94-145)
     LocalCsc<T> Asel, Ypanel;
     const LocalCsc<T>* Ysrc = &Al;
@@ -927,7 +937,9 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
       set_rules(fa, fb);
     }
     // ---- local product
-    spgemm<T>(*Xsrc, *Ysrc, alpha, wthr, rv, loc<T>(AB), &st, want_shift ? &ds : nullptr);
+    // deferred entries only for a plain replacement of C on a single slice
+    const unsigned w = (S == 1 && (std::fabs(beta) < 2.2250738585072014e-308 || !C.constructed)) ? want : WANT_ALL;
+    spgemm<T>(*Xsrc, *Ysrc, alpha, wthr, rv, loc<T>(AB), &st, want_shift ? &ds : nullptr, w);
   }
   rt().flops_useful += st.flops;
   rt().multiplies++;
@@ -946,7 +958,7 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
 }
 
 void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
-                  MemoryPool* pool) {
+                  MemoryPool* pool, unsigned want) {
   NTB_CHECK(A.constructed && B.constructed, "MatrixMultiply on an unconstructed matrix");
   NTB_CHECK(A.logical_dim == B.logical_dim && A.grid == B.grid, "MatrixMultiply: operands live on different grids/sizes");
   if (pool) { pool->rows = A.local_rows; pool->cols = A.local_cols; pool->is_complex = A.is_complex || B.is_complex; pool->constructed = true; }
@@ -959,7 +971,7 @@ void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, dou
     if (C.constructed && !C.is_complex && std::fabs(beta) > 0) { Matrix tc; mat_to_complex(C, tc); C = std::move(tc); }
     multiply_t<cplx>(*pa, *pb, C, alpha, beta, threshold);
   } else {
-    multiply_t<double>(A, B, C, alpha, beta, threshold);
+    multiply_t<double>(A, B, C, alpha, beta, threshold, 0.0, want);
   }
 }
 
@@ -967,12 +979,12 @@ void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, dou
 // Newton-Schulz style driver issues (e.g. SignSolversModule.F90:226-229). The shift is fused into the product's
 // emit pass when the product runs on the tile path; otherwise the two reference calls are made.
 void mat_multiply_shift(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double threshold, double sigma,
-                        const Matrix& Identity, MemoryPool* pool) {
+                        const Matrix& Identity, MemoryPool* pool, unsigned want) {
   NTB_CHECK(A.constructed && B.constructed, "MatrixMultiply on an unconstructed matrix");
   if (!A.is_complex && !B.is_complex && sigma != 0.0 && fused_shift_enabled()) {
     NTB_CHECK(A.logical_dim == B.logical_dim && A.grid == B.grid, "MatrixMultiply: operands live on different grids/sizes");
     if (pool) { pool->rows = A.local_rows; pool->cols = A.local_cols; pool->is_complex = false; pool->constructed = true; }
-    if (multiply_t<double>(A, B, C, alpha, 0.0, threshold, sigma)) return;
+    if (multiply_t<double>(A, B, C, alpha, 0.0, threshold, sigma, want)) return;
   } else {
     mat_multiply(A, B, C, alpha, 0.0, threshold, pool);
   }

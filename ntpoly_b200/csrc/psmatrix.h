@@ -85,10 +85,13 @@ long long mat_global_nnz(const Matrix& M);
 bool mat_is_identity(const Matrix& M);
 
 // PSMatrixAlgebraModule
+// want (csc.cuh: WANT_*): what the caller will read of C. A driver intermediate that only feeds the next product as
+// its right operand asks for WANT_RIGHT alone; C is valid for every later use either way (entries are materialized
+// on demand).
 void mat_multiply(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
-                  MemoryPool* pool);
+                  MemoryPool* pool, unsigned want = WANT_ALL);
 void mat_multiply_shift(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double threshold, double sigma,
-                        const Matrix& Identity, MemoryPool* pool);
+                        const Matrix& Identity, MemoryPool* pool, unsigned want = WANT_ALL);
 void set_fused_shift(int on);
 void set_halo_path(int on);
 void mat_increment(const Matrix& A, Matrix& B, double alpha, double threshold);

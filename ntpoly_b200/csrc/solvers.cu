@@ -413,19 +413,28 @@ void mcweeny_step(const Matrix& D, Matrix& Dout, const Matrix* S, double thresho
 // sign function / polar decomposition core (SignSolversModule.F90:150-258)
 // One pass of the loop body (:213-234): X <- 0.5*a*X*(3I - a^2 X^T X); returns ||X_new - X_old||.
 // "Gemm then IncrementMatrix(Identity, T1, 3)" is issued as one fused product (mat_multiply_shift).
-double sign_iteration(Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& T2, Matrix& OutT, double alpha_k,
-                      double threshold, bool needs_transpose, MemoryPool* pool) {
+// One pass of the loop body of SignFunction / PolarDecomposition (SignSolversModule.F90:207-240), out of place:
+// Xn = 1/2 a X (3I - a^2 X^T X), X untouched; returns ||Xn - X||. T1 = 3I - a^2 X^T X only ever feeds the second
+// product as its right operand, so it is emitted as a right tile form with deferred entries (csc.cuh).
+double sign_step(const Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& Xn, Matrix& OutT, double alpha_k,
+                 double threshold, bool needs_transpose, MemoryPool* pool) {
   if (needs_transpose) {
     mat_transpose(X, OutT);
     if (OutT.is_complex) mat_conjugate(OutT);
-    mat_multiply_shift(OutT, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool);
+    mat_multiply_shift(OutT, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool, WANT_RIGHT);
   } else {
-    mat_multiply_shift(X, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool);   // T1 = 3I - a^2 X^2
+    mat_multiply_shift(X, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool, WANT_RIGHT);
   }
-  mat_multiply(X, T1, T2, 0.5 * alpha_k, 0.0, threshold, pool);
+  mat_multiply(X, T1, Xn, 0.5 * alpha_k, 0.0, threshold, pool);
   // reference: IncrementMatrix(T2, X, -1); norm = MatrixNorm(X); CopyMatrix(T2, X) — X - T2 is never needed itself
-  const double norm_value = mat_diff_norm(T2, X, -1.0);
-  mat_copy(T2, X);
+  return mat_diff_norm(Xn, X, -1.0);
+}
+// ... and in place, as the drivers use it: X becomes the next iterate by exchanging it with the work matrix T2
+// (the reference copies Temp2 into X; T2 is scratch either way and holds the previous iterate afterwards).
+double sign_iteration(Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& T2, Matrix& OutT, double alpha_k,
+                      double threshold, bool needs_transpose, MemoryPool* pool) {
+  const double norm_value = sign_step(X, Identity, T1, T2, OutT, alpha_k, threshold, needs_transpose, pool);
+  std::swap(X, T2);
   return norm_value;
 }
 

@@ -60,6 +60,8 @@ void solve_pm(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, doubl
 void solve_hpcp(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, double* energy_out, double* chempot_out,
                 const SolverParameters& params);
 void solve_sign(const Matrix& In, Matrix& Out, const SolverParameters& params);
+double sign_step(const Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& Xn, Matrix& OutT, double alpha_k,
+                 double threshold, bool needs_transpose, MemoryPool* pool);
 double sign_iteration(Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& T2, Matrix& OutT, double alpha_k,
                       double threshold, bool needs_transpose, MemoryPool* pool);
 void solve_polar(const Matrix& In, Matrix& U, Matrix* Hmat, const SolverParameters& params);

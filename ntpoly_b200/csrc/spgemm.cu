@@ -25,7 +25,7 @@
 namespace ntb {
 
 bool spgemm_tile(const LocalCsc<double>& X, const LocalCsc<double>& Y, double alpha, double thr, const RuleView& rules,
-                 LocalCsc<double>& Z, double useful_products, const DiagShift* shift);
+                 LocalCsc<double>& Z, double useful_products, const DiagShift* shift, unsigned want);
 
 static int g_tile_mode = -1;   // -1: read NTB_TILE once; 0 off; 1 on
 void set_tile_path(int on) { g_tile_mode = on ? 1 : 0; }
@@ -311,12 +311,32 @@ double useful_products_from_lengths(const LocalCsc<double>& X, const int* d_ylen
 // ---------------------------------------------------------------------------
 template <typename T>
 void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double thr, const RuleView& rules,
-            LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift) {
-  const CscView<T> X = Xl.view(), Y = Yl.view();
-  NTB_CHECK(X.rows == Y.cols, "spgemm: inner dimensions differ");
+            LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift, unsigned want) {
+  NTB_CHECK(Xl.rows == Yl.cols, "spgemm: inner dimensions differ");
   if (stats) stats->shift_applied = false;
-  const int ncols = X.cols;
-  const int nrows = Y.rows;
+  const int ncols = Xl.cols;
+  const int nrows = Yl.rows;
+
+  auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
+  auto account_bytes = [&](long long nnz_out) {
+    double b = csc_bytes(Xl.nnz, Xl.cols) + csc_bytes(nnz_out, ncols);
+    if (Yl.outer.get() != Xl.outer.get()) b += csc_bytes(Yl.nnz, Yl.cols);   // A counted once when A == B
+    rt().alg_bytes += b;
+  };
+
+  // ---- operands that already carry their tile forms (results of earlier tile products): with the flop accounting
+  // switched off nothing needs the CSC entries, which may even be deferred (LocalCsc::deferred)
+  if constexpr (!scalar_traits<T>::is_complex) {
+    if (tile_path_enabled() && !rt().count_flops && ncols > 0 && Xl.nnz > 0 && Yl.nnz > 0 && Xl.forms && Yl.forms &&
+        Xl.forms->has_right == 1 && Yl.forms->has_left == 1 &&
+        spgemm_tile_core(Yl.forms->left, Xl.forms->right, ncols, nrows, alpha, thr, rules, Z, -1.0, shift, false, want)) {
+      if (stats) { stats->shift_applied = shift && shift->sigma != 0.0; stats->flops = 0.0; stats->tmp_entries = 0; }
+      account_bytes(Z.nnz);
+      return;
+    }
+  }
+
+  const CscView<T> X = Xl.view(), Y = Yl.view();
   Z.rows = nrows;
   Z.cols = ncols;
   Z.outer.alloc((size_t)ncols + 1);
@@ -331,13 +351,6 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   cfg.wmax[5] = (int)(SMEM_BUDGET / sizeof(T));
   cfg.wmax[6] = INT_MAX;
 
-  auto csc_bytes = [](long long nnz, int cols) { return (double)nnz * (sizeof(T) + 4) + ((double)cols + 1) * 4; };
-  auto account_bytes = [&](long long nnz_out) {
-    double b = csc_bytes(Xl.nnz, X.cols) + csc_bytes(nnz_out, ncols);
-    if (Y.val != X.val) b += csc_bytes(Yl.nnz, Y.cols);   // A counted once when A == B
-    rt().alg_bytes += b;
-  };
-
   // ---- tile path first: it needs only the useful-product count, not the per-column windows
   if constexpr (!scalar_traits<T>::is_complex) {
     if (tile_path_enabled() && Xl.nnz > 0 && Yl.nnz > 0) {
@@ -347,7 +360,7 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
       unsigned long long h_fl = 0;
       d2h(&h_fl, fl.get(), 1);
       // worth it only when columns are long enough to fill tiles
-      if ((double)h_fl >= 16.0 * (double)ncols && spgemm_tile(Xl, Yl, alpha, thr, rules, Z, (double)h_fl, shift)) {
+      if ((double)h_fl >= 16.0 * (double)ncols && spgemm_tile(Xl, Yl, alpha, thr, rules, Z, (double)h_fl, shift, want)) {
         if (stats) {
           stats->shift_applied = shift && shift->sigma != 0.0;
           stats->flops = 2.0 * (double)h_fl;
@@ -447,8 +460,8 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
 }
 
 template void spgemm<double>(const LocalCsc<double>&, const LocalCsc<double>&, double, double, const RuleView&,
-                             LocalCsc<double>&, GemmStats*, const DiagShift*);
+                             LocalCsc<double>&, GemmStats*, const DiagShift*, unsigned);
 template void spgemm<cplx>(const LocalCsc<cplx>&, const LocalCsc<cplx>&, double, double, const RuleView&,
-                           LocalCsc<cplx>&, GemmStats*, const DiagShift*);
+                           LocalCsc<cplx>&, GemmStats*, const DiagShift*, unsigned);
 
 }  // namespace ntb

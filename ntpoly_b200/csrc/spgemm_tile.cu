@@ -838,7 +838,7 @@ k_forms_fill(int nJ, int nrows, int ncols, const int2* __restrict__ tasks, const
              const int* __restrict__ imin8, const int* __restrict__ nI8, const long long* __restrict__ stg_off,
              const double* __restrict__ stg, EmitSpec es, const unsigned long long* __restrict__ fmA,
              const unsigned long long* __restrict__ fmB, const int* __restrict__ stoffL, const int* __restrict__ stoffR,
-             double* __restrict__ tvalL, double* __restrict__ tvalR) {
+             double* __restrict__ tvalL, double* __restrict__ tvalR, unsigned want) {
   const int task = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int2 tk = tasks[task];
@@ -849,7 +849,7 @@ k_forms_fill(int nJ, int nrows, int ncols, const int2* __restrict__ tasks, const
   const int wlen = nI * 8;
   const double* src = stg + stg_off[J] * 64 + (size_t)(I0 - iw0) * 8;
   // right form: tiles (h, jj = w, kk): rows 32h + 4kk + lane%4, column lane/4
-  {
+  if (want & WANT_RIGHT) {
     const int c = lane >> 2, r = lane & 3, col = J * 8 + c;
     for (int h = 0; h < 2; ++h) {
       const unsigned long long m = fmB[(size_t)task * 2 + h];
@@ -868,7 +868,7 @@ k_forms_fill(int nJ, int nrows, int ncols, const int2* __restrict__ tasks, const
     }
   }
   // left form: chunk column c = w/4, inner tiles kk = 2(w%4) + ch: rows 8ii + lane/4, column 4ch + lane%4
-  {
+  if (want & WANT_LEFT) {
     const int cch = w >> 2, r = lane >> 2, c4 = lane & 3;
     const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
     const unsigned long long m = fmA[(size_t)task * 2 + cch];
@@ -890,6 +890,52 @@ k_forms_fill(int nJ, int nrows, int ncols, const int2* __restrict__ tasks, const
       }
     }
   }
+}
+
+// Deferred CSC entries of a product, from its right form (the kept entries of a product are exactly its non-zero
+// values: |alpha*v| > thr >= 0, or a non-zero shifted diagonal entry). One warp per column; a lane is one row of a
+// super-tile (inner tile lane/4, row lane%4), so entries come out in ascending row order.
+__global__ void __launch_bounds__(256)
+k_right_to_csc(int ncols, CtView R, const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ val,
+               int* __restrict__ mismatch) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int j = gw; j < ncols; j += nw) {
+    const int4 cm = R.colmeta[j >> 6];
+    const int bit = ((j >> 3) & 7) * 8 + (lane >> 2);
+    const int fr = (j & 7) * 4 + (lane & 3);
+    int pos = outer[j];
+    const int end = outer[j + 1];
+    for (int e = 0; e < cm.y; ++e) {
+      const int4 en = R.ent[cm.x + e];
+      const unsigned long long m = mask64(en);
+      double v = 0.0;
+      if ((m >> bit) & 1ull) v = R.tval[((size_t)en.y + popc64(m & ((1ull << bit) - 1ull))) * 32 + fr];
+      const bool keep = v != 0.0;
+      const unsigned b = __ballot_sync(0xffffffffu, keep);
+      const int p = pos + __popc(b & ((1u << lane) - 1u));
+      if (keep && p < end) { inner[p] = en.x * 32 + lane; val[p] = v; }
+      pos += __popc(b);
+    }
+    if (lane == 0 && pos != end) atomicExch(mismatch, 1);
+  }
+}
+void tile_materialize_entries(const LocalCsc<double>& M) {
+  NTB_CHECK(M.forms && M.forms->has_right == 1, "deferred entries without a right tile form");
+  const ChunkTiles& R = M.forms->right;
+  M.inner.alloc((size_t)M.nnz);
+  M.val.alloc((size_t)M.nnz);
+  rt().deferred_materialized++;
+  if (M.nnz == 0 || M.cols == 0) return;
+  const CtView Rv{R.colmeta.get(), R.ent.get(), R.tval.get(), nullptr, R.ncc};
+  DevBuf<int> bad(1);
+  bad.zero();
+  NTB_LAUNCH(k_right_to_csc, max(1, min(div_up((long long)M.cols * 32, 256), kNumSMs * 16)), 256, 0, M.cols, Rv,
+             M.outer.get(), M.inner.get(), M.val.get(), bad.get());
+  int h = 0;
+  d2h(&h, bad.get(), 1);
+  NTB_CHECK(h == 0, "deferred entries: the right form does not match the column counts");
 }
 
 // the cached (or freshly built) tile form of an operand; nullptr when its pattern cannot be tiled
@@ -931,18 +977,20 @@ void tile_fixup_gathered_left(ChunkTiles& G, const LeftPiece* pieces, int npiece
 // returns false when the operands are not locally dense enough (caller falls back to the
 // scalar window kernels). useful_products = sum over B entries of the A column lengths.
 bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double alpha, double thr, const RuleView& rules,
-                 LocalCsc<double>& Z, double useful_products, const DiagShift* shift) {
+                 LocalCsc<double>& Z, double useful_products, const DiagShift* shift, unsigned want) {
   if (Xl.cols == 0 || Xl.nnz == 0 || Yl.nnz == 0 || !(thr >= 0.0)) return false;
   const ChunkTiles* A = tile_operand_form(Yl, true);
   if (!A || (double)Yl.nnz < 0.20 * 32.0 * (double)A->ntiles) return false;   // tiles mostly padding
   const ChunkTiles* B = tile_operand_form(Xl, false);
   if (!B || (double)Xl.nnz < 0.20 * 32.0 * (double)B->ntiles) return false;
-  return spgemm_tile_core(*A, *B, Xl.cols, Yl.rows, alpha, thr, rules, Z, useful_products, shift, false);
+  return spgemm_tile_core(*A, *B, Xl.cols, Yl.rows, alpha, thr, rules, Z, useful_products, shift, false, want);
 }
 
 bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncols, int nrows, double alpha, double thr,
                       const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
-                      bool force) {
+                      bool force, unsigned want) {
+  // entries can be deferred only when the kept entries are exactly the non-zero values (no dense-rule blocks)
+  if (!(want & WANT_CSC)) { if (rules.tbl != nullptr) want = WANT_ALL; else want |= WANT_RIGHT; }
   const ChunkTiles* A = &Aform;
   const ChunkTiles* B = &Bform;
   static const bool timing = std::getenv("NTB_TILE_TIMING") != nullptr;      // developer probe: wall time per phase
@@ -975,7 +1023,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   CUDA_CHECK(cudaMemcpyAsync(&h_tasks, gtask_off.get() + nG, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
   // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
-  if (!force && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
+  if (!force && useful_products >= 0.0 && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
 
   const auto t1 = now();
   DevBuf<double> stg((size_t)h_stg * 64);
@@ -1045,27 +1093,39 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   CUDA_CHECK(cudaMemcpyAsync(h_tot, totals.get(), sizeof(h_tot), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
   const auto t4 = now();
-  Z.alloc_entries(h_nnz);
-  if (h_nnz > 0)
-    NTB_LAUNCH(k_tile_emit, egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(), es,
-               Z.outer.get(), Z.inner.get(), Z.val.get());
+  const bool with_forms = h_tasks > 0 && h_nnz > 0;
+  const bool defer = with_forms && !(want & WANT_CSC);
+  if (defer) {
+    Z.alloc_entries(0);
+    Z.nnz = h_nnz;                             // inner/val are filled from the right form on first use
+  } else {
+    Z.alloc_entries(h_nnz);
+    if (h_nnz > 0)
+      NTB_LAUNCH(k_tile_emit, egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(), es,
+                 Z.outer.get(), Z.inner.get(), Z.val.get());
+  }
   const auto t5 = now();
-  if (h_tasks > 0 && h_nnz > 0) {
+  if (with_forms) {
     L.ncc = div_up(ncols, 32); L.nsuper = h_tot[0]; L.ntiles = h_tot[1];
     R.ncc = nG; R.nsuper = h_tot[2]; R.ntiles = h_tot[3];
-    L.tval.alloc((size_t)L.ntiles * 32);
-    R.tval.alloc((size_t)R.ntiles * 32);
-    NTB_LAUNCH(k_forms_fill, h_tasks, 256, 0, nJ, nrows, ncols, tasks.get(), gtask_off.get(), imin8.get(), nI8.get(),
-               stg_off.get(), stg.get(), es, fmA.get(), fmB.get(), stoffL.get(), stoffR.get(), L.tval.get(), R.tval.get());
-    forms->has_left = 1;
-    forms->has_right = 1;
+    const bool wl = (want & WANT_LEFT) != 0, wr = (want & WANT_RIGHT) != 0;
+    if (wl) L.tval.alloc((size_t)L.ntiles * 32);
+    if (wr) R.tval.alloc((size_t)R.ntiles * 32);
+    if (wl || wr)
+      NTB_LAUNCH(k_forms_fill, h_tasks, 256, 0, nJ, nrows, ncols, tasks.get(), gtask_off.get(), imin8.get(), nI8.get(),
+                 stg_off.get(), stg.get(), es, fmA.get(), fmB.get(), stoffL.get(), stoffR.get(), L.tval.get(), R.tval.get(),
+                 want);
+    forms->has_left = wl ? 1 : 0;              // a form that was not asked for is rebuilt from CSC if it is ever needed
+    forms->has_right = wr ? 1 : 0;
     Z.forms = forms;
+    Z.deferred = defer;
   }
   const auto t6 = now();
   if (timing)
     std::fprintf(stderr, "[tile] bounds %.3f  alloc+tasks %.3f  numeric %.3f  index %.3f  emit %.3f  fill %.3f ms  (tasks %d, stg %.0f MB, nnz %d)\n",
                  ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), ms(t5, t6), h_tasks, (double)h_stg * 512.0 / 1e6, h_nnz);
   rt().tile_products++;
+  if (Z.deferred) rt().deferred_products++;
   rt().dmma_issued += (double)h_ndmma;
   return true;
 }

@@ -83,7 +83,9 @@ def test_multiply_banded_config1_small(nt, oracle):
     a = banded(n)
     A, C = to_gpu(nt, a), nt.Matrix_ps(n)
     nt.reset_counters()
+    nt.set_flop_counting(True)
     C.Gemm(A, A, None, threshold=1e-8)
+    nt.set_flop_counting(False)
     st = oracle.MultiplyStats()
     ref = oracle.multiply(oracle.PSMatrix.from_scipy(a), oracle.PSMatrix.from_scipy(a), thr=1e-8, stats=st)
     compare_sparse(C.to_scipy(), ref.to_scipy(), 1e-8)
@@ -251,3 +253,77 @@ def test_fused_shift_empty_product_columns(nt):
     r.sort_indices(); f.sort_indices()
     assert np.array_equal(r.indptr, f.indptr) and np.array_equal(r.indices, f.indices)
     assert np.array_equal(r.data, f.data)
+
+
+# ---- driver intermediates: right tile form + deferred CSC entries -------------------------------------------------
+def _bits_equal(a, b):
+    a, b = a.to_scipy().tocsc(), b.to_scipy().tocsc()
+    a.sort_indices(); b.sort_indices()
+    return (np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+            and np.array_equal(a.data, b.data))
+
+
+@pytest.mark.parametrize("n,hb,thr", [(2048, 40, 1e-7), (1111, 25, 0.0), (4096, 82, 1e-6)])
+def test_sign_step_deferred_intermediate_is_bit_exact(nt, n, hb, thr):
+    """ntb_SignStep emits T1 = 3I - a^2 X^2 as outer index + right tile form only (its CSC entries are deferred).
+    The next iterate, the convergence norm and T1 itself (materialized on demand) must equal, bit for bit, what the
+    separate MatrixMultiply / IncrementMatrix / MatrixNorm calls of the reference loop body give."""
+    ak = 1.3
+    x = banded(n, half_bandwidth=hb) * 0.3
+    X, I = to_gpu(nt, x), nt.Matrix_ps(n)
+    I.FillIdentity()
+    T1r, X1r = nt.Matrix_ps(n), nt.Matrix_ps(n)
+    T1r.GemmShift(X, X, I, 3.0, None, alpha=-ak * ak, threshold=thr)
+    X1r.Gemm(X, T1r, None, alpha=0.5 * ak, threshold=thr)
+    D = nt.Matrix_ps(X)
+    D.Increment(X1r, -1.0)
+    norm_ref = D.Norm()
+
+    T1, X1 = nt.Matrix_ps(n), nt.Matrix_ps(n)
+    nt.reset_counters()
+    nv = nt.sign_step(X, I, T1, X1, ak, thr)
+    dc = nt.deferred_counters()
+    assert dc["products"] == 1 and dc["materialized"] == 0, dc
+    assert nt.tile_counters()["tile_products"] == 2
+    assert _bits_equal(X1, X1r)
+    assert nv == pytest.approx(norm_ref, rel=1e-12)
+    assert _bits_equal(X, to_gpu(nt, x))                       # X untouched
+    assert T1.GetSize() == T1r.GetSize()                       # nnz is known without the entries
+    assert nt.deferred_counters()["materialized"] == 0
+    assert _bits_equal(T1, T1r)                                # reading T1 materializes its entries
+    assert nt.deferred_counters()["materialized"] == 1
+    assert T1.Trace() == T1r.Trace() and T1.Norm() == T1r.Norm()
+
+    # the in-place driver form: X advances, T2 is scratch
+    X2, T2 = nt.Matrix_ps(X), nt.Matrix_ps(n)
+    nv2 = nt.sign_iteration(X2, I, T1, T2, ak, thr)
+    assert nv2 == nv and _bits_equal(X2, X1r)
+    # a deferred matrix survives copy / scale / use as a LEFT operand (its left form is rebuilt from the entries)
+    nt.sign_step(X, I, T1, X1, ak, thr)
+    C1, C2, P, Pr = nt.Matrix_ps(T1), nt.Matrix_ps(T1r), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    C1.Scale(0.5); C2.Scale(0.5)
+    assert _bits_equal(C1, C2)
+    P.Gemm(T1, X, None, threshold=thr)
+    Pr.Gemm(T1r, X, None, threshold=thr)
+    assert _bits_equal(P, Pr)
+
+
+def test_flop_counting_is_optional_instrumentation(nt, oracle):
+    """useful-product counts are exact when switched on and never change a result"""
+    n, thr = 1536, 1e-7
+    a = banded(n, half_bandwidth=30)
+    A, C, D, E = to_gpu(nt, a), nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    C.Gemm(A, A, None, threshold=thr)            # C and A now carry tile forms
+    try:
+        nt.set_flop_counting(True)
+        nt.reset_counters()
+        D.Gemm(C, A, None, threshold=thr)
+        st = oracle.MultiplyStats()
+        oracle.multiply(oracle.PSMatrix.from_scipy(C.to_scipy()), oracle.PSMatrix.from_scipy(a), thr=thr, stats=st)
+        assert nt.counters()["flops"] == pytest.approx(st.flops, rel=1e-12)
+    finally:
+        nt.set_flop_counting(False)
+    nt.reset_counters()
+    E.Gemm(C, A, None, threshold=thr)
+    assert nt.tile_counters()["tile_products"] == 1
+    assert _bits_equal(D, E)
