@@ -314,12 +314,12 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 
 // pipeline shape: a stage = one A super-tile (<= 64 tiles, 16 KB) + one B super-tile (16 KB); 3 stages = 96 KB per
 // CTA, two CTAs per SM
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE_DEFAULT = 3;
 constexpr int SLAB_DOUBLES = 64 * 32;                        // one super-tile, all tiles present
 constexpr int STAGE_DOUBLES = 2 * SLAB_DOUBLES;
 constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;               // 32 KB
 constexpr int META_BYTES = 32;                               // maskA (8 B), maskB (8 B), flags, g, Ib, pad
-constexpr int NUMERIC_SMEM = NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES + 2 * NSTAGE * 8;
+constexpr int numeric_smem(int nstage) { return nstage * STAGE_BYTES + nstage * META_BYTES + 2 * nstage * 8; }
 constexpr int CW = 8;                                        // DMMA warps: one per tile column of the group
 constexpr int NUMERIC_THREADS = (CW + 1) * 32;               // + 1 copy warp
 
@@ -368,7 +368,8 @@ __device__ __forceinline__ void ct_pair(const int4& ea, const int4& eb, int Ib, 
 // are skipped with real branches (a predicated-off DMMA occupies the pipe for its full 16 cycles). The strip is
 // written to the dense staging window and the kept-entry counts of its 8 columns are accumulated on the fly
 // (threshold rule fused), so the emit pass is a single sweep.
-__global__ void __launch_bounds__(NUMERIC_THREADS, 2)
+template <int NSTAGE, int MINB>
+__global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
 k_tile_numeric(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const int* __restrict__ nI8,
                const long long* __restrict__ stg_off, const int2* __restrict__ tasks, int ntasks,
                int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
@@ -1044,14 +1045,20 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
     CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
   }
   if (h_tasks > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_CHECK(cudaFuncSetAttribute(k_tile_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, NUMERIC_SMEM));
-      attr_set = true;
-    }
-    NTB_LAUNCH(k_tile_numeric, min(h_tasks, kNumSMs * 2), NUMERIC_THREADS, NUMERIC_SMEM, Av, Bv, nJ, imin8.get(),
-               nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
-               reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
+    // pipeline shape: 3 stages x 2 CTAs per SM (default) or 2 stages x 3 CTAs per SM (NTB_NUMERIC_SHAPE=23)
+    static const int shape = [] { const char* e = std::getenv("NTB_NUMERIC_SHAPE"); return e ? std::atoi(e) : 32; }();
+    auto launch = [&](auto kern, int nstage, int per_sm) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem(nstage)));
+        attr_set = true;
+      }
+      NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem(nstage), Av, Bv, nJ, imin8.get(),
+                 nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
+                 reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
+    };
+    if (shape == 23) launch(k_tile_numeric<2, 3>, 2, 3);
+    else launch(k_tile_numeric<NSTAGE_DEFAULT, 2>, NSTAGE_DEFAULT, 2);
   }
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
