@@ -134,6 +134,8 @@ const ChunkTiles* tile_operand_form(const LocalCsc<double>& M, bool left);
 bool spgemm_tile_core(const ChunkTiles& A, const ChunkTiles& B, int ncols, int nrows, double alpha, double thr,
                       const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
                       bool force, unsigned want = WANT_ALL);
+// column sums of |alpha*A + B| from the right tile forms of both blocks; false when either has none (use the CSC kernel)
+bool tile_diff_col_abs_sums(const LocalCsc<double>& A, const LocalCsc<double>& B, double alpha, double* d_colsum);
 // assemble the left form of a row of column blocks from per-rank pieces (see psmatrix.cu: halo gather)
 struct LeftPiece {          // one rank's contribution, all offsets in units of that rank / of the gathered arrays
   int ent_base;             // first entry of this rank in the gathered entry array

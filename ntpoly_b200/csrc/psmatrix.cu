@@ -524,7 +524,8 @@ double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha) {
   }
   DevBuf<double> colsum((size_t)B.local_cols), d(1);
   if (A.is_complex) csc_diff_col_abs_sums<cplx>(A.c.view(), B.c.view(), alpha, colsum.get());
-  else csc_diff_col_abs_sums<double>(A.r.view(), B.r.view(), alpha, colsum.get());
+  else if (!(tile_path_on() && tile_diff_col_abs_sums(A.r, B.r, alpha, colsum.get())))   // iterates that live as tile forms
+    csc_diff_col_abs_sums<double>(A.r.view(), B.r.view(), alpha, colsum.get());
   comm_allreduce_f64(B.grid->column, colsum.get(), (size_t)B.local_cols, RedOp::Sum);
   reduce_max(colsum.get(), B.local_cols, d.get());
   comm_allreduce_f64(B.grid->row, d.get(), 1, RedOp::Max);

@@ -425,7 +425,9 @@ double sign_step(const Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& Xn
   } else {
     mat_multiply_shift(X, X, T1, -1.0 * alpha_k * alpha_k, threshold, 3.0, Identity, pool, WANT_RIGHT);
   }
-  mat_multiply(X, T1, Xn, 0.5 * alpha_k, 0.0, threshold, pool);
+  // the next iterate is read by the norm below and by the products of the next pass, all of which work on tile
+  // forms: its CSC entries stay deferred until somebody asks for them (the caller reading the result)
+  mat_multiply(X, T1, Xn, 0.5 * alpha_k, 0.0, threshold, pool, WANT_LEFT | WANT_RIGHT);
   // reference: IncrementMatrix(T2, X, -1); norm = MatrixNorm(X); CopyMatrix(T2, X) — X - T2 is never needed itself
   return mat_diff_norm(Xn, X, -1.0);
 }

@@ -649,6 +649,325 @@ k_tile_numeric(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const 
   }
 }
 
+// ---- v9 of the numeric kernel: same pipeline, same results, leaner DMMA warps ---------------------------------------
+// ncu's per-instruction samples of the kernel above (profiles/r01b_numeric_source_top.txt) show the DMMA warps spending
+// 18 % of their time in per-stage mask arithmetic and barrier turn-around, 18 % in the per-inner-tile address chain
+// (BREV/FLO/POPC run on the quarter-rate XU pipe and sit on the critical path of every DMMA burst) and 22 % in the
+// epilogue (two dependent global loads before the first store). Here
+//   * the COPY WARP digests the masks once per stage (it idles on the empty barrier 95 % of the time anyway): per
+//     inner tile kk of the A super-tile a descriptor {presence byte, first tile, first/last row tile, kind}, per
+//     (tile column, kk) the index of the B tile in the slab; the DMMA warps only extract bit fields;
+//   * the inner loop counts kk up instead of bit-scanning, and prefetches the next descriptor;
+//   * the window constants of the epilogue are loaded when a task STARTS, so their latency hides behind the DMMAs;
+//   * the presence bytes of the result's tile forms come from two warp-wide OR reductions instead of 8 ballots.
+constexpr int META9 = 128;
+constexpr int numeric_smem9(int nstage) { return nstage * STAGE_BYTES + nstage * META9 + 2 * nstage * 8; }
+//  per stage: +0   int4 {flags | nzA << 8, g, Ib, task}   flags: 1 = last stage of the task, 2 = no more tasks
+//             +16  u32 adesc[8]  ma | first tile << 8 | l0 << 16 | h0 << 19 | kind << 22   (kind: 0 full, 1 prefix
+//                                run 0..h0, 2 suffix run l0..7, 3 anything else)
+//             +48  u8 mbyte[8]   presence bits over kk of tile column jj of the B super-tile
+//             +64  u8 boff[64]   [jj*8+kk] index of B tile (jj,kk) in the slab
+template <int NSTAGE, int MINB>
+__global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
+k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const int* __restrict__ nI8,
+                const long long* __restrict__ stg_off, const int2* __restrict__ tasks, int ntasks,
+                int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
+                unsigned char* __restrict__ fmA, unsigned char* __restrict__ fmB, int nrows, int ncols, EmitSpec es) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* slab = reinterpret_cast<double*>(smem);
+  unsigned char* meta = smem + NSTAGE * STAGE_BYTES;
+  const unsigned bar0 = smem_u32(smem + NSTAGE * STAGE_BYTES + NSTAGE * META9);   // full[s] at +8s, empty[s] at +8(NSTAGE+s)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * (NSTAGE + s), CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  int st = 0;
+  unsigned ph = 0;
+  if (warp == CW) {
+    // ------------------------------------------------------------------ copy warp (look-up chain as in v8)
+    const int4 none = make_int4(0, 0, 0, -1);
+    int task_raw = 0;
+    int pstep = 0;
+    bool valid_n = false, have_n = false, found_n = false;
+    int tid_n = 0;
+    int2 tk_n = make_int2(0, 0);
+    int4 cmB_n = none, eb_n = none, ca_n = none, ea_n = none;
+    unsigned long long mA_n = 0ull, mB_n = 0ull;
+    int offA_n = 0, offB_n = 0;
+    auto advance = [&]() {
+      switch (pstep) {
+        case 0: {
+          const int t = __shfl_sync(0xffffffffu, task_raw, 0);
+          tid_n = t;
+          valid_n = t < ntasks;
+          tk_n = valid_n ? tasks[t] : make_int2(0, 0);
+          break;
+        }
+        case 1: cmB_n = valid_n ? B.colmeta[tk_n.x] : none; break;
+        case 2: have_n = valid_n && lane < cmB_n.y; eb_n = have_n ? B.ent[cmB_n.x + lane] : none; break;
+        case 3: ca_n = have_n ? A.colmeta[eb_n.x] : none; break;
+        case 4: {
+          const int idx = have_n ? ct_find(A, ca_n, tk_n.y) : -1;
+          found_n = idx >= 0;
+          ea_n = found_n ? A.ent[idx] : none;
+          break;
+        }
+        case 5: ct_pair(ea_n, eb_n, tk_n.y, found_n, mA_n, mB_n, offA_n, offB_n); break;
+        default: break;
+      }
+      ++pstep;
+    };
+    if (lane == 0) task_raw = atomicAdd(task_counter, 1);
+    while (pstep < 6) advance();
+    for (;;) {
+      const bool done = !valid_n;
+      const int g = tk_n.x, Ib = tk_n.y, task = tid_n;
+      const int4 cmB = cmB_n;
+      unsigned long long mA = mA_n, mB = mB_n;
+      int offA = offA_n, offB = offB_n;
+      if (!done) {
+        if (lane == 0) task_raw = atomicAdd(task_counter, 1);
+        pstep = 0;
+      }
+      const int nb = done ? 1 : max(1, (cmB.y + 31) / 32);
+      for (int bb = 0; bb < nb; ++bb) {
+        if (bb > 0) {
+          const int e = bb * 32 + lane;
+          const bool have = e < cmB.y;
+          const int4 eb = have ? B.ent[cmB.x + e] : none;
+          const int4 ca = have ? A.colmeta[eb.x] : none;
+          const int idx = have ? ct_find(A, ca, Ib) : -1;
+          const int4 ea = (idx >= 0) ? A.ent[idx] : none;
+          ct_pair(ea, eb, Ib, idx >= 0, mA, mB, offA, offB);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, mA != 0ull);
+        const bool final_batch = (bb == nb - 1);
+        if (todo == 0u && final_batch) todo = 1u;
+        while (todo) {
+          const int l = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const bool last = final_batch && todo == 0u;
+          const unsigned long long sA = __shfl_sync(0xffffffffu, mA, l), sB = __shfl_sync(0xffffffffu, mB, l);
+          const int oA = __shfl_sync(0xffffffffu, offA, l), oB = __shfl_sync(0xffffffffu, offB, l);
+          // digest the masks while the slot may still be busy
+          unsigned desc = 0;
+          if (lane < 8) {
+            const unsigned ma = (unsigned)(sA >> (8 * lane)) & 0xffu;
+            if (ma) {
+              const unsigned aoff = (unsigned)popc64(sA & ((1ull << (8 * lane)) - 1ull));
+              const unsigned l0 = (unsigned)__ffs(ma) - 1u, h0 = 31u - (unsigned)__clz(ma), pc = (unsigned)__popc(ma);
+              unsigned kind = 3u;
+              if (ma == 0xffu) kind = 0u;
+              else if (l0 == 0u && pc == h0 + 1u) kind = 1u;
+              else if (h0 == 7u && pc == 8u - l0) kind = 2u;
+              desc = ma | (aoff << 8) | (l0 << 16) | (h0 << 19) | (kind << 22);
+            }
+          }
+          const unsigned b0 = (unsigned)popc64(sB & ((1ull << (2 * lane)) - 1ull));
+          const unsigned b1 = b0 + (unsigned)((sB >> (2 * lane)) & 1ull);
+          const unsigned nzA = nonzero_bytes(sA);
+          mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
+          unsigned char* mt = meta + st * META9;
+          if (lane < 8) reinterpret_cast<unsigned*>(mt + 16)[lane] = desc;
+          reinterpret_cast<unsigned short*>(mt + 64)[lane] = (unsigned short)(b0 | (b1 << 8));
+          if (lane == 0) {
+            *reinterpret_cast<unsigned long long*>(mt + 48) = sB;
+            *reinterpret_cast<int4*>(mt) = make_int4((int)((last ? 1u : 0u) | (done ? 2u : 0u) | (nzA << 8)), g, Ib, task);
+          }
+          __syncwarp();                                        // the other lanes' meta stores happen before the arrive
+          if (lane == 0) {
+            const unsigned bA = (unsigned)popc64(sA) * 256u, bB = (unsigned)popc64(sB) * 256u;
+            mbar_arrive_expect_tx(bar0 + 8 * st, bA + bB);
+            const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
+            if (bA) bulk_g2s(slab_s, A.tval + (size_t)oA * 32, bA, bar0 + 8 * st);
+            if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + (size_t)oB * 32, bB, bar0 + 8 * st);
+          }
+          __syncwarp();
+          if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+          if (!done) advance();
+        }
+      }
+      if (done) break;
+      while (pstep < 6) advance();
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- DMMA warps
+  const int wj = warp;                              // tile column of the group
+  for (;;) {
+    double acc[8][2];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
+    int g = 0, Ib = 0, task = 0;
+    unsigned fl = 0;
+    bool fresh = true;
+    int iw0 = 0, nI = 0;
+    long long so = 0;
+    do {
+      mbar_wait(bar0 + 8 * st, ph);
+      const unsigned char* mt = meta + st * META9;
+      const int4 mi = *reinterpret_cast<const int4*>(mt);
+      fl = (unsigned)mi.x & 0xffu; g = mi.y; Ib = mi.z; task = mi.w;
+      if (fresh) {                                   // a task starts: issue the loads its epilogue will need
+        fresh = false;
+        const int J = g * 8 + wj;
+        if (!(fl & 2u) && J < nJ) { iw0 = imin8[J]; nI = nI8[J]; so = stg_off[J]; }
+      }
+      const unsigned mb = mt[48 + wj];
+      const unsigned live = mb & ((unsigned)mi.x >> 8) & 0xffu;
+      if (live != 0u) {
+        const unsigned long long bo = *reinterpret_cast<const unsigned long long*>(mt + 64 + 8 * wj);
+        const unsigned* adesc = reinterpret_cast<const unsigned*>(mt + 16);
+        const double* As = slab + (size_t)st * STAGE_DOUBLES + lane;
+        const double* Bs = As + SLAB_DOUBLES;
+        unsigned dn = adesc[0];
+#pragma unroll 1
+        for (int kk = 0; (live >> kk) != 0u; ++kk) {
+          const unsigned d = dn;
+          dn = adesc[(kk + 1) & 7];
+          if (((live >> kk) & 1u) == 0u) continue;
+          const unsigned ma = d & 0xffu;
+          const double bv = Bs[((unsigned)(bo >> (8 * kk)) & 0xffu) * 32];
+          const double* ap = As + ((d >> 8) & 0xffu) * 32;
+          const unsigned kind = (d >> 22) & 3u;
+          double av[8];
+#define NTB_D(i) dmma884(acc[i][0], acc[i][1], av[i], bv);
+          if (kind == 0u) {
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) av[ii] = ap[ii * 32];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
+          } else if (kind == 1u) {
+            // prefix run (row tiles 0..h0): one jump into a descending sequence (real branches: a predicated-off DMMA
+            // still holds the FP64 tensor pipe for 16 cycles)
+            const int h0 = (int)((d >> 19) & 7u);
+#pragma unroll
+            for (int ii = 0; ii < 7; ++ii)
+              if (ii <= h0) av[ii] = ap[ii * 32];
+            switch (h0) {
+              case 6: NTB_D(6)
+              case 5: NTB_D(5)
+              case 4: NTB_D(4)
+              case 3: NTB_D(3)
+              case 2: NTB_D(2)
+              case 1: NTB_D(1)
+              default: NTB_D(0)
+            }
+          } else if (kind == 2u) {
+            // suffix run (row tiles l0..7): one jump into an ascending sequence
+            const int l0 = (int)((d >> 16) & 7u);
+            const double* aq = ap - l0 * 32;
+#pragma unroll
+            for (int ii = 1; ii < 8; ++ii)
+              if (ii >= l0) av[ii] = aq[ii * 32];
+            switch (l0) {
+              case 1: NTB_D(1)
+              case 2: NTB_D(2)
+              case 3: NTB_D(3)
+              case 4: NTB_D(4)
+              case 5: NTB_D(5)
+              case 6: NTB_D(6)
+              default: NTB_D(7)
+            }
+          } else {
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii)
+              if ((ma >> ii) & 1u) av[ii] = ap[__popc(ma & ((1u << ii) - 1u)) * 32];
+            unsigned m = ma;
+#define NTB_RUN_STEP(i) dmma884(acc[i][0], acc[i][1], av[i], bv); if (h0 == i) break;
+            do {
+              const int l0 = __ffs(m) - 1;
+              const int len = __ffs(~(m >> l0)) - 1;
+              const int h0 = l0 + len - 1;
+              m &= ~(((1u << len) - 1u) << l0);
+              switch (l0) {
+                case 0: NTB_RUN_STEP(0)
+                case 1: NTB_RUN_STEP(1)
+                case 2: NTB_RUN_STEP(2)
+                case 3: NTB_RUN_STEP(3)
+                case 4: NTB_RUN_STEP(4)
+                case 5: NTB_RUN_STEP(5)
+                case 6: NTB_RUN_STEP(6)
+                default: dmma884(acc[7][0], acc[7][1], av[7], bv);
+              }
+            } while (m);
+#undef NTB_RUN_STEP
+          }
+#undef NTB_D
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (NSTAGE + st));
+      if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+    } while ((fl & 1u) == 0u);
+    if (fl & 2u) break;
+    const int J = g * 8 + wj;
+    if (J >= nJ) continue;
+    const int I0 = Ib << 3;
+    if (I0 < iw0 || I0 >= iw0 + nI) continue;
+    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column.
+    const int wlen = nI * 8;
+    const int r = lane >> 2, cc = (lane & 3) * 2;
+    double* o = stg + so * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
+    const int j0 = J * 8 + cc;
+    const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
+    const bool on_diag = es.sigma != 0.0 && (I0 * 8 <= J * 8 + 7 + es.dd) && (I0 * 8 + 63 >= J * 8 + es.dd);
+    const bool plain = es.rules.tbl == nullptr && !on_diag;
+    int c0 = 0, c1 = 0;
+    unsigned km = 0;                               // bit ii: this lane keeps an entry of row tile ii
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const double v0 = acc[ii][0], v1 = acc[ii][1];
+      o[ii * 8] = v0;
+      o[wlen + ii * 8] = v1;
+      const int row = (I0 + ii) * 8 + r;
+      bool k0 = false, k1 = false;
+      if (row < nrows) {
+        if (plain) {                            // sparse rule everywhere, no shift: |alpha*v| > thr
+          k0 = in0 && fabs(es.alpha * v0) > es.thr;
+          k1 = in1 && fabs(es.alpha * v1) > es.thr;
+        } else {
+          if (in0) k0 = keep_general(es, v0, row, j0);
+          if (in1) k1 = keep_general(es, v1, row, j0 + 1);
+        }
+      }
+      c0 += k0 ? 1 : 0;
+      c1 += k1 ? 1 : 0;
+      km |= ((k0 || k1) ? 1u : 0u) << ii;
+    }
+    // presence bytes of the strip's tiles in the two forms of the RESULT: right form = (rows 0-31 / 32-63) x inner
+    // tiles of 4 rows (lanes 0-15 hold rows 0-3 of a row tile, lanes 16-31 rows 4-7); left form = (columns 0-3 /
+    // 4-7) x row tiles (lanes with lane%4 < 2 hold columns 0-3)
+    unsigned x = km;
+    x = (x | (x << 4)) & 0x0f0fu;
+    x = (x | (x << 2)) & 0x3333u;
+    x = (x | (x << 1)) & 0x5555u;                  // bit ii -> bit 2*ii
+    const unsigned bR = __reduce_or_sync(0xffffffffu, (lane & 16) ? (x << 1) : x);
+    const unsigned bL = __reduce_or_sync(0xffffffffu, (lane & 2) ? (km << 8) : km);
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+    }
+    if (lane < 4) {
+      if (c0) atomicAdd(&cnt[j0], c0);
+      if (c1) atomicAdd(&cnt[j0 + 1], c1);
+    }
+    if (lane == 0) {
+      fmB[((size_t)task * 2 + 0) * 8 + wj] = (unsigned char)(bR & 0xffu);
+      fmB[((size_t)task * 2 + 1) * 8 + wj] = (unsigned char)((bR >> 8) & 0xffu);
+      unsigned char* fa = fmA + ((size_t)task * 2 + (wj >> 2)) * 8 + 2 * (wj & 3);
+      fa[0] = (unsigned char)(bL & 0xffu);
+      fa[1] = (unsigned char)((bL >> 8) & 0xffu);
+    }
+  }
+}
+
 // ordered emit of the kept entries of every output column into CSC (counts came from the numeric kernel)
 __global__ void __launch_bounds__(256)
 k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __restrict__ nI8,
@@ -939,6 +1258,61 @@ void tile_materialize_entries(const LocalCsc<double>& M) {
   NTB_CHECK(h == 0, "deferred entries: the right form does not match the column counts");
 }
 
+// Column sums of |alpha*A + B| from the RIGHT tile forms of two blocks of equal shape: the convergence norm of the
+// Newton-Schulz style drivers on iterates that live as tile forms (their CSC entries may be deferred). One warp per
+// tile column (8 matrix columns): it walks the two id-sorted super-tile lists of its chunk column like a merge; a
+// lane is one fragment position (column lane/4, row lane%4 of a 4x8 tile). Absent tiles and dropped entries are
+// zeros, so the value equals the CSC kernel's (ops.cu: k_diff_col_abs) up to summation order.
+__global__ void __launch_bounds__(256)
+k_form_diff_col_abs(CtView A, CtView B, int nJ, int ncols, double alpha, double* __restrict__ colsum) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const int4 none = make_int4(INT_MAX, 0, 0, 0);
+  for (int J = gw; J < nJ; J += nw) {
+    const int q = J >> 3, sh = (J & 7) * 8;
+    const int4 ca = A.colmeta[q], cb = B.colmeta[q];
+    int ia = 0, ib = 0;
+    int4 ea = (ca.y > 0) ? A.ent[ca.x] : none, eb = (cb.y > 0) ? B.ent[cb.x] : none;
+    double s = 0.0;
+    while (ea.x != INT_MAX || eb.x != INT_MAX) {
+      const int id = min(ea.x, eb.x);
+      const bool ta = ea.x == id, tb = eb.x == id;
+      const unsigned long long wa = ta ? mask64(ea) : 0ull, wb = tb ? mask64(eb) : 0ull;
+      const unsigned ma = (unsigned)(wa >> sh) & 0xffu, mb = (unsigned)(wb >> sh) & 0xffu;
+      const size_t ba = (size_t)ea.y + popc64(wa & ((1ull << sh) - 1ull)), bb = (size_t)eb.y + popc64(wb & ((1ull << sh) - 1ull));
+      unsigned m = ma | mb;
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1u;
+        const unsigned below = (1u << kk) - 1u;
+        double a = 0.0, b = 0.0;
+        if ((ma >> kk) & 1u) a = A.tval[(ba + __popc(ma & below)) * 32 + lane];
+        if ((mb >> kk) & 1u) b = B.tval[(bb + __popc(mb & below)) * 32 + lane];
+        s += fabs(alpha * a + b);
+      }
+      if (ta) { ++ia; ea = (ia < ca.y) ? A.ent[ca.x + ia] : none; }
+      if (tb) { ++ib; eb = (ib < cb.y) ? B.ent[cb.x + ib] : none; }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const int col = J * 8 + (lane >> 2);
+    if ((lane & 3) == 0 && col < ncols) colsum[col] = s;
+  }
+}
+bool tile_diff_col_abs_sums(const LocalCsc<double>& A, const LocalCsc<double>& B, double alpha, double* d_colsum) {
+  if (!A.forms || !B.forms || A.forms->has_right != 1 || B.forms->has_right != 1) return false;
+  const ChunkTiles& Ra = A.forms->right;
+  const ChunkTiles& Rb = B.forms->right;
+  if (A.cols != B.cols || A.rows != B.rows || Ra.ncc != Rb.ncc || A.cols == 0) return false;
+  const CtView Av{Ra.colmeta.get(), Ra.ent.get(), Ra.tval.get(), nullptr, Ra.ncc};
+  const CtView Bv{Rb.colmeta.get(), Rb.ent.get(), Rb.tval.get(), nullptr, Rb.ncc};
+  const int nJ = div_up(A.cols, 8);
+  NTB_LAUNCH(k_form_diff_col_abs, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, nJ, A.cols,
+             alpha, d_colsum);
+  return true;
+}
+
 // the cached (or freshly built) tile form of an operand; nullptr when its pattern cannot be tiled
 const ChunkTiles* tile_operand_form(const LocalCsc<double>& M, bool left) {
   if (!M.forms) M.forms = std::make_shared<TileForms>();
@@ -1057,7 +1431,20 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
                  nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
                  reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
     };
-    if (shape == 23) launch(k_tile_numeric<2, 3>, 2, 3);
+    static const int ver = [] { const char* e = std::getenv("NTB_NUMERIC_VER"); return e ? std::atoi(e) : 8; }();
+    auto launch9 = [&](auto kern, int nstage, int per_sm) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem9(nstage)));
+        attr_set = true;
+      }
+      NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, imin8.get(),
+                 nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
+                 reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
+    };
+    if (ver == 9 && shape == 23) launch9(k_tile_numeric9<2, 3>, 2, 3);
+    else if (ver == 9) launch9(k_tile_numeric9<NSTAGE_DEFAULT, 2>, NSTAGE_DEFAULT, 2);
+    else if (shape == 23) launch(k_tile_numeric<2, 3>, 2, 3);
     else launch(k_tile_numeric<NSTAGE_DEFAULT, 2>, NSTAGE_DEFAULT, 2);
   }
   if (rt().profile) {

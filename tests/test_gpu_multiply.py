@@ -283,16 +283,20 @@ def test_sign_step_deferred_intermediate_is_bit_exact(nt, n, hb, thr):
     nt.reset_counters()
     nv = nt.sign_step(X, I, T1, X1, ak, thr)
     dc = nt.deferred_counters()
-    assert dc["products"] == 1 and dc["materialized"] == 0, dc
+    assert dc["products"] == 2 and dc["materialized"] == 0, dc     # T1 and the next iterate live as tile forms
     assert nt.tile_counters()["tile_products"] == 2
-    assert _bits_equal(X1, X1r)
-    assert nv == pytest.approx(norm_ref, rel=1e-12)
-    assert _bits_equal(X, to_gpu(nt, x))                       # X untouched
-    assert T1.GetSize() == T1r.GetSize()                       # nnz is known without the entries
+    assert nv == pytest.approx(norm_ref, rel=1e-12)                # norm taken from the right tile forms
+    assert T1.GetSize() == T1r.GetSize() and X1.GetSize() == X1r.GetSize()   # nnz is known without the entries
     assert nt.deferred_counters()["materialized"] == 0
-    assert _bits_equal(T1, T1r)                                # reading T1 materializes its entries
+    assert _bits_equal(X1, X1r)                                # reading a matrix materializes its entries
     assert nt.deferred_counters()["materialized"] == 1
+    assert _bits_equal(T1, T1r)
+    assert nt.deferred_counters()["materialized"] == 2
+    assert _bits_equal(X, to_gpu(nt, x))                       # X untouched
     assert T1.Trace() == T1r.Trace() and T1.Norm() == T1r.Norm()
+    D2 = nt.Matrix_ps(X)
+    D2.Increment(X1, -1.0)
+    assert D2.Norm() == norm_ref                               # CSC route on the materialized entries
 
     # the in-place driver form: X advances, T2 is scratch
     X2, T2 = nt.Matrix_ps(X), nt.Matrix_ps(n)
