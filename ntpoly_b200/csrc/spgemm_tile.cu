@@ -312,6 +312,10 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// HBM -> L2 prefetch of a byte range that a later bulk copy will read (no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // pipeline shape: a stage = one A super-tile (<= 64 tiles, 16 KB) + one B super-tile (16 KB); 3 stages = 96 KB per
 // CTA, two CTAs per SM
 constexpr int NSTAGE_DEFAULT = 3;
@@ -716,7 +720,16 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
           ea_n = found_n ? A.ent[idx] : none;
           break;
         }
-        case 5: ct_pair(ea_n, eb_n, tk_n.y, found_n, mA_n, mB_n, offA_n, offB_n); break;
+        case 5:
+          ct_pair(ea_n, eb_n, tk_n.y, found_n, mA_n, mB_n, offA_n, offB_n);
+          // the stages of the NEXT task are now known: pull their tiles into L2 while this task is still being
+          // consumed, so that their bulk copies find them there (the DMMA warps were waiting 12 % of their time for
+          // a full barrier, i.e. for HBM latency at the short band-edge stages)
+          if (mA_n != 0ull) {
+            bulk_prefetch_l2(A.tval + (size_t)offA_n * 32, (unsigned)popc64(mA_n) * 256u);
+            bulk_prefetch_l2(B.tval + (size_t)offB_n * 32, (unsigned)popc64(mB_n) * 256u);
+          }
+          break;
         default: break;
       }
       ++pstep;
@@ -917,7 +930,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
     const int j0 = J * 8 + cc;
     const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
     const bool on_diag = es.sigma != 0.0 && (I0 * 8 <= J * 8 + 7 + es.dd) && (I0 * 8 + 63 >= J * 8 + es.dd);
-    const bool plain = es.rules.tbl == nullptr && !on_diag;
+    const bool norules = es.rules.tbl == nullptr;
     int c0 = 0, c1 = 0;
     unsigned km = 0;                               // bit ii: this lane keeps an entry of row tile ii
 #pragma unroll
@@ -928,9 +941,14 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
       const int row = (I0 + ii) * 8 + r;
       bool k0 = false, k1 = false;
       if (row < nrows) {
-        if (plain) {                            // sparse rule everywhere, no shift: |alpha*v| > thr
-          k0 = in0 && fabs(es.alpha * v0) > es.thr;
-          k1 = in1 && fabs(es.alpha * v1) > es.thr;
+        if (norules) {                          // sparse rule everywhere: |alpha*v| > thr
+          const double s0 = es.alpha * v0, s1 = es.alpha * v1;
+          k0 = in0 && fabs(s0) > es.thr;
+          k1 = in1 && fabs(s1) > es.thr;
+          if (on_diag) {                        // a shifted diagonal entry is kept iff it is non-zero (final_value)
+            if (in0 && row == j0 + es.dd && j0 < es.ncols_diag) k0 = ((k0 ? s0 : 0.0) + es.sigma) != 0.0;
+            if (in1 && row == j0 + 1 + es.dd && j0 + 1 < es.ncols_diag) k1 = ((k1 ? s1 : 0.0) + es.sigma) != 0.0;
+          }
         } else {
           if (in0) k0 = keep_general(es, v0, row, j0);
           if (in1) k1 = keep_general(es, v1, row, j0 + 1);
@@ -1032,7 +1050,8 @@ k_forms_slots(int ntasks, const int2* __restrict__ tasks, const int* __restrict_
   (left ? smaskL : smaskR)[s] = m;
 }
 
-// (2) one CTA per form: exclusive scans of (non-empty, tile count) over the slots
+// (2) one CTA per form: exclusive scans of (non-empty, tile count) over the slots. Every thread owns one contiguous
+// chunk of slots: chunk totals -> one block-wide scan -> outputs (two sweeps over L2-resident data, three barriers)
 __global__ void __launch_bounds__(FI_T)
 k_forms_scan(int ntasks, const unsigned long long* __restrict__ smaskL, const unsigned long long* __restrict__ smaskR,
              int* __restrict__ seidxL, int* __restrict__ seidxR, int* __restrict__ stoffL, int* __restrict__ stoffR,
@@ -1043,51 +1062,39 @@ k_forms_scan(int ntasks, const unsigned long long* __restrict__ smaskL, const un
   int* stoff = left ? stoffL : stoffR;
   const int n = 2 * ntasks;
   __shared__ int wsum[2][32];
-  __shared__ int carry[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
-  __syncthreads();
-  for (int base = 0; base < n; base += FI_T * FI_ITEMS) {
-    const int s0 = base + threadIdx.x * FI_ITEMS;
-    unsigned long long m[FI_ITEMS];
-    int f = 0, pc = 0;
+  const int per = (n + FI_T - 1) / FI_T;
+  const int s0 = min(n, (int)threadIdx.x * per), s1 = min(n, s0 + per);
+  int f = 0, pc = 0;
+#pragma unroll 4
+  for (int i = s0; i < s1; ++i) { const unsigned long long m = smask[i]; f += (m != 0ull); pc += popc64(m); }
+  int fi = f, pi = pc;
 #pragma unroll
-    for (int k = 0; k < FI_ITEMS; ++k) {
-      m[k] = (s0 + k < n) ? smask[s0 + k] : 0ull;
-      f += (m[k] != 0ull); pc += popc64(m[k]);
-    }
-    int fi = f, pi = pc;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, fi, d), b = __shfl_up_sync(0xffffffffu, pi, d);
+    if (lane >= d) { fi += a; pi += b; }
+  }
+  if (lane == 31) { wsum[0][warp] = fi; wsum[1][warp] = pi; }
+  __syncthreads();
+  if (warp == 0) {
+    const int a = wsum[0][lane], b = wsum[1][lane];
+    int ai = a, bi = b;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, fi, d), b = __shfl_up_sync(0xffffffffu, pi, d);
-      if (lane >= d) { fi += a; pi += b; }
+      const int x = __shfl_up_sync(0xffffffffu, ai, d), y = __shfl_up_sync(0xffffffffu, bi, d);
+      if (lane >= d) { ai += x; bi += y; }
     }
-    if (lane == 31) { wsum[0][warp] = fi; wsum[1][warp] = pi; }
-    __syncthreads();
-    if (warp == 0) {
-      const int a = wsum[0][lane], b = wsum[1][lane];
-      int ai = a, bi = b;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int x = __shfl_up_sync(0xffffffffu, ai, d), y = __shfl_up_sync(0xffffffffu, bi, d);
-        if (lane >= d) { ai += x; bi += y; }
-      }
-      wsum[0][lane] = ai - a; wsum[1][lane] = bi - b;      // exclusive warp offsets
-    }
-    __syncthreads();
-    int e = carry[0] + wsum[0][warp] + fi - f, t = carry[1] + wsum[1][warp] + pi - pc;
-#pragma unroll
-    for (int k = 0; k < FI_ITEMS; ++k) {
-      if (s0 + k < n) {
-        seidx[s0 + k] = e; stoff[s0 + k] = t;
-        if (m[k] != 0ull) { ++e; t += popc64(m[k]); }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == FI_T - 1) { carry[0] = e; carry[1] = t; }   // the last thread ends at the running totals
-    __syncthreads();
+    wsum[0][lane] = ai - a; wsum[1][lane] = bi - b;      // exclusive warp offsets
   }
-  if (threadIdx.x == 0) { seidx[n] = carry[0]; totals[left ? 0 : 2] = carry[0]; totals[left ? 1 : 3] = carry[1]; }
+  __syncthreads();
+  int e = wsum[0][warp] + fi - f, t = wsum[1][warp] + pi - pc;
+#pragma unroll 4
+  for (int i = s0; i < s1; ++i) {
+    const unsigned long long m = smask[i];
+    seidx[i] = e; stoff[i] = t;
+    if (m != 0ull) { ++e; t += popc64(m); }
+  }
+  if (threadIdx.x == FI_T - 1) { seidx[n] = e; totals[left ? 0 : 2] = e; totals[left ? 1 : 3] = t; }
 }
 
 // (3) entries and chunk-column meta (blockIdx.y: 0 = left, 1 = right); threads beyond the slots mark empty columns
@@ -1431,7 +1438,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
                  nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
                  reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
     };
-    static const int ver = [] { const char* e = std::getenv("NTB_NUMERIC_VER"); return e ? std::atoi(e) : 8; }();
+    static const int ver = [] { const char* e = std::getenv("NTB_NUMERIC_VER"); return e ? std::atoi(e) : 9; }();
     auto launch9 = [&](auto kern, int nstage, int per_sm) {
       static bool attr_set = false;
       if (!attr_set) {
