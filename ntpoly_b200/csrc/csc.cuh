@@ -19,6 +19,7 @@ struct ChunkTiles {
   DevBuf<double> tval;                       // [ntiles*32] fragment-ordered values
   DevBuf<int4> kmeta;                        // left form only: per inner tile K {0, tile count, first row tile, last row tile}
   DevBuf<int> coltile;                       // left form only: [ncc+1] first tile of every chunk column (halo exchange)
+  bool emitted = false;                      // written by a product (fixed 64-tile slots), not built from CSC
 };
 // Both forms of one matrix, built on first use as a product operand or emitted together with a product's result.
 // Immutable once built, so copies of a matrix share them; any change of the entries drops them.
@@ -48,6 +49,7 @@ template <typename T> struct LocalCsc {
     if (!deferred) return;
     if constexpr (std::is_same<T, double>::value) tile_materialize_entries(*this);
     deferred = false;
+    rt().deferred_materialized++;
   }
   void init_empty(int r, int c) {
     forms.reset();

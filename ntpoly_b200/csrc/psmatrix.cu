@@ -685,7 +685,12 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   // ---- records: who can play, sizes, and which global chunk columns of A each rank needs (the needed range is
   // written into the device copy of the record by a kernel: one all-gather, one read-back)
   HaloRecord mine{};
-  mine.ok = (Lf && Rf) ? 1 : 0;
+  // forms built from CSC must be reasonably full (mostly-padding tiles are the scalar kernels' business); forms written
+  // by a product have fixed 64-tile slots, their tile count says nothing about the fill
+  auto dense_enough = [](const ChunkTiles* f, long long nnz) {
+    return f->emitted || (double)nnz >= 0.20 * 32.0 * (double)f->ntiles;
+  };
+  mine.ok = (Lf && Rf && dense_enough(Lf, Al.nnz) && dense_enough(Rf, Bl.nnz)) ? 1 : 0;
   mine.qlo = INT_MAX; mine.qhi = -1;
   if (mine.ok) { mine.nsuper = Lf->nsuper; mine.ntiles = Lf->ntiles; mine.nnzA = Al.nnz; mine.nnzB = Bl.nnz; mine.ntilesB = Rf->ntiles; }
   std::vector<HaloRecord> rec(C);
@@ -710,7 +715,6 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
     nnzA += rec[p].nnzA; ntilesA += rec[p].ntiles; nnzB += rec[p].nnzB; ntilesB += rec[p].ntilesB;
   }
   if (nnzA == 0 || nnzB == 0) return false;
-  if ((double)nnzA < 0.20 * 32.0 * (double)ntilesA || (double)nnzB < 0.20 * 32.0 * (double)ntilesB) return false;
   // A row block of A's panel cannot be more than 10 % full when the whole panel holds fewer entries than 10 % of
   // ONE row block: only past that bound is the per-block histogram (and its all-reduce) needed for the rule table
   if ((double)nnzA > 0.1 * (double)A.row_block() * (double)Bl.rows) full_rules();

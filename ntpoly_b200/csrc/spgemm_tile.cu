@@ -49,6 +49,19 @@ template <bool ISA> struct CtGeom {
 };
 
 __device__ __forceinline__ int popc64(unsigned long long v) { return __popcll(v); }
+// ---- storage of a super-tile ("byte-packed"): its 64-bit presence mask has 8 groups of 8 tiles (one byte each: the
+// row tiles of one inner tile in a left form, the inner tiles of one tile column in a right form). Group b starts at
+// tile origin + 8*b, its present tiles are rank-packed behind that. Everything from the first present group to the
+// last present tile is one contiguous range (one bulk copy); a product can therefore write the tiles of its result
+// straight from the accumulators, every warp knowing the offsets of its own groups without any cross-warp scan.
+__device__ __forceinline__ int first_group(unsigned long long m) { return m ? ((__ffsll((long long)m) - 1) >> 3) : 0; }
+__device__ __forceinline__ int last_group(unsigned long long m) { return m ? ((63 - __clzll((long long)m)) >> 3) : 0; }
+// tiles between the start of the first present group and the last present tile
+__device__ __forceinline__ int span_tiles(unsigned long long m) {
+  if (m == 0ull) return 0;
+  const int gl = last_group(m);
+  return 8 * (gl - first_group(m)) + __popc((unsigned)(m >> (8 * gl)) & 0xffu);
+}
 
 // pass 1 (FILL=false): super-tile and tile counts per chunk column (+ per-K meta for A);
 // pass 2 (FILL=true): entries + values. One warp per chunk column.
@@ -97,7 +110,7 @@ k_ct_build(CscView<double> M, int ncc, int* __restrict__ scount, int* __restrict
     // lane owns IPL consecutive ids: prefix of non-empty super-tiles and of tiles
     int ns = 0, nt = 0;
 #pragma unroll
-    for (int w = 0; w < IPL; ++w) { const unsigned long long m = b[lane * IPL + w]; ns += (m != 0ull); nt += popc64(m); }
+    for (int w = 0; w < IPL; ++w) { const unsigned long long m = b[lane * IPL + w]; ns += (m != 0ull); nt += span_tiles(m); }
     int is = ns, it = nt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -139,10 +152,12 @@ k_ct_build(CscView<double> M, int ncc, int* __restrict__ scount, int* __restrict
 #pragma unroll
     for (int w = 0; w < IPL; ++w) {
       const unsigned long long m = b[lane * IPL + w];
-      pre[warp][lane * IPL + w] = rt_;
+      // virtual origin of the super-tile: tile (group b, rank r) lives at origin + 8*b + r
+      const int origin = base_t + rt_ - 8 * first_group(m);
+      pre[warp][lane * IPL + w] = origin;
       if (m != 0ull) {
-        ent[rs++] = make_int4(idmin + lane * IPL + w, base_t + rt_, (int)(unsigned)(m & 0xffffffffull), (int)(unsigned)(m >> 32));
-        rt_ += popc64(m);
+        ent[rs++] = make_int4(idmin + lane * IPL + w, origin, (int)(unsigned)(m & 0xffffffffull), (int)(unsigned)(m >> 32));
+        rt_ += span_tiles(m);
       }
     }
     __syncwarp();
@@ -151,8 +166,9 @@ k_ct_build(CscView<double> M, int ncc, int* __restrict__ scount, int* __restrict
         const int r = M.inner[p];
         const int id = r / G::RB - idmin;
         const int bit = G::bit(r, c);
-        const int rk = pre[warp][id] + popc64(b[id] & ((1ull << bit) - 1ull));
-        tval[((size_t)(base_t + rk)) * 32 + G::frag(r, c)] = M.val[p];
+        const unsigned grp = (unsigned)(b[id] >> (bit & 56)) & 0xffu;
+        const int tile = pre[warp][id] + (bit & 56) + __popc(grp & ((1u << (bit & 7)) - 1u));
+        tval[(size_t)tile * 32 + G::frag(r, c)] = M.val[p];
       }
     __syncwarp();
   }
@@ -161,6 +177,7 @@ k_ct_build(CscView<double> M, int ncc, int* __restrict__ scount, int* __restrict
 template <bool ISA>
 static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
   using G = CtGeom<ISA>;
+  T.emitted = false;
   T.ncc = div_up(M.cols, G::CW);
   const int ncc = T.ncc;
   const int nk = ISA ? div_up(M.cols, 4) : 0;
@@ -287,6 +304,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ... and the value itself (result entry, or 0 with keep = false)
+__device__ __noinline__ double value_general(const EmitSpec& e, double v, int row, int col, bool& keep) {
+  return final_value<true>(e, v, row, col, keep);
+}
 // ---- mbarrier + bulk-copy (TMA, 1-D) primitives; SASS: SYNCS.*, UBLKCP.S.G
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -362,321 +383,47 @@ __device__ __forceinline__ void ct_pair(const int4& ea, const int4& eb, int Ib, 
   }
 }
 
-// Persistent CTAs; task = 64x64 output block (8 tile columns x 8 row tiles), handed out by an atomic counter.
-// Warp 8 (copy warp): at the start of a task each lane looks up one inner chunk: the B super-tile (chunk, group)
-// and the A super-tile (row block, chunk). For every chunk where both exist and share an inner tile, one lane
-// publishes the two 64-bit presence masks and issues TWO 1-D bulk copies (TMA) into a 3-stage shared-memory ring
-// guarded by full/empty mbarriers. Warps 0-7: warp w owns tile column 8g + w, i.e. a 64x8 strip of the block with
-// its 8 accumulator tiles in registers, and issues one DMMA.8x8x4 per (present A tile, present B tile) pair from
-// conflict-free 256-byte shared-memory fragments; tiles are located by popcount rank in the masks. Absent tiles
-// are skipped with real branches (a predicated-off DMMA occupies the pipe for its full 16 cycles). The strip is
-// written to the dense staging window and the kept-entry counts of its 8 columns are accumulated on the fly
-// (threshold rule fused), so the emit pass is a single sweep.
-template <int NSTAGE, int MINB>
-__global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
-k_tile_numeric(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const int* __restrict__ nI8,
-               const long long* __restrict__ stg_off, const int2* __restrict__ tasks, int ntasks,
-               int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
-               unsigned char* __restrict__ fmA, unsigned char* __restrict__ fmB, int nrows, int ncols, EmitSpec es) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  double* slab = reinterpret_cast<double*>(smem);
-  unsigned char* meta = smem + NSTAGE * STAGE_BYTES;
-  const unsigned bar0 = smem_u32(smem + NSTAGE * STAGE_BYTES + NSTAGE * META_BYTES);   // full[s] at +8s, empty[s] at +8(NSTAGE+s)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * (NSTAGE + s), CW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  int st = 0;
-  unsigned ph = 0;
-  if (warp == CW) {
-    // ------------------------------------------------------------------ copy warp
-    // The look-ups of a task are a chain of five dependent global loads (task -> B column meta -> B super-tile
-    // -> A column meta -> A super-tile). They are software-pipelined: while the stages of task n are pushed,
-    // one link of the chain of task n+1 is advanced per pushed stage, so the latency hides behind the ring.
-    const int4 none = make_int4(0, 0, 0, -1);
-    int task_raw = 0;                               // lane 0: task id returned by the atomic counter
-    int pstep = 0;
-    bool valid_n = false, have_n = false, found_n = false;
-    int tid_n = 0;
-    int2 tk_n = make_int2(0, 0);
-    int4 cmB_n = none, eb_n = none, ca_n = none, ea_n = none;
-    unsigned long long mA_n = 0ull, mB_n = 0ull;
-    int offA_n = 0, offB_n = 0;
-    auto advance = [&]() {
-      switch (pstep) {
-        case 0: {
-          const int t = __shfl_sync(0xffffffffu, task_raw, 0);
-          tid_n = t;
-          valid_n = t < ntasks;
-          tk_n = valid_n ? tasks[t] : make_int2(0, 0);
-          break;
-        }
-        case 1: cmB_n = valid_n ? B.colmeta[tk_n.x] : none; break;
-        case 2: have_n = valid_n && lane < cmB_n.y; eb_n = have_n ? B.ent[cmB_n.x + lane] : none; break;
-        case 3: ca_n = have_n ? A.colmeta[eb_n.x] : none; break;
-        case 4: {
-          const int idx = have_n ? ct_find(A, ca_n, tk_n.y) : -1;
-          found_n = idx >= 0;
-          ea_n = found_n ? A.ent[idx] : none;
-          break;
-        }
-        case 5: ct_pair(ea_n, eb_n, tk_n.y, found_n, mA_n, mB_n, offA_n, offB_n); break;
-        default: break;
-      }
-      ++pstep;
-    };
-    if (lane == 0) task_raw = atomicAdd(task_counter, 1);
-    while (pstep < 6) advance();
-    for (;;) {
-      const bool done = !valid_n;
-      const int g = tk_n.x, Ib = tk_n.y, task = tid_n;
-      const int4 cmB = cmB_n;
-      unsigned long long mA = mA_n, mB = mB_n;
-      int offA = offA_n, offB = offB_n;
-      if (!done) {
-        if (lane == 0) task_raw = atomicAdd(task_counter, 1);
-        pstep = 0;
-      }
-      const int nb = done ? 1 : max(1, (cmB.y + 31) / 32);
-      for (int bb = 0; bb < nb; ++bb) {
-        if (bb > 0) {                               // more than 32 inner chunks in this group: synchronous look-up
-          const int e = bb * 32 + lane;
-          const bool have = e < cmB.y;
-          const int4 eb = have ? B.ent[cmB.x + e] : none;
-          const int4 ca = have ? A.colmeta[eb.x] : none;
-          const int idx = have ? ct_find(A, ca, Ib) : -1;
-          const int4 ea = (idx >= 0) ? A.ent[idx] : none;
-          ct_pair(ea, eb, Ib, idx >= 0, mA, mB, offA, offB);
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, mA != 0ull);
-        const bool final_batch = (bb == nb - 1);
-        if (todo == 0u && final_batch) todo = 1u;             // a task always ends with a (possibly empty) last stage
-        while (todo) {
-          const int l = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const bool last = final_batch && todo == 0u;
-          const unsigned long long sA = __shfl_sync(0xffffffffu, mA, l), sB = __shfl_sync(0xffffffffu, mB, l);
-          const int oA = __shfl_sync(0xffffffffu, offA, l), oB = __shfl_sync(0xffffffffu, offB, l);
-          mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
-          if (lane == 0) {
-            unsigned char* mt = meta + st * META_BYTES;
-            *reinterpret_cast<unsigned long long*>(mt) = sA;
-            *reinterpret_cast<unsigned long long*>(mt + 8) = sB;
-            *reinterpret_cast<int4*>(mt + 16) = make_int4((last ? 1 : 0) | (done ? 2 : 0), g, Ib, task);
-            const unsigned bA = (unsigned)popc64(sA) * 256u, bB = (unsigned)popc64(sB) * 256u;
-            mbar_arrive_expect_tx(bar0 + 8 * st, bA + bB);
-            const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
-            if (bA) bulk_g2s(slab_s, A.tval + (size_t)oA * 32, bA, bar0 + 8 * st);
-            if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + (size_t)oB * 32, bB, bar0 + 8 * st);
-          }
-          __syncwarp();
-          if (++st == NSTAGE) { st = 0; ph ^= 1u; }
-          if (!done) advance();
-        }
-      }
-      if (done) break;
-      while (pstep < 6) advance();
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------------- DMMA warps
-  const int wj = warp;                              // tile column of the group
-  for (;;) {
-    double acc[8][2];
-#pragma unroll
-    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
-    int g = 0, Ib = 0, task = 0;
-    unsigned fl = 0;
-    do {
-      mbar_wait(bar0 + 8 * st, ph);
-      const unsigned char* mt = meta + st * META_BYTES;
-      const ulonglong2 mm = *reinterpret_cast<const ulonglong2*>(mt);     // maskA, maskB
-      const int4 mi = *reinterpret_cast<const int4*>(mt + 16);
-      fl = (unsigned)mi.x; g = mi.y; Ib = mi.z; task = mi.w;
-      const unsigned mb = (unsigned)(mm.y >> (8 * wj)) & 0xffu;           // my tile column: bits over kk
-      if (mb != 0u && mm.x != 0ull) {
-        // tiles are rank-packed: byte kk of `excl` = number of A tiles stored before inner tile kk
-        unsigned long long x = mm.x - ((mm.x >> 1) & 0x5555555555555555ull);
-        x = (x & 0x3333333333333333ull) + ((x >> 2) & 0x3333333333333333ull);
-        x = (x + (x >> 4)) & 0x0f0f0f0f0f0f0f0full;
-        const unsigned long long excl = (x * 0x0101010101010101ull) << 8;
-        const double* As = slab + (size_t)st * STAGE_DOUBLES + lane;
-        const double* Bs = As + SLAB_DOUBLES + popc64(mm.y & ((1ull << (8 * wj)) - 1ull)) * 32;
-        // one copy of the loop body (not unrolled over kk): the four code paths below times eight would not
-        // fit the instruction cache (measured: stall_no_instruction dominated)
-        unsigned live = mb & nonzero_bytes(mm.x);
-#pragma unroll 1
-        while (live) {
-          const int kk = __ffs(live) - 1;
-          live &= live - 1u;
-          const unsigned ma = (unsigned)(mm.x >> (8 * kk)) & 0xffu;
-          const double bv = Bs[__popc(mb & ((1u << kk) - 1u)) * 32];
-          const double* ap = As + ((unsigned)(excl >> (8 * kk)) & 0xffu) * 32;
-          double av[8];
-          if (ma == 0xffu) {
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii) av[ii] = ap[ii * 32];
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], av[ii], bv);
-          } else if ((ma & (ma + 1u)) == 0u) {
-            // Absent tiles are skipped with branches, not predicates: a predicated-off DMMA still holds the FP64
-            // tensor pipe for 16 cycles (scripts/micro/dmma_shapes.cu).
-            // prefix run (row tiles 0..h0, the band edge leaving the block): one jump into a descending sequence
-            const int h0 = __popc(ma) - 1;
-#pragma unroll
-            for (int ii = 0; ii < 7; ++ii)
-              if (ii <= h0) av[ii] = ap[ii * 32];
-#define NTB_D(i) dmma884(acc[i][0], acc[i][1], av[i], bv);
-            switch (h0) {
-              case 6: NTB_D(6)
-              case 5: NTB_D(5)
-              case 4: NTB_D(4)
-              case 3: NTB_D(3)
-              case 2: NTB_D(2)
-              case 1: NTB_D(1)
-              default: NTB_D(0)
-            }
-          } else if (((ma | (ma - 1u)) & 0xffu) == 0xffu) {
-            // suffix run (row tiles l0..7, the band edge entering the block): one jump into an ascending sequence
-            const int l0 = __ffs(ma) - 1;
-            const double* aq = ap - l0 * 32;
-#pragma unroll
-            for (int ii = 1; ii < 8; ++ii)
-              if (ii >= l0) av[ii] = aq[ii * 32];
-            switch (l0) {
-              case 1: NTB_D(1)
-              case 2: NTB_D(2)
-              case 3: NTB_D(3)
-              case 4: NTB_D(4)
-              case 5: NTB_D(5)
-              case 6: NTB_D(6)
-              default: NTB_D(7)
-            }
-#undef NTB_D
-          } else {
-            // general pattern: load the present tiles (rank-packed), then enter the unrolled DMMA sequence at the
-            // first tile of each id run and leave it after the last
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii)
-              if ((ma >> ii) & 1u) av[ii] = ap[__popc(ma & ((1u << ii) - 1u)) * 32];
-            unsigned m = ma;
-#define NTB_RUN_STEP(i) dmma884(acc[i][0], acc[i][1], av[i], bv); if (h0 == i) break;
-            do {
-              const int l0 = __ffs(m) - 1;
-              const int len = __ffs(~(m >> l0)) - 1;
-              const int h0 = l0 + len - 1;
-              m &= ~(((1u << len) - 1u) << l0);
-              switch (l0) {
-                case 0: NTB_RUN_STEP(0)
-                case 1: NTB_RUN_STEP(1)
-                case 2: NTB_RUN_STEP(2)
-                case 3: NTB_RUN_STEP(3)
-                case 4: NTB_RUN_STEP(4)
-                case 5: NTB_RUN_STEP(5)
-                case 6: NTB_RUN_STEP(6)
-                default: dmma884(acc[7][0], acc[7][1], av[7], bv);
-              }
-            } while (m);
-#undef NTB_RUN_STEP
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (NSTAGE + st));
-      if (++st == NSTAGE) { st = 0; ph ^= 1u; }
-    } while ((fl & 1u) == 0u);
-    if (fl & 2u) break;
-    const int J = g * 8 + wj;
-    if (J >= nJ) continue;
-    const int I0 = Ib << 3;
-    const int iw0 = imin8[J], nI = nI8[J];
-    if (I0 < iw0 || I0 >= iw0 + nI) continue;
-    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column.
-    // Alongside the raw strip: kept-entry counts of the 8 columns and the presence bytes of the strip's tiles in
-    // the two tile forms of the RESULT (the next product reads them without ever rebuilding tiles from CSC).
-    const int wlen = nI * 8;
-    const int r = lane >> 2, cc = (lane & 3) * 2;
-    double* o = stg + stg_off[J] * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
-    const int j0 = J * 8 + cc;
-    const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
-    // the shifted diagonal touches only the strips that cross it: everything else takes the plain test
-    const bool on_diag = es.sigma != 0.0 && (I0 * 8 <= J * 8 + 7 + es.dd) && (I0 * 8 + 63 >= J * 8 + es.dd);
-    const bool plain = es.rules.tbl == nullptr && !on_diag;
-    int c0 = 0, c1 = 0;
-    unsigned bR0 = 0, bR1 = 0, bL0 = 0, bL1 = 0;   // right-form bytes (rows 0-31 / 32-63), left-form bytes (cols 0-3 / 4-7)
-#pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {
-      const double v0 = acc[ii][0], v1 = acc[ii][1];
-      o[ii * 8] = v0;
-      o[wlen + ii * 8] = v1;
-      const int row = (I0 + ii) * 8 + r;
-      bool k0 = false, k1 = false;
-      if (row < nrows) {
-        if (plain) {                            // sparse rule everywhere, no shift: |alpha*v| > thr
-          k0 = in0 && fabs(es.alpha * v0) > es.thr;
-          k1 = in1 && fabs(es.alpha * v1) > es.thr;
-        } else {
-          if (in0) k0 = keep_general(es, v0, row, j0);
-          if (in1) k1 = keep_general(es, v1, row, j0 + 1);
-        }
-      }
-      c0 += k0 ? 1 : 0;
-      c1 += k1 ? 1 : 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, k0 || k1);
-      const unsigned lo = (bal & 0x0000ffffu) ? 1u : 0u, hi = (bal & 0xffff0000u) ? 1u : 0u;
-      if (ii < 4) bR0 |= (lo << (2 * ii)) | (hi << (2 * ii + 1));
-      else bR1 |= (lo << (2 * (ii - 4))) | (hi << (2 * (ii - 4) + 1));
-      bL0 |= ((bal & 0x33333333u) ? 1u : 0u) << ii;
-      bL1 |= ((bal & 0xccccccccu) ? 1u : 0u) << ii;
-    }
-#pragma unroll
-    for (int d = 4; d < 32; d <<= 1) {
-      c0 += __shfl_xor_sync(0xffffffffu, c0, d);
-      c1 += __shfl_xor_sync(0xffffffffu, c1, d);
-    }
-    if (lane < 4) {
-      if (c0) atomicAdd(&cnt[j0], c0);
-      if (c1) atomicAdd(&cnt[j0 + 1], c1);
-    }
-    if (lane == 0) {
-      fmB[((size_t)task * 2 + 0) * 8 + wj] = (unsigned char)bR0;
-      fmB[((size_t)task * 2 + 1) * 8 + wj] = (unsigned char)bR1;
-      unsigned char* fa = fmA + ((size_t)task * 2 + (wj >> 2)) * 8 + 2 * (wj & 3);
-      fa[0] = (unsigned char)bL0;
-      fa[1] = (unsigned char)bL1;
-    }
-  }
-}
-
-// ---- v9 of the numeric kernel: same pipeline, same results, leaner DMMA warps ---------------------------------------
-// ncu's per-instruction samples of the kernel above (profiles/r01b_numeric_source_top.txt) show the DMMA warps spending
-// 18 % of their time in per-stage mask arithmetic and barrier turn-around, 18 % in the per-inner-tile address chain
-// (BREV/FLO/POPC run on the quarter-rate XU pipe and sit on the critical path of every DMMA burst) and 22 % in the
-// epilogue (two dependent global loads before the first store). Here
-//   * the COPY WARP digests the masks once per stage (it idles on the empty barrier 95 % of the time anyway): per
-//     inner tile kk of the A super-tile a descriptor {presence byte, first tile, first/last row tile, kind}, per
-//     (tile column, kk) the index of the B tile in the slab; the DMMA warps only extract bit fields;
-//   * the inner loop counts kk up instead of bit-scanning, and prefetches the next descriptor;
-//   * the window constants of the epilogue are loaded when a task STARTS, so their latency hides behind the DMMAs;
-//   * the presence bytes of the result's tile forms come from two warp-wide OR reductions instead of 8 ballots.
+// ---- the numeric kernel -------------------------------------------------------------------------------------------
+// Persistent CTAs (2 per SM); task = 64x64 output block (8 tile columns x 8 row tiles), handed out by an atomic counter.
+//
+// Warp 8 = COPY WARP. At the start of a task each lane looks up one inner chunk: the B super-tile (chunk, group) and
+// the A super-tile (row block, chunk); the five-load look-up chain of task n+1 is software-pipelined behind the stage
+// pushes of task n, and as soon as it completes the tiles of task n+1 are prefetched into L2. For every chunk where
+// both super-tiles exist and share an inner tile it pushes one STAGE into a 3-stage shared-memory ring guarded by
+// full/empty mbarriers: TWO 1-D bulk copies (TMA) - the contiguous tile span of each super-tile - plus a 128-byte
+// digest of the two presence masks, so that the DMMA warps only extract bit fields (the address arithmetic used to
+// sit on the critical path of every DMMA burst: BREV/FLO/POPC run on the quarter-rate XU pipe):
+//     +0   int4 {flags | nzA << 8, g, Ib, task}   flags: 1 = last stage of the task, 2 = no more tasks
+//     +16  u32 adesc[8]  per inner tile kk of the A super-tile:  presence byte | first tile of the group in the slab
+//                        << 8 | l0 << 16 | h0 << 19 | kind << 22   (kind 0 full, 1 prefix run 0..h0, 2 suffix run
+//                        l0..7, 3 anything else)
+//     +48  u8 mbyte[8]   presence bits over kk of tile column jj of the B super-tile
+//     +56  int2 {t0, nn} first task and task count of group g (slot arithmetic of the result's left form)
+//     +64  u8 boff[64]   [jj*8+kk] index of B tile (jj,kk) in the slab
+//
+// Warps 0-7 = DMMA WARPS: warp w owns tile column 8g+w, i.e. a 64x8 strip of the block with its 8 accumulator tiles in
+// registers, and issues one DMMA.8x8x4 per (present A tile, present B tile) pair from conflict-free 256-byte
+// shared-memory fragments. Absent tiles are skipped with real branches (a predicated-off DMMA occupies the pipe for
+// its full 16 cycles, scripts/micro/dmma_shapes.cu).
+//
+// EPILOGUE = the result, finished: threshold rule, alpha and the optional identity shift are applied to the
+// accumulators, the kept-entry counts of the 8 columns are added up (CSC outer index of the result), and the strip is
+// written STRAIGHT INTO THE TWO TILE FORMS OF THE RESULT (byte-packed layout, see first_group): a warp owns whole
+// groups of both forms - tile column w of the two right-form super-tiles of the task, inner tiles 2(w%4), 2(w%4)+1 of
+// the left-form super-tile w/4 - so it knows every tile offset from its own presence bytes. No staging buffer, no
+// second pass; the next product reads these forms as they are.
 constexpr int META9 = 128;
 constexpr int numeric_smem9(int nstage) { return nstage * STAGE_BYTES + nstage * META9 + 2 * nstage * 8; }
-//  per stage: +0   int4 {flags | nzA << 8, g, Ib, task}   flags: 1 = last stage of the task, 2 = no more tasks
-//             +16  u32 adesc[8]  ma | first tile << 8 | l0 << 16 | h0 << 19 | kind << 22   (kind: 0 full, 1 prefix
-//                                run 0..h0, 2 suffix run l0..7, 3 anything else)
-//             +48  u8 mbyte[8]   presence bits over kk of tile column jj of the B super-tile
-//             +64  u8 boff[64]   [jj*8+kk] index of B tile (jj,kk) in the slab
+// where the strip of a task goes
+struct ResultForms {
+  int4* entL; double* tvalL;                 // left form: slot s <-> entry s, tiles s*64 ...
+  int4* entR; double* tvalR;                 // right form: slot 2*task + h
+  unsigned want;                             // WANT_LEFT | WANT_RIGHT
+};
 template <int NSTAGE, int MINB>
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
-k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const int* __restrict__ nI8,
-                const long long* __restrict__ stg_off, const int2* __restrict__ tasks, int ntasks,
-                int* __restrict__ task_counter, double* __restrict__ stg, int* __restrict__ cnt,
-                unsigned char* __restrict__ fmA, unsigned char* __restrict__ fmB, int nrows, int ncols, EmitSpec es) {
+k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
+                int* __restrict__ task_counter, int* __restrict__ cnt, ResultForms out, int nrows, int ncols, EmitSpec es) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* slab = reinterpret_cast<double*>(smem);
   unsigned char* meta = smem + NSTAGE * STAGE_BYTES;
@@ -702,6 +449,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
     int4 cmB_n = none, eb_n = none, ca_n = none, ea_n = none;
     unsigned long long mA_n = 0ull, mB_n = 0ull;
     int offA_n = 0, offB_n = 0;
+    int gt0_n = 0, gt1_n = 0;
     auto advance = [&]() {
       switch (pstep) {
         case 0: {
@@ -711,9 +459,17 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
           tk_n = valid_n ? tasks[t] : make_int2(0, 0);
           break;
         }
-        case 1: cmB_n = valid_n ? B.colmeta[tk_n.x] : none; break;
+        case 1:
+          cmB_n = valid_n ? B.colmeta[tk_n.x] : none;
+          gt0_n = valid_n ? gtask_off[tk_n.x] : 0;
+          gt1_n = valid_n ? gtask_off[tk_n.x + 1] : 0;
+          break;
         case 2: have_n = valid_n && lane < cmB_n.y; eb_n = have_n ? B.ent[cmB_n.x + lane] : none; break;
-        case 3: ca_n = have_n ? A.colmeta[eb_n.x] : none; break;
+        case 3:
+          // an entry of a product-written form may carry an empty mask (and an id past the last chunk column of A)
+          have_n = have_n && mask64(eb_n) != 0ull;
+          ca_n = have_n ? A.colmeta[eb_n.x] : none;
+          break;
         case 4: {
           const int idx = have_n ? ct_find(A, ca_n, tk_n.y) : -1;
           found_n = idx >= 0;
@@ -726,8 +482,8 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
           // consumed, so that their bulk copies find them there (the DMMA warps were waiting 12 % of their time for
           // a full barrier, i.e. for HBM latency at the short band-edge stages)
           if (mA_n != 0ull) {
-            bulk_prefetch_l2(A.tval + (size_t)offA_n * 32, (unsigned)popc64(mA_n) * 256u);
-            bulk_prefetch_l2(B.tval + (size_t)offB_n * 32, (unsigned)popc64(mB_n) * 256u);
+            bulk_prefetch_l2(A.tval + ((long long)offA_n + 8 * first_group(mA_n)) * 32, (unsigned)span_tiles(mA_n) * 256u);
+            bulk_prefetch_l2(B.tval + ((long long)offB_n + 8 * first_group(mB_n)) * 32, (unsigned)span_tiles(mB_n) * 256u);
           }
           break;
         default: break;
@@ -739,6 +495,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
     for (;;) {
       const bool done = !valid_n;
       const int g = tk_n.x, Ib = tk_n.y, task = tid_n;
+      const int gt0 = gt0_n, gtn = gt1_n - gt0_n;
       const int4 cmB = cmB_n;
       unsigned long long mA = mA_n, mB = mB_n;
       int offA = offA_n, offB = offB_n;
@@ -750,8 +507,9 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
       for (int bb = 0; bb < nb; ++bb) {
         if (bb > 0) {
           const int e = bb * 32 + lane;
-          const bool have = e < cmB.y;
+          bool have = e < cmB.y;
           const int4 eb = have ? B.ent[cmB.x + e] : none;
+          have = have && mask64(eb) != 0ull;
           const int4 ca = have ? A.colmeta[eb.x] : none;
           const int idx = have ? ct_find(A, ca, Ib) : -1;
           const int4 ea = (idx >= 0) ? A.ent[idx] : none;
@@ -767,11 +525,12 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
           const unsigned long long sA = __shfl_sync(0xffffffffu, mA, l), sB = __shfl_sync(0xffffffffu, mB, l);
           const int oA = __shfl_sync(0xffffffffu, offA, l), oB = __shfl_sync(0xffffffffu, offB, l);
           // digest the masks while the slot may still be busy
+          const int gfA = first_group(sA), gfB = first_group(sB);
           unsigned desc = 0;
           if (lane < 8) {
             const unsigned ma = (unsigned)(sA >> (8 * lane)) & 0xffu;
             if (ma) {
-              const unsigned aoff = (unsigned)popc64(sA & ((1ull << (8 * lane)) - 1ull));
+              const unsigned aoff = (unsigned)(8 * (lane - gfA));     // group kk starts at tile 8*(kk - first group) of the slab
               const unsigned l0 = (unsigned)__ffs(ma) - 1u, h0 = 31u - (unsigned)__clz(ma), pc = (unsigned)__popc(ma);
               unsigned kind = 3u;
               if (ma == 0xffu) kind = 0u;
@@ -780,24 +539,27 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
               desc = ma | (aoff << 8) | (l0 << 16) | (h0 << 19) | (kind << 22);
             }
           }
-          const unsigned b0 = (unsigned)popc64(sB & ((1ull << (2 * lane)) - 1ull));
-          const unsigned b1 = b0 + (unsigned)((sB >> (2 * lane)) & 1ull);
+          // B tiles (jj, kk), jj = lane / 4, kk = 2 (lane % 4) and + 1
+          const unsigned bbyte = (unsigned)(sB >> (8 * (lane >> 2))) & 0xffu;
+          const unsigned b0 = (unsigned)(8 * ((lane >> 2) - gfB)) + (unsigned)__popc(bbyte & ((1u << (2 * (lane & 3))) - 1u));
+          const unsigned b1 = b0 + ((bbyte >> (2 * (lane & 3))) & 1u);
           const unsigned nzA = nonzero_bytes(sA);
           mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
           unsigned char* mt = meta + st * META9;
           if (lane < 8) reinterpret_cast<unsigned*>(mt + 16)[lane] = desc;
-          reinterpret_cast<unsigned short*>(mt + 64)[lane] = (unsigned short)(b0 | (b1 << 8));
+          reinterpret_cast<unsigned short*>(mt + 64)[lane] = (unsigned short)((b0 & 0xffu) | ((b1 & 0xffu) << 8));
           if (lane == 0) {
             *reinterpret_cast<unsigned long long*>(mt + 48) = sB;
+            *reinterpret_cast<int2*>(mt + 56) = make_int2(gt0, gtn);
             *reinterpret_cast<int4*>(mt) = make_int4((int)((last ? 1u : 0u) | (done ? 2u : 0u) | (nzA << 8)), g, Ib, task);
           }
           __syncwarp();                                        // the other lanes' meta stores happen before the arrive
           if (lane == 0) {
-            const unsigned bA = (unsigned)popc64(sA) * 256u, bB = (unsigned)popc64(sB) * 256u;
+            const unsigned bA = (unsigned)span_tiles(sA) * 256u, bB = (unsigned)span_tiles(sB) * 256u;
             mbar_arrive_expect_tx(bar0 + 8 * st, bA + bB);
             const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
-            if (bA) bulk_g2s(slab_s, A.tval + (size_t)oA * 32, bA, bar0 + 8 * st);
-            if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + (size_t)oB * 32, bB, bar0 + 8 * st);
+            if (bA) bulk_g2s(slab_s, A.tval + ((long long)oA + 8 * gfA) * 32, bA, bar0 + 8 * st);
+            if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + ((long long)oB + 8 * gfB) * 32, bB, bar0 + 8 * st);
           }
           __syncwarp();
           if (++st == NSTAGE) { st = 0; ph ^= 1u; }
@@ -818,19 +580,13 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
     for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.0; acc[ii][1] = 0.0; }
     int g = 0, Ib = 0, task = 0;
     unsigned fl = 0;
-    bool fresh = true;
-    int iw0 = 0, nI = 0;
-    long long so = 0;
+    int gt0 = 0, gtn = 0;
     do {
       mbar_wait(bar0 + 8 * st, ph);
       const unsigned char* mt = meta + st * META9;
       const int4 mi = *reinterpret_cast<const int4*>(mt);
       fl = (unsigned)mi.x & 0xffu; g = mi.y; Ib = mi.z; task = mi.w;
-      if (fresh) {                                   // a task starts: issue the loads its epilogue will need
-        fresh = false;
-        const int J = g * 8 + wj;
-        if (!(fl & 2u) && J < nJ) { iw0 = imin8[J]; nI = nI8[J]; so = stg_off[J]; }
-      }
+      { const int2 gt = *reinterpret_cast<const int2*>(mt + 56); gt0 = gt.x; gtn = gt.y; }
       const unsigned mb = mt[48 + wj];
       const unsigned live = mb & ((unsigned)mi.x >> 8) & 0xffu;
       if (live != 0u) {
@@ -921,14 +677,12 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
     if (fl & 2u) break;
     const int J = g * 8 + wj;
     if (J >= nJ) continue;
+    // C fragment: row = lane/4, cols = 2*(lane%4), +1
     const int I0 = Ib << 3;
-    if (I0 < iw0 || I0 >= iw0 + nI) continue;
-    // C fragment: row = lane/4, cols = 2*(lane%4), +1 ; staging is column-major per tile column.
-    const int wlen = nI * 8;
     const int r = lane >> 2, cc = (lane & 3) * 2;
-    double* o = stg + so * 64 + (size_t)cc * wlen + (size_t)(I0 - iw0) * 8 + r;
     const int j0 = J * 8 + cc;
     const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
+    // the shifted diagonal touches only the strips that cross it
     const bool on_diag = es.sigma != 0.0 && (I0 * 8 <= J * 8 + 7 + es.dd) && (I0 * 8 + 63 >= J * 8 + es.dd);
     const bool norules = es.rules.tbl == nullptr;
     int c0 = 0, c1 = 0;
@@ -936,24 +690,27 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
       const double v0 = acc[ii][0], v1 = acc[ii][1];
-      o[ii * 8] = v0;
-      o[wlen + ii * 8] = v1;
       const int row = (I0 + ii) * 8 + r;
       bool k0 = false, k1 = false;
+      double f0 = 0.0, f1 = 0.0;                   // what the result holds at these two positions (0 = no entry)
       if (row < nrows) {
         if (norules) {                          // sparse rule everywhere: |alpha*v| > thr
           const double s0 = es.alpha * v0, s1 = es.alpha * v1;
           k0 = in0 && fabs(s0) > es.thr;
           k1 = in1 && fabs(s1) > es.thr;
+          f0 = k0 ? s0 : 0.0;
+          f1 = k1 ? s1 : 0.0;
           if (on_diag) {                        // a shifted diagonal entry is kept iff it is non-zero (final_value)
-            if (in0 && row == j0 + es.dd && j0 < es.ncols_diag) k0 = ((k0 ? s0 : 0.0) + es.sigma) != 0.0;
-            if (in1 && row == j0 + 1 + es.dd && j0 + 1 < es.ncols_diag) k1 = ((k1 ? s1 : 0.0) + es.sigma) != 0.0;
+            if (in0 && row == j0 + es.dd && j0 < es.ncols_diag) { f0 += es.sigma; k0 = f0 != 0.0; }
+            if (in1 && row == j0 + 1 + es.dd && j0 + 1 < es.ncols_diag) { f1 += es.sigma; k1 = f1 != 0.0; }
           }
         } else {
-          if (in0) k0 = keep_general(es, v0, row, j0);
-          if (in1) k1 = keep_general(es, v1, row, j0 + 1);
+          if (in0) f0 = value_general(es, v0, row, j0, k0);
+          if (in1) f1 = value_general(es, v1, row, j0 + 1, k1);
         }
       }
+      acc[ii][0] = k0 ? f0 : 0.0;
+      acc[ii][1] = k1 ? f1 : 0.0;
       c0 += k0 ? 1 : 0;
       c1 += k1 ? 1 : 0;
       km |= ((k0 || k1) ? 1u : 0u) << ii;
@@ -967,6 +724,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
     x = (x | (x << 1)) & 0x5555u;                  // bit ii -> bit 2*ii
     const unsigned bR = __reduce_or_sync(0xffffffffu, (lane & 16) ? (x << 1) : x);
     const unsigned bL = __reduce_or_sync(0xffffffffu, (lane & 2) ? (km << 8) : km);
+    if (bL == 0u) continue;                        // nothing of this strip survives
 #pragma unroll
     for (int d = 4; d < 32; d <<= 1) {
       c0 += __shfl_xor_sync(0xffffffffu, c0, d);
@@ -976,170 +734,91 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ imin8, const
       if (c0) atomicAdd(&cnt[j0], c0);
       if (c1) atomicAdd(&cnt[j0 + 1], c1);
     }
-    if (lane == 0) {
-      fmB[((size_t)task * 2 + 0) * 8 + wj] = (unsigned char)(bR & 0xffu);
-      fmB[((size_t)task * 2 + 1) * 8 + wj] = (unsigned char)((bR >> 8) & 0xffu);
-      unsigned char* fa = fmA + ((size_t)task * 2 + (wj >> 2)) * 8 + 2 * (wj & 3);
-      fa[0] = (unsigned char)(bL & 0xffu);
-      fa[1] = (unsigned char)((bL >> 8) & 0xffu);
-    }
-  }
-}
-
-// ordered emit of the kept entries of every output column into CSC (counts came from the numeric kernel)
-__global__ void __launch_bounds__(256)
-k_tile_emit(int ncols, int nrows, const int* __restrict__ imin8, const int* __restrict__ nI8,
-            const long long* __restrict__ stg_off, const double* __restrict__ stg, EmitSpec es,
-            const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ val) {
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int j = gw; j < ncols; j += nw) {
-    const int J = j >> 3, jj = j & 7;
-    const int wlen = nI8[J] * 8;
-    const int base = imin8[J] * 8;
-    const double* src = stg + stg_off[J] * 64 + (size_t)jj * wlen;
-    int count = 0;
-    const int dst = outer[j];
-    for (int t0 = 0; t0 < wlen; t0 += 32) {
-      const int t = t0 + lane;
-      bool keep = false;
-      double sv = 0.0;
-      if (t < wlen && base + t < nrows) sv = final_value<true>(es, src[t], base + t, j, keep);
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const int pos = dst + count + __popc(m & ((1u << lane) - 1));
-        inner[pos] = base + t;
-        val[pos] = sv;
+    const int slotL = 2 * gt0 + (wj >> 2) * gtn + (task - gt0);
+    if (out.want & WANT_RIGHT) {
+      // 4x8 tiles (h, jj = wj, kk): rows 32h + 4kk + row%4, fragment position (col%8)*4 + row%4. Row tile ii holds
+      // inner tiles kk = 2(ii%4) (rows 0-3: lanes 0-15) and 2(ii%4)+1 (rows 4-7: lanes 16-31) of super-tile h = ii/4
+      const unsigned half = (unsigned)lane >> 4;
+      double* base = out.tvalR + ((long long)task * 2 * 64 + 8 * wj) * 32 + cc * 4 + (r & 3);
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const unsigned byte = (bR >> (8 * (ii >> 2))) & 0xffu;
+        const unsigned kk = 2u * (ii & 3) + half;
+        if ((byte >> kk) & 1u) {
+          double* t = base + ((ii >> 2) * 64 + __popc(byte & ((1u << kk) - 1u))) * 32;
+          t[0] = acc[ii][0];
+          t[4] = acc[ii][1];
+        }
       }
-      count += __popc(m);
+    }
+    if (out.want & WANT_LEFT) {
+      // 8x4 tiles (kk' = 2(wj%4) + ch, ii) of super-tile (Ib, chunk column 2g + wj/4): columns 4ch + col%4, fragment
+      // position (row%8)*4 + col%4; lanes with lane%4 < 2 hold ch = 0
+      const unsigned ch = ((unsigned)lane & 3u) >> 1;
+      const unsigned byte = (bL >> (8 * ch)) & 0xffu;
+      double* base = out.tvalL + ((long long)slotL * 64 + 8 * (2 * (wj & 3) + (int)ch)) * 32 + r * 4 + (cc & 3);
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii)
+        if ((byte >> ii) & 1u)
+          *reinterpret_cast<double2*>(base + __popc(byte & ((1u << ii) - 1u)) * 32) = make_double2(acc[ii][0], acc[ii][1]);
+    }
+    if (lane == 0) {
+      // presence masks: byte wj of the two right-form entries, bytes 2(wj%4), 2(wj%4)+1 of the left-form entry
+      // (little endian: .z/.w of the int4 are the low / high word of the 64-bit mask)
+      unsigned char* mR = reinterpret_cast<unsigned char*>(out.entR + (size_t)task * 2) + 8;
+      mR[wj] = (unsigned char)(bR & 0xffu);
+      mR[16 + wj] = (unsigned char)((bR >> 8) & 0xffu);
+      unsigned char* mL = reinterpret_cast<unsigned char*>(out.entL + slotL) + 8 + 2 * (wj & 3);
+      mL[0] = (unsigned char)(bL & 0xffu);
+      mL[1] = (unsigned char)((bL >> 8) & 0xffu);
     }
   }
 }
 
-// ---- tile forms of the result, straight from the staging strips --------------------------------------------
-// Every task (group g, row block Ib) owns two super-tiles of each form: left form (Ib, chunk column 2g+c), right
-// form (inner chunk 2Ib+h, group g); their presence masks were written by the numeric kernel (fmA / fmB).
-// Slots are enumerated in chunk-column order: right form slot = 2*task + h; left form slot = 2*t0(g) + c*n(g) + b.
-constexpr int FI_T = 1024, FI_ITEMS = 8;
-
-// slot s of a form -> its task-owned mask, super-tile id and the slot range [sa, sb) of its chunk column
-__device__ __forceinline__ void form_slot(bool left, int s, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
-                                          const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
-                                          unsigned long long& mask, int& id, int& q, int& sa, int& sb) {
-  const int t = s >> 1;
-  const int2 tk = tasks[t];
-  const int t0 = gtask_off[tk.x], nn = gtask_off[tk.x + 1] - t0;
-  if (!left) { mask = fmB[s]; id = 2 * tk.y + (s & 1); q = tk.x; sa = 2 * t0; sb = sa + 2 * nn; return; }
-  const int local = s - 2 * t0, c = local / nn, b = local - c * nn;
-  mask = fmA[(size_t)(t0 + b) * 2 + c];
-  id = tasks[t0 + b].y;
-  q = 2 * tk.x + c; sa = 2 * t0 + c * nn; sb = sa + nn;
-}
-
-// (1) masks in slot order, both forms (blockIdx.y: 0 = left, 1 = right)
+// ---- index of the result's tile forms: known BEFORE the numeric kernel runs ------------------------------------------
+// Every task (group g, row block Ib) owns two super-tiles of each form, each with a fixed slot of 64 tiles:
+//   right form (chunk column g):        slot 2*task + h         <-> inner chunk 2*Ib + h
+//   left form  (chunk column 2g + c):   slot 2*t0(g) + c*n(g) + (task - t0(g))   <-> row block Ib
+// i.e. slots are enumerated in chunk-column order with ascending ids, as the look-ups of the next product expect.
+// Entries start with an empty mask; the numeric kernel fills in the presence bytes (an entry whose mask stays empty
+// is skipped by every reader).
 __global__ void __launch_bounds__(256)
-k_forms_slots(int ntasks, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
-              const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
-              unsigned long long* __restrict__ smaskL, unsigned long long* __restrict__ smaskR) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= 2 * ntasks) return;
-  const bool left = blockIdx.y == 0;
-  unsigned long long m; int id, q, sa, sb;
-  form_slot(left, s, tasks, gtask_off, fmA, fmB, m, id, q, sa, sb);
-  (left ? smaskL : smaskR)[s] = m;
-}
-
-// (2) one CTA per form: exclusive scans of (non-empty, tile count) over the slots. Every thread owns one contiguous
-// chunk of slots: chunk totals -> one block-wide scan -> outputs (two sweeps over L2-resident data, three barriers)
-__global__ void __launch_bounds__(FI_T)
-k_forms_scan(int ntasks, const unsigned long long* __restrict__ smaskL, const unsigned long long* __restrict__ smaskR,
-             int* __restrict__ seidxL, int* __restrict__ seidxR, int* __restrict__ stoffL, int* __restrict__ stoffR,
-             int* __restrict__ totals) {
-  const bool left = blockIdx.x == 0;
-  const unsigned long long* smask = left ? smaskL : smaskR;
-  int* seidx = left ? seidxL : seidxR;
-  int* stoff = left ? stoffL : stoffR;
-  const int n = 2 * ntasks;
-  __shared__ int wsum[2][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (n + FI_T - 1) / FI_T;
-  const int s0 = min(n, (int)threadIdx.x * per), s1 = min(n, s0 + per);
-  int f = 0, pc = 0;
-#pragma unroll 4
-  for (int i = s0; i < s1; ++i) { const unsigned long long m = smask[i]; f += (m != 0ull); pc += popc64(m); }
-  int fi = f, pi = pc;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int a = __shfl_up_sync(0xffffffffu, fi, d), b = __shfl_up_sync(0xffffffffu, pi, d);
-    if (lane >= d) { fi += a; pi += b; }
-  }
-  if (lane == 31) { wsum[0][warp] = fi; wsum[1][warp] = pi; }
-  __syncthreads();
-  if (warp == 0) {
-    const int a = wsum[0][lane], b = wsum[1][lane];
-    int ai = a, bi = b;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int x = __shfl_up_sync(0xffffffffu, ai, d), y = __shfl_up_sync(0xffffffffu, bi, d);
-      if (lane >= d) { ai += x; bi += y; }
-    }
-    wsum[0][lane] = ai - a; wsum[1][lane] = bi - b;      // exclusive warp offsets
-  }
-  __syncthreads();
-  int e = wsum[0][warp] + fi - f, t = wsum[1][warp] + pi - pc;
-#pragma unroll 4
-  for (int i = s0; i < s1; ++i) {
-    const unsigned long long m = smask[i];
-    seidx[i] = e; stoff[i] = t;
-    if (m != 0ull) { ++e; t += popc64(m); }
-  }
-  if (threadIdx.x == FI_T - 1) { seidx[n] = e; totals[left ? 0 : 2] = e; totals[left ? 1 : 3] = t; }
-}
-
-// (3) entries and chunk-column meta (blockIdx.y: 0 = left, 1 = right); threads beyond the slots mark empty columns
-__global__ void __launch_bounds__(256)
-k_forms_write(int ntasks, int nG, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
-              const unsigned long long* __restrict__ fmA, const unsigned long long* __restrict__ fmB,
-              const int* __restrict__ seidxL, const int* __restrict__ seidxR, const int* __restrict__ stoffL,
-              const int* __restrict__ stoffR, int4* __restrict__ entL, int4* __restrict__ entR,
-              int4* __restrict__ colmetaL, int4* __restrict__ colmetaR, int* __restrict__ coltileL,
-              const int* __restrict__ totals) {
-  const bool left = blockIdx.y == 0;
-  const int* seidx = left ? seidxL : seidxR;
-  const int* stoff = left ? stoffL : stoffR;
-  int4* ent = left ? entL : entR;
-  int* cm = reinterpret_cast<int*>(left ? colmetaL : colmetaR);
+k_forms_layout(int ntasks, int nG, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
+               int4* __restrict__ entL, int4* __restrict__ entR, int4* __restrict__ colmetaL, int4* __restrict__ colmetaR,
+               int* __restrict__ coltileL) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = 2 * ntasks;
-  if (i < n) {
-    unsigned long long m; int id, q, sa, sb;
-    form_slot(left, i, tasks, gtask_off, fmA, fmB, m, id, q, sa, sb);
-    if (m != 0ull) {
-      const int e = seidx[i], e0 = seidx[sa], e1 = seidx[sb];
-      ent[e] = make_int4(id, stoff[i], (int)(unsigned)(m & 0xffffffffull), (int)(unsigned)(m >> 32));
-      if (e == e0) { cm[4 * q + 0] = e0; cm[4 * q + 1] = e1 - e0; cm[4 * q + 2] = id; }
-      if (e + 1 == e1) cm[4 * q + 3] = id;
-    }
+  if (i < ntasks) {
+    const int2 tk = tasks[i];
+    const int t0 = gtask_off[tk.x], nn = gtask_off[tk.x + 1] - t0;
+    entR[2 * i] = make_int4(2 * tk.y, (2 * i) * 64, 0, 0);
+    entR[2 * i + 1] = make_int4(2 * tk.y + 1, (2 * i + 1) * 64, 0, 0);
+    const int s0 = 2 * t0 + (i - t0), s1 = s0 + nn;
+    entL[s0] = make_int4(tk.y, s0 * 64, 0, 0);
+    entL[s1] = make_int4(tk.y, s1 * 64, 0, 0);
     return;
   }
-  const int q = i - n;                       // one extra thread per chunk column: empty columns
-  const int ncc = left ? 2 * nG : nG;
-  if (q >= ncc) return;
-  const int g = left ? (q >> 1) : q;
+  const int g = i - ntasks;                    // one extra thread per group: chunk-column meta
+  if (g >= nG) return;
   const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
-  const int sa = left ? 2 * t0 + (q & 1) * nn : 2 * t0, sb = sa + (left ? nn : 2 * nn);
-  if (seidx[sa] == seidx[sb]) reinterpret_cast<int4*>(cm)[q] = make_int4(0, 0, 0, -1);
-  if (left) {
-    coltileL[q] = (sa < n) ? stoff[sa] : totals[1];
-    if (q == ncc - 1) coltileL[ncc] = totals[1];
+  if (nn > 0) {
+    const int ib0 = tasks[t0].y, ib1 = tasks[t0 + nn - 1].y;
+    colmetaR[g] = make_int4(2 * t0, 2 * nn, 2 * ib0, 2 * ib1 + 1);
+    colmetaL[2 * g] = make_int4(2 * t0, nn, ib0, ib1);
+    colmetaL[2 * g + 1] = make_int4(2 * t0 + nn, nn, ib0, ib1);
+  } else {
+    colmetaR[g] = make_int4(0, 0, 0, -1);
+    colmetaL[2 * g] = make_int4(0, 0, 0, -1);
+    colmetaL[2 * g + 1] = make_int4(0, 0, 0, -1);
   }
+  coltileL[2 * g] = 2 * t0 * 64;
+  coltileL[2 * g + 1] = (2 * t0 + nn) * 64;
+  if (g == nG - 1) coltileL[2 * nG] = 2 * ntasks * 64;
 }
 
-// left form: per inner tile K of the result (4 columns): tile count, first and last row tile
+// left form: per inner tile K of the result (4 columns): tile count, first and last row tile (after the numeric kernel)
 __global__ void __launch_bounds__(256)
 k_forms_kmeta(int nk, int nG, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
-              const unsigned long long* __restrict__ fmA, int4* __restrict__ kmeta) {
+              const int4* __restrict__ entL, int4* __restrict__ kmeta) {
   const int K = blockIdx.x * blockDim.x + threadIdx.x;
   if (K >= nk) return;
   const int g = K >> 4, c = (K >> 3) & 1, kk = K & 7;
@@ -1147,7 +826,7 @@ k_forms_kmeta(int nk, int nG, const int2* __restrict__ tasks, const int* __restr
   if (g < nG) {
     const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
     for (int b = 0; b < nn; ++b) {
-      const unsigned byte = (unsigned)(fmA[(size_t)(t0 + b) * 2 + c] >> (8 * kk)) & 0xffu;
+      const unsigned byte = (unsigned)(mask64(entL[2 * t0 + c * nn + b]) >> (8 * kk)) & 0xffu;
       if (byte) {
         const int base = tasks[t0 + b].y * 8;
         cnt += __popc(byte);
@@ -1157,66 +836,6 @@ k_forms_kmeta(int nk, int nG, const int2* __restrict__ tasks, const int* __restr
     }
   }
   kmeta[K] = (cnt > 0) ? make_int4(0, cnt, fk, lk) : make_int4(0, 0, 0, -1);
-}
-
-// one CTA per task, warp w <-> tile column 8g+w: thresholded, scaled (and shifted) values into both tile forms
-__global__ void __launch_bounds__(256)
-k_forms_fill(int nJ, int nrows, int ncols, const int2* __restrict__ tasks, const int* __restrict__ gtask_off,
-             const int* __restrict__ imin8, const int* __restrict__ nI8, const long long* __restrict__ stg_off,
-             const double* __restrict__ stg, EmitSpec es, const unsigned long long* __restrict__ fmA,
-             const unsigned long long* __restrict__ fmB, const int* __restrict__ stoffL, const int* __restrict__ stoffR,
-             double* __restrict__ tvalL, double* __restrict__ tvalR, unsigned want) {
-  const int task = blockIdx.x;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int2 tk = tasks[task];
-  const int g = tk.x, I0 = tk.y << 3, J = g * 8 + w;
-  if (J >= nJ) return;
-  const int iw0 = imin8[J], nI = nI8[J];
-  if (I0 < iw0 || I0 >= iw0 + nI) return;
-  const int wlen = nI * 8;
-  const double* src = stg + stg_off[J] * 64 + (size_t)(I0 - iw0) * 8;
-  // right form: tiles (h, jj = w, kk): rows 32h + 4kk + lane%4, column lane/4
-  if (want & WANT_RIGHT) {
-    const int c = lane >> 2, r = lane & 3, col = J * 8 + c;
-    for (int h = 0; h < 2; ++h) {
-      const unsigned long long m = fmB[(size_t)task * 2 + h];
-      unsigned byte = (unsigned)(m >> (8 * w)) & 0xffu;
-      long long t = (long long)stoffR[task * 2 + h] + popc64(m & ((1ull << (8 * w)) - 1ull));
-      while (byte) {
-        const int kk = __ffs(byte) - 1;
-        byte &= byte - 1;
-        const int lr = 32 * h + 4 * kk + r, row = I0 * 8 + lr;
-        bool keep = false;
-        double v = 0.0;
-        if (row < nrows && col < ncols) v = final_value<true>(es, src[(size_t)c * wlen + lr], row, col, keep);
-        tvalR[t * 32 + lane] = keep ? v : 0.0;
-        ++t;
-      }
-    }
-  }
-  // left form: chunk column c = w/4, inner tiles kk = 2(w%4) + ch: rows 8ii + lane/4, column 4ch + lane%4
-  if (want & WANT_LEFT) {
-    const int cch = w >> 2, r = lane >> 2, c4 = lane & 3;
-    const int t0 = gtask_off[g], nn = gtask_off[g + 1] - t0;
-    const unsigned long long m = fmA[(size_t)task * 2 + cch];
-    const int slot = 2 * t0 + cch * nn + (task - t0);
-    for (int ch = 0; ch < 2; ++ch) {
-      const int kk = 2 * (w & 3) + ch;
-      unsigned byte = (unsigned)(m >> (8 * kk)) & 0xffu;
-      long long t = (long long)stoffL[slot] + popc64(m & ((1ull << (8 * kk)) - 1ull));
-      const int lc = 4 * ch + c4, col = J * 8 + lc;
-      while (byte) {
-        const int ii = __ffs(byte) - 1;
-        byte &= byte - 1;
-        const int lr = 8 * ii + r, row = I0 * 8 + lr;
-        bool keep = false;
-        double v = 0.0;
-        if (row < nrows && col < ncols) v = final_value<true>(es, src[(size_t)lc * wlen + lr], row, col, keep);
-        tvalL[t * 32 + lane] = keep ? v : 0.0;
-        ++t;
-      }
-    }
-  }
 }
 
 // Deferred CSC entries of a product, from its right form (the kept entries of a product are exactly its non-zero
@@ -1230,15 +849,16 @@ k_right_to_csc(int ncols, CtView R, const int* __restrict__ outer, int* __restri
   const int nw = (gridDim.x * blockDim.x) >> 5;
   for (int j = gw; j < ncols; j += nw) {
     const int4 cm = R.colmeta[j >> 6];
-    const int bit = ((j >> 3) & 7) * 8 + (lane >> 2);
+    const int sh = ((j >> 3) & 7) * 8, kk = lane >> 2;            // group = tile column of j, inner tile of this lane
     const int fr = (j & 7) * 4 + (lane & 3);
     int pos = outer[j];
     const int end = outer[j + 1];
     for (int e = 0; e < cm.y; ++e) {
       const int4 en = R.ent[cm.x + e];
       const unsigned long long m = mask64(en);
+      const unsigned byte = (unsigned)(m >> sh) & 0xffu;
       double v = 0.0;
-      if ((m >> bit) & 1ull) v = R.tval[((size_t)en.y + popc64(m & ((1ull << bit) - 1ull))) * 32 + fr];
+      if ((byte >> kk) & 1u) v = R.tval[((long long)en.y + sh + __popc(byte & ((1u << kk) - 1u))) * 32 + fr];
       const bool keep = v != 0.0;
       const unsigned b = __ballot_sync(0xffffffffu, keep);
       const int p = pos + __popc(b & ((1u << lane) - 1u));
@@ -1253,7 +873,6 @@ void tile_materialize_entries(const LocalCsc<double>& M) {
   const ChunkTiles& R = M.forms->right;
   M.inner.alloc((size_t)M.nnz);
   M.val.alloc((size_t)M.nnz);
-  rt().deferred_materialized++;
   if (M.nnz == 0 || M.cols == 0) return;
   const CtView Rv{R.colmeta.get(), R.ent.get(), R.tval.get(), nullptr, R.ncc};
   DevBuf<int> bad(1);
@@ -1287,7 +906,7 @@ k_form_diff_col_abs(CtView A, CtView B, int nJ, int ncols, double alpha, double*
       const bool ta = ea.x == id, tb = eb.x == id;
       const unsigned long long wa = ta ? mask64(ea) : 0ull, wb = tb ? mask64(eb) : 0ull;
       const unsigned ma = (unsigned)(wa >> sh) & 0xffu, mb = (unsigned)(wb >> sh) & 0xffu;
-      const size_t ba = (size_t)ea.y + popc64(wa & ((1ull << sh) - 1ull)), bb = (size_t)eb.y + popc64(wb & ((1ull << sh) - 1ull));
+      const long long ba = (long long)ea.y + sh, bb = (long long)eb.y + sh;      // start of this tile column's group
       unsigned m = ma | mb;
       while (m) {
         const int kk = __ffs(m) - 1;
@@ -1362,17 +981,18 @@ bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double 
                  LocalCsc<double>& Z, double useful_products, const DiagShift* shift, unsigned want) {
   if (Xl.cols == 0 || Xl.nnz == 0 || Yl.nnz == 0 || !(thr >= 0.0)) return false;
   const ChunkTiles* A = tile_operand_form(Yl, true);
-  if (!A || (double)Yl.nnz < 0.20 * 32.0 * (double)A->ntiles) return false;   // tiles mostly padding
+  if (!A || (!A->emitted && (double)Yl.nnz < 0.20 * 32.0 * (double)A->ntiles)) return false;   // tiles mostly padding
   const ChunkTiles* B = tile_operand_form(Xl, false);
-  if (!B || (double)Xl.nnz < 0.20 * 32.0 * (double)B->ntiles) return false;
+  if (!B || (!B->emitted && (double)Xl.nnz < 0.20 * 32.0 * (double)B->ntiles)) return false;
   return spgemm_tile_core(*A, *B, Xl.cols, Yl.rows, alpha, thr, rules, Z, useful_products, shift, false, want);
 }
 
 bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncols, int nrows, double alpha, double thr,
                       const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
                       bool force, unsigned want) {
-  // entries can be deferred only when the kept entries are exactly the non-zero values (no dense-rule blocks)
-  if (!(want & WANT_CSC)) { if (rules.tbl != nullptr) want = WANT_ALL; else want |= WANT_RIGHT; }
+  // the CSC entries are produced from the right form (kept entries = non-zero values)
+  if (want & WANT_CSC) want |= WANT_RIGHT;
+  if (!(want & (WANT_LEFT | WANT_RIGHT))) want |= WANT_RIGHT;
   const ChunkTiles* A = &Aform;
   const ChunkTiles* B = &Bform;
   static const bool timing = std::getenv("NTB_TILE_TIMING") != nullptr;      // developer probe: wall time per phase
@@ -1388,36 +1008,49 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   es.sigma = shift ? shift->sigma : 0.0;
   es.dd = shift ? shift->dd : 0;
   es.ncols_diag = shift ? shift->ncols_diag : 0;
+  // ---- symbolic: row-tile window of every tile column -> 64-row blocks of every group -> task table
   DevBuf<int> imin8((size_t)nJ), nI8((size_t)nJ), gbmin((size_t)nG), gnb((size_t)nG), gtask_off((size_t)nG + 1);
-  DevBuf<long long> stg_off((size_t)nJ + 1);
   DevBuf<unsigned long long> ndmma(1);
   ndmma.zero();
   NTB_LAUNCH(k_tile_bounds, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, nJ, imin8.get(),
              nI8.get(), ndmma.get(), es.sigma != 0.0 ? 1 : 0, es.dd, es.ncols_diag, nrows);
   NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), gbmin.get(), gnb.get());
-  exclusive_scan(nI8.get(), stg_off.get(), nJ);        // staging in units of 64 doubles (8 cols x 8 rows per row tile)
   exclusive_scan(gnb.get(), gtask_off.get(), nG);
-  long long h_stg = 0;
   unsigned long long h_ndmma = 0;
   int h_tasks = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&h_stg, stg_off.get() + nJ, sizeof(long long), cudaMemcpyDeviceToHost, rt().stream));
   CUDA_CHECK(cudaMemcpyAsync(&h_ndmma, ndmma.get(), sizeof(h_ndmma), cudaMemcpyDeviceToHost, rt().stream));
   CUDA_CHECK(cudaMemcpyAsync(&h_tasks, gtask_off.get() + nG, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
   // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
   if (!force && useful_products >= 0.0 && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
+  NTB_CHECK((long long)h_tasks * 128 < (1ll << 31), "tile product: more than 2^31 tile slots in the result");
 
   const auto t1 = now();
-  DevBuf<double> stg((size_t)h_stg * 64);
+  // ---- the result's tile forms: fixed slots of 64 tiles per (task, super-tile); index known up front
+  auto forms = std::make_shared<TileForms>();
+  ChunkTiles& L = forms->left;
+  ChunkTiles& R = forms->right;
+  const bool wl = (want & WANT_LEFT) != 0, wr = (want & WANT_RIGHT) != 0;
+  const size_t ns = (size_t)max(h_tasks, 1) * 2;
+  const int nk = div_up(ncols, 4);
   DevBuf<int2> tasks((size_t)max(h_tasks, 1));
   DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
-  DevBuf<unsigned long long> fmA((size_t)max(h_tasks, 1) * 2), fmB((size_t)max(h_tasks, 1) * 2);
   cnt.zero();
   task_counter.zero();
-  fmA.zero();
-  fmB.zero();
+  L.ent.alloc(ns); R.ent.alloc(ns);
+  L.colmeta.alloc((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
+  L.kmeta.alloc((size_t)nk);
+  L.coltile.alloc((size_t)nG * 2 + 1);
+  L.ncc = div_up(ncols, 32); R.ncc = nG;
+  L.nsuper = R.nsuper = 2 * h_tasks;
+  L.ntiles = R.ntiles = (long long)h_tasks * 128;
+  L.emitted = R.emitted = true;
+  if (wl) L.tval.alloc((size_t)max(L.ntiles, 1ll) * 32);     // never read outside present tiles: no memset
+  if (wr) R.tval.alloc((size_t)max(R.ntiles, 1ll) * 32);
   if (h_tasks > 0)
     NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, gbmin.get(), gtask_off.get(), tasks.get());
+  NTB_LAUNCH(k_forms_layout, div_up(h_tasks + nG, 256), 256, 0, h_tasks, nG, tasks.get(), gtask_off.get(), L.ent.get(),
+             R.ent.get(), L.colmeta.get(), R.colmeta.get(), L.coltile.get());
   const auto t2 = now();
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (rt().profile) {
@@ -1428,105 +1061,47 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   if (h_tasks > 0) {
     // pipeline shape: 3 stages x 2 CTAs per SM (default) or 2 stages x 3 CTAs per SM (NTB_NUMERIC_SHAPE=23)
     static const int shape = [] { const char* e = std::getenv("NTB_NUMERIC_SHAPE"); return e ? std::atoi(e) : 32; }();
+    const ResultForms out{L.ent.get(), L.tval.get(), R.ent.get(), R.tval.get(), want & (WANT_LEFT | WANT_RIGHT)};
     auto launch = [&](auto kern, int nstage, int per_sm) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem(nstage)));
-        attr_set = true;
-      }
-      NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem(nstage), Av, Bv, nJ, imin8.get(),
-                 nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
-                 reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
-    };
-    static const int ver = [] { const char* e = std::getenv("NTB_NUMERIC_VER"); return e ? std::atoi(e) : 9; }();
-    auto launch9 = [&](auto kern, int nstage, int per_sm) {
       static bool attr_set = false;
       if (!attr_set) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem9(nstage)));
         attr_set = true;
       }
-      NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, imin8.get(),
-                 nI8.get(), stg_off.get(), tasks.get(), h_tasks, task_counter.get(), stg.get(), cnt.get(),
-                 reinterpret_cast<unsigned char*>(fmA.get()), reinterpret_cast<unsigned char*>(fmB.get()), nrows, ncols, es);
+      NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, gtask_off.get(),
+                 tasks.get(), h_tasks, task_counter.get(), cnt.get(), out, nrows, ncols, es);
     };
-    if (ver == 9 && shape == 23) launch9(k_tile_numeric9<2, 3>, 2, 3);
-    else if (ver == 9) launch9(k_tile_numeric9<NSTAGE_DEFAULT, 2>, NSTAGE_DEFAULT, 2);
-    else if (shape == 23) launch(k_tile_numeric<2, 3>, 2, 3);
-    else launch(k_tile_numeric<NSTAGE_DEFAULT, 2>, NSTAGE_DEFAULT, 2);
+    if (shape == 23) launch(k_tile_numeric9<2, 3>, 2, 3);
+    else launch(k_tile_numeric9<NSTAGE_DEFAULT, 2>, NSTAGE_DEFAULT, 2);
   }
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
     rt().prof_events.emplace_back(ev0, ev1);
   }
   const auto t3 = now();
-  // ---- CSC of the result
-  const int egrid = max(1, min(div_up((long long)ncols * 32, 256), kNumSMs * 16));
+  // ---- outer index of the result (kept-entry counts came from the numeric kernel); per-K meta of the left form
   Z.rows = nrows; Z.cols = ncols;
   Z.outer.alloc((size_t)ncols + 1);
   exclusive_scan(cnt.get(), Z.outer.get(), ncols);
-  // ---- index of the result's tile forms (same read-back as the entry count)
-  auto forms = std::make_shared<TileForms>();
-  ChunkTiles& L = forms->left;
-  ChunkTiles& R = forms->right;
-  DevBuf<int> seidxL, seidxR, stoffL, stoffR, totals(4);
-  const int nk = div_up(ncols, 4);
-  if (h_tasks > 0) {
-    const size_t ns = (size_t)h_tasks * 2;
-    L.ent.alloc(ns); R.ent.alloc(ns);
-    L.colmeta.alloc((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
-    L.kmeta.alloc((size_t)nk);
-    L.coltile.alloc((size_t)nG * 2 + 1);
-    seidxL.alloc(ns + 1); seidxR.alloc(ns + 1); stoffL.alloc(ns); stoffR.alloc(ns);
-    DevBuf<unsigned long long> smaskL(ns), smaskR(ns);
-    NTB_LAUNCH(k_forms_slots, dim3(div_up((long long)ns, 256), 2), 256, 0, h_tasks, tasks.get(), gtask_off.get(), fmA.get(),
-               fmB.get(), smaskL.get(), smaskR.get());
-    NTB_LAUNCH(k_forms_scan, 2, FI_T, 0, h_tasks, smaskL.get(), smaskR.get(), seidxL.get(), seidxR.get(), stoffL.get(),
-               stoffR.get(), totals.get());
-    NTB_LAUNCH(k_forms_write, dim3(div_up((long long)ns + 2 * nG, 256), 2), 256, 0, h_tasks, nG, tasks.get(), gtask_off.get(),
-               fmA.get(), fmB.get(), seidxL.get(), seidxR.get(), stoffL.get(), stoffR.get(), L.ent.get(), R.ent.get(),
-               L.colmeta.get(), R.colmeta.get(), L.coltile.get(), totals.get());
-    NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), fmA.get(), L.kmeta.get());
-  } else {
-    totals.zero();
-  }
-  int h_nnz = 0, h_tot[4] = {0, 0, 0, 0};
+  if (wl) NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), L.ent.get(), L.kmeta.get());
+  int h_nnz = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_nnz, Z.outer.get() + ncols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-  CUDA_CHECK(cudaMemcpyAsync(h_tot, totals.get(), sizeof(h_tot), cudaMemcpyDeviceToHost, rt().stream));
   stream_sync();
   const auto t4 = now();
-  const bool with_forms = h_tasks > 0 && h_nnz > 0;
-  const bool defer = with_forms && !(want & WANT_CSC);
-  if (defer) {
-    Z.alloc_entries(0);
-    Z.nnz = h_nnz;                             // inner/val are filled from the right form on first use
-  } else {
-    Z.alloc_entries(h_nnz);
-    if (h_nnz > 0)
-      NTB_LAUNCH(k_tile_emit, egrid, 256, 0, ncols, nrows, imin8.get(), nI8.get(), stg_off.get(), stg.get(), es,
-                 Z.outer.get(), Z.inner.get(), Z.val.get());
+  Z.alloc_entries(0);
+  Z.nnz = h_nnz;
+  forms->has_left = wl ? 1 : 0;                // a form that was not asked for is rebuilt from CSC if it is ever needed
+  forms->has_right = wr ? 1 : 0;
+  Z.forms = forms;
+  if (h_nnz > 0) {
+    if (want & WANT_CSC) tile_materialize_entries(Z);        // inner/val from the right form right away ...
+    else { Z.deferred = true; rt().deferred_products++; }    // ... or on first use
   }
   const auto t5 = now();
-  if (with_forms) {
-    L.ncc = div_up(ncols, 32); L.nsuper = h_tot[0]; L.ntiles = h_tot[1];
-    R.ncc = nG; R.nsuper = h_tot[2]; R.ntiles = h_tot[3];
-    const bool wl = (want & WANT_LEFT) != 0, wr = (want & WANT_RIGHT) != 0;
-    if (wl) L.tval.alloc((size_t)L.ntiles * 32);
-    if (wr) R.tval.alloc((size_t)R.ntiles * 32);
-    if (wl || wr)
-      NTB_LAUNCH(k_forms_fill, h_tasks, 256, 0, nJ, nrows, ncols, tasks.get(), gtask_off.get(), imin8.get(), nI8.get(),
-                 stg_off.get(), stg.get(), es, fmA.get(), fmB.get(), stoffL.get(), stoffR.get(), L.tval.get(), R.tval.get(),
-                 want);
-    forms->has_left = wl ? 1 : 0;              // a form that was not asked for is rebuilt from CSC if it is ever needed
-    forms->has_right = wr ? 1 : 0;
-    Z.forms = forms;
-    Z.deferred = defer;
-  }
-  const auto t6 = now();
   if (timing)
-    std::fprintf(stderr, "[tile] bounds %.3f  alloc+tasks %.3f  numeric %.3f  index %.3f  emit %.3f  fill %.3f ms  (tasks %d, stg %.0f MB, nnz %d)\n",
-                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), ms(t5, t6), h_tasks, (double)h_stg * 512.0 / 1e6, h_nnz);
+    std::fprintf(stderr, "[tile] bounds %.3f  layout %.3f  numeric %.3f  index %.3f  csc %.3f ms  (tasks %d, nnz %d)\n",
+                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), h_tasks, h_nnz);
   rt().tile_products++;
-  if (Z.deferred) rt().deferred_products++;
   rt().dmma_issued += (double)h_ndmma;
   return true;
 }
