@@ -755,28 +755,40 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
     tl = ct[(size_t)p * (nccl + 1) + a];
     th = ct[(size_t)p * (nccl + 1) + b];
   };
+  // The rank's own tiles are used where they are; only the tiles received from the peers go into a new buffer. Both
+  // are addressed through ONE base pointer (the own form's): a received tile gets the index
+  // (halo buffer - own buffer) / 256 B + its position, which fits an int on any single device.
   std::vector<LeftPiece> pieces(C);
-  long long total_tiles = 0;
+  long long halo_tiles = 0, total_tiles = 0;
   for (int p = 0; p < C; ++p) {
     int a, b, tl, th;
     run_of((int)mine.qlo, (int)mine.qhi, p, a, b, tl, th);
-    pieces[p] = LeftPiece{ent_base[p], nccl, a, b, tl, (int)total_tiles, (int)rec[p].nsuper};
     total_tiles += th - tl;
+    if (p != me) halo_tiles += th - tl;
   }
-  NTB_CHECK(total_tiles < (1ll << 26), "halo of the left operand exceeds 2^26 tiles");
+  NTB_CHECK(halo_tiles < (1ll << 26), "halo of the left operand exceeds 2^26 tiles");
   G.ntiles = total_tiles;
-  G.tval.alloc((size_t)std::max(total_tiles, 1ll) * 32);
+  G.tval.alloc((size_t)std::max(halo_tiles, 1ll) * 32);
+  G.tval_view = Lf->tval.get();
+  const long long halo_origin = (G.tval.get() - Lf->tval.get()) / 32;      // in tiles; blocks are at least 512-byte aligned
+  NTB_CHECK((G.tval.get() - Lf->tval.get()) % 32 == 0 && std::llabs(halo_origin) < (1ll << 30), "halo buffer not addressable from the own form");
+  {
+    long long at = 0;
+    for (int p = 0; p < C; ++p) {
+      int a, b, tl, th;
+      run_of((int)mine.qlo, (int)mine.qhi, p, a, b, tl, th);
+      const int base = (p == me) ? tl : (int)(halo_origin + at);
+      pieces[p] = LeftPiece{ent_base[p], nccl, a, b, tl, base, (int)rec[p].nsuper};
+      if (p != me) at += th - tl;
+    }
+  }
   comm_group_start();
   for (int p = 0; p < C; ++p) {
+    if (p == me) continue;
     int a, b, tl, th;
     run_of((int)mine.qlo, (int)mine.qhi, p, a, b, tl, th);                        // what I take from p
     const size_t rbytes = (size_t)(th - tl) * 256;
-    if (p == me) {
-      if (rbytes) CUDA_CHECK(cudaMemcpyAsync(G.tval.get() + (size_t)pieces[p].recv_base * 32, Lf->tval.get() + (size_t)tl * 32,
-                                             rbytes, cudaMemcpyDeviceToDevice, rt().stream));
-      continue;
-    }
-    if (rbytes) comm_recv_bytes(g.row, G.tval.get() + (size_t)pieces[p].recv_base * 32, rbytes, p);
+    if (rbytes) comm_recv_bytes(g.row, G.tval.get() + ((long long)pieces[p].recv_base - halo_origin) * 32, rbytes, p);
     run_of((int)rec[p].qlo, (int)rec[p].qhi, me, a, b, tl, th);                   // what p takes from me
     const size_t sbytes = (size_t)(th - tl) * 256;
     if (sbytes) comm_send_bytes(g.row, Lf->tval.get() + (size_t)tl * 32, sbytes, p);
@@ -793,7 +805,7 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   const auto t5 = now();
   if (timing && me == 0)
     std::fprintf(stderr, "[halo] records %.3f  index gather %.3f  tiles %.3f (%.1f MB)  flops %.3f  product %.3f ms\n",
-                 ms(t0, t1), ms(t1, t2), ms(t2, t3), (double)total_tiles * 256.0 / 1e6, ms(t3, t4), ms(t4, t5));
+                 ms(t0, t1), ms(t1, t2), ms(t2, t3), (double)halo_tiles * 256.0 / 1e6, ms(t3, t4), ms(t4, t5));
   NTB_CHECK(done, "forced tile product declined");
   st.flops = count ? 2.0 * useful : 0.0;
   st.shift_applied = ds && ds->sigma != 0.0;
@@ -806,7 +818,7 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   }
   rt().alg_bytes += a_bytes + (double)Bl.bytes() + (double)out.bytes();
   rt().halo_products++;
-  rt().halo_bytes += (double)total_tiles * 256.0;
+  rt().halo_bytes += (double)halo_tiles * 256.0;
   return true;
 }
 

@@ -292,11 +292,15 @@ __device__ __forceinline__ double final_value(const EmitSpec& e, double v, int r
   return sv;
 }
 
-// out-of-line: keeps the (rare) rule-table / shifted-diagonal test out of the numeric kernel's hot code
-__device__ __noinline__ bool keep_general(const EmitSpec& e, double v, int row, int col) {
+// out-of-line (keeps the rare rule-table test out of the numeric kernel's hot code): the result entry, or 0 when there
+// is none. (An entry that is kept with the value 0 - only possible under the dense-block rule with alpha*v
+// underflowing - does not exist for the tile forms: kept <=> non-zero.)
+// By value and without reference arguments on purpose: anything whose address is taken here lives in local memory and
+// is re-loaded in the hot epilogue (a long-scoreboard stall per row tile in the ncu source view).
+__device__ __noinline__ double value_general(EmitSpec e, double v, int row, int col) {
   bool keep;
-  (void)final_value<true>(e, v, row, col, keep);
-  return keep;
+  const double sv = final_value<true>(e, v, row, col, keep);
+  return keep ? sv : 0.0;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -304,10 +308,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// ... and the value itself (result entry, or 0 with keep = false)
-__device__ __noinline__ double value_general(const EmitSpec& e, double v, int row, int col, bool& keep) {
-  return final_value<true>(e, v, row, col, keep);
-}
 // ---- mbarrier + bulk-copy (TMA, 1-D) primitives; SASS: SYNCS.*, UBLKCP.S.G
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -563,7 +563,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
           }
           __syncwarp();
           if (++st == NSTAGE) { st = 0; ph ^= 1u; }
-          if (!done) advance();
+          if (!done) { advance(); advance(); }                 // two links per stage: the L2 prefetch of the next task goes out early
         }
       }
       if (done) break;
@@ -705,8 +705,8 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
             if (in1 && row == j0 + 1 + es.dd && j0 + 1 < es.ncols_diag) { f1 += es.sigma; k1 = f1 != 0.0; }
           }
         } else {
-          if (in0) f0 = value_general(es, v0, row, j0, k0);
-          if (in1) f1 = value_general(es, v1, row, j0 + 1, k1);
+          if (in0) { f0 = value_general(es, v0, row, j0); k0 = f0 != 0.0; }
+          if (in1) { f1 = value_general(es, v1, row, j0 + 1); k1 = f1 != 0.0; }
         }
       }
       acc[ii][0] = k0 ? f0 : 0.0;
@@ -1001,7 +1001,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
     return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto t0 = now();
   const int nJ = div_up(ncols, 8), nG = B->ncc;
-  const CtView Av{A->colmeta.get(), A->ent.get(), A->tval.get(), A->kmeta.get(), A->ncc};
+  const CtView Av{A->colmeta.get(), A->ent.get(), A->tval_view ? A->tval_view : A->tval.get(), A->kmeta.get(), A->ncc};
   const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc};
   EmitSpec es;
   es.alpha = alpha; es.thr = thr; es.rules = rules;

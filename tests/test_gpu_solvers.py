@@ -208,3 +208,53 @@ def test_trs4_block_sparse_tile_path(nt, oracle):
     assert rec["loop_counter"] == info.iterations
     assert e == pytest.approx(info.energy, rel=1e-8)
     compare_sparse(K.to_scipy(), Kref.to_scipy(), thr, tol=1e-7)
+
+
+# ---- full-size style checks through size-independent properties (the oracle does not finish these in seconds) -------
+def test_sign_function_c4_shape_properties(nt):
+    """config-4 matrix at N=32768 (one eighth of the bench size; the whole iteration runs in tile space):
+    sign(M)^2 = I, sign(M) symmetric, integer trace (= #positive - #negative eigenvalues), entries read back once"""
+    from ntpoly_b200.workloads import banded_sign_input
+    n, thr = 32768, 1e-6
+    m = banded_sign_input(n)
+    M, S, I, P = to_gpu(nt, m), nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    I.FillIdentity()
+    nt.reset_counters()
+    nt.SignSolvers.ComputeSign(M, S, params(nt, 1e-5, thr))
+    rec = nt.last_solve()
+    assert 3 <= rec["loop_counter"] <= 40
+    dc = nt.deferred_counters()
+    assert dc["products"] >= 2 * rec["loop_counter"] - 1 and dc["materialized"] == 0, dc   # nothing left tile space
+    assert nt.tile_counters()["tile_products"] == 2 * rec["loop_counter"]
+    tr = S.Trace()                                                  # first read of the entries
+    assert nt.deferred_counters()["materialized"] == 1
+    assert abs(tr - round(tr)) < 1e-2 and abs(tr) < n
+    assert S.MeasureAsymmetry() < 5e-3                              # thresholded products are not symmetric to the bit
+    P.Gemm(S, S, None, threshold=thr)
+    P.Increment(I, -1.0)
+    assert P.Norm() < 1e-3
+
+
+def test_trs4_c3_shape_properties(nt):
+    """config-3 matrix (32x32 dense blocks, block band) at N=8192: TRS4 density is idempotent, has the requested
+    trace and commutes with H"""
+    from ntpoly_b200.workloads import block_sparse
+    n, thr, nel = 8192, 1e-6, 4096
+    # gapped (alternating on-site energies), so that the density matrix is well defined and stays block-sparse
+    h = block_sparse(n, neighbours=12, band_blocks=24) * 0.3
+    h = sp.csc_matrix(h + sp.diags(np.where(np.arange(n) % 2 == 0, 0.5, -0.5)))
+    H, ISQ, K, K2, C1, C2 = (to_gpu(nt, h), nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n), nt.Matrix_ps(n),
+                             nt.Matrix_ps(n))
+    ISQ.FillIdentity()
+    nt.reset_counters()
+    e, mu = nt.DensityMatrixSolvers.TRS4(H, ISQ, nel, K, params(nt, 1e-6, thr))
+    assert nt.tile_counters()["tile_products"] > 0
+    assert K.Trace() == pytest.approx(nel, abs=1e-2)                # the requested trace
+    K2.Gemm(K, K, None, threshold=thr)
+    K2.Increment(K, -1.0)
+    assert K2.Norm() < 1e-2                                         # idempotent
+    C1.Gemm(K, H, None, threshold=thr)
+    C2.Gemm(H, K, None, threshold=thr)
+    C1.Increment(C2, -1.0)
+    assert C1.Norm() < 1e-2                                         # [K, H] = 0
+    assert e == pytest.approx(K.Dot(H), rel=1e-5)                   # E = Tr(K H) (identity overlap)
