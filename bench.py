@@ -34,7 +34,7 @@ UNIT = "GFLOP/s"
 GRIDS = {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 4, 1), 8: (1, 8, 1)}   # column split: tile halo exchange, no panel gather
 ALPHA_MAX = 1.69770248526
 FP64_PEAK_TFLOPS = 37.2          # DMMA.8x8x4 issue peak measured on this pool's B200 (scripts/micro/dmma_shapes.cu)
-TRAFFIC_PER_LAUNCH = 1.69e9       # dram read+write bytes of one numeric launch, ncu --set full (profiles/r01_prof_tile_numeric_bench.keys.txt)
+TRAFFIC_PER_LAUNCH = 1.531e9      # dram read+write bytes per numeric launch, mean of the step's two products, ncu --set full (profiles/r01d_numeric.keys.txt)
 
 
 def workload_name(n, thr, iterate):
@@ -345,7 +345,7 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (prof["numeric_ms"] * 1e-3) / 1e9 if prof["numeric_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": TRAFFIC_PER_LAUNCH, "kernel": "k_tile_numeric (numeric SpGEMM, one launch per product)",
+                "traffic": TRAFFIC_PER_LAUNCH, "kernel": "k_tile_numeric9 (numeric SpGEMM incl. threshold and tile-form output, one launch per product)",
                 "launches_timed": prof["products"], "peak_source": peak_src,
                 "numeric_share_of_step": prof["numeric_ms"] / (ms_total if world == 1 else float(t[0])),
                 "fp64_tflops_useful": flops_local / (prof["numeric_ms"] * 1e-3) / 1e12 if prof["numeric_ms"] > 0 else 0.0,

@@ -219,7 +219,8 @@ void ntb_set_tile_path(int on);
 void ntb_set_fused_shift(int on);
 /* CSC -> tile-form conversions since the last reset (0 per product once operands carry their tile forms) */
 double ntb_tile_builds(void);
-/* distributed products whose left operand was fetched as a tile halo (1 x C x 1 grids): {count, tile bytes} */
+/* distributed products whose left operand was fetched as a tile halo (1 x C x 1 grids): {count, tile bytes received
+ * from the peers (the rank's own tiles are used in place)} */
 void ntb_get_halo_counters(double *out2);
 /* 1 (default): column-split grids use the tile halo exchange; 0: always the reference-style CSC panel gather */
 void ntb_set_halo_path(int on);

@@ -19,7 +19,7 @@ struct Runtime {
   unsigned long long tile_products = 0;  // local products that ran on the DMMA tile path
   unsigned long long tile_builds = 0;    // CSC -> tile-form conversions (0 per product once operands carry their forms)
   unsigned long long halo_products = 0;  // distributed products that fetched the left operand as a tile halo
-  double halo_bytes = 0.0;               // tile bytes of those halos (own part included)
+  double halo_bytes = 0.0;               // tile bytes received from the peers for those halos
   double dmma_issued = 0.0;              // DMMA.8x8x4 instructions (x256 FMAs) issued by the tile path
   unsigned long long deferred_products = 0;      // tile products emitted without CSC entries (outer + right form only)
   unsigned long long deferred_materialized = 0; // ... whose entries had to be produced later after all
