@@ -20,10 +20,11 @@ struct ChunkTiles {
   DevBuf<int4> kmeta;                        // left form only: per inner tile K {0, tile count, first row tile, last row tile}
   DevBuf<int> coltile;                       // left form only: [ncc+1] first tile of every chunk column (halo exchange)
   bool emitted = false;                      // written by a product (fixed 64-tile slots), not built from CSC
-  // tile indices of `ent` are relative to this address when set (a gathered left form addresses the rank's own tiles
-  // in place and the received halo tiles in `tval` through one base pointer)
+  // a gathered left form (halo exchange) addresses the rank's own tiles in place: tile indices below HALO_TILE_BIAS
+  // are relative to tval_view (the own form's tiles), indices from HALO_TILE_BIAS on to `tval` (the received tiles)
   const double* tval_view = nullptr;
 };
+constexpr long long HALO_TILE_BIAS = 1ll << 30;
 // Both forms of one matrix, built on first use as a product operand or emitted together with a product's result.
 // Immutable once built, so copies of a matrix share them; any change of the entries drops them.
 struct TileForms {

@@ -755,9 +755,8 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
     tl = ct[(size_t)p * (nccl + 1) + a];
     th = ct[(size_t)p * (nccl + 1) + b];
   };
-  // The rank's own tiles are used where they are; only the tiles received from the peers go into a new buffer. Both
-  // are addressed through ONE base pointer (the own form's): a received tile gets the index
-  // (halo buffer - own buffer) / 256 B + its position, which fits an int on any single device.
+  // The rank's own tiles are used where they are; only the tiles received from the peers go into a new buffer, which
+  // the entries address with indices from HALO_TILE_BIAS on (csc.cuh).
   std::vector<LeftPiece> pieces(C);
   long long halo_tiles = 0, total_tiles = 0;
   for (int p = 0; p < C; ++p) {
@@ -766,12 +765,11 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
     total_tiles += th - tl;
     if (p != me) halo_tiles += th - tl;
   }
-  NTB_CHECK(halo_tiles < (1ll << 26), "halo of the left operand exceeds 2^26 tiles");
+  NTB_CHECK(halo_tiles < (1ll << 26) && Lf->ntiles < HALO_TILE_BIAS - 64, "left operand too large for the halo exchange");
   G.ntiles = total_tiles;
   G.tval.alloc((size_t)std::max(halo_tiles, 1ll) * 32);
   G.tval_view = Lf->tval.get();
-  const long long halo_origin = (G.tval.get() - Lf->tval.get()) / 32;      // in tiles; blocks are at least 512-byte aligned
-  NTB_CHECK((G.tval.get() - Lf->tval.get()) % 32 == 0 && std::llabs(halo_origin) < (1ll << 30), "halo buffer not addressable from the own form");
+  const long long halo_origin = HALO_TILE_BIAS;
   {
     long long at = 0;
     for (int p = 0; p < C; ++p) {

@@ -35,7 +35,11 @@ constexpr int IPL = MAXR / 32;               // bitmap words owned by a lane
 
 struct CtView {
   const int4* colmeta; const int4* ent; const double* tval; const int4* kmeta; int ncc;
+  const double* tval2;   // tiles with index >= HALO_TILE_BIAS (minus the slack of a virtual origin) live here (halo buffer)
 };
+__device__ __forceinline__ const double* tile_ptr(const CtView& V, long long tile) {
+  return (tile >= HALO_TILE_BIAS - 64) ? V.tval2 + (tile - HALO_TILE_BIAS) * 32 : V.tval + tile * 32;
+}
 
 // A: super-tile id = row/64, bit = ((col%32)/4)*8 + (row/8)%8, fragment lane = (row%8)*4 + col%4
 // B: super-tile id = row/32, bit = ((col%64)/8)*8 + (row/4)%8, fragment lane = (col%8)*4 + row%4
@@ -482,7 +486,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
           // consumed, so that their bulk copies find them there (the DMMA warps were waiting 12 % of their time for
           // a full barrier, i.e. for HBM latency at the short band-edge stages)
           if (mA_n != 0ull) {
-            bulk_prefetch_l2(A.tval + ((long long)offA_n + 8 * first_group(mA_n)) * 32, (unsigned)span_tiles(mA_n) * 256u);
+            bulk_prefetch_l2(tile_ptr(A, (long long)offA_n + 8 * first_group(mA_n)), (unsigned)span_tiles(mA_n) * 256u);
             bulk_prefetch_l2(B.tval + ((long long)offB_n + 8 * first_group(mB_n)) * 32, (unsigned)span_tiles(mB_n) * 256u);
           }
           break;
@@ -558,7 +562,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
             const unsigned bA = (unsigned)span_tiles(sA) * 256u, bB = (unsigned)span_tiles(sB) * 256u;
             mbar_arrive_expect_tx(bar0 + 8 * st, bA + bB);
             const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
-            if (bA) bulk_g2s(slab_s, A.tval + ((long long)oA + 8 * gfA) * 32, bA, bar0 + 8 * st);
+            if (bA) bulk_g2s(slab_s, tile_ptr(A, (long long)oA + 8 * gfA), bA, bar0 + 8 * st);
             if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + ((long long)oB + 8 * gfB) * 32, bB, bar0 + 8 * st);
           }
           __syncwarp();
@@ -874,7 +878,7 @@ void tile_materialize_entries(const LocalCsc<double>& M) {
   M.inner.alloc((size_t)M.nnz);
   M.val.alloc((size_t)M.nnz);
   if (M.nnz == 0 || M.cols == 0) return;
-  const CtView Rv{R.colmeta.get(), R.ent.get(), R.tval.get(), nullptr, R.ncc};
+  const CtView Rv{R.colmeta.get(), R.ent.get(), R.tval.get(), nullptr, R.ncc, nullptr};
   DevBuf<int> bad(1);
   bad.zero();
   NTB_LAUNCH(k_right_to_csc, max(1, min(div_up((long long)M.cols * 32, 256), kNumSMs * 16)), 256, 0, M.cols, Rv,
@@ -931,8 +935,8 @@ bool tile_diff_col_abs_sums(const LocalCsc<double>& A, const LocalCsc<double>& B
   const ChunkTiles& Ra = A.forms->right;
   const ChunkTiles& Rb = B.forms->right;
   if (A.cols != B.cols || A.rows != B.rows || Ra.ncc != Rb.ncc || A.cols == 0) return false;
-  const CtView Av{Ra.colmeta.get(), Ra.ent.get(), Ra.tval.get(), nullptr, Ra.ncc};
-  const CtView Bv{Rb.colmeta.get(), Rb.ent.get(), Rb.tval.get(), nullptr, Rb.ncc};
+  const CtView Av{Ra.colmeta.get(), Ra.ent.get(), Ra.tval.get(), nullptr, Ra.ncc, nullptr};
+  const CtView Bv{Rb.colmeta.get(), Rb.ent.get(), Rb.tval.get(), nullptr, Rb.ncc, nullptr};
   const int nJ = div_up(A.cols, 8);
   NTB_LAUNCH(k_form_diff_col_abs, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, nJ, A.cols,
              alpha, d_colsum);
@@ -1001,8 +1005,9 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
     return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto t0 = now();
   const int nJ = div_up(ncols, 8), nG = B->ncc;
-  const CtView Av{A->colmeta.get(), A->ent.get(), A->tval_view ? A->tval_view : A->tval.get(), A->kmeta.get(), A->ncc};
-  const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc};
+  const CtView Av{A->colmeta.get(), A->ent.get(), A->tval_view ? A->tval_view : A->tval.get(), A->kmeta.get(), A->ncc,
+                  A->tval_view ? A->tval.get() : nullptr};
+  const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc, nullptr};
   EmitSpec es;
   es.alpha = alpha; es.thr = thr; es.rules = rules;
   es.sigma = shift ? shift->sigma : 0.0;
