@@ -193,6 +193,11 @@ void ntb_FillMatrixFromArrays_ps(int *ih_this, long long n, const int *rows, con
                                  const double *vals, int is_complex_interleaved);
 long long ntb_GetMatrixLocalSize_ps(const int *ih_this);
 void ntb_GetMatrixArrays_ps(const int *ih_this, int *rows, int *cols, double *vals);
+/* The same for a real matrix without waiting for the device-to-host copies (they run on a second stream and overlap
+ * whatever is enqueued next, e.g. the ingest of the next matrix); returns the local entry count. The host arrays
+ * (pinned memory, or the copies serialise) are complete after ntb_EgressWait(). */
+long long ntb_GetMatrixArraysAsync_ps(const int *ih_this, int *rows, int *cols, double *vals);
+void ntb_EgressWait(void);
 void ntb_ConstructEmptyMatrixComplex_ps(int *ih_this, const int *matrix_dim, const int *is_complex);
 int ntb_MatrixIsComplex_ps(const int *ih_this);
 void ntb_FilterMatrix_ps(int *ih_this, const double *threshold);

@@ -59,7 +59,7 @@ PolarDecomposition_wrp Invert_wrp SquareRoot_wrp InverseSquareRoot_wrp ComputeEx
 PowerBounds_wrp
 ntb_nccl_unique_id ntb_world_init ntb_world_rank ntb_world_size ntb_set_stream ntb_synchronize
 ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletList_c_get
-ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_ConstructEmptyMatrixComplex_ps
+ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
 ntb_set_fused_shift ntb_get_halo_counters ntb_set_halo_path ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
@@ -82,6 +82,7 @@ def lib():
         L.MeasureAsymmetry_ps_wrp.restype = c_double
         L.GetGlobalIsRoot_wrp.restype = c_bool
         L.ntb_GetMatrixLocalSize_ps.restype = c_longlong
+        L.ntb_GetMatrixArraysAsync_ps.restype = c_longlong
         L.ntb_MatrixAlgorithmicBytes_ps.restype = c_longlong
         L.ntb_version.restype = c_char_p
         L.ntb_algorithmic_bytes.restype = c_double
@@ -542,6 +543,13 @@ class Matrix_ps:
                                          vals.view(np.float64).ctypes.data_as(POINTER(c_double)))
         return rows, cols, vals
 
+    def get_arrays_async(self, out):
+        """real matrices: like get_arrays(out=...) but the device-to-host copies run on a second stream; the (pinned)
+        buffers are complete after egress_wait()"""
+        n = int(lib().ntb_GetMatrixArraysAsync_ps(self.ih, _ip(out[0]), _ip(out[1]),
+                                                  out[2].ctypes.data_as(POINTER(c_double))))
+        return tuple(a[:n] for a in out)
+
     def fill_from_scipy(self, m):
         import scipy.sparse as sp
         m = sp.coo_matrix(m)
@@ -722,6 +730,10 @@ def deferred_counters():
     out = (c_double * 2)()
     lib().ntb_get_deferred_counters(out)
     return {"products": int(out[0]), "materialized": int(out[1])}
+
+
+def egress_wait():
+    lib().ntb_EgressWait()
 
 
 def algorithmic_bytes():

@@ -362,6 +362,10 @@ void ntb_GetMatrixArrays_ps(const int* ih, int* rows, int* cols, double* vals) {
   if (M.is_complex) mat_get_triplets(M, rows, cols, nullptr, reinterpret_cast<cplx*>(vals));
   else mat_get_triplets(M, rows, cols, vals, nullptr);
 }
+long long ntb_GetMatrixArraysAsync_ps(const int* ih, int* rows, int* cols, double* vals) {
+  return mat_get_triplets_async(*get<Matrix>(ih), rows, cols, vals);
+}
+void ntb_EgressWait(void) { mat_egress_wait(); }
 void ntb_ConstructEmptyMatrixComplex_ps(int* ih, const int* n, const int* is_complex) { auto* M = new Matrix(); mat_construct_empty(*M, *n, nullptr, *is_complex != 0); put(ih, M); }
 int ntb_MatrixIsComplex_ps(const int* ih) { return get<Matrix>(ih)->is_complex ? 1 : 0; }
 void ntb_FilterMatrix_ps(int* ih, const double* thr) { mat_filter(*get<Matrix>(ih), *thr); }

@@ -373,6 +373,43 @@ long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r
   return nnz;
 }
 
+// ---- asynchronous egress: the device side (entries -> global triplets) runs on the library stream, the device-to-host
+// copies on a second stream behind an event, so they overlap whatever the caller enqueues next (e.g. the host-to-device
+// copy of the next input: PCIe is full duplex). The staged device arrays live until mat_egress_wait().
+namespace {
+struct PendingEgress { DevBuf<int> row, col; DevBuf<double> val; };
+std::vector<PendingEgress> g_pending_egress;
+cudaStream_t g_copy_stream = nullptr;
+cudaEvent_t g_egress_ready = nullptr;
+}  // namespace
+long long mat_get_triplets_async(const Matrix& M, int* rows, int* cols, double* vals_r) {
+  NTB_CHECK(!M.is_complex, "asynchronous egress: real matrices only");
+  const long long nnz = M.local_nnz();
+  if (nnz == 0) return 0;
+  if (!g_copy_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_egress_ready, cudaEventDisableTiming));
+  }
+  PendingEgress pe;
+  pe.row.alloc((size_t)nnz); pe.col.alloc((size_t)nnz); pe.val.alloc((size_t)nnz);
+  const CscView<double> v = M.r.view();
+  csc_to_device_triplets<double>(v, nnz, pe.row.get(), pe.col.get());
+  NTB_LAUNCH(k_add_const2, std::min(div_up(nnz, 256), kNumSMs * 16), 256, 0, pe.row.get(), pe.col.get(), nnz, M.start_row + 1,
+             M.start_col + 1);
+  d2d(pe.val.get(), v.val, (size_t)nnz);       // the matrix may be overwritten before the copy has run
+  CUDA_CHECK(cudaEventRecord(g_egress_ready, rt().stream));
+  CUDA_CHECK(cudaStreamWaitEvent(g_copy_stream, g_egress_ready, 0));
+  CUDA_CHECK(cudaMemcpyAsync(rows, pe.row.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, g_copy_stream));
+  CUDA_CHECK(cudaMemcpyAsync(cols, pe.col.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, g_copy_stream));
+  CUDA_CHECK(cudaMemcpyAsync(vals_r, pe.val.get(), nnz * sizeof(double), cudaMemcpyDeviceToHost, g_copy_stream));
+  g_pending_egress.push_back(std::move(pe));
+  return nnz;
+}
+void mat_egress_wait() {
+  if (g_copy_stream) CUDA_CHECK(cudaStreamSynchronize(g_copy_stream));
+  g_pending_egress.clear();                    // blocks go back to the arena only now
+}
+
 void mat_fill_identity(Matrix& M) {
   // distributed_includes/FillMatrixIdentity.f90:9-22: only indices <= actual dimension
   std::vector<int> rows, cols;

@@ -76,6 +76,9 @@ void mat_fill_from_triplets(Matrix& M, const int* rows, const int* cols, const d
                             const cplx* vals_c, long long n, bool preduplicated, bool prepartitioned);
 // local block as global 1-based triplets, column-major order. Call with nullptrs to get the count.
 long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r, cplx* vals_c);
+// the same for a real matrix without waiting: host buffers (pinned) are complete after mat_egress_wait()
+long long mat_get_triplets_async(const Matrix& M, int* rows, int* cols, double* vals_r);
+void mat_egress_wait();
 void mat_transpose(const Matrix& A, Matrix& out);
 void mat_conjugate(Matrix& M);
 void mat_to_complex(const Matrix& in, Matrix& out);
