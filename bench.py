@@ -162,6 +162,8 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all host cores (torchrun exports OMP_NUM_THREADS=1 to its workers; the OpenMP runtime has not been loaded yet)
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("BENCH_CPU_THREADS", str(os.cpu_count() or 1))
     n = args.cpu_n
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 3))
     r = run_cpu(n, args.threshold, args.iterate, steps, warmup)
