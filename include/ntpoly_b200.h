@@ -80,6 +80,10 @@ void GetTripletAt_c_wrp(const int *ih_this, const int *index, int *index_column,
                         double *point_value_real, double *point_value_imag);
 void DestructTripletList_c_wrp(int *ih_this);
 int GetTripletListSize_c_wrp(const int *ih_this);
+/* sorted copy (by column, then row). Argument list of the Fortran binding (TripletListModule_wrp.F90:135-151);
+ * the reference's C header declares one size argument fewer than the shim takes. */
+void SortTripletList_r_wrp(const int *ih_this, const int *matrix_columns, const int *matrix_rows, int *ih_sorted);
+void SortTripletList_c_wrp(const int *ih_this, const int *matrix_columns, const int *matrix_rows, int *ih_sorted);
 
 /* ---- 3. distributed matrix container (Source/C/PSMatrix_c.h:4-49; PSMatrixModule_wrp.F90) */
 void ConstructEmptyMatrix_ps_wrp(int *ih_this, const int *matrix_dim);
@@ -118,10 +122,72 @@ void DotMatrix_psc_wrp(const int *ih_matA, const int *ih_matB, double *product_r
 void MatrixPairwiseMultiply_ps_wrp(const int *ih_matA, const int *ih_matB, int *ih_matC);
 double MeasureAsymmetry_ps_wrp(const int *ih_this);
 void SymmetrizeMatrix_ps_wrp(int *ih_this);
+/* column j scaled by every listed (index_column = j, point_value); PSMatrixAlgebraModule.F90:507-532 */
+void MatrixDiagonalScale_psr_wrp(int *ih_mat, const int *ih_tlist);
+void MatrixDiagonalScale_psc_wrp(int *ih_mat, const int *ih_tlist);
 
-/* ---- 5. memory pool (Source/C/PMatrixMemoryPool_c.h:4-5) */
+/* ---- 4b. THE LOCAL KERNEL: Matrix_lsr / Matrix_lsc and SMatrixAlgebraModule (Source/C/SMatrix_c.h:3-83;
+ *          SMatrixModule_wrp.F90, SMatrixAlgebraModule_wrp.F90 -> SMatrixAlgebraModule.F90:116-287,
+ *          sparse_includes/{GemmMatrix,SparseBranch,DenseBranch,MultiplyBlock,PruneList}.f90).
+ *          One device-resident CSC block per handle; MatrixMultiply_ls*_wrp is the local product the
+ *          distributed multiply runs per block pair: C = alpha*op(A)*op(B) + beta*C, op(X) = X^T when the
+ *          flag is set, entries kept by the dense rule (|v| > threshold before alpha) when both operands are
+ *          more than 10 % full and by the sparse rule (|alpha*v| > threshold) otherwise. */
+void ConstructMatrixFromFile_lsr_wrp(int *ih_this, const char *file_name, const int *name_size);
+void ConstructMatrixFromTripletList_lsr_wrp(int *ih_this, const int *ih_triplet_list, const int *rows,
+                                            const int *columns);
+void ConstructZeroMatrix_lsr_wrp(int *ih_this, const int *rows, const int *columns);
+void DestructMatrix_lsr_wrp(int *ih_this);
+void CopyMatrix_lsr_wrp(const int *ih_matA, int *ih_matB);
+void GetMatrixRows_lsr_wrp(const int *ih_this, int *rows);
+void GetMatrixColumns_lsr_wrp(const int *ih_this, int *columns);
+void ExtractMatrixRow_lsr_wrp(const int *ih_this, int *row_number, int *ih_row_out);
+void ExtractMatrixColumn_lsr_wrp(const int *ih_this, int *column_number, int *ih_column_out);
+void ScaleMatrix_lsr_wrp(int *ih_this, const double *constant);
+void IncrementMatrix_lsr_wrp(const int *ih_matA, int *ih_matB, const double *alpha_in, const double *threshold_in);
+void DotMatrix_lsr_wrp(const int *ih_matA, const int *ih_matB, double *product);
+void PairwiseMultiplyMatrix_lsr_wrp(const int *ih_matA, const int *ih_matB, int *ih_matC);
+void MatrixMultiply_lsr_wrp(const int *ih_matA, const int *ih_matB, int *ih_matC, const bool *IsATransposed,
+                            const bool *IsBTransposed, const double *alpha, const double *beta,
+                            const double *threshold, int *ih_matrix_memory_pool);
+void TransposeMatrix_lsr_wrp(const int *ih_matA, int *ih_matAT);
+void PrintMatrix_lsr_wrp(const int *ih_this);
+void PrintMatrixF_lsr_wrp(const int *ih_this, const char *file_name, const int *name_size);
+void MatrixToTripletList_lsr_wrp(const int *ih_this, int *ih_triplet_list);
+void MatrixDiagonalScale_lsr_wrp(int *ih_mat, const int *ih_tlist);
+void ConstructMatrixFromFile_lsc_wrp(int *ih_this, const char *file_name, const int *name_size);
+void ConstructMatrixFromTripletList_lsc_wrp(int *ih_this, const int *ih_triplet_list, const int *rows,
+                                            const int *columns);
+void ConstructZeroMatrix_lsc_wrp(int *ih_this, const int *rows, const int *columns);
+void DestructMatrix_lsc_wrp(int *ih_this);
+void CopyMatrix_lsc_wrp(const int *ih_matA, int *ih_matB);
+void GetMatrixRows_lsc_wrp(const int *ih_this, int *rows);
+void GetMatrixColumns_lsc_wrp(const int *ih_this, int *columns);
+void ExtractMatrixRow_lsc_wrp(const int *ih_this, int *row_number, int *ih_row_out);
+void ExtractMatrixColumn_lsc_wrp(const int *ih_this, int *column_number, int *ih_column_out);
+void ScaleMatrix_lsc_wrp(int *ih_this, const double *constant);
+void IncrementMatrix_lsc_wrp(const int *ih_matA, int *ih_matB, const double *alpha_in, const double *threshold_in);
+void DotMatrix_lsc_wrp(const int *ih_matA, const int *ih_matB, double *product_real, double *product_complex);
+void PairwiseMultiplyMatrix_lsc_wrp(const int *ih_matA, const int *ih_matB, int *ih_matC);
+void MatrixMultiply_lsc_wrp(const int *ih_matA, const int *ih_matB, int *ih_matC, const bool *IsATransposed,
+                            const bool *IsBTransposed, const double *alpha, const double *beta,
+                            const double *threshold, int *ih_matrix_memory_pool);
+void TransposeMatrix_lsc_wrp(const int *ih_matA, int *ih_matAT);
+void ConjugateMatrix_lsc_wrp(int *ih_matA);
+void PrintMatrix_lsc_wrp(const int *ih_this);
+void PrintMatrixF_lsc_wrp(const int *ih_this, const char *file_name, const int *name_size);
+void MatrixToTripletList_lsc_wrp(const int *ih_this, int *ih_triplet_list);
+void MatrixDiagonalScale_lsc_wrp(int *ih_mat, const int *ih_tlist);
+
+/* ---- 5. memory pools (Source/C/PMatrixMemoryPool_c.h:4-5, MatrixMemoryPool_c.h:3-8). The reference's pools
+ *         hold 36 B per element of the dense local block (MatrixMemoryPoolModule.F90:13-53); here the scratch of a
+ *         product comes from the device arena and the handles only keep the API and the shape. */
 void ConstructMatrixMemoryPool_p_wrp(int *ih_this, const int *ih_matrix);
 void DestructMatrixMemoryPool_p_wrp(int *ih_this);
+void ConstructMatrixMemoryPool_lr_wrp(int *ih_this, const int *columns, const int *rows);
+void DestructMatrixMemoryPool_lr_wrp(int *ih_this);
+void ConstructMatrixMemoryPool_lc_wrp(int *ih_this, const int *columns, const int *rows);
+void DestructMatrixMemoryPool_lc_wrp(int *ih_this);
 
 /* ---- 6. solver parameters / permutation / load balancer
  *         (Source/C/SolverParameters_c.h, Permutation_c.h, LoadBalancer_c.h) */
@@ -159,6 +225,9 @@ void PM_wrp(const int *ih_Hamiltonian, const int *ih_InverseSquareRoot, const do
 void HPCP_wrp(const int *ih_Hamiltonian, const int *ih_InverseSquareRoot, const double *trace,
               int *ih_Density, double *energy_value_out, double *chemical_potential_out,
               const int *ih_solver_parameters);
+void ScaleAndFold_wrp(const int *ih_Hamiltonian, const int *ih_InverseSquareRoot, const double *trace,
+                      int *ih_Density, const double *homo, const double *lumo, double *energy_value_out,
+                      const int *ih_solver_parameters);
 void EnergyDensityMatrix_wrp(const int *ih_Hamiltonian, const int *ih_Density, int *ih_EnergyDensity,
                              const double *threshold);
 void McWeenyStep_wrp(const int *ih_D, int *ih_DOut, const double *threshold);
@@ -166,6 +235,7 @@ void McWeenyStepS_wrp(const int *ih_D, int *ih_DOut, const int *ih_S, const doub
 void SignFunction_wrp(const int *ih_mat1, int *ih_signmat, const int *ih_solver_parameters);
 void PolarDecomposition_wrp(const int *ih_mat1, int *ih_umat, int *ih_hmat, const int *ih_solver_parameters);
 void Invert_wrp(const int *ih_Hamiltonian, int *ih_Inverse, const int *ih_solver_parameters);
+void PseudoInverse_wrp(const int *ih_Hamiltonian, int *ih_Inverse, const int *ih_solver_parameters);
 void SquareRoot_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters);
 void InverseSquareRoot_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters);
 void ComputeExponential_wrp(const int *ih_Input, int *ih_Output, const int *ih_solver_parameters);

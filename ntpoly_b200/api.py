@@ -57,6 +57,20 @@ UndoPermuteMatrix_wrp
 TRS2_wrp TRS4_wrp PM_wrp HPCP_wrp EnergyDensityMatrix_wrp McWeenyStep_wrp McWeenyStepS_wrp SignFunction_wrp
 PolarDecomposition_wrp Invert_wrp SquareRoot_wrp InverseSquareRoot_wrp ComputeExponential_wrp GershgorinBounds_wrp
 PowerBounds_wrp
+SortTripletList_r_wrp SortTripletList_c_wrp MatrixDiagonalScale_psr_wrp MatrixDiagonalScale_psc_wrp
+ScaleAndFold_wrp PseudoInverse_wrp
+ConstructMatrixFromFile_lsr_wrp ConstructMatrixFromTripletList_lsr_wrp ConstructZeroMatrix_lsr_wrp
+DestructMatrix_lsr_wrp CopyMatrix_lsr_wrp GetMatrixRows_lsr_wrp GetMatrixColumns_lsr_wrp ExtractMatrixRow_lsr_wrp
+ExtractMatrixColumn_lsr_wrp ScaleMatrix_lsr_wrp IncrementMatrix_lsr_wrp DotMatrix_lsr_wrp
+PairwiseMultiplyMatrix_lsr_wrp MatrixMultiply_lsr_wrp TransposeMatrix_lsr_wrp PrintMatrix_lsr_wrp
+PrintMatrixF_lsr_wrp MatrixToTripletList_lsr_wrp MatrixDiagonalScale_lsr_wrp
+ConstructMatrixFromFile_lsc_wrp ConstructMatrixFromTripletList_lsc_wrp ConstructZeroMatrix_lsc_wrp
+DestructMatrix_lsc_wrp CopyMatrix_lsc_wrp GetMatrixRows_lsc_wrp GetMatrixColumns_lsc_wrp ExtractMatrixRow_lsc_wrp
+ExtractMatrixColumn_lsc_wrp ScaleMatrix_lsc_wrp IncrementMatrix_lsc_wrp DotMatrix_lsc_wrp
+PairwiseMultiplyMatrix_lsc_wrp MatrixMultiply_lsc_wrp TransposeMatrix_lsc_wrp ConjugateMatrix_lsc_wrp
+PrintMatrix_lsc_wrp PrintMatrixF_lsc_wrp MatrixToTripletList_lsc_wrp MatrixDiagonalScale_lsc_wrp
+ConstructMatrixMemoryPool_lr_wrp DestructMatrixMemoryPool_lr_wrp ConstructMatrixMemoryPool_lc_wrp
+DestructMatrixMemoryPool_lc_wrp
 ntb_nccl_unique_id ntb_world_init ntb_world_rank ntb_world_size ntb_set_stream ntb_synchronize
 ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletList_c_get
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_ConstructEmptyMatrixComplex_ps
@@ -265,6 +279,13 @@ class TripletList_r:
     def GetSize(self):
         return lib().GetTripletListSize_r_wrp(self.ih)
 
+    def Sort(self, matrix_columns=0, matrix_rows=0):
+        """sorted copy (by column, then row)"""
+        out = TripletList_r.__new__(TripletList_r)
+        out.ih = _handle()
+        lib().SortTripletList_r_wrp(self.ih, _i(matrix_columns), _i(matrix_rows), out.ih)
+        return out
+
     # bulk (extension)
     def set_arrays(self, rows, cols, vals):
         rows = np.ascontiguousarray(rows, np.int32)
@@ -303,6 +324,12 @@ class TripletList_c:
 
     def GetSize(self):
         return lib().GetTripletListSize_c_wrp(self.ih)
+
+    def Sort(self, matrix_columns=0, matrix_rows=0):
+        out = TripletList_c.__new__(TripletList_c)
+        out.ih = _handle()
+        lib().SortTripletList_c_wrp(self.ih, _i(matrix_columns), _i(matrix_rows), out.ih)
+        return out
 
     def set_arrays(self, rows, cols, vals):
         rows = np.ascontiguousarray(rows, np.int32)
@@ -385,6 +412,152 @@ class PMatrixMemoryPool:
             lib().DestructMatrixMemoryPool_p_wrp(self.ih)
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------
+# local matrices (reference Source/CPlusPlus/SMatrix.h, MatrixMemoryPool.h)
+# ---------------------------------------------------------------------------
+class _MatrixMemoryPool:
+    _sfx = "lr"
+
+    def __init__(self, columns, rows):
+        self.ih = _handle()
+        getattr(lib(), f"ConstructMatrixMemoryPool_{self._sfx}_wrp")(self.ih, _i(columns), _i(rows))
+
+    def __del__(self):
+        try:
+            getattr(lib(), f"DestructMatrixMemoryPool_{self._sfx}_wrp")(self.ih)
+        except Exception:
+            pass
+
+
+class MatrixMemoryPool_r(_MatrixMemoryPool):
+    _sfx = "lr"
+
+
+class MatrixMemoryPool_c(_MatrixMemoryPool):
+    _sfx = "lc"
+
+
+class _Matrix_ls:
+    """Local sparse matrix living in GPU memory as one CSC block; same constructor overloads and method names as the
+    reference class: (columns, rows) | (file_name) | (triplet_list, rows, columns) | (other matrix)."""
+    _sfx = "lsr"
+    is_complex = False
+
+    def _fn(self, name):
+        return getattr(lib(), f"{name}_{self._sfx}_wrp")
+
+    def __init__(self, *args):
+        self.ih = _handle()
+        if len(args) == 1 and isinstance(args[0], _Matrix_ls):
+            other = args[0]
+            self._fn("ConstructZeroMatrix")(self.ih, _i(other.GetRows()), _i(other.GetColumns()))
+            self._fn("CopyMatrix")(other.ih, self.ih)
+        elif len(args) == 1 and isinstance(args[0], str):
+            b = args[0].encode()
+            self._fn("ConstructMatrixFromFile")(self.ih, c_char_p(b), _i(len(b)))
+        elif len(args) == 3:
+            tl, rows, columns = args
+            self._fn("ConstructMatrixFromTripletList")(self.ih, tl.ih, _i(rows), _i(columns))
+        else:
+            columns, rows = args
+            self._fn("ConstructZeroMatrix")(self.ih, _i(rows), _i(columns))
+
+    def __del__(self):
+        try:
+            self._fn("DestructMatrix")(self.ih)
+        except Exception:
+            pass
+
+    def GetRows(self):
+        v = c_int()
+        self._fn("GetMatrixRows")(self.ih, byref(v))
+        return v.value
+
+    def GetColumns(self):
+        v = c_int()
+        self._fn("GetMatrixColumns")(self.ih, byref(v))
+        return v.value
+
+    def ExtractRow(self, row_number, row_out):
+        """row_number is 0-based like in the reference C++ class; row_out receives a 1 x columns matrix"""
+        self._fn("DestructMatrix")(row_out.ih)       # the C entry point allocates a fresh object for the output
+        self._fn("ExtractMatrixRow")(self.ih, byref(c_int(row_number + 1)), row_out.ih)
+
+    def ExtractColumn(self, column_number, column_out):
+        self._fn("DestructMatrix")(column_out.ih)
+        self._fn("ExtractMatrixColumn")(self.ih, byref(c_int(column_number + 1)), column_out.ih)
+
+    def Scale(self, constant):
+        self._fn("ScaleMatrix")(self.ih, _d(constant))
+
+    def Increment(self, matB, alpha=1.0, threshold=0.0):
+        """this = alpha*matB + this"""
+        self._fn("IncrementMatrix")(matB.ih, self.ih, _d(alpha), _d(threshold))
+
+    def Dot(self, matB):
+        if self.is_complex:
+            re, im = c_double(), c_double()
+            self._fn("DotMatrix")(self.ih, matB.ih, byref(re), byref(im))
+            return complex(re.value, im.value)
+        v = c_double()
+        self._fn("DotMatrix")(self.ih, matB.ih, byref(v))
+        return v.value
+
+    def PairwiseMultiply(self, matA, matB):
+        self._fn("PairwiseMultiplyMatrix")(matA.ih, matB.ih, self.ih)
+
+    def Gemm(self, matA, matB, isATransposed, isBTransposed, alpha, beta, threshold, memory_pool=None):
+        """this = alpha*op(matA)*op(matB) + beta*this"""
+        self._fn("MatrixMultiply")(matA.ih, matB.ih, self.ih, byref(c_bool(bool(isATransposed))),
+                                   byref(c_bool(bool(isBTransposed))), _d(alpha), _d(beta), _d(threshold),
+                                   memory_pool.ih if memory_pool is not None else None)
+
+    def DiagonalScale(self, tlist):
+        self._fn("MatrixDiagonalScale")(self.ih, tlist.ih)
+
+    def Transpose(self, matA):
+        self._fn("TransposeMatrix")(matA.ih, self.ih)
+
+    def Print(self):
+        self._fn("PrintMatrix")(self.ih)
+
+    def WriteToMatrixMarket(self, file_name):
+        b = file_name.encode()
+        self._fn("PrintMatrixF")(self.ih, c_char_p(b), _i(len(b)))
+
+    def MatrixToTripletList(self, triplet_list):
+        self._fn("MatrixToTripletList")(self.ih, triplet_list.ih)
+
+    # bulk host transfer (extension)
+    @classmethod
+    def from_scipy(cls, m):
+        import scipy.sparse as sp
+        m = sp.coo_matrix(m)
+        tl = TripletList_c() if cls.is_complex else TripletList_r()
+        tl.set_arrays(m.row + 1, m.col + 1, m.data)
+        return cls(tl, m.shape[0], m.shape[1])
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        tl = TripletList_c() if self.is_complex else TripletList_r()
+        self.MatrixToTripletList(tl)
+        rows, cols, vals = tl.get_arrays()
+        return sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(self.GetRows(), self.GetColumns())).tocsc()
+
+
+class Matrix_lsr(_Matrix_ls):
+    _sfx = "lsr"
+    is_complex = False
+
+
+class Matrix_lsc(_Matrix_ls):
+    _sfx = "lsc"
+    is_complex = True
+
+    def Conjugate(self):
+        lib().ConjugateMatrix_lsc_wrp(self.ih)
 
 
 # ---------------------------------------------------------------------------
@@ -515,6 +688,12 @@ class Matrix_ps:
     def Symmetrize(self):
         lib().SymmetrizeMatrix_ps_wrp(self.ih)
 
+    def DiagonalScale(self, tlist):
+        if tlist.is_complex:
+            lib().MatrixDiagonalScale_psc_wrp(self.ih, tlist.ih)
+        else:
+            lib().MatrixDiagonalScale_psr_wrp(self.ih, tlist.ih)
+
     def Filter(self, threshold):
         lib().ntb_FilterMatrix_ps(self.ih, _d(threshold))
 
@@ -594,6 +773,12 @@ class DensityMatrixSolvers:
         return _density(lib().HPCP_wrp, H, ISQ, trace, K, sp)
 
     @staticmethod
+    def ScaleAndFold(H, ISQ, trace, K, homo, lumo, sp):
+        e = c_double()
+        lib().ScaleAndFold_wrp(H.ih, ISQ.ih, _d(trace), K.ih, _d(homo), _d(lumo), byref(e), sp.ih)
+        return e.value
+
+    @staticmethod
     def EnergyDensityMatrix(H, D, ED, threshold=0.0):
         lib().EnergyDensityMatrix_wrp(H.ih, D.ih, ED.ih, _d(threshold))
 
@@ -619,6 +804,10 @@ class InverseSolvers:
     @staticmethod
     def Invert(M, Out, sp):
         lib().Invert_wrp(M.ih, Out.ih, sp.ih)
+
+    @staticmethod
+    def PseudoInverse(M, Out, sp):
+        lib().PseudoInverse_wrp(M.ih, Out.ih, sp.ih)
 
 
 class SquareRootSolvers:

@@ -1,6 +1,6 @@
 // extern "C" surface: NTPoly's `*_wrp` symbols over the CUDA hot path.
 // See include/ntpoly_b200.h for the per-section reference citations.
-#include "../../include/ntpoly_b200.h"
+#include "c_api_common.h"
 #include "ops.cuh"
 #include "solvers.h"
 #include <algorithm>
@@ -11,61 +11,11 @@
 
 using namespace ntb;
 
+using namespace ntb::capi;
+
 namespace {
-// opaque handle = caller-owned int[12]; first 8 bytes carry the object pointer
-// (the reference TRANSFERs a derived type holding one POINTER, WrapperModule.F90:8)
-template <typename T> T* get(const int* ih) {
-  T* p;
-  std::memcpy(&p, ih, sizeof(p));
-  NTB_CHECK(p != nullptr, "null handle passed to ntpoly_b200");
-  return p;
-}
-template <typename T> void put(int* ih, T* p) {
-  std::memset(ih, 0, NTB_SIZE_wrp * sizeof(int));
-  std::memcpy(ih, &p, sizeof(p));
-}
 SolverParameters default_params;
 const SolverParameters& params_of(const int* ih) { return *get<SolverParameters>(ih); }
-
-// ---- MatrixMarket (host side; PSMatrixModule.F90:351-570, WriteToMatrixMarket.f90)
-struct MMData {
-  int n = 0;
-  bool is_complex = false;
-  std::vector<int> rows, cols;
-  std::vector<double> re, im;
-};
-MMData read_matrix_market(const std::string& path, int rank, int size) {
-  std::ifstream f(path);
-  NTB_CHECK(f.good(), "cannot open MatrixMarket file");
-  std::string line;
-  std::getline(f, line);
-  std::string lower = line;
-  std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
-  MMData d;
-  d.is_complex = lower.find("complex") != std::string::npos;
-  const bool pattern = lower.find("pattern") != std::string::npos;
-  const bool symmetric = lower.find(" symmetric") != std::string::npos;
-  const bool skew = lower.find("skew-symmetric") != std::string::npos;
-  const bool hermitian = lower.find("hermitian") != std::string::npos;
-  while (std::getline(f, line)) if (!line.empty() && line[0] != '%') break;
-  long long nr, nc, nnz;
-  { std::istringstream ss(line); ss >> nr >> nc >> nnz; }
-  d.n = (int)nr;
-  for (long long i = 0; i < nnz; ++i) {
-    int r, c;
-    double vr = 1.0, vi = 0.0;
-    f >> r >> c;
-    if (!pattern) { f >> vr; if (d.is_complex) f >> vi; }
-    if ((i % size) != rank) continue;  // every rank parses, each keeps a disjoint share
-    d.rows.push_back(r); d.cols.push_back(c); d.re.push_back(vr); d.im.push_back(vi);
-    if ((symmetric || skew || hermitian) && r != c) {
-      d.rows.push_back(c); d.cols.push_back(r);
-      d.re.push_back(skew ? -vr : vr);
-      d.im.push_back(hermitian ? -vi : (skew ? -vi : vi));
-    }
-  }
-  return d;
-}
 void construct_from_mm(int* ih_this, const char* file_name, int name_size, ProcessGrid* grid) {
   std::string path(file_name, (size_t)name_size);
   world_init_from_env();
@@ -305,12 +255,15 @@ void TRS2_wrp(const int* H, const int* ISQ, const double* trace, int* K, double*
 void TRS4_wrp(const int* H, const int* ISQ, const double* trace, int* K, double* e, double* mu, const int* sp) { solve_trs4(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), e, mu, params_of(sp)); }
 void PM_wrp(const int* H, const int* ISQ, const double* trace, int* K, double* e, double* mu, const int* sp) { solve_pm(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), e, mu, params_of(sp)); }
 void HPCP_wrp(const int* H, const int* ISQ, const double* trace, int* K, double* e, double* mu, const int* sp) { solve_hpcp(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), e, mu, params_of(sp)); }
+void ScaleAndFold_wrp(const int* H, const int* ISQ, const double* trace, int* K, const double* homo, const double* lumo, double* e, const int* sp) { solve_scale_and_fold(*get<Matrix>(H), *get<Matrix>(ISQ), *trace, *get<Matrix>(K), *homo, *lumo, e, params_of(sp)); }
 void EnergyDensityMatrix_wrp(const int* H, const int* D, int* ED, const double* thr) { energy_density_matrix(*get<Matrix>(H), *get<Matrix>(D), *get<Matrix>(ED), *thr); }
 void McWeenyStep_wrp(const int* D, int* Dout, const double* thr) { mcweeny_step(*get<Matrix>(D), *get<Matrix>(Dout), nullptr, *thr); }
 void McWeenyStepS_wrp(const int* D, int* Dout, const int* S, const double* thr) { mcweeny_step(*get<Matrix>(D), *get<Matrix>(Dout), get<Matrix>(S), *thr); }
 void SignFunction_wrp(const int* in, int* out, const int* sp) { solve_sign(*get<Matrix>(in), *get<Matrix>(out), params_of(sp)); }
 void PolarDecomposition_wrp(const int* in, int* u, int* h, const int* sp) { solve_polar(*get<Matrix>(in), *get<Matrix>(u), h ? get<Matrix>(h) : nullptr, params_of(sp)); }
 void Invert_wrp(const int* in, int* out, const int* sp) { solve_invert(*get<Matrix>(in), *get<Matrix>(out), params_of(sp)); }
+// InverseSolversModule.F90:187-298: the same Hotelling iteration as Invert (the reference's two routines differ in their log text only)
+void PseudoInverse_wrp(const int* in, int* out, const int* sp) { solve_invert(*get<Matrix>(in), *get<Matrix>(out), params_of(sp)); }
 void SquareRoot_wrp(const int* in, int* out, const int* sp) { solve_sqrt(*get<Matrix>(in), *get<Matrix>(out), params_of(sp), false, 5); }
 void InverseSquareRoot_wrp(const int* in, int* out, const int* sp) { solve_sqrt(*get<Matrix>(in), *get<Matrix>(out), params_of(sp), true, 5); }
 void ComputeExponential_wrp(const int* in, int* out, const int* sp) { solve_exponential(*get<Matrix>(in), *get<Matrix>(out), params_of(sp)); }

@@ -179,6 +179,56 @@ void solve_trs2(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, dou
 }
 
 // ---------------------------------------------------------------------------
+// Scale and Fold  (DensityMatrixSolversModule.F90:953-1117)
+void solve_scale_and_fold(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, double homo, double lumo,
+                          double* energy_out, const SolverParameters& p) {
+  SolveScope scope;
+  Monitor mon;
+  mon.construct(p.monitor_convergence, p.converge_diff);
+  DensitySetup s;
+  density_setup(H, ISQ, p, s);
+  double e_min, e_max;
+  mat_gershgorin(s.WH, &e_min, &e_max);
+  Matrix X, X2;
+  mat_copy(s.WH, X);
+  mat_scale(X, -1.0);
+  mat_increment(s.IMat, X, e_max, 0.0);
+  mat_scale(X, 1.0 / (e_max - e_min));
+  double Beta = (e_max - lumo) / (e_max - e_min);
+  double BetaBar = (e_max - homo) / (e_max - e_min);
+  double energy = 0.0;
+  int II = 1;
+  for (II = 1; II <= p.max_iterations; ++II) {
+    const double tv = mat_trace(X);
+    if (tv > trace) {
+      const double alpha = 2.0 / (2.0 - Beta);
+      mat_scale(X, alpha);
+      mat_increment(s.IMat, X, 1.0 - alpha, 0.0);
+      mat_multiply(X, X, X2, 1.0, 0.0, p.threshold, &s.pool);
+      mat_copy(X2, X);
+      Beta = (alpha * Beta + 1 - alpha) * (alpha * Beta + 1 - alpha);
+      BetaBar = (alpha * BetaBar + 1 - alpha) * (alpha * BetaBar + 1 - alpha);
+    } else {
+      const double alpha = 2.0 / (1.0 + BetaBar);
+      mat_multiply(X, X, X2, 1.0, 0.0, p.threshold, &s.pool);
+      mat_scale(X, 2 * alpha);
+      mat_increment(X2, X, -1.0 * alpha * alpha, 0.0);
+      Beta = 2.0 * alpha * Beta - alpha * alpha * Beta * Beta;
+      BetaBar = 2.0 * alpha * BetaBar - alpha * alpha * BetaBar * BetaBar;
+    }
+    const double old = energy;
+    energy = 2.0 * dot_real(X, s.WH);
+    mon.append(energy - old);
+    g_last.last_value = energy - old;
+    if (mon.converged(p.be_verbose)) break;
+  }
+  g_last.loop_counter = II;
+  g_last.energy = energy;
+  if (energy_out) *energy_out = energy;
+  density_finish(X, ISQ, s, p, K);
+}
+
+// ---------------------------------------------------------------------------
 // TRS4  (DensityMatrixSolversModule.F90:485-716)
 void solve_trs4(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, double* energy_out, double* chempot_out,
                 const SolverParameters& p) {

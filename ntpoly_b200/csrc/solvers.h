@@ -59,6 +59,8 @@ void solve_pm(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, doubl
               const SolverParameters& params);
 void solve_hpcp(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, double* energy_out, double* chempot_out,
                 const SolverParameters& params);
+void solve_scale_and_fold(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, double homo, double lumo,
+                          double* energy_out, const SolverParameters& params);
 void solve_sign(const Matrix& In, Matrix& Out, const SolverParameters& params);
 double sign_step(const Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& Xn, Matrix& OutT, double alpha_k,
                  double threshold, bool needs_transpose, MemoryPool* pool);

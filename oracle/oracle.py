@@ -663,6 +663,50 @@ def trs2(H, ISQ, trace_target, p: SolverParameters | None = None):
     return K, info
 
 
+def scale_and_fold(H, ISQ, trace_target, homo, lumo, p: SolverParameters | None = None):
+    """Scale and Fold (DensityMatrixSolversModule.F90:953-1117). Returns (K, SolveInfo)."""
+    p = p or SolverParameters()
+    mon = p.monitor()
+    info = SolveInfo()
+    I, ISQT, WH = _density_setup(H, ISQ, p)
+    e_min, e_max = gershgorin(WH)
+    X = scale(WH, -1.0)
+    X = increment(I, X, alpha=e_max)
+    X = scale(X, 1.0 / (e_max - e_min))
+    beta = (e_max - lumo) / (e_max - e_min)
+    beta_bar = (e_max - homo) / (e_max - e_min)
+    energy = 0.0
+    broke = False
+    ii = 0
+    for ii in range(1, p.max_iterations + 1):
+        tv = trace(X)
+        if tv > trace_target:                                   # :1051-1059
+            alpha = 2.0 / (2.0 - beta)
+            X = scale(X, alpha)
+            X = increment(I, X, alpha=1.0 - alpha)
+            X = multiply(X, X, thr=p.threshold)
+            beta = (alpha * beta + 1 - alpha) ** 2
+            beta_bar = (alpha * beta_bar + 1 - alpha) ** 2
+        else:                                                   # :1060-1068
+            alpha = 2.0 / (1.0 + beta_bar)
+            X2 = multiply(X, X, thr=p.threshold)
+            X = scale(X, 2 * alpha)
+            X = increment(X2, X, alpha=-1.0 * alpha ** 2)
+            beta = 2.0 * alpha * beta - alpha ** 2 * beta ** 2
+            beta_bar = 2.0 * alpha * beta_bar - alpha ** 2 * beta_bar ** 2
+        old = energy
+        energy = 2.0 * dot_real(X, WH)
+        mon.append(energy - old)
+        info.history.append(energy - old)
+        if mon.converged():
+            broke = True
+            break
+    info.iterations = _loop_counter(ii, p.max_iterations, broke)
+    info.energy = energy
+    K = _density_finish(X, ISQT, ISQ, p)
+    return K, info
+
+
 def trs4(H, ISQ, trace_target, p: SolverParameters | None = None):
     """TRS4 (DensityMatrixSolversModule.F90:485-716)."""
     p = p or SolverParameters()

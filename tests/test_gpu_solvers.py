@@ -55,6 +55,46 @@ def test_premade_matrix_density_golden(nt, oracle):
         assert np.linalg.norm(K.to_scipy().toarray() - D) <= 1e-4, name
 
 
+def test_premade_scale_and_fold(nt, oracle):
+    """ScaleAndFold_wrp (DensityMatrixSolversModule.F90:953-1117) fed with the HOMO/LUMO of the generalised
+    eigenproblem like the reference's own test (UnitTests/test_chemistry.py:236-264): golden density, and the same
+    iteration count and energy as the oracle's restatement"""
+    import scipy.linalg as la
+    O = oracle
+    Hs, Ss = (sp.csc_matrix(sio.mmread(os.path.join(GOLD, f))) for f in ("premade_Hamiltonian.mtx", "premade_Overlap.mtx"))
+    D = sio.mmread(os.path.join(GOLD, "premade_Density-Reference.mtx")).toarray()
+    w = la.eigh(Hs.toarray(), Ss.toarray(), eigvals_only=True)
+    H, S = to_gpu(nt, Hs), to_gpu(nt, Ss)
+    ISQ, K = nt.Matrix_ps(7), nt.Matrix_ps(7)
+    p = params(nt, 1e-3, 1e-6)
+    nt.SquareRootSolvers.InverseSquareRoot(S, ISQ, p)
+    p.SetConvergeDiff(1e-5)
+    e = nt.DensityMatrixSolvers.ScaleAndFold(H, ISQ, 5.0, K, w[4], w[5], p)
+    rec = nt.last_solve()
+    po = O.SolverParameters(converge_diff=1e-3, threshold=1e-6)
+    ISQo, _ = O.inverse_square_root(O.PSMatrix.from_scipy(Ss), po)
+    po.converge_diff = 1e-5
+    Ko, info = O.scale_and_fold(O.PSMatrix.from_scipy(Hs), ISQo, 5.0, w[4], w[5], po)
+    assert rec["loop_counter"] == info.iterations
+    assert e == pytest.approx(info.energy, rel=1e-8)
+    assert np.linalg.norm(K.to_scipy().toarray() - D) <= 1e-4
+    assert np.linalg.norm(K.to_scipy().toarray() - Ko.todense()) <= 1e-8
+
+
+def test_pseudo_inverse_is_the_hotelling_iteration(nt, oracle):
+    """PseudoInverse (InverseSolversModule.F90:187-298) runs the same iteration as Invert"""
+    n = 200
+    m = spd_banded(n, seed=4)
+    M, P, Inv = to_gpu(nt, m), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    p = params(nt, 1e-8, 1e-10)
+    nt.InverseSolvers.PseudoInverse(M, P, p)
+    it = nt.last_solve()["loop_counter"]
+    nt.InverseSolvers.Invert(M, Inv, p)
+    assert it == nt.last_solve()["loop_counter"]
+    assert abs(P.to_scipy() - Inv.to_scipy()).sum() == 0.0
+    assert abs(P.to_scipy() @ m - sp.identity(n)).max() < 1e-6
+
+
 def test_premade_with_load_balancing_permutation(nt):
     """every reference example runs with a random permutation: results are permutation invariant up to
     threshold effects"""

@@ -55,6 +55,22 @@ def test_premade_other_density_solvers(oracle, solver):
     assert np.linalg.norm(K.todense() - D) <= 1e-4
 
 
+def test_premade_scale_and_fold(oracle):
+    """Scale and Fold with the HOMO/LUMO of the generalised eigenproblem, as the reference's own test feeds it
+    (UnitTests/test_chemistry.py:236-264), must land on the shipped Density-Reference.mtx too."""
+    O = oracle
+    H, S = O.PSMatrix.from_scipy(mm("premade_Hamiltonian.mtx")), O.PSMatrix.from_scipy(mm("premade_Overlap.mtx"))
+    D = mm("premade_Density-Reference.mtx").toarray()
+    w = la.eigh(H.todense(), S.todense(), eigvals_only=True)
+    p = O.SolverParameters(converge_diff=1e-3, threshold=1e-6)
+    ISQ, _ = O.inverse_square_root(S, p)
+    p.converge_diff = 1e-5
+    K, info = O.scale_and_fold(H, ISQ, 5.0, w[4], w[5], p)
+    assert np.linalg.norm(K.todense() - D) <= 1e-4
+    assert np.trace(K.todense() @ S.todense()) == pytest.approx(5.0, abs=1e-4)
+    assert info.iterations < 19                                  # the acceleration must beat plain TRS2 (19)
+
+
 GRIDS = [(1, 1, 1, 1), (2, 1, 1, 1), (1, 2, 1, 1), (2, 2, 1, 1), (1, 1, 2, 1), (2, 1, 2, 1), (1, 2, 2, 1), (2, 2, 2, 1),
          (3, 2, 1, 1), (2, 1, 3, 1), (6, 1, 1, 1), (1, 1, 1, 8)]
 
