@@ -268,6 +268,15 @@ void ntb_GetMatrixArrays_ps(const int *ih_this, int *rows, int *cols, double *va
  * (pinned memory, or the copies serialise) are complete after ntb_EgressWait(). */
 long long ntb_GetMatrixArraysAsync_ps(const int *ih_this, int *rows, int *cols, double *vals);
 void ntb_EgressWait(void);
+/* Ingest in two halves, so that the host-to-device copies of the NEXT matrix overlap the work on the current one:
+ * ntb_StageArrays only enqueues the copies of a real 1-based global list (pinned host arrays, valid until the fill) on a
+ * copy stream and returns; ntb_FillMatrixFromStaged_ps makes the library stream wait for them, builds the matrix like
+ * ntb_FillMatrixFromArrays_ps and releases the stage (handle zeroed). */
+void ntb_StageArrays(int *ih_stage, long long n, const int *rows, const int *cols, const double *vals);
+void ntb_FillMatrixFromStaged_ps(int *ih_this, int *ih_stage);
+/* triplet lists since the last reset that were taken as they came (every rank's list its own block in column-major
+ * order without duplicates): no sort, no gather */
+double ntb_sorted_ingests(void);
 void ntb_ConstructEmptyMatrixComplex_ps(int *ih_this, const int *matrix_dim, const int *is_complex);
 int ntb_MatrixIsComplex_ps(const int *ih_this);
 void ntb_FilterMatrix_ps(int *ih_this, const double *threshold);

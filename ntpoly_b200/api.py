@@ -73,7 +73,7 @@ ConstructMatrixMemoryPool_lr_wrp DestructMatrixMemoryPool_lr_wrp ConstructMatrix
 DestructMatrixMemoryPool_lc_wrp
 ntb_nccl_unique_id ntb_world_init ntb_world_rank ntb_world_size ntb_set_stream ntb_synchronize
 ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletList_c_get
-ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_ConstructEmptyMatrixComplex_ps
+ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_StageArrays ntb_FillMatrixFromStaged_ps ntb_sorted_ingests ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
 ntb_set_fused_shift ntb_get_halo_counters ntb_set_halo_path ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
@@ -91,6 +91,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
         L.MatrixNorm_ps_wrp.restype = c_double
         L.ntb_tile_builds.restype = c_double
+        L.ntb_sorted_ingests.restype = c_double
         L.ntb_SignIteration.restype = c_double
         L.ntb_SignStep.restype = c_double
         L.MeasureAsymmetry_ps_wrp.restype = c_double
@@ -707,6 +708,11 @@ class Matrix_ps:
                                           vals.view(np.float64).ctypes.data_as(POINTER(c_double)),
                                           c_int(1 if cplx else 0))
 
+    def fill_from_staged(self, staged):
+        """second half of the two-stage ingest: the matrix is built from a list staged with stage_arrays()"""
+        lib().ntb_FillMatrixFromStaged_ps(self.ih, staged.ih)
+        staged.keep = None
+
     def get_arrays(self, out=None):
         """local block as global 1-based triplets; `out` = (rows, cols, vals) buffers to fill (e.g. pinned memory,
         at least GetMatrixLocalSize entries each) instead of fresh arrays"""
@@ -919,6 +925,25 @@ def deferred_counters():
     out = (c_double * 2)()
     lib().ntb_get_deferred_counters(out)
     return {"products": int(out[0]), "materialized": int(out[1])}
+
+
+class StagedArrays:
+    """a real global 1-based (rows, cols, vals) list whose host-to-device copies are in flight on the library's copy
+    stream (first half of the two-stage ingest); the host arrays should be pinned and are kept alive here"""
+
+    def __init__(self, rows, cols, vals):
+        assert rows.dtype == np.int32 and cols.dtype == np.int32 and vals.dtype == np.float64
+        self.keep = (rows, cols, vals)
+        self.ih = _handle()
+        lib().ntb_StageArrays(self.ih, c_longlong(len(rows)), _ip(rows), _ip(cols), _dp(vals))
+
+
+def stage_arrays(rows, cols, vals):
+    return StagedArrays(rows, cols, vals)
+
+
+def sorted_ingests():
+    return int(lib().ntb_sorted_ingests())
 
 
 def egress_wait():

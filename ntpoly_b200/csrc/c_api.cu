@@ -319,6 +319,18 @@ long long ntb_GetMatrixArraysAsync_ps(const int* ih, int* rows, int* cols, doubl
   return mat_get_triplets_async(*get<Matrix>(ih), rows, cols, vals);
 }
 void ntb_EgressWait(void) { mat_egress_wait(); }
+void ntb_StageArrays(int* ih_stage, long long n, const int* rows, const int* cols, const double* vals) {
+  auto* S = new StagedTriplets();
+  stage_triplets(*S, rows, cols, vals, n);
+  put(ih_stage, S);
+}
+void ntb_FillMatrixFromStaged_ps(int* ih, int* ih_stage) {
+  StagedTriplets* S = get<StagedTriplets>(ih_stage);
+  mat_fill_from_staged(*get<Matrix>(ih), *S);
+  delete S;
+  std::memset(ih_stage, 0, NTB_SIZE_wrp * sizeof(int));
+}
+double ntb_sorted_ingests(void) { return (double)rt().sorted_ingests; }
 void ntb_ConstructEmptyMatrixComplex_ps(int* ih, const int* n, const int* is_complex) { auto* M = new Matrix(); mat_construct_empty(*M, *n, nullptr, *is_complex != 0); put(ih, M); }
 int ntb_MatrixIsComplex_ps(const int* ih) { return get<Matrix>(ih)->is_complex ? 1 : 0; }
 void ntb_FilterMatrix_ps(int* ih, const double* thr) { mat_filter(*get<Matrix>(ih), *thr); }
@@ -336,7 +348,7 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
 // C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when

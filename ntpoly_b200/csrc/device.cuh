@@ -23,6 +23,7 @@ struct Runtime {
   double dmma_issued = 0.0;              // DMMA.8x8x4 instructions (x256 FMAs) issued by the tile path
   unsigned long long deferred_products = 0;      // tile products emitted without CSC entries (outer + right form only)
   unsigned long long deferred_materialized = 0; // ... whose entries had to be produced later after all
+  unsigned long long sorted_ingests = 0;        // triplet lists taken as they were (own block, column-major): no sort, no gather
   bool count_flops = false;        // instrumentation: count the useful products of every multiply (one extra sweep + read-back)
   double alg_bytes = 0.0;          // compulsory bytes of the local products: bytes(A)+bytes(B)+bytes(C_kept)
   // optional device timing of the dominant (numeric SpGEMM) kernels, for bench.py's roofline

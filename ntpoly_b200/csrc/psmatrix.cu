@@ -256,6 +256,15 @@ template <> const LocalCsc<cplx>& loc<cplx>(const Matrix& M) { return M.c; }
 // ===========================================================================
 // ingest / egress
 // ===========================================================================
+// Bulk host<->device copies are issued in pieces: a copy engine serves its queue in order, so a small read-back of
+// the library stream (task counts, nnz, norms: ~10 per solver step) would otherwise wait behind a whole multi-hundred-MB
+// transfer of a copy stream. With 4 MB pieces it waits for at most one piece (< 0.1 ms).
+static void copy_in_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
+  constexpr size_t PIECE = 4u << 20;
+  for (size_t off = 0; off < bytes; off += PIECE)
+    CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off,
+                               std::min(PIECE, bytes - off), kind, stream));
+}
 template <typename T>
 __global__ void __launch_bounds__(256) k_local_filter(const int* __restrict__ row, const int* __restrict__ col, long long n,
                                                       int r0, int r1, int c0, int c1, int* __restrict__ flag) {
@@ -319,6 +328,84 @@ __global__ void __launch_bounds__(256) k_add_const2(int* __restrict__ a, int* __
   }
 }
 
+// ---- fast ingest of lists that are already this rank's block in column-major order (what GetMatrixTripletList
+// hands out and what host codes that keep CSC/CSR data produce): no sort, no gather. One pass decides, the rest is
+// two streaming copies and a binary search per column.
+// bad[0] != 0 unless every (global 0-based) entry lies in [r0,r1) x [c0,c1) and (col,row) is strictly ascending
+__global__ void __launch_bounds__(256) k_check_sorted_local(const int* __restrict__ row, const int* __restrict__ col, long long n,
+                                                            int r0, int r1, int c0, int c1, int* __restrict__ bad) {
+  bool ok = true;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = row[i], c = col[i];
+    ok = ok && r >= r0 && r < r1 && c >= c0 && c < c1;
+    if (i > 0) {
+      const int pr = row[i - 1], pc = col[i - 1];
+      ok = ok && (pc < c || (pc == c && pr < r));
+    }
+  }
+  if (!ok) *bad = 1;
+}
+__global__ void __launch_bounds__(256) k_sub_const(const int* __restrict__ in, int* __restrict__ out, long long n, int d) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = in[i] - d;
+}
+// outer[j] = first position whose column is >= c0 + j (col ascending)
+__global__ void __launch_bounds__(256) k_outer_from_sorted_cols(const int* __restrict__ col, int n, int cols, int c0,
+                                                                int* __restrict__ outer) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > cols) return;
+  const int key = c0 + j;
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < key) lo = mid + 1; else hi = mid; }
+  outer[j] = lo;
+}
+// collective over the slice: true when every rank's list is its own block, sorted and duplicate free
+static bool lists_are_local_blocks(const Matrix& M, const int* d_row, const int* d_col, long long n) {
+  DevBuf<int> bad(1);
+  bad.zero();
+  if (n >= (1ll << 31)) { const int one = 1; h2d(bad.get(), &one, 1); stream_sync(); }
+  else if (n > 0)
+    NTB_LAUNCH(k_check_sorted_local, std::min(div_up(n, 256), kNumSMs * 16), 256, 0, d_row, d_col, n, M.start_row,
+               M.start_row + M.local_rows, M.start_col, M.start_col + M.local_cols, bad.get());
+  int h = 0;
+  d2h(&h, bad.get(), 1);
+  double v = h ? 1.0 : 0.0;
+  if (comm_size(M.grid->within_slice) > 1) {
+    DevBuf<double> d(1);
+    h2d(d.get(), &v, 1);
+    comm_allreduce_f64(M.grid->within_slice, d.get(), 1, RedOp::Max);
+    d2h(&v, d.get(), 1);
+  }
+  return v == 0.0;
+}
+template <typename T>
+static void build_local_from_sorted_block(Matrix& M, const int* d_row, const int* d_col, const T* d_val, long long n) {
+  LocalCsc<T>& L = loc<T>(M);
+  if (n == 0) { L.init_empty(M.local_rows, M.local_cols); return; }
+  L.rows = M.local_rows; L.cols = M.local_cols;
+  L.outer.alloc((size_t)L.cols + 1);
+  L.alloc_entries(n);
+  NTB_LAUNCH(k_outer_from_sorted_cols, div_up(L.cols + 1, 256), 256, 0, d_col, (int)n, L.cols, M.start_col, L.outer.get());
+  NTB_LAUNCH(k_sub_const, std::min(div_up(n, 256), kNumSMs * 16), 256, 0, d_row, L.inner.get(), n, M.start_row);
+  d2d(L.val.get(), d_val, (size_t)n);
+}
+
+// d_*: this rank's list on the device, GLOBAL 0-based indices
+template <typename T>
+static void ingest_device_triplets(Matrix& M, DevBuf<int>& d_row, DevBuf<int>& d_col, DevBuf<T>& d_val, long long n,
+                                   bool preduplicated, bool prepartitioned) {
+  if (lists_are_local_blocks(M, d_row.get(), d_col.get(), n)) {
+    build_local_from_sorted_block<T>(M, d_row.get(), d_col.get(), d_val.get(), n);
+    rt().sorted_ingests++;
+  } else {
+    long long total = n;
+    if (!prepartitioned) total = allgather_triplets<T>(M.grid->within_slice, d_row, d_col, d_val, n);
+    build_local_from_global_triplets<T>(M, d_row.get(), d_col.get(), d_val.get(), total);
+  }
+  if (!prepartitioned && !preduplicated && M.grid->S > 1)   // FillMatrixFromTripletList.f90:37-42
+    reduce_and_sum<T>(loc<T>(M), M.grid->between_slice, 0.0, M.row_block());
+}
+
 template <typename T>
 static void fill_from_triplets_t(Matrix& M, const int* rows, const int* cols, const T* vals, long long n,
                                  bool preduplicated, bool prepartitioned) {
@@ -330,11 +417,47 @@ static void fill_from_triplets_t(Matrix& M, const int* rows, const int* cols, co
     NTB_LAUNCH(k_add_const2, std::min(div_up(n, 256), kNumSMs * 16), 256, 0, d_row.get(), d_col.get(), n, -1, -1);
   }
   stream_sync();
-  long long total = n;
-  if (!prepartitioned) total = allgather_triplets<T>(M.grid->within_slice, d_row, d_col, d_val, n);
-  build_local_from_global_triplets<T>(M, d_row.get(), d_col.get(), d_val.get(), total);
-  if (!prepartitioned && !preduplicated && M.grid->S > 1)   // FillMatrixFromTripletList.f90:37-42
-    reduce_and_sum<T>(loc<T>(M), M.grid->between_slice, 0.0, M.row_block());
+  ingest_device_triplets<T>(M, d_row, d_col, d_val, n, preduplicated, prepartitioned);
+}
+
+// ---- staged (asynchronous) ingest: the host-to-device copies of a list run on a copy stream of their own while the
+// library stream computes on an earlier matrix; the list becomes a matrix later, with mat_fill_from_staged
+namespace {
+cudaStream_t g_h2d_stream = nullptr;
+}
+StagedTriplets::~StagedTriplets() {
+  if (!ready) return;
+  if (row.get()) cudaEventSynchronize(ready);    // never consumed: the copies must be over before the buffers are recycled
+  cudaEventDestroy(ready);
+}
+void stage_triplets(StagedTriplets& S, const int* rows, const int* cols, const double* vals, long long n) {
+  ensure_init();
+  if (!g_h2d_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&g_h2d_stream, cudaStreamNonBlocking));
+  S.n = n;
+  S.row.alloc((size_t)n); S.col.alloc((size_t)n); S.val.alloc((size_t)n);
+  if (!S.ready) CUDA_CHECK(cudaEventCreateWithFlags(&S.ready, cudaEventDisableTiming));
+  // arena blocks are recycled in library-stream order: the copies must not start before the work already enqueued there
+  cudaEvent_t now;
+  CUDA_CHECK(cudaEventCreateWithFlags(&now, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(now, rt().stream));
+  CUDA_CHECK(cudaStreamWaitEvent(g_h2d_stream, now, 0));
+  CUDA_CHECK(cudaEventDestroy(now));
+  if (n) {
+    copy_in_pieces(S.row.get(), rows, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, g_h2d_stream);
+    copy_in_pieces(S.col.get(), cols, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, g_h2d_stream);
+    copy_in_pieces(S.val.get(), vals, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g_h2d_stream);
+  }
+  CUDA_CHECK(cudaEventRecord(S.ready, g_h2d_stream));
+}
+void mat_fill_from_staged(Matrix& M, StagedTriplets& S) {
+  NTB_CHECK(M.constructed, "FillMatrixFromStaged on an unconstructed matrix");
+  NTB_CHECK(S.ready != nullptr, "FillMatrixFromStaged: nothing was staged");
+  if (M.is_complex) { Matrix t; mat_construct_empty(t, M.actual_dim, M.grid, false); M = std::move(t); }
+  CUDA_CHECK(cudaStreamWaitEvent(rt().stream, S.ready, 0));
+  if (S.n) NTB_LAUNCH(k_add_const2, std::min(div_up(S.n, 256), kNumSMs * 16), 256, 0, S.row.get(), S.col.get(), S.n, -1, -1);
+  ingest_device_triplets<double>(M, S.row, S.col, S.val, S.n, false, false);
+  S.row.release(); S.col.release(); S.val.release();       // back to the arena, in library-stream order
+  S.n = 0;
 }
 
 void mat_fill_from_triplets(Matrix& M, const int* rows, const int* cols, const double* vals_r, const cplx* vals_c,
@@ -399,9 +522,9 @@ long long mat_get_triplets_async(const Matrix& M, int* rows, int* cols, double* 
   d2d(pe.val.get(), v.val, (size_t)nnz);       // the matrix may be overwritten before the copy has run
   CUDA_CHECK(cudaEventRecord(g_egress_ready, rt().stream));
   CUDA_CHECK(cudaStreamWaitEvent(g_copy_stream, g_egress_ready, 0));
-  CUDA_CHECK(cudaMemcpyAsync(rows, pe.row.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, g_copy_stream));
-  CUDA_CHECK(cudaMemcpyAsync(cols, pe.col.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, g_copy_stream));
-  CUDA_CHECK(cudaMemcpyAsync(vals_r, pe.val.get(), nnz * sizeof(double), cudaMemcpyDeviceToHost, g_copy_stream));
+  copy_in_pieces(rows, pe.row.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, g_copy_stream);
+  copy_in_pieces(cols, pe.col.get(), nnz * sizeof(int), cudaMemcpyDeviceToHost, g_copy_stream);
+  copy_in_pieces(vals_r, pe.val.get(), nnz * sizeof(double), cudaMemcpyDeviceToHost, g_copy_stream);
   g_pending_egress.push_back(std::move(pe));
   return nnz;
 }

@@ -79,6 +79,18 @@ long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r
 // the same for a real matrix without waiting: host buffers (pinned) are complete after mat_egress_wait()
 long long mat_get_triplets_async(const Matrix& M, int* rows, int* cols, double* vals_r);
 void mat_egress_wait();
+// Staged ingest (real matrices): stage_triplets only enqueues the host-to-device copies of a global 1-based list on a
+// copy stream and returns; mat_fill_from_staged later turns the staged list into the matrix (the library stream waits
+// for the copies). The host arrays (pinned memory, or the copies are not asynchronous) must stay valid until then.
+struct StagedTriplets {
+  DevBuf<int> row, col;
+  DevBuf<double> val;
+  long long n = 0;
+  cudaEvent_t ready = nullptr;
+  ~StagedTriplets();
+};
+void stage_triplets(StagedTriplets& S, const int* rows, const int* cols, const double* vals, long long n);
+void mat_fill_from_staged(Matrix& M, StagedTriplets& S);
 void mat_transpose(const Matrix& A, Matrix& out);
 void mat_conjugate(Matrix& M);
 void mat_to_complex(const Matrix& in, Matrix& out);
