@@ -308,6 +308,9 @@ double ntb_tile_builds(void);
 void ntb_get_halo_counters(double *out2);
 /* 1 (default): column-split grids use the tile halo exchange; 0: always the reference-style CSC panel gather */
 void ntb_set_halo_path(int on);
+/* 0 (default): PermuteMatrix / UndoPermuteMatrix relabel the indices on the device; 1: the reference's two products by
+ * permutation matrices (LoadBalancerModule.F90:38-47, 77-86). Same result bit for bit. */
+void ntb_set_permute_gemm(int on);
 /* C = alpha*A*B (thresholded), then IncrementMatrix(Identity, C, sigma) with threshold 0 — the call pair of
  * SignSolversModule.F90:226-229 / SquareRootSolversModule.F90 as one entry point. */
 void ntb_MatrixMultiplyShift_ps(const int *ih_matA, const int *ih_matB, int *ih_matC, const double *alpha,

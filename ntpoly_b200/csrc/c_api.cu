@@ -386,6 +386,7 @@ void ntb_get_tile_counters(double* out2) { out2[0] = (double)rt().tile_products;
 double ntb_tile_builds(void) { return (double)rt().tile_builds; }
 void ntb_get_halo_counters(double* out2) { out2[0] = (double)rt().halo_products; out2[1] = rt().halo_bytes; }
 void ntb_set_halo_path(int on) { ntb::set_halo_path(on); }
+void ntb_set_permute_gemm(int on) { ntb::set_permute_gemm(on); }
 double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }
 void ntb_profile_enable(int on) { ensure_init(); rt().profile = on != 0; }
 void ntb_profile_read(double* out2) {

@@ -1,4 +1,5 @@
 #include "device.cuh"
+#include <cstring>
 #include <map>
 #include <unordered_map>
 
@@ -95,7 +96,61 @@ void dfree(void* p) {
   g_arena.free_blocks.emplace(it->second, p);
 }
 size_t arena_bytes_reserved() { return g_arena.bytes_reserved; }
-void stream_sync() { CUDA_CHECK(cudaStreamSynchronize(g_rt.stream)); }
+
+// ---------------------------------------------------------------------------
+// Small read-backs (task counts, nnz, norms, flags: about ten per solver step) do not use a copy engine: a copy
+// engine serves its queue in order, so a 4-byte cudaMemcpyAsync of the library stream waits behind a whole bulk
+// device-to-host transfer that another stream has queued (the asynchronous egress of the previous result) - measured:
+// the step of a pipelined host loop could not start before the previous result had left completely. Instead one
+// thread block stores the bytes straight into mapped pinned host memory; stream_sync() hands them to the caller.
+// ---------------------------------------------------------------------------
+namespace {
+constexpr size_t RB_SCRATCH = 64 << 10, RB_MAX = 4096;
+struct PendingReadback { void* host; size_t off, bytes; };
+unsigned char* g_rb_host = nullptr;                  // mapped pinned scratch (host address)
+unsigned char* g_rb_dev = nullptr;                   // the same memory as seen from the device
+size_t g_rb_used = 0;
+std::vector<PendingReadback> g_rb_pending;
+
+__global__ void __launch_bounds__(128) k_readback(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst,
+                                                  unsigned bytes, int words) {
+  if (words) {
+    const unsigned n = bytes >> 2;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
+      reinterpret_cast<unsigned*>(dst)[i] = reinterpret_cast<const unsigned*>(src)[i];
+  } else {
+    for (unsigned i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+}
+}  // namespace
+
+void readback_async(void* host, const void* dev, size_t bytes) {
+  if (bytes == 0) return;
+  const size_t padded = (bytes + 15) & ~size_t(15);
+  if (bytes > RB_MAX || g_rb_used + padded > RB_SCRATCH) {          // bulk, or scratch exhausted: the copy engine
+    CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g_rt.stream));
+    return;
+  }
+  if (!g_rb_host) {
+    CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&g_rb_host), RB_SCRATCH, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_rb_dev), g_rb_host, 0));
+  }
+  const int words = ((reinterpret_cast<uintptr_t>(dev) & 3u) == 0 && (bytes & 3u) == 0) ? 1 : 0;
+  k_readback<<<1, 128, 0, g_rt.stream>>>(static_cast<const unsigned char*>(dev), g_rb_dev + g_rb_used, (unsigned)bytes, words);
+  CUDA_CHECK(cudaGetLastError());
+  g_rt.launches++;
+  g_rb_pending.push_back(PendingReadback{host, g_rb_used, bytes});
+  g_rb_used += padded;
+}
+void stream_sync() {
+  CUDA_CHECK(cudaStreamSynchronize(g_rt.stream));
+  if (!g_rb_pending.empty()) {
+    for (const PendingReadback& r : g_rb_pending) std::memcpy(r.host, g_rb_host + r.off, r.bytes);
+    g_rb_pending.clear();
+  }
+  g_rb_used = 0;
+}
 
 // ---------------------------------------------------------------------------
 // device-wide exclusive scan: block partials -> single-block top scan -> final

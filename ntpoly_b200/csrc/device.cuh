@@ -36,7 +36,11 @@ void set_stream(cudaStream_t s);
 
 void* dmalloc(size_t bytes);
 void dfree(void* p);
+// waits for the library stream and completes the read-backs enqueued with readback_async()
 void stream_sync();
+// device -> host copy on the library stream whose result is valid after the next stream_sync(); small sizes bypass the
+// copy engines (see device.cu)
+void readback_async(void* host, const void* dev, size_t bytes);
 size_t arena_bytes_reserved();
 
 // RAII device array on the library stream
@@ -64,7 +68,7 @@ template <typename T> struct DevBuf {
 };
 
 template <typename T> inline void d2h(T* host, const T* dev, size_t count) {
-  CUDA_CHECK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, rt().stream));
+  readback_async(host, dev, count * sizeof(T));
   stream_sync();
 }
 template <typename T> inline void h2d(T* dev, const T* host, size_t count) {

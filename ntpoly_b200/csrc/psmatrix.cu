@@ -595,6 +595,42 @@ void mat_transpose(const Matrix& A, Matrix& out) {
   if (A.is_complex) transpose_t<cplx>(A, out); else transpose_t<double>(A, out);
 }
 
+// ---- symmetric relabelling out(map[r], map[c]) = A(r, c): what PermuteMatrix / UndoPermuteMatrix compute with two
+// products by permutation matrices (LoadBalancerModule.F90:38-47, 77-86), done as an index gather and a re-sort
+// (SURVEY 8f row 3). Every result entry of those products is 1*v*1 with a single term and the products keep |v| > 0,
+// so relabelling and dropping exact zeros gives the same matrix bit for bit.
+__global__ void __launch_bounds__(256) k_relabel(int* __restrict__ row, int* __restrict__ col, long long n, int roff, int coff,
+                                                 const int* __restrict__ map) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    row[i] = map[row[i] + roff];
+    col[i] = map[col[i] + coff];
+  }
+}
+template <typename T> static void relabel_t(const Matrix& A, Matrix& out, const int* h_map0) {
+  Matrix res;
+  mat_construct_empty(res, A.actual_dim, A.grid, A.is_complex);
+  const LocalCsc<T>& L = loc<T>(A);
+  const long long n = L.nnz;
+  DevBuf<int> d_row((size_t)n), d_col((size_t)n), d_map((size_t)A.logical_dim);
+  DevBuf<T> d_val((size_t)n);
+  h2d(d_map.get(), h_map0, (size_t)A.logical_dim);
+  if (n) {
+    const CscView<T> v = L.view();
+    csc_to_device_triplets<T>(v, n, d_row.get(), d_col.get());
+    d2d(d_val.get(), v.val, (size_t)n);
+    NTB_LAUNCH(k_relabel, std::min(div_up(n, 256), kNumSMs * 16), 256, 0, d_row.get(), d_col.get(), n, A.start_row,
+               A.start_col, d_map.get());
+  }
+  stream_sync();                                 // h_map0 is the copy's source
+  ingest_device_triplets<T>(res, d_row, d_col, d_val, n, true, false);
+  csc_filter<T>(loc<T>(res), 0.0);               // the products would not keep an exact zero
+  out = std::move(res);
+}
+void mat_relabel(const Matrix& A, Matrix& out, const int* h_map0) {
+  NTB_CHECK(A.constructed, "PermuteMatrix on an unconstructed matrix");
+  if (A.is_complex) relabel_t<cplx>(A, out, h_map0); else relabel_t<double>(A, out, h_map0);
+}
+
 void mat_conjugate(Matrix& M) { if (M.is_complex) csc_conjugate<cplx>(M.c); }
 
 void mat_filter(Matrix& M, double threshold) {
@@ -1046,7 +1082,7 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
     fb.assign(nJ, 0.0);
     if (nJ == 1) { fb[0] = (double)Xpan.nnz / ((double)cb * inner_dim); return; }
     std::vector<int> marks(nJ + 1);
-    for (int j = 0; j <= nJ; ++j) CUDA_CHECK(cudaMemcpyAsync(&marks[j], Xpan.outer.get() + (size_t)j * cb, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+    for (int j = 0; j <= nJ; ++j) readback_async(&marks[j], Xpan.outer.get() + (size_t)j * cb, sizeof(int));
     stream_sync();
     for (int j = 0; j < nJ; ++j) fb[j] = (double)(marks[j + 1] - marks[j]) / ((double)cb * inner_dim);
   };

@@ -92,6 +92,8 @@ struct StagedTriplets {
 void stage_triplets(StagedTriplets& S, const int* rows, const int* cols, const double* vals, long long n);
 void mat_fill_from_staged(Matrix& M, StagedTriplets& S);
 void mat_transpose(const Matrix& A, Matrix& out);
+// out(map[r], map[c]) = A(r, c), exact zeros dropped; map has logical_dim 0-based entries (host)
+void mat_relabel(const Matrix& A, Matrix& out, const int* h_map0);
 void mat_conjugate(Matrix& M);
 void mat_to_complex(const Matrix& in, Matrix& out);
 void mat_to_real(const Matrix& in, Matrix& out);

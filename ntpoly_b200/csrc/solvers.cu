@@ -77,7 +77,30 @@ bool Monitor::converged(bool be_verbose) const {              // :122-191
 }
 
 // ---------------------------------------------------------------------------
-void permute_matrix(const Matrix& in, Matrix& out, const Permutation& p, MemoryPool* pool) {   // LoadBalancerModule.F90:16-52
+// LoadBalancerModule.F90:16-92. The reference forms the row and column permutation matrices and multiplies twice
+// (out = PR*in*PC resp. PC*in*PR); the same matrix is obtained here by relabelling the indices on the device
+// (psmatrix.cu: mat_relabel): in(r,c) lands at (rev[r], rev[c]) for PermuteMatrix and at (fwd[r], fwd[c]) for
+// UndoPermuteMatrix. NTB_PERMUTE_GEMM=1 / ntb_set_permute_gemm(1) selects the reference's two products instead.
+static int g_permute_gemm = -1;
+void set_permute_gemm(int on) { g_permute_gemm = on ? 1 : 0; }
+static bool permute_gemm() {
+  if (g_permute_gemm < 0) { const char* e = std::getenv("NTB_PERMUTE_GEMM"); g_permute_gemm = (e && e[0] == '1') ? 1 : 0; }
+  return g_permute_gemm == 1;
+}
+// only index_lookup is used, like the reference's FillMatrixPermutation (ConstructReversePermutation leaves an identity
+// in reverse_index_lookup, PermutationModule.F90:64-67, so the inverse is formed here)
+static void relabel_with(const Matrix& in, Matrix& out, const Permutation& p, bool inverse) {
+  NTB_CHECK((int)p.index_lookup.size() >= in.logical_dim, "permutation shorter than the logical matrix dimension");
+  std::vector<int> map0((size_t)in.logical_dim, 0);
+  for (int i = 0; i < in.logical_dim; ++i) {
+    const int l = p.index_lookup[(size_t)i] - 1;
+    NTB_CHECK(l >= 0 && l < in.logical_dim, "permutation entry outside the logical matrix dimension");
+    if (inverse) map0[(size_t)l] = i; else map0[(size_t)i] = l;
+  }
+  mat_relabel(in, out, map0.data());
+}
+void permute_matrix(const Matrix& in, Matrix& out, const Permutation& p, MemoryPool* pool) {   // :16-52
+  if (!permute_gemm()) { relabel_with(in, out, p, true); return; }
   Matrix PR, PC, T;
   mat_construct_like(PR, in);
   mat_construct_like(PC, in);
@@ -87,6 +110,7 @@ void permute_matrix(const Matrix& in, Matrix& out, const Permutation& p, MemoryP
   mat_multiply(T, PC, out, 1.0, 0.0, 0.0, pool);
 }
 void undo_permute_matrix(const Matrix& in, Matrix& out, const Permutation& p, MemoryPool* pool) {  // :55-92
+  if (!permute_gemm()) { relabel_with(in, out, p, false); return; }
   Matrix PR, PC, T;
   mat_construct_like(PR, in);
   mat_construct_like(PC, in);

@@ -392,9 +392,9 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   int h_bins[NBINS];
   long long h_tmp_total = 0;
   unsigned long long h_flops = 0;
-  CUDA_CHECK(cudaMemcpyAsync(h_bins, bin_count.get(), sizeof(h_bins), cudaMemcpyDeviceToHost, rt().stream));
-  CUDA_CHECK(cudaMemcpyAsync(&h_tmp_total, tmp_off.get() + ncols, sizeof(long long), cudaMemcpyDeviceToHost, rt().stream));
-  CUDA_CHECK(cudaMemcpyAsync(&h_flops, flops.get(), sizeof(h_flops), cudaMemcpyDeviceToHost, rt().stream));
+  readback_async(h_bins, bin_count.get(), sizeof(h_bins));
+  readback_async(&h_tmp_total, tmp_off.get() + ncols, sizeof(long long));
+  readback_async(&h_flops, flops.get(), sizeof(h_flops));
   stream_sync();
 
   auto account = [&](long long nnz_out) {

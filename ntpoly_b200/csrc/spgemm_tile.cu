@@ -196,9 +196,9 @@ static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
   exclusive_scan(scount.get(), sptr.get(), ncc);
   exclusive_scan(tcount.get(), tptr.get(), ncc);
   int h[3] = {0, 0, 0};
-  CUDA_CHECK(cudaMemcpyAsync(&h[0], sptr.get() + ncc, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-  CUDA_CHECK(cudaMemcpyAsync(&h[1], tptr.get() + ncc, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
-  CUDA_CHECK(cudaMemcpyAsync(&h[2], overflow.get(), sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  readback_async(&h[0], sptr.get() + ncc, sizeof(int));
+  readback_async(&h[1], tptr.get() + ncc, sizeof(int));
+  readback_async(&h[2], overflow.get(), sizeof(int));
   stream_sync();
   if (h[2]) return false;
   T.nsuper = h[0];
@@ -1023,8 +1023,8 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   exclusive_scan(gnb.get(), gtask_off.get(), nG);
   unsigned long long h_ndmma = 0;
   int h_tasks = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&h_ndmma, ndmma.get(), sizeof(h_ndmma), cudaMemcpyDeviceToHost, rt().stream));
-  CUDA_CHECK(cudaMemcpyAsync(&h_tasks, gtask_off.get() + nG, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  readback_async(&h_ndmma, ndmma.get(), sizeof(h_ndmma));
+  readback_async(&h_tasks, gtask_off.get() + nG, sizeof(int));
   stream_sync();
   // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
   if (!force && useful_products >= 0.0 && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
@@ -1090,7 +1090,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   exclusive_scan(cnt.get(), Z.outer.get(), ncols);
   if (wl) NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), L.ent.get(), L.kmeta.get());
   int h_nnz = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&h_nnz, Z.outer.get() + ncols, sizeof(int), cudaMemcpyDeviceToHost, rt().stream));
+  readback_async(&h_nnz, Z.outer.get() + ncols, sizeof(int));
   stream_sync();
   const auto t4 = now();
   Z.alloc_entries(0);

@@ -122,6 +122,43 @@ def test_identity_permutation_and_triplet_roundtrip(nt):
     assert abs(B.to_scipy() - a).sum() == 0.0
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("kind", ["random", "reverse", "default"])
+def test_permutation_by_relabelling_equals_the_two_products(nt, cplx, kind):
+    """PermuteMatrix / UndoPermuteMatrix as an index relabelling on the device against the
+    reference's form, two products by permutation matrices (LoadBalancerModule.F90:38-47, 77-86): same matrix bit
+    for bit, also with a padded logical dimension and with an explicit zero among the entries"""
+    n = 123
+    a = random_sparse(n, 0.08, 21, cplx).tolil()
+    a[3, 7] = 0.0
+    a = sp.csc_matrix(a)
+    p = nt.Permutation(n)
+    if kind == "random":
+        p.SetRandomPermutation(seed=11)
+    elif kind == "reverse":
+        p.SetReversePermutation()
+    A = to_gpu(nt, a)
+    res = {}
+    for gemm in (True, False):
+        nt.set_permute_gemm(gemm)
+        P, U = nt.Matrix_ps(n), nt.Matrix_ps(n)
+        nt.reset_counters()
+        nt.LoadBalancer.PermuteMatrix(A, P, p)
+        nt.LoadBalancer.UndoPermuteMatrix(P, U, p)
+        assert nt.counters()["multiplies"] == (4 if gemm else 0)
+        res[gemm] = (P.get_arrays(), U.get_arrays())
+    nt.set_permute_gemm(False)
+    for k in range(2):
+        for x, y in zip(res[True][k], res[False][k]):
+            assert np.array_equal(x, y)
+    rows, cols, vals = res[False][1]
+    back = sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(n, n)).tocsc()
+    assert abs(back - a).sum() == 0.0
+    if kind != "default":
+        prow, pcol, _ = res[False][0]
+        assert not (np.array_equal(prow, rows) and np.array_equal(pcol, cols))
+
+
 def test_matrix_market_roundtrip(nt, tmp_path):
     import os
     import scipy.io as sio
