@@ -107,6 +107,18 @@ void TransposeMatrix_ps_wrp(const int *ih_matA, int *ih_transmat);
 void ConjugateMatrix_ps_wrp(int *ih_matA);
 void GetMatrixProcessGrid_ps_wrp(const int *ih_this, int *ih_grid);
 int IsIdentity_ps_wrp(const int *ih_this);
+/* container utilities either side of the path (host-side logic over the ingest / egress primitives):
+ * PSMatrixModule.F90:958-990, 1153-1225, 1718-1741, distributed_includes/{FillMatrixDense,GetMatrixBlock,SliceMatrix,
+ * ResizeMatrix}.f90; Source/C/MatrixConversion_c.h:4 (MatrixConversionModule.F90:21-61) */
+void FillMatrixDense_ps_wrp(int *ih_this);
+void GetMatrixBlock_psr_wrp(const int *ih_this, int *ih_triplet_list, int *start_row, int *end_row,
+                            int *start_column, int *end_column);
+void GetMatrixBlock_psc_wrp(const int *ih_this, int *ih_triplet_list, int *start_row, int *end_row,
+                            int *start_column, int *end_column);
+void GetMatrixSlice_wrp(const int *ih_this, int *ih_submatrix, int *start_row, int *end_row, int *start_column,
+                        int *end_column);
+void ResizeMatrix_ps_wrp(int *ih_this, const int *new_size);
+void SnapMatrixToSparsityPattern_wrp(int *ih_matA, const int *ih_matB);
 
 /* ---- 4. THE HOT PATH: distributed algebra (Source/C/PSMatrix_c.h:51-68;
  *         PSMatrixAlgebraModule_wrp.F90:29-198 -> PSMatrixAlgebraModule.F90) */

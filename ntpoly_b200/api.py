@@ -45,7 +45,8 @@ ConstructMatrixFromMatrixMarket_ps_wrp ConstructMatrixFromMatrixMarketPG_ps_wrp 
 FillMatrixFromTripletList_psr_wrp FillMatrixFromTripletList_psc_wrp FillMatrixPermutation_ps_wrp
 FillMatrixIdentity_ps_wrp GetMatrixActualDimension_ps_wrp GetMatrixLogicalDimension_ps_wrp GetMatrixSize_ps_wrp
 GetMatrixTripletList_psr_wrp GetMatrixTripletList_psc_wrp TransposeMatrix_ps_wrp ConjugateMatrix_ps_wrp
-GetMatrixProcessGrid_ps_wrp IsIdentity_ps_wrp
+GetMatrixProcessGrid_ps_wrp IsIdentity_ps_wrp FillMatrixDense_ps_wrp GetMatrixBlock_psr_wrp GetMatrixBlock_psc_wrp
+GetMatrixSlice_wrp ResizeMatrix_ps_wrp SnapMatrixToSparsityPattern_wrp
 MatrixMultiply_ps_wrp IncrementMatrix_ps_wrp ScaleMatrix_ps_wrp MatrixTrace_ps_wrp MatrixNorm_ps_wrp
 DotMatrix_psr_wrp DotMatrix_psc_wrp MatrixPairwiseMultiply_ps_wrp MeasureAsymmetry_ps_wrp SymmetrizeMatrix_ps_wrp
 ConstructMatrixMemoryPool_p_wrp DestructMatrixMemoryPool_p_wrp
@@ -605,6 +606,27 @@ class Matrix_ps:
 
     def FillIdentity(self):
         lib().FillMatrixIdentity_ps_wrp(self.ih)
+
+    def FillDense(self):
+        lib().FillMatrixDense_ps_wrp(self.ih)
+
+    def Resize(self, new_size):
+        lib().ResizeMatrix_ps_wrp(self.ih, _i(new_size))
+
+    def GetMatrixBlock(self, tl, start_row, end_row, start_column, end_column):
+        """0-based bounds, ends exclusive, like the reference C++ class (PSMatrix.cc:129-150 adds 1 to all four before
+        the C call; distributed_includes/GetMatrixBlock.f90 tests start <= index < end)"""
+        fn = lib().GetMatrixBlock_psc_wrp if tl.is_complex else lib().GetMatrixBlock_psr_wrp
+        fn(self.ih, tl.ih, _i(start_row + 1), _i(end_row + 1), _i(start_column + 1), _i(end_column + 1))
+
+    def GetMatrixSlice(self, submatrix, start_row, end_row, start_column, end_column):
+        """0-based inclusive bounds like the reference C++ class (PSMatrix.cc adds 1 before the C call)"""
+        lib().GetMatrixSlice_wrp(self.ih, submatrix.ih, _i(start_row + 1), _i(end_row + 1), _i(start_column + 1),
+                                 _i(end_column + 1))
+
+    def SnapToSparsityPattern(self, pattern):
+        """reference MatrixConversion::SnapMatrixToSparsityPattern(mata, matb)"""
+        lib().SnapMatrixToSparsityPattern_wrp(self.ih, pattern.ih)
 
     def GetActualDimension(self):
         v = c_int()

@@ -197,6 +197,32 @@ void GetMatrixTripletList_psc_wrp(const int* ih, int* ih_tl) {
   d.resize((size_t)n);
   for (long long i = 0; i < n; ++i) d[i] = Triplet_c{cols[i], rows[i], vals[i].x, vals[i].y};
 }
+void FillMatrixDense_ps_wrp(int* ih) { mat_fill_dense(*get<Matrix>(ih)); }
+void ResizeMatrix_ps_wrp(int* ih, const int* new_size) { mat_resize(*get<Matrix>(ih), *new_size); }
+void GetMatrixSlice_wrp(const int* ih, int* ih_sub, int* start_row, int* end_row, int* start_column, int* end_column) {
+  mat_get_slice(*get<Matrix>(ih), *get<Matrix>(ih_sub), *start_row, *end_row, *start_column, *end_column);
+}
+void GetMatrixBlock_psr_wrp(const int* ih, int* ih_tl, int* start_row, int* end_row, int* start_column, int* end_column) {
+  const Matrix& M = *get<Matrix>(ih);
+  NTB_CHECK(!M.is_complex, "GetMatrixBlock_psr on a complex matrix");
+  std::vector<int> r, c;
+  std::vector<double> v;
+  const long long n = mat_get_block(M, *start_row, *end_row, *start_column, *end_column, r, c, v);
+  auto& d = get<TripletList_r>(ih_tl)->data;
+  d.resize((size_t)n);
+  for (long long i = 0; i < n; ++i) d[i] = Triplet_r{c[i], r[i], v[i]};
+}
+void GetMatrixBlock_psc_wrp(const int* ih, int* ih_tl, int* start_row, int* end_row, int* start_column, int* end_column) {
+  const Matrix& M = *get<Matrix>(ih);
+  NTB_CHECK(M.is_complex, "GetMatrixBlock_psc on a real matrix");
+  std::vector<int> r, c;
+  std::vector<double> v;
+  const long long n = mat_get_block(M, *start_row, *end_row, *start_column, *end_column, r, c, v);
+  auto& d = get<TripletList_c>(ih_tl)->data;
+  d.resize((size_t)n);
+  for (long long i = 0; i < n; ++i) d[i] = Triplet_c{c[i], r[i], v[2 * i], v[2 * i + 1]};
+}
+void SnapMatrixToSparsityPattern_wrp(int* ih_a, const int* ih_b) { mat_snap_to_pattern(*get<Matrix>(ih_a), *get<Matrix>(ih_b)); }
 void TransposeMatrix_ps_wrp(const int* ih_a, int* ih_t) { mat_transpose(*get<Matrix>(ih_a), *get<Matrix>(ih_t)); }
 void ConjugateMatrix_ps_wrp(int* ih) { mat_conjugate(*get<Matrix>(ih)); }
 void GetMatrixProcessGrid_ps_wrp(const int* ih, int* ih_grid) { put(ih_grid, get<Matrix>(ih)->grid); }

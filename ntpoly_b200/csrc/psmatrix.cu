@@ -1210,4 +1210,158 @@ void mat_similarity_transform(const Matrix& A, const Matrix& P, const Matrix& PI
   mat_multiply(tmp, PInv, Res, 1.0, 0.0, threshold, pool);
 }
 
+// ===========================================================================
+// container utilities either side of the path (host-side logic over the ingest / egress primitives; not per-iteration)
+// ===========================================================================
+namespace {
+struct HostTriplets { std::vector<int> rows, cols; std::vector<double> re; std::vector<cplx> cx; };
+// local block as global 1-based host triplets
+HostTriplets local_host_triplets(const Matrix& M) {
+  HostTriplets t;
+  const long long n = M.local_nnz();
+  t.rows.resize((size_t)n); t.cols.resize((size_t)n);
+  if (M.is_complex) { t.cx.resize((size_t)n); mat_get_triplets(M, t.rows.data(), t.cols.data(), nullptr, t.cx.data()); }
+  else { t.re.resize((size_t)n); mat_get_triplets(M, t.rows.data(), t.cols.data(), t.re.data(), nullptr); }
+  return t;
+}
+// keep the entries for which pred(row, col) holds, renumbered by (row - dr, col - dc)
+template <typename P> HostTriplets select_triplets(const HostTriplets& in, bool cx, int dr, int dc, P pred) {
+  HostTriplets o;
+  for (size_t i = 0; i < in.rows.size(); ++i)
+    if (pred(in.rows[i], in.cols[i])) {
+      o.rows.push_back(in.rows[i] - dr); o.cols.push_back(in.cols[i] - dc);
+      if (cx) o.cx.push_back(in.cx[i]); else o.re.push_back(in.re[i]);
+    }
+  return o;
+}
+void fill_host_triplets(Matrix& M, const HostTriplets& t, bool preduplicated, bool prepartitioned) {
+  mat_fill_from_triplets(M, t.rows.data(), t.cols.data(), M.is_complex ? nullptr : t.re.data(),
+                         M.is_complex ? t.cx.data() : nullptr, (long long)t.rows.size(), preduplicated, prepartitioned);
+}
+}  // namespace
+
+// distributed_includes/FillMatrixDense.f90: 1.0 at every position of the local block inside the actual dimension
+void mat_fill_dense(Matrix& M) {
+  NTB_CHECK(M.constructed, "FillMatrixDense on an unconstructed matrix");
+  HostTriplets t;
+  for (int c = M.start_col; c < M.start_col + M.local_cols && c < M.actual_dim; ++c)
+    for (int r = M.start_row; r < M.start_row + M.local_rows && r < M.actual_dim; ++r) {
+      t.rows.push_back(r + 1); t.cols.push_back(c + 1);
+      if (M.is_complex) t.cx.push_back(cplx{1.0, 0.0}); else t.re.push_back(1.0);
+    }
+  fill_host_triplets(M, t, true, true);
+}
+
+// distributed_includes/ResizeMatrix.f90: entries inside the new size survive; the result lives on the GLOBAL grid
+// (the reference calls ConstructEmptyMatrix without a grid there)
+void mat_resize(Matrix& M, int new_size) {
+  NTB_CHECK(M.constructed, "ResizeMatrix on an unconstructed matrix");
+  const bool cx = M.is_complex;
+  const HostTriplets kept = select_triplets(local_host_triplets(M), cx, 0, 0,
+                                            [&](int r, int c) { return r <= new_size && c <= new_size; });
+  Matrix res;
+  mat_construct_empty(res, new_size, nullptr, cx);
+  fill_host_triplets(res, kept, true, false);
+  M = std::move(res);
+}
+
+// distributed_includes/SliceMatrix.f90: rows [start_row, end_row] x columns [start_column, end_column] (1-based,
+// inclusive) as a new matrix of dimension max(height, width) on the same grid
+void mat_get_slice(const Matrix& M, Matrix& sub, int start_row, int end_row, int start_col, int end_col) {
+  NTB_CHECK(M.constructed, "GetMatrixSlice on an unconstructed matrix");
+  const bool cx = M.is_complex;
+  const HostTriplets kept = select_triplets(local_host_triplets(M), cx, start_row - 1, start_col - 1, [&](int r, int c) {
+    return r >= start_row && r <= end_row && c >= start_col && c <= end_col; });
+  const int new_dim = std::max(end_row - start_row + 1, end_col - start_col + 1);
+  Matrix res;
+  mat_construct_empty(res, new_dim, M.grid, cx);
+  fill_host_triplets(res, kept, true, false);
+  sub = std::move(res);
+}
+
+// every entry held by the ranks of M's slice as global 1-based host triplets (the same on every rank of the slice)
+template <typename T>
+static void slice_triplets_to_host(const Matrix& M, const LocalCsc<T>& L, std::vector<int>& rows, std::vector<int>& cols,
+                                   std::vector<T>& vals) {
+  const long long n = L.nnz;
+  DevBuf<int> d_row((size_t)n), d_col((size_t)n);
+  DevBuf<T> d_val((size_t)n);
+  if (n) {
+    const CscView<T> v = L.view();
+    csc_to_device_triplets<T>(v, n, d_row.get(), d_col.get());
+    d2d(d_val.get(), v.val, (size_t)n);
+    NTB_LAUNCH(k_add_const2, std::min(div_up(n, 256), kNumSMs * 16), 256, 0, d_row.get(), d_col.get(), n, M.start_row + 1,
+               M.start_col + 1);
+  }
+  const long long total = allgather_triplets<T>(M.grid->within_slice, d_row, d_col, d_val, n);
+  rows.resize((size_t)total); cols.resize((size_t)total); vals.resize((size_t)total);
+  if (total) {
+    d2h(rows.data(), d_row.get(), (size_t)total);
+    d2h(cols.data(), d_col.get(), (size_t)total);
+    d2h(vals.data(), d_val.get(), (size_t)total);
+  }
+}
+
+// distributed_includes/GetMatrixBlock.f90: every rank names a block [start_row, end_row) x [start_column, end_column)
+// (1-based, end exclusive) and receives the entries of the whole matrix that fall into it; an entry wanted by several
+// ranks of a slice goes to the first of them
+long long mat_get_block(const Matrix& M, int start_row, int end_row, int start_col, int end_col, std::vector<int>& rows,
+                        std::vector<int>& cols, std::vector<double>& vals_interleaved) {
+  NTB_CHECK(M.constructed, "GetMatrixBlock on an unconstructed matrix");
+  CommHandle* comm = M.grid->within_slice;
+  const int np = comm_size(comm), me = comm_rank(comm);
+  std::vector<int> ranges((size_t)np * 4);
+  {
+    const int mine[4] = {start_row, end_row, start_col, end_col};
+    if (np == 1) { std::copy(mine, mine + 4, ranges.begin()); }
+    else {
+      DevBuf<int> d_mine(4), d_all((size_t)np * 4);
+      h2d(d_mine.get(), mine, 4);
+      stream_sync();
+      comm_allgather_bytes(comm, d_mine.get(), d_all.get(), 4 * sizeof(int));
+      d2h(ranges.data(), d_all.get(), (size_t)np * 4);
+    }
+  }
+  // all entries of the slice, global 1-based, on the host
+  HostTriplets all;
+  const bool cx = M.is_complex;
+  if (np == 1) all = local_host_triplets(M);
+  else if (cx) slice_triplets_to_host<cplx>(M, M.c, all.rows, all.cols, all.cx);
+  else slice_triplets_to_host<double>(M, M.r, all.rows, all.cols, all.re);
+  auto wanted_by = [&](int r, int c) {
+    for (int p = 0; p < np; ++p) {
+      const int* q = &ranges[(size_t)p * 4];
+      if (r >= q[0] && r < q[1] && c >= q[2] && c < q[3]) return p;
+    }
+    return -1;
+  };
+  rows.clear(); cols.clear(); vals_interleaved.clear();
+  for (size_t i = 0; i < all.rows.size(); ++i)
+    if (wanted_by(all.rows[i], all.cols[i]) == me) {
+      rows.push_back(all.rows[i]); cols.push_back(all.cols[i]);
+      if (cx) { vals_interleaved.push_back(all.cx[i].x); vals_interleaved.push_back(all.cx[i].y); }
+      else vals_interleaved.push_back(all.re[i]);
+    }
+  return (long long)rows.size();
+}
+
+// MatrixConversionModule.F90:21-61: mat takes the sparsity pattern of `pattern` - positions of the pattern that mat
+// lacks become explicit zeros (an addition with a negative threshold never drops anything), values outside are removed
+void mat_snap_to_pattern(Matrix& mat, const Matrix& pattern) {
+  NTB_CHECK(mat.constructed && pattern.constructed, "SnapMatrixToSparsityPattern on an unconstructed matrix");
+  Matrix ones, zeros, filtered;
+  {
+    HostTriplets t = local_host_triplets(pattern);
+    t.cx.clear();
+    t.re.assign(t.rows.size(), 1.0);
+    mat_construct_empty(ones, pattern.actual_dim, pattern.grid, false);
+    fill_host_triplets(ones, t, true, true);
+  }
+  mat_copy(ones, zeros);
+  mat_scale(zeros, 0.0);
+  mat_increment(zeros, mat, 1.0, -1.0);
+  mat_copy(mat, filtered);
+  mat_pairwise(ones, filtered, mat);
+}
+
 }  // namespace ntb

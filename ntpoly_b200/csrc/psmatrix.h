@@ -98,6 +98,13 @@ void mat_conjugate(Matrix& M);
 void mat_to_complex(const Matrix& in, Matrix& out);
 void mat_to_real(const Matrix& in, Matrix& out);
 void mat_filter(Matrix& M, double threshold);
+// container utilities of PSMatrixModule / MatrixConversionModule that sit either side of the path
+void mat_fill_dense(Matrix& M);
+void mat_resize(Matrix& M, int new_size);
+void mat_get_slice(const Matrix& M, Matrix& sub, int start_row, int end_row, int start_col, int end_col);
+long long mat_get_block(const Matrix& M, int start_row, int end_row, int start_col, int end_col, std::vector<int>& rows,
+                        std::vector<int>& cols, std::vector<double>& vals_interleaved);
+void mat_snap_to_pattern(Matrix& mat, const Matrix& pattern);
 long long mat_global_nnz(const Matrix& M);
 bool mat_is_identity(const Matrix& M);
 

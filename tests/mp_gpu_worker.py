@@ -66,6 +66,28 @@ def main():
             T = nt.Matrix_ps(n)
             T.Transpose(A)
             assert abs(local_block(T) - oracle_block(O, O.transpose(OA), rank)).sum() < 1e-14
+            # a list that is the rank's own block in column-major order is taken without sort or gather (collective
+            # decision inside the slice); the ranks of the other slices contribute nothing and receive the replica
+            rows, cols, vals = T.get_arrays()
+            if nt.GetGlobalMySlice() != 0:
+                rows, cols, vals = rows[:0], cols[:0], vals[:0]
+            T2 = nt.Matrix_ps(n, is_complex=cplx)
+            before = nt.sorted_ingests()
+            T2.fill_from_arrays(rows, cols, vals)
+            assert nt.sorted_ingests() == before + 1
+            assert abs(local_block(T2) - local_block(T)).sum() == 0.0 and T2.GetSize() == T.GetSize()
+            # load balancing by relabelling == by two products, on this grid
+            perm = nt.Permutation(T.GetLogicalDimension()); perm.SetRandomPermutation(seed=3)
+            blocks = []
+            for gemm in (True, False):
+                nt.set_permute_gemm(gemm)
+                P1, U1 = nt.Matrix_ps(n), nt.Matrix_ps(n)
+                nt.LoadBalancer.PermuteMatrix(T, P1, perm)
+                nt.LoadBalancer.UndoPermuteMatrix(P1, U1, perm)
+                blocks.append((local_block(P1), local_block(U1)))
+            nt.set_permute_gemm(False)
+            assert abs(blocks[0][0] - blocks[1][0]).sum() == 0.0 and abs(blocks[0][1] - blocks[1][1]).sum() == 0.0
+            assert abs(blocks[1][1] - local_block(T)).sum() == 0.0
         # banded product on the tile path + a solver with identical iteration count
         n = 2048
         a = banded(n, half_bandwidth=24).tocoo()
