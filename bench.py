@@ -369,6 +369,7 @@ def main():
                 "fp64_tflops_useful": flops_local / (prof["numeric_ms"] * 1e-3) / 1e12 if prof["numeric_ms"] > 0 else 0.0,
                 "fp64_tensor_peak_tflops": FP64_PEAK_TFLOPS,
                 "fp64_frac": (flops_local / (prof["numeric_ms"] * 1e-3) / 1e12 / FP64_PEAK_TFLOPS) if prof["numeric_ms"] > 0 else 0.0,
+                "gustavson_upper_bytes_per_launch": (flops_local / max(prof["products"], 1)) / 2.0 * 12.0,
                 "tile_form_builds_in_timed_region": builds_timed,
                 "deferred_csc_products_in_timed_region": dfr["products"],
                 "deferred_csc_materialized_in_timed_region": dfr["materialized"],
