@@ -98,7 +98,6 @@ void ConstructMatrixFromMatrixMarket_ps_wrp(int* ih, const char* file_name, cons
 void ConstructMatrixFromMatrixMarketPG_ps_wrp(int* ih, const char* file_name, const int* name_size, const int* ih_grid) { construct_from_mm(ih, file_name, *name_size, get<ProcessGrid>(ih_grid)); }
 void WriteMatrixToMatrixMarket_ps_wrp(const int* ih, const char* file_name, const int* name_size) {
   const Matrix& M = *get<Matrix>(ih);
-  NTB_CHECK(M.grid->size == 1 || true, "");
   // every rank of slice 0 appends its block in turn is not possible without host messaging;
   // the blocks are therefore collected on the device side and written by global rank 0.
   std::string path(file_name, (size_t)*name_size);
