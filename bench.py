@@ -348,6 +348,9 @@ def main():
                "overlap": "three streams: every step copies its own input in (copy stream 1) and its own result out "
                           "(copy stream 2); the input copy of step i+1 and the result copy of step i-1 run while step i "
                           "computes (PCIe is full duplex)",
+               "api": "C ABI with pinned host arrays: ntb_StageArrays + ntb_FillMatrixFromStaged_ps (triplets in), "
+                      "ntb_SignStep (the SignFunction driver's loop body), ntb_GetMatrixArraysAsync_ps + ntb_EgressWait "
+                      "(triplets out)",
                "sorted_ingests": nt.sorted_ingests()}
 
     if rank != 0:
