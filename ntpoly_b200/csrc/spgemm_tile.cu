@@ -424,7 +424,7 @@ struct ResultForms {
   int4* entR; double* tvalR;                 // right form: slot 2*task + h
   unsigned want;                             // WANT_LEFT | WANT_RIGHT
 };
-template <int NSTAGE, int MINB>
+template <int NSTAGE, int MINB, bool DENSE>
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
 k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
                 int* __restrict__ task_counter, int* __restrict__ cnt, ResultForms out, int nrows, int ncols, EmitSpec es) {
@@ -555,7 +555,8 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
           if (lane == 0) {
             *reinterpret_cast<unsigned long long*>(mt + 48) = sB;
             *reinterpret_cast<int2*>(mt + 56) = make_int2(gt0, gtn);
-            *reinterpret_cast<int4*>(mt) = make_int4((int)((last ? 1u : 0u) | (done ? 2u : 0u) | (nzA << 8)), g, Ib, task);
+            *reinterpret_cast<int4*>(mt) = make_int4((int)((last ? 1u : 0u) | (done ? 2u : 0u) | ((sA == ~0ull) ? 4u : 0u) | (nzA << 8)),
+                                                     g, Ib, task);
           }
           __syncwarp();                                        // the other lanes' meta stores happen before the arrive
           if (lane == 0) {
@@ -593,7 +594,22 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
       { const int2 gt = *reinterpret_cast<const int2*>(mt + 56); gt0 = gt.x; gtn = gt.y; }
       const unsigned mb = mt[48 + wj];
       const unsigned live = mb & ((unsigned)mi.x >> 8) & 0xffu;
-      if (live != 0u) {
+      if (DENSE && (fl & 4u) != 0u && mb == 0xffu) {
+        // DENSE STAGE: all 64 tiles of the A super-tile and all 8 inner tiles of this warp's B tile column are present
+        // (the interior of a band or of a filled-in block). Every fragment sits at a compile-time offset from two
+        // base pointers - A tile (kk, ii) at 8 kk + ii, B tile (wj, kk) at the column's first tile + kk - so the 64
+        // DMMAs need no mask arithmetic, no branches and no per-tile address chain (the generic loop below spends
+        // ~13 instructions per DMMA, this block ~2), and ptxas is free to hoist the loads of the next inner tile
+        // above the DMMAs of the current one. Same accumulation order as the generic loop: bit-identical results.
+        const double* Ad = slab + (size_t)st * STAGE_DOUBLES + lane;
+        const double* Bd = Ad + SLAB_DOUBLES + (unsigned)mt[64 + 8 * wj] * 32;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const double bv = Bd[kk * 32];
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], Ad[(8 * kk + ii) * 32], bv);
+        }
+      } else if (live != 0u) {
         const unsigned long long bo = *reinterpret_cast<const unsigned long long*>(mt + 64 + 8 * wj);
         const unsigned* adesc = reinterpret_cast<const unsigned*>(mt + 16);
         const double* As = slab + (size_t)st * STAGE_DOUBLES + lane;
@@ -1076,8 +1092,11 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
       NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, gtask_off.get(),
                  tasks.get(), h_tasks, task_counter.get(), cnt.get(), out, nrows, ncols, es);
     };
-    if (shape == 23) launch(k_tile_numeric9<2, 3>, 2, 3);
-    else launch(k_tile_numeric9<NSTAGE_DEFAULT, 2>, NSTAGE_DEFAULT, 2);
+    // dense-stage fast path of the DMMA warps (NTB_DENSE_STAGE=0 switches it off)
+    static const bool dense = [] { const char* e = std::getenv("NTB_DENSE_STAGE"); return !(e && e[0] == '0'); }();
+    if (shape == 23) launch(k_tile_numeric9<2, 3, false>, 2, 3);
+    else if (dense) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, true>, NSTAGE_DEFAULT, 2);
+    else launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, false>, NSTAGE_DEFAULT, 2);
   }
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
