@@ -1,0 +1,53 @@
+"""Offline (CPU, test infrastructure): how the DMMAs of the bench step's two products distribute over stage kinds.
+Builds the bench iterate X_3 of a banded N (default 8192; the band structure is translation invariant) with the CPU
+restatement, lays the tile masks of the numeric kernel over A and B (8x4 / 4x8 tiles, 64x32 / 32x64 super-tiles) and
+counts, per (stage, DMMA warp): DMMAs in 'dense' stages (A super-tile complete and the warp's B tile column complete:
+the fast path of k_tile_numeric9), in 'A complete, B column partial' stages, and the rest."""
+import os, sys
+import numpy as np, scipy.sparse as sp
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+thr, iterate = 1e-6, 3
+from oracle import oracle as O
+from ntpoly_b200.workloads import banded_sign_input
+O.build()
+M = O.PSMatrix.from_scipy(banded_sign_input(n)); I = O.identity(M)
+e_min, e_max = O.gershgorin(M)
+al = bench.alpha_sequence(e_min, e_max, iterate)
+X = O.scale(M, 1.0 / abs(e_max))
+def step(X, ak):
+    T1 = O.increment(I, O.multiply(X, X, alpha=-ak * ak, thr=thr), alpha=3.0)
+    return T1, O.multiply(X, T1, alpha=0.5 * ak, thr=thr)
+for k in range(iterate - 1):
+    _, X = step(X, al[k])
+T1, Xn = step(X, al[iterate - 1])
+Xs, T1s = X.to_scipy().tocsc(), T1.to_scipy().tocsc()
+print(f"n={n} nnz/col X={Xs.nnz / n:.1f} T1={T1s.nnz / n:.1f} Xnext={Xn.to_scipy().nnz / n:.1f}")
+
+def tile_grid(m, th, tw):
+    """boolean grid of th x tw tiles holding at least one entry"""
+    c = m.tocoo()
+    g = np.zeros((-(-m.shape[0] // th), -(-m.shape[1] // tw)), bool)
+    g[c.row // th, c.col // tw] = True
+    return g
+
+def stats(Am, Bm, name):
+    A = tile_grid(Am, 8, 4)          # A tiles: 8 rows x 4 inner
+    B = tile_grid(Bm, 4, 8)          # B tiles: 4 inner x 8 cols
+    nIb, nc, nJ = A.shape[0] // 8, A.shape[1] // 8, B.shape[1]
+    tot = dense = afull = 0
+    for c in range(nc):
+        Ac = A[:, 8 * c:8 * c + 8].reshape(nIb, 8, 8)          # [Ib, ii, kk]
+        Bc = B[8 * c:8 * c + 8, :]                               # [kk, J]
+        a_cnt = Ac.sum(axis=1)                                   # [Ib, kk] tiles per inner tile
+        a_full = Ac.reshape(nIb, 64).all(axis=1)                 # [Ib]
+        b_full = Bc.all(axis=0)                                  # [J]
+        d = a_cnt.astype(np.int64) @ Bc.astype(np.int64)         # [Ib, J] DMMAs of (row block, tile column) in this stage
+        tot += d.sum()
+        dense += d[np.ix_(a_full, b_full)].sum()
+        afull += d[a_full, :].sum()
+    print(f"{name}: DMMAs {tot}  dense stages {dense / tot:.3f}  A complete (any B column) {afull / tot:.3f}")
+
+stats(Xs, Xs, "X * X ")
+stats(Xs, T1s, "X * T1")
