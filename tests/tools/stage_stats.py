@@ -1,11 +1,11 @@
-"""Offline (CPU, test infrastructure): how the DMMAs of the bench step's two products distribute over stage kinds.
+"""Offline analysis (CPU, TEST INFRASTRUCTURE: lives under tests/ because it runs the CPU checker): how the DMMAs of the bench step's two products distribute over stage kinds.
 Builds the bench iterate X_3 of a banded N (default 8192; the band structure is translation invariant) with the CPU
 restatement, lays the tile masks of the numeric kernel over A and B (8x4 / 4x8 tiles, 64x32 / 32x64 super-tiles) and
 counts, per (stage, DMMA warp): DMMAs in 'dense' stages (A super-tile complete and the warp's B tile column complete:
 the fast path of k_tile_numeric9), in 'A complete, B column partial' stages, and the rest."""
 import os, sys
 import numpy as np, scipy.sparse as sp
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 thr, iterate = 1e-6, 3
