@@ -51,3 +51,34 @@ def stats(Am, Bm, name):
 
 stats(Xs, Xs, "X * X ")
 stats(Xs, T1s, "X * T1")
+
+
+def ragged_histogram(Am, Bm, name):
+    """DMMAs per (stage, warp) pair outside the dense stages: how much work a warp finds per stage it has to visit"""
+    A = tile_grid(Am, 8, 4); B = tile_grid(Bm, 4, 8)
+    nIb, nc = A.shape[0] // 8, A.shape[1] // 8
+    hist = np.zeros(65, np.int64)
+    visited_empty = 0
+    for c in range(nc):
+        Ac = A[:, 8 * c:8 * c + 8].reshape(nIb, 8, 8)
+        Bc = B[8 * c:8 * c + 8, :]
+        a_cnt = Ac.sum(axis=1)
+        a_full = Ac.reshape(nIb, 64).all(axis=1)
+        b_full = Bc.all(axis=0)
+        d = a_cnt.astype(np.int64) @ Bc.astype(np.int64)                 # [Ib, J]
+        # a stage exists for task (g, Ib) when the A super-tile and the B super-tile of the group share an inner tile
+        Bg = Bc.reshape(8, -1, 8).any(axis=2)                            # [kk, g]
+        stage = (Ac.any(axis=1).astype(np.int64) @ Bg.astype(np.int64)) > 0   # [Ib, g]
+        stage_J = np.repeat(stage, 8, axis=1)[:, :d.shape[1]]
+        dense = np.outer(a_full, b_full)
+        sel = stage_J & ~dense
+        np.add.at(hist, d[sel], 1)
+    tot_pairs = hist.sum()
+    work = (hist * np.arange(65)).sum()
+    print(f"{name}: ragged (stage, warp) pairs {tot_pairs}, mean DMMAs per pair {work / tot_pairs:.1f} of 64; "
+          f"pairs with 0 DMMAs {hist[0] / tot_pairs:.2f}, 1-16: {hist[1:17].sum() / tot_pairs:.2f}, "
+          f"17-48: {hist[17:49].sum() / tot_pairs:.2f}, 49-64: {hist[49:].sum() / tot_pairs:.2f}")
+
+
+ragged_histogram(Xs, Xs, "X * X ")
+ragged_histogram(Xs, T1s, "X * T1")
