@@ -707,6 +707,113 @@ def scale_and_fold(H, ISQ, trace_target, homo, lumo, p: SolverParameters | None 
     return K, info
 
 
+def hpcp(H, ISQ, trace_target, p: SolverParameters | None = None):
+    """HPCP (DensityMatrixSolversModule.F90:720-950). Returns (K, SolveInfo)."""
+    p = p or SolverParameters()
+    mon = p.monitor()
+    info = SolveInfo()
+    I, ISQT, WH = _density_setup(H, ISQ, p)
+    n = float(H.n)
+    e_min, e_max = gershgorin(WH)
+    mu = trace(WH) / n
+    sigma_bar = (n - trace_target) / n
+    sigma = 1.0 - sigma_bar
+    beta = sigma / (e_max - mu)
+    beta_bar = sigma_bar / (mu - e_min)
+    beta_1, beta_2 = sigma, min(beta, beta_bar)
+    D1 = scale(I, beta_1)                                        # :812-818
+    T = scale(I, mu)
+    T = increment(WH, T, alpha=-1.0)
+    T = scale(T, beta_2)
+    D1 = increment(T, D1)
+    energy = 0.0
+    broke = False
+    ii = 0
+    for ii in range(1, p.max_iterations + 1):
+        DH = increment(I, D1.copy(), alpha=-1.0)                 # :830-832
+        DH = scale(DH, -1.0)
+        DDH = multiply(D1, DH, thr=p.threshold)
+        tv = trace(DDH)
+        D2DH = multiply(D1, DDH, thr=p.threshold)
+        sg = trace(D2DH) / tv
+        info.sigmas.append(sg)
+        D1 = increment(D2DH, D1, alpha=2.0)
+        D1 = increment(DDH, D1, alpha=-1.0 * 2.0 * sg)
+        old = energy
+        energy = dot_real(D1, WH)
+        mon.append(energy - old)
+        info.history.append(energy - old)
+        if mon.converged():
+            broke = True
+            break
+    info.iterations = _loop_counter(ii, p.max_iterations, broke)
+    total = info.iterations - 1
+    info.energy = energy
+    K = _density_finish(D1, ISQT, ISQ, p)
+    a, b, mid = 0.0, 1.0, 0.0
+    for _ in range(p.max_iterations):                            # :905-925
+        mid = (b - a) / 2.0 + a
+        z = mid
+        for jj in range(total):
+            z = z + 2.0 * ((z * z) * (1.0 - z) - info.sigmas[jj] * z * (1.0 - z))
+        if z < 0.5:
+            a = mid
+        else:
+            b = mid
+        if abs(z - 0.5) < p.converge_diff:
+            break
+    info.chemical_potential = mu + (beta_1 - mid) / beta_2
+    return K, info
+
+
+def mcweeny_step(D, S=None, thr=0.0):
+    """McWeenyStep (DensityMatrixSolversModule.F90:1190-1231): 3 DSD - 2 DSDSD."""
+    DS = multiply(D, S, thr=thr) if S is not None else D.copy()
+    DSD = multiply(DS, D, thr=thr)
+    out = multiply(DS, DSD, alpha=-2.0, thr=thr)
+    return increment(DSD, out, alpha=3.0)
+
+
+def energy_density_matrix(H, D, thr=0.0):
+    """EnergyDensityMatrix (DensityMatrixSolversModule.F90:1165-1187): D H D via SimilarityTransform(H, D, D)."""
+    return similarity_transform(H, D, D, thr)
+
+
+def power_bounds(M, p: SolverParameters | None = None):
+    """PowerBounds (EigenBoundsModule.F90:60-189): power iteration with Aitken extrapolation. Returns (value, SolveInfo)."""
+    default = p is None
+    p = p or SolverParameters()
+    maxit = 10 if default else p.max_iterations
+    mon = p.monitor()
+    info = SolveInfo()
+    n = M.n
+    v = sp.csc_matrix((np.full(n, 1.0 / n), (np.zeros(n, int), np.arange(n))), shape=(n, n))   # :97-108: first row
+    vec = PSMatrix.from_scipy(v, M.grid)
+    ritz, ait = [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+    broke = False
+    ii = 0
+    for ii in range(1, maxit + 1):
+        vec2 = multiply(M, vec, thr=p.threshold)
+        sv = dot_real(vec, vec)
+        mv = dot_real(vec, vec2) / sv
+        vec = scale(vec2, 1.0 / norm(vec2))
+        ritz = [ritz[1], ritz[2], mv]
+        ait = [ait[1], ait[2], 0.0]
+        if ii >= 3:
+            num = ritz[2] * ritz[0] - ritz[1] ** 2
+            den = ritz[2] - 2 * ritz[1] + ritz[0]
+            ait[2] = num / den if abs(den) > 1e-14 else ritz[2]
+        else:
+            ait[2] = ritz[2]
+        mon.append(-(ait[2] - ait[1]))
+        info.history.append(-(ait[2] - ait[1]))
+        if mon.converged() and abs(ait[2] - ritz[2]) < mon.loose:
+            broke = True
+            break
+    info.iterations = _loop_counter(ii, maxit, broke)
+    return ait[2], info
+
+
 def trs4(H, ISQ, trace_target, p: SolverParameters | None = None):
     """TRS4 (DensityMatrixSolversModule.F90:485-716)."""
     p = p or SolverParameters()

@@ -55,6 +55,17 @@ def test_hpcp_premade_density(nt):
     assert abs(e - np.trace(k @ Hd)) <= 1e-3
     w = la.eigh(Hd, Sd, eigvals_only=True)
     assert w[4] < mu < w[5]
+    # same iteration count and energy as the CPU restatement (oracle.hpcp, pinned on the golden density on the CPU side)
+    from oracle import oracle as O
+    rec = nt.last_solve()
+    po = O.SolverParameters(converge_diff=1e-3, threshold=1e-6)
+    Ho, So = O.PSMatrix.from_scipy(sp.csc_matrix(Hd)), O.PSMatrix.from_scipy(sp.csc_matrix(Sd))
+    ISQo, _ = O.inverse_square_root(So, po)
+    po.converge_diff = 1e-5
+    Ko, info = O.hpcp(Ho, ISQo, 5.0, po)
+    assert rec["loop_counter"] == info.iterations, (rec, info.iterations)
+    assert abs(e - info.energy) <= 1e-8 * abs(info.energy)
+    assert abs(mu - info.chemical_potential) <= 1e-6 * abs(info.chemical_potential)
 
 
 def test_polar_decomposition(nt):

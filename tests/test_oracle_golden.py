@@ -71,6 +71,43 @@ def test_premade_scale_and_fold(oracle):
     assert info.iterations < 19                                  # the acceleration must beat plain TRS2 (19)
 
 
+def test_premade_hpcp(oracle):
+    """HPCP (DensityMatrixSolversModule.F90:720-950) on the shipped example: golden density, chemical potential in the
+    HOMO-LUMO gap (UnitTests/test_chemistry.py basic_solver / check_cp)"""
+    O = oracle
+    H, S = O.PSMatrix.from_scipy(mm("premade_Hamiltonian.mtx")), O.PSMatrix.from_scipy(mm("premade_Overlap.mtx"))
+    D = mm("premade_Density-Reference.mtx").toarray()
+    p = O.SolverParameters(converge_diff=1e-3, threshold=1e-6)
+    ISQ, _ = O.inverse_square_root(S, p)
+    p.converge_diff = 1e-5
+    K, info = O.hpcp(H, ISQ, 5.0, p)
+    assert np.linalg.norm(K.todense() - D) <= 1e-4
+    assert info.energy == pytest.approx(np.trace(K.todense() @ H.todense()), abs=1e-3)
+    w = la.eigh(H.todense(), S.todense(), eigvals_only=True)
+    assert w[4] < info.chemical_potential < w[5]
+
+
+def test_power_bounds_mcweeny_energy_density(oracle):
+    """PowerBounds vs the dominant eigenvalue (UnitTests/test_solvers.py:826-843), McWeenyStep and EnergyDensityMatrix vs
+    their dense definitions (test_chemistry.py)"""
+    O = oracle
+    rng = np.random.default_rng(5)
+    n = 31
+    a = rng.uniform(0.0, 1.0, (n, n))
+    a = a + a.T
+    val, info = O.power_bounds(O.PSMatrix.from_scipy(sp.csc_matrix(a)), O.SolverParameters(monitor_convergence=False))
+    assert abs(val - np.abs(la.eigvalsh(a)).max()) <= 1e-4
+    d = sp.random(n, n, 0.3, random_state=rng, format="csc")
+    d = sp.csc_matrix((d + d.T) * 0.1)
+    s = sp.csc_matrix(sp.identity(n) + 0.01 * sp.csc_matrix(a))
+    Dm, Sm, Hm = (O.PSMatrix.from_scipy(x) for x in (d, s, sp.csc_matrix(a)))
+    dd, sd = d.toarray(), s.toarray()
+    assert np.linalg.norm(O.mcweeny_step(Dm).todense() - (3 * dd @ dd - 2 * dd @ dd @ dd)) <= 1e-13
+    dsd = dd @ sd @ dd
+    assert np.linalg.norm(O.mcweeny_step(Dm, Sm).todense() - (3 * dsd - 2 * dd @ sd @ dsd)) <= 1e-13
+    assert np.linalg.norm(O.energy_density_matrix(Hm, Dm).todense() - dd @ a @ dd) <= 1e-12
+
+
 GRIDS = [(1, 1, 1, 1), (2, 1, 1, 1), (1, 2, 1, 1), (2, 2, 1, 1), (1, 1, 2, 1), (2, 1, 2, 1), (1, 2, 2, 1), (2, 2, 2, 1),
          (3, 2, 1, 1), (2, 1, 3, 1), (6, 1, 1, 1), (1, 1, 1, 8)]
 
