@@ -312,7 +312,7 @@ def main():
         pout = [(torch.empty(cap, dtype=torch.int32).pin_memory().numpy(),
                  torch.empty(cap, dtype=torch.int32).pin_memory().numpy(),
                  torch.empty(cap, dtype=torch.float64).pin_memory().numpy()) for _ in range(2)]
-        e2e_steps = max(2, min(args.steps, 24))          # a pipeline: fill and drain are inside the timed region
+        e2e_steps = min(max(args.steps, 16), 24)         # a pipeline: fill and drain are inside the timed region
 
         def e2e_loop(count):
             d2h = 0
