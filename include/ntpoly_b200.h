@@ -80,10 +80,11 @@ void GetTripletAt_c_wrp(const int *ih_this, const int *index, int *index_column,
                         double *point_value_real, double *point_value_imag);
 void DestructTripletList_c_wrp(int *ih_this);
 int GetTripletListSize_c_wrp(const int *ih_this);
-/* sorted copy (by column, then row). Argument list of the Fortran binding (TripletListModule_wrp.F90:135-151);
- * the reference's C header declares one size argument fewer than the shim takes. */
-void SortTripletList_r_wrp(const int *ih_this, const int *matrix_columns, const int *matrix_rows, int *ih_sorted);
-void SortTripletList_c_wrp(const int *ih_this, const int *matrix_columns, const int *matrix_rows, int *ih_sorted);
+/* sorted copy (by column, then row) in a freshly allocated list whose handle is written to h_sorted. Three arguments
+ * like the reference's C header and C++ caller (TripletList_c.h:15-16, TripletList.cc:88-96); the Fortran shim behind
+ * them takes four (TripletListModule_wrp.F90:135-151), a mismatch inside the reference. */
+void SortTripletList_r_wrp(const int *ih_this, const int *matrix_size, int *h_sorted);
+void SortTripletList_c_wrp(const int *ih_this, const int *matrix_size, int *h_sorted);
 
 /* ---- 3. distributed matrix container (Source/C/PSMatrix_c.h:4-49; PSMatrixModule_wrp.F90) */
 void ConstructEmptyMatrix_ps_wrp(int *ih_this, const int *matrix_dim);

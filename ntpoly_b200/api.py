@@ -237,6 +237,9 @@ class ProcessGrid:
     def GetNumRows(self):
         return lib().GetNumRows_wrp(self.ih)
 
+    def WriteInfo(self):
+        lib().WriteProcessGridInfo_wrp(self.ih)
+
 
 # ---------------------------------------------------------------------------
 # triplets
@@ -281,11 +284,15 @@ class TripletList_r:
     def GetSize(self):
         return lib().GetTripletListSize_r_wrp(self.ih)
 
-    def Sort(self, matrix_columns=0, matrix_rows=0):
-        """sorted copy (by column, then row)"""
-        out = TripletList_r.__new__(TripletList_r)
-        out.ih = _handle()
-        lib().SortTripletList_r_wrp(self.ih, _i(matrix_columns), _i(matrix_rows), out.ih)
+    @staticmethod
+    def SortTripletList(input_list, matrix_columns, sorted_list):
+        """sorted copy of input_list (by column, then row) into sorted_list (reference TripletList.h:42-43)"""
+        lib().DestructTripletList_r_wrp(sorted_list.ih)      # the C entry point allocates a fresh list for the result
+        lib().SortTripletList_r_wrp(input_list.ih, _i(matrix_columns), sorted_list.ih)
+
+    def Sort(self, matrix_columns=0):
+        out = TripletList_r()
+        TripletList_r.SortTripletList(self, matrix_columns, out)
         return out
 
     # bulk (extension)
@@ -327,10 +334,21 @@ class TripletList_c:
     def GetSize(self):
         return lib().GetTripletListSize_c_wrp(self.ih)
 
-    def Sort(self, matrix_columns=0, matrix_rows=0):
-        out = TripletList_c.__new__(TripletList_c)
-        out.ih = _handle()
-        lib().SortTripletList_c_wrp(self.ih, _i(matrix_columns), _i(matrix_rows), out.ih)
+    def Resize(self, size):
+        lib().ResizeTripletList_c_wrp(self.ih, _i(size))
+
+    def SetTripletAt(self, index, t):
+        v = complex(t.point_value)
+        lib().SetTripletAt_c_wrp(self.ih, _i(index + 1), _i(t.index_column), _i(t.index_row), _d(v.real), _d(v.imag))
+
+    @staticmethod
+    def SortTripletList(input_list, matrix_columns, sorted_list):
+        lib().DestructTripletList_c_wrp(sorted_list.ih)
+        lib().SortTripletList_c_wrp(input_list.ih, _i(matrix_columns), sorted_list.ih)
+
+    def Sort(self, matrix_columns=0):
+        out = TripletList_c()
+        TripletList_c.SortTripletList(self, matrix_columns, out)
         return out
 
     def set_arrays(self, rows, cols, vals):
@@ -872,6 +890,12 @@ class EigenBounds:
         v = c_double()
         lib().PowerBounds_wrp(M.ih, byref(v), sp.ih)
         return v.value
+
+
+class MatrixConversion:
+    @staticmethod
+    def SnapMatrixToSparsityPattern(mata, matb):
+        lib().SnapMatrixToSparsityPattern_wrp(mata.ih, matb.ih)
 
 
 class LoadBalancer:

@@ -163,9 +163,13 @@ void DestructMatrixMemoryPool_lr_wrp(int* ih) { delete get<LocalMemoryPool>(ih);
 void ConstructMatrixMemoryPool_lc_wrp(int* ih, const int* columns, const int* rows) { auto* p = new LocalMemoryPool(); p->rows = *rows; p->cols = *columns; p->is_complex = true; put(ih, p); }
 void DestructMatrixMemoryPool_lc_wrp(int* ih) { delete get<LocalMemoryPool>(ih); clear(ih); }
 
-// ---------------------------------------------------------------- triplet list sort (TripletListModule_wrp.F90:135-151)
-void SortTripletList_r_wrp(const int* ih, const int*, const int*, int* ih_sorted) { auto* t = new TripletList_r(); sort_list(*get<TripletList_r>(ih), *t); put(ih_sorted, t); }
-void SortTripletList_c_wrp(const int* ih, const int*, const int*, int* ih_sorted) { auto* t = new TripletList_c(); sort_list(*get<TripletList_c>(ih), *t); put(ih_sorted, t); }
+// ---------------------------------------------------------------- triplet list sort
+// Signature of the reference's C header and of its C++ caller (Source/C/TripletList_c.h:15-16,
+// Source/CPlusPlus/TripletList.cc:88-96): three arguments. (The Fortran shim behind them takes four - columns, rows,
+// sorted - TripletListModule_wrp.F90:135-151; the callers of the C ABI pass three, so three it is.) Like the shim, a
+// fresh list is allocated for the result and its handle written to ih_sorted.
+void SortTripletList_r_wrp(const int* ih, const int*, int* ih_sorted) { auto* t = new TripletList_r(); sort_list(*get<TripletList_r>(ih), *t); put(ih_sorted, t); }
+void SortTripletList_c_wrp(const int* ih, const int*, int* ih_sorted) { auto* t = new TripletList_c(); sort_list(*get<TripletList_c>(ih), *t); put(ih_sorted, t); }
 
 // ---------------------------------------------------------------- column scaling of a distributed matrix
 // (PSMatrixAlgebraModule.F90:507-532, distributed_algebra_includes/ScaleDiagonal.f90): every rank passes the whole

@@ -63,7 +63,7 @@ def test_construct_roundtrip_copy_and_files(nt, cplx, tmp_path):
     coo = sp.coo_matrix(rnd(31, 57, 0.2, 8, cplx))
     perm = np.random.default_rng(0).permutation(coo.nnz)
     tl.set_arrays(coo.row[perm] + 1, coo.col[perm] + 1, coo.data[perm])
-    rows, cols, _ = tl.Sort(57, 31).get_arrays()
+    rows, cols, _ = tl.Sort(57).get_arrays()
     key = cols.astype(np.int64) * 100 + rows
     assert np.all(np.diff(key) > 0)
 
