@@ -424,7 +424,7 @@ struct ResultForms {
   int4* entR; double* tvalR;                 // right form: slot 2*task + h
   unsigned want;                             // WANT_LEFT | WANT_RIGHT
 };
-template <int NSTAGE, int MINB, bool DENSE>
+template <int NSTAGE, int MINB, int DENSE>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
 k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
                 int* __restrict__ task_counter, int* __restrict__ cnt, ResultForms out, int nrows, int ncols, EmitSpec es) {
@@ -594,7 +594,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
       { const int2 gt = *reinterpret_cast<const int2*>(mt + 56); gt0 = gt.x; gtn = gt.y; }
       const unsigned mb = mt[48 + wj];
       const unsigned live = mb & ((unsigned)mi.x >> 8) & 0xffu;
-      if (DENSE && (fl & 4u) != 0u && mb == 0xffu) {
+      if (DENSE >= 1 && (fl & 4u) != 0u && mb == 0xffu) {
         // DENSE STAGE: all 64 tiles of the A super-tile and all 8 inner tiles of this warp's B tile column are present
         // (the interior of a band or of a filled-in block). Every fragment sits at a compile-time offset from two
         // base pointers - A tile (kk, ii) at 8 kk + ii, B tile (wj, kk) at the column's first tile + kk - so the 64
@@ -608,6 +608,20 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
           const double bv = Bd[kk * 32];
 #pragma unroll
           for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], Ad[(8 * kk + ii) * 32], bv);
+        }
+      } else if (DENSE >= 2 && (fl & 4u) != 0u && mb != 0u) {
+        // A COMPLETE, B COLUMN PARTIAL (NTB_DENSE_STAGE=2, not measured yet): the A fragments of inner tile kk sit at
+        // compile-time offsets from one pointer that advances by a constant; only the B tile index comes from the stage
+        // descriptor. One short non-unrolled loop over the present inner tiles.
+        const unsigned long long bo = *reinterpret_cast<const unsigned long long*>(mt + 64 + 8 * wj);
+        const double* Ad = slab + (size_t)st * STAGE_DOUBLES + lane;
+        const double* Bd = Ad + SLAB_DOUBLES;
+#pragma unroll 1
+        for (int kk = 0; (mb >> kk) != 0u; ++kk, Ad += 8 * 32) {
+          if (((mb >> kk) & 1u) == 0u) continue;
+          const double bv = Bd[((unsigned)(bo >> (8 * kk)) & 0xffu) * 32];
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) dmma884(acc[ii][0], acc[ii][1], Ad[ii * 32], bv);
         }
       } else if (live != 0u) {
         const unsigned long long bo = *reinterpret_cast<const unsigned long long*>(mt + 64 + 8 * wj);
@@ -1092,11 +1106,13 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
       NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, gtask_off.get(),
                  tasks.get(), h_tasks, task_counter.get(), cnt.get(), out, nrows, ncols, es);
     };
-    // dense-stage fast path of the DMMA warps (NTB_DENSE_STAGE=0 switches it off)
-    static const bool dense = [] { const char* e = std::getenv("NTB_DENSE_STAGE"); return !(e && e[0] == '0'); }();
-    if (shape == 23) launch(k_tile_numeric9<2, 3, false>, 2, 3);
-    else if (dense) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, true>, NSTAGE_DEFAULT, 2);
-    else launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, false>, NSTAGE_DEFAULT, 2);
+    // fast paths of the DMMA warps: NTB_DENSE_STAGE=0 generic loop only, 1 (default) dense-stage block, 2 also the
+    // A-complete block (experimental)
+    static const int dense = [] { const char* e = std::getenv("NTB_DENSE_STAGE"); return e ? std::atoi(e) : 1; }();
+    if (shape == 23) launch(k_tile_numeric9<2, 3, 0>, 2, 3);
+    else if (dense >= 2) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 2>, NSTAGE_DEFAULT, 2);
+    else if (dense == 1) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 1>, NSTAGE_DEFAULT, 2);
+    else launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 0>, NSTAGE_DEFAULT, 2);
   }
   if (rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
