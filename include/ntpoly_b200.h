@@ -255,6 +255,12 @@ void ComputeExponential_wrp(const int *ih_Input, int *ih_Output, const int *ih_s
 void GershgorinBounds_wrp(const int *ih_Hamiltonian, double *max_value, double *min_value);
 void PowerBounds_wrp(const int *ih_Hamiltonian, double *max_value, const int *ih_solver_parameters);
 
+/* ---- 7b. logging (Source/C/Logging_c.h:4-7): accepted so that front ends which activate NTPoly's YAML logger link and
+ *          run; the logger itself (host text output) is outside the path */
+void ActivateLogger_wrp(const bool *start_document);
+void ActivateLoggerFile_wrp(const bool *start_document, const char *file_name, const int *name_size);
+void DeactivateLogger_wrp(void);
+
 /* ---- 8. ntb_ extensions (no counterpart in the reference) ------------------- */
 /* bootstrap: rank/size of this process and, for size>1, the 128-byte ncclUniqueId that
  * rank 0 obtained from ntb_nccl_unique_id() and the host broadcast (e.g. torch.distributed). */

@@ -59,7 +59,7 @@ TRS2_wrp TRS4_wrp PM_wrp HPCP_wrp EnergyDensityMatrix_wrp McWeenyStep_wrp McWeen
 PolarDecomposition_wrp Invert_wrp SquareRoot_wrp InverseSquareRoot_wrp ComputeExponential_wrp GershgorinBounds_wrp
 PowerBounds_wrp
 SortTripletList_r_wrp SortTripletList_c_wrp MatrixDiagonalScale_psr_wrp MatrixDiagonalScale_psc_wrp
-ScaleAndFold_wrp PseudoInverse_wrp
+ScaleAndFold_wrp PseudoInverse_wrp ActivateLogger_wrp ActivateLoggerFile_wrp DeactivateLogger_wrp
 ConstructMatrixFromFile_lsr_wrp ConstructMatrixFromTripletList_lsr_wrp ConstructZeroMatrix_lsr_wrp
 DestructMatrix_lsr_wrp CopyMatrix_lsr_wrp GetMatrixRows_lsr_wrp GetMatrixColumns_lsr_wrp ExtractMatrixRow_lsr_wrp
 ExtractMatrixColumn_lsr_wrp ScaleMatrix_lsr_wrp IncrementMatrix_lsr_wrp DotMatrix_lsr_wrp
@@ -206,6 +206,19 @@ def GetGlobalNumRows():
 
 def WriteGridInfo():
     lib().WriteGlobalProcessGridInfo_wrp()
+
+
+def ActivateLogger(file_name=None, start_document=False):
+    """reference Source/CPlusPlus/Logging.h; the YAML logger itself is outside the path (accepted, no output)"""
+    if file_name is None or isinstance(file_name, bool):
+        lib().ActivateLogger_wrp(byref(c_bool(bool(file_name) if isinstance(file_name, bool) else start_document)))
+    else:
+        b = file_name.encode()
+        lib().ActivateLoggerFile_wrp(byref(c_bool(start_document)), c_char_p(b), _i(len(b)))
+
+
+def DeactivateLogger():
+    lib().DeactivateLogger_wrp()
 
 
 class ProcessGrid:

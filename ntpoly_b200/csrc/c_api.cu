@@ -303,6 +303,14 @@ void GershgorinBounds_wrp(const int* ih, double* max_value, double* min_value) {
 }
 void PowerBounds_wrp(const int* ih, double* max_value, const int* sp) { solve_power_bounds(*get<Matrix>(ih), max_value, params_of(sp), false); }
 
+// ---------------------------------------------------------------- 8. logging (Source/C/Logging_c.h)
+// NTPoly's YAML logger is host text output outside the path; the three entry points exist so that front ends which
+// switch it on (every shipped example does) link and run. Solver verbosity (SetParametersBeVerbose_wrp) prints regardless.
+static bool g_logger_active = false;
+void ActivateLogger_wrp(const bool*) { g_logger_active = true; }
+void ActivateLoggerFile_wrp(const bool*, const char*, const int*) { g_logger_active = true; }
+void DeactivateLogger_wrp(void) { g_logger_active = false; }
+
 // ---------------------------------------------------------------- 9. extensions
 void ntb_nccl_unique_id(void* out128) { world_get_unique_id(out128); }
 void ntb_world_init(int rank, int size, const void* id) { world_init_explicit(rank, size, id); }

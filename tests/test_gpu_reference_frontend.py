@@ -1,0 +1,36 @@
+"""NTPoly's OWN C++ front end and its OWN PremadeMatrix example (Examples/PremadeMatrix/main.cc, unmodified), compiled in
+the build container from where they lie in the reference checkout and linked against libntpoly_b200.so
+(`make -C oracle ref` -> oracle/_ref/premade_example; the binary travels to the GPU box, the reference does not).
+The example is run with the command of the reference's ReadMe (Examples/PremadeMatrix/ReadMe.md:72-77) with the electron
+count of the shipped reference density (5) and must reproduce Density-Reference.mtx at the reference's own
+tolerance.
+
+First hardware run pending (written after the round-1 GPU budget was spent): non-strict xfail until then; skipped when
+the binary was not built."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.io as sio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "premade_example")
+GOLD = os.path.join(ROOT, "tests", "golden")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/premade_example was not built (no reference checkout at build time)"),
+              pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: first hardware run pending")]
+
+
+def test_reference_premade_example_runs_on_the_cuda_library(tmp_path):
+    out = str(tmp_path / "Density.mtx")
+    cmd = [EXE, "--hamiltonian", os.path.join(GOLD, "premade_Hamiltonian.mtx"), "--overlap", os.path.join(GOLD, "premade_Overlap.mtx"),
+           "--density", out, "--process_rows", "1", "--process_columns", "1", "--process_slices", "1",
+           "--number_of_electrons", "5", "--threshold", "1e-6", "--converge_overlap", "1e-3", "--converge_density", "1e-5"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    got = sio.mmread(out).toarray()
+    ref = sio.mmread(os.path.join(GOLD, "premade_Density-Reference.mtx")).toarray()
+    assert got.shape == ref.shape
+    assert np.linalg.norm(got - ref) <= 1e-4
