@@ -12,3 +12,7 @@ OUT_OF_SCOPE(DenseSignFunction_wrp)
 OUT_OF_SCOPE(DenseInvert_wrp)
 OUT_OF_SCOPE(DenseSquareRoot_wrp)
 OUT_OF_SCOPE(DenseInverseSquareRoot_wrp)
+OUT_OF_SCOPE(ComputeDenseExponential_wrp)
+OUT_OF_SCOPE(ComputeDenseLogarithm_wrp)
+OUT_OF_SCOPE(ComputeExponentialPade_wrp)
+OUT_OF_SCOPE(ComputeLogarithm_wrp)

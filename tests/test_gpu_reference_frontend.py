@@ -1,6 +1,7 @@
-"""NTPoly's OWN C++ front end and its OWN PremadeMatrix example (Examples/PremadeMatrix/main.cc, unmodified), compiled in
+"""NTPoly's OWN C++ front end and its OWN examples (Examples/PremadeMatrix/main.cc, Examples/ComplexMatrix/main.cc,
+unmodified), compiled in
 the build container from where they lie in the reference checkout and linked against libntpoly_b200.so
-(`make -C oracle ref` -> oracle/_ref/premade_example; the binary travels to the GPU box, the reference does not).
+(`make -C oracle ref` -> oracle/_ref/example_PremadeMatrix; the binary travels to the GPU box, the reference does not).
 The example is run with the command of the reference's ReadMe (Examples/PremadeMatrix/ReadMe.md:72-77) with the electron
 count of the shipped reference density (5) and must reproduce Density-Reference.mtx at the reference's own
 tolerance.
@@ -15,10 +16,11 @@ import pytest
 import scipy.io as sio
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXE = os.path.join(ROOT, "oracle", "_ref", "premade_example")
+EXE = os.path.join(ROOT, "oracle", "_ref", "example_PremadeMatrix")
+EXE_COMPLEX = os.path.join(ROOT, "oracle", "_ref", "example_ComplexMatrix")
 GOLD = os.path.join(ROOT, "tests", "golden")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/premade_example was not built (no reference checkout at build time)"),
+              pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/example_PremadeMatrix was not built (no reference checkout at build time)"),
               pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: first hardware run pending")]
 
 
@@ -34,3 +36,24 @@ def test_reference_premade_example_runs_on_the_cuda_library(tmp_path):
     ref = sio.mmread(os.path.join(GOLD, "premade_Density-Reference.mtx")).toarray()
     assert got.shape == ref.shape
     assert np.linalg.norm(got - ref) <= 1e-4
+
+
+def test_reference_complex_example_runs_on_the_cuda_library(tmp_path):
+    """Examples/ComplexMatrix (BASELINE config 5 at the shipped size): the example builds the Hermitian Guo matrix from the
+    directed graph through the triplet-list API, scales it by 0.5 and calls ComputeExponential; the file it writes must
+    be exp(0.5 G)"""
+    import sys
+    import scipy.linalg as la
+    sys.path.insert(0, ROOT)
+    from ntpoly_b200.workloads import guo_transform
+    out = str(tmp_path / "Exponential.mtx")
+    cmd = [EXE_COMPLEX, "--input_file", os.path.join(GOLD, "complex_input.mtx"), "--exponential_file", out,
+           "--process_rows", "1", "--process_columns", "1", "--process_slices", "1", "--threshold", "1e-6"]   # ReadMe.md:72-74
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    got = sio.mmread(out).toarray()
+    g = guo_transform(sio.mmread(os.path.join(GOLD, "complex_input.mtx")))
+    want = la.expm(0.5 * g.toarray())
+    assert got.shape == want.shape
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-6
