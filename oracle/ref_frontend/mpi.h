@@ -13,3 +13,7 @@ static inline int MPI_Init_thread(int *argc, char ***argv, int required, int *pr
   return 0;
 }
 static inline int MPI_Finalize(void) { return 0; }
+/* one process per GPU: rank and size come from the launcher's environment (torchrun, srun --export, mpirun -x) */
+#include <stdlib.h>
+static inline int MPI_Comm_rank(MPI_Comm c, int *rank) { const char *e = getenv("RANK"); (void)c; *rank = e ? atoi(e) : 0; return 0; }
+static inline int MPI_Comm_size(MPI_Comm c, int *size) { const char *e = getenv("WORLD_SIZE"); (void)c; *size = e ? atoi(e) : 1; return 0; }

@@ -18,6 +18,7 @@ import scipy.io as sio
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "oracle", "_ref", "example_PremadeMatrix")
 EXE_COMPLEX = os.path.join(ROOT, "oracle", "_ref", "example_ComplexMatrix")
+EXE_HYDROGEN = os.path.join(ROOT, "oracle", "_ref", "example_HydrogenAtom")
 GOLD = os.path.join(ROOT, "tests", "golden")
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/example_PremadeMatrix was not built (no reference checkout at build time)"),
@@ -57,3 +58,34 @@ def test_reference_complex_example_runs_on_the_cuda_library(tmp_path):
     want = la.expm(0.5 * g.toarray())
     assert got.shape == want.shape
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-6
+
+
+def test_reference_hydrogen_example_runs_on_the_cuda_library(tmp_path, oracle):
+    """Examples/HydrogenAtom with the ReadMe's command (ReadMe.md:73-76): the example assembles a finite-difference
+    Hamiltonian through the triplet-list API and calls TRS2 with an identity overlap and one electron. The density it
+    writes must equal the CPU restatement's for the same matrix and thresholds, have trace 1
+    and be idempotent to the convergence threshold."""
+    import scipy.sparse as sp
+    n, x0, x1 = 100, -6.28, 6.28
+    out = str(tmp_path / "Density.mtx")
+    cmd = [EXE_HYDROGEN, "--process_rows", "1", "--process_columns", "1", "--process_slices", "1", "--threshold", "1e-6",
+           "--convergence_threshold", "1e-5", "--grid_points", str(n), "--density", out]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    got = sio.mmread(out).toarray()
+    # the same matrix as Examples/HydrogenAtom/main.cc:93-143 builds
+    h = (x1 - x0) / (n - 1)
+    rows, cols, vals = [], [], []
+    for row in range(1, n + 1):
+        for d, c, ok in ((-2, -1.0, row > 2), (-1, 16.0, row > 1), (0, -30.0, True), (1, 16.0, row + 1 < n), (2, -1.0, row + 2 < n)):
+            if ok:
+                rows.append(row - 1); cols.append(row - 1 + d); vals.append(-0.5 * c / (12.0 * h * h))
+    x = x0 + np.arange(n) * h
+    H = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsc() + sp.diags(-1.0 / np.abs(x))
+    O = oracle
+    Hm = O.PSMatrix.from_scipy(sp.csc_matrix(H))
+    K, info = O.trs2(Hm, O.identity(Hm), 1.0, O.SolverParameters(converge_diff=1e-5, threshold=1e-6))
+    assert np.linalg.norm(got - K.todense()) <= 1e-5           # entries at the 1e-6 threshold may fall on either side
+    assert abs(np.trace(got) - 1.0) <= 1e-4
+    assert np.linalg.norm(got @ got - got) <= 1e-3
