@@ -130,3 +130,30 @@ def test_triplet_list_host_api():
         assert len(r) == 200 and np.all(np.diff(c.astype(np.int64) * 100 + r) >= 0)
         key = lambda t: (t[1], t[0], t[2].real, t[2].imag)
         assert sorted(zip(r, c, [complex(x) for x in v]), key=key) == sorted(zip(rows, cols, [complex(x) for x in vals]), key=key)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/ntpoly_b200.h is the boundary for C, C++ and Fortran hosts: it must compile as strict C99 and as C++, and a
+    C program using it must link against the library"""
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "ntpoly_b200.h"\n'
+                   'int main(void) {\n'
+                   '  int ih[NTB_SIZE_wrp]; int n = 3; int col = 1, row = 2; double v = 0.5; int c, r; double out;\n'
+                   '  ConstructTripletList_r_wrp(ih, &n);\n'
+                   '  SetTripletAt_r_wrp(ih, &n, &col, &row, &v);\n'
+                   '  GetTripletAt_r_wrp(ih, &n, &c, &r, &out);\n'
+                   '  n = GetTripletListSize_r_wrp(ih);\n'
+                   '  DestructTripletList_r_wrp(ih);\n'
+                   '  return (c == 1 && r == 2 && out == 0.5 && n == 3) ? 0 : 1;\n'
+                   '}\n')
+    from ntpoly_b200 import build
+    lib = build.build()
+    inc, libdir = os.path.join(ROOT, "include"), os.path.dirname(lib)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{inc}", "-c", str(src), "-o", str(tmp_path / "c.o")],
+                   check=True, capture_output=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", f"-I{inc}", "-x", "c++", "-c", str(src), "-o", str(tmp_path / "cxx.o")],
+                   check=True, capture_output=True)
+    exe = str(tmp_path / "use_header")
+    subprocess.run(["gcc", str(tmp_path / "c.o"), "-o", exe, f"-L{libdir}", "-lntpoly_b200", f"-Wl,-rpath,{libdir}"],
+                   check=True, capture_output=True)
+    assert subprocess.run([exe], timeout=60).returncode == 0
