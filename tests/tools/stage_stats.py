@@ -82,3 +82,34 @@ def ragged_histogram(Am, Bm, name):
 
 ragged_histogram(Xs, Xs, "X * X ")
 ragged_histogram(Xs, T1s, "X * T1")
+
+
+def ownership_balance(Am, Bm, name):
+    """Sum over stages of the busiest warp's DMMA count (the stage advances at that warp's pace) for different ways of
+    giving the 8x8 tiles of a 64x64 block to 8 warps; the ideal is total/8."""
+    A = tile_grid(Am, 8, 4); B = tile_grid(Bm, 4, 8)
+    nIb, nc, nG = A.shape[0] // 8, A.shape[1] // 8, B.shape[1] // 8
+    schemes = {"8x1 (tile column per warp, today)": (8, 1), "4x2": (4, 2), "2x4": (2, 4), "1x8 (row tile per warp)": (1, 8)}
+    busiest = {k: 0 for k in schemes}
+    busiest_diag = [0]
+    total = 0
+    for c in range(nc):
+        Ac = A[:, 8 * c:8 * c + 8].reshape(nIb, 8, 8).astype(np.int64)      # [Ib, ii, kk]
+        Bc = B[8 * c:8 * c + 8, :nG * 8].reshape(8, nG, 8).astype(np.int64)  # [kk, g, jj]
+        # d[Ib, g, ii, jj] = number of inner tiles kk with A(ii,kk) and B(kk,jj) present
+        d = np.einsum("aik,kgj->agij", Ac, Bc)
+        total += d.sum()
+        for k, (hr, wc) in schemes.items():
+            per_warp = d.reshape(nIb, nG, 8 // hr, hr, 8 // wc, wc).sum(axis=(3, 5))   # [Ib, g, row group, col group]
+            busiest[k] += per_warp.reshape(nIb, nG, -1).max(axis=2).sum()
+        # wrapped diagonals: warp w owns the tiles (ii, (ii + w) mod 8)
+        ii = np.arange(8)
+        diag = np.stack([d[:, :, ii, (ii + w) % 8].sum(axis=2) for w in range(8)], axis=2)   # [Ib, g, w]
+        busiest_diag[0] += diag.max(axis=2).sum()
+    print(f"{name}: DMMAs {total}, ideal busiest-warp sum {total / 8:.0f}; " +
+          "; ".join(f"{k}: {v / (total / 8):.3f}x" for k, v in busiest.items()) +
+          f"; wrapped diagonals: {busiest_diag[0] / (total / 8):.3f}x")
+
+
+ownership_balance(Xs, Xs, "X * X ")
+ownership_balance(Xs, T1s, "X * T1")
