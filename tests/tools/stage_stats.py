@@ -113,3 +113,13 @@ def ownership_balance(Am, Bm, name):
 
 ownership_balance(Xs, Xs, "X * X ")
 ownership_balance(Xs, T1s, "X * T1")
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "block":
+    # the block-sparse workload (config 3: 32x32 dense blocks) under the same masks, first product of a purification
+    from ntpoly_b200.workloads import block_sparse
+    Hb = block_sparse(n=n, block=32, neighbours=20, band_blocks=64, seed=1234).tocsc()
+    print(f"block-sparse n={n} nnz/col {Hb.nnz / n:.1f}")
+    stats(Hb, Hb, "H * H ")
+    ragged_histogram(Hb, Hb, "H * H ")
+    ownership_balance(Hb, Hb, "H * H ")
