@@ -814,6 +814,79 @@ def power_bounds(M, p: SolverParameters | None = None):
     return ait[2], info
 
 
+# --------------------------------------------------------------------------
+# Chebyshev polynomials and the exponential (ChebyshevSolversModule.F90, ExponentialSolversModule.F90)
+# --------------------------------------------------------------------------
+EXP_CHEBYSHEV_COEFFICIENTS = [                 # ExponentialSolversModule.F90:98-113
+    1.266065877752007e+00, 1.130318207984970e+00, 2.714953395340771e-01, 4.433684984866504e-02,
+    5.474240442092110e-03, 5.429263119148932e-04, 4.497732295351912e-05, 3.198436462630565e-06,
+    1.992124801999838e-07, 1.103677287249654e-08, 5.505891628277851e-10, 2.498021534339559e-11,
+    1.038827668772902e-12, 4.032447357431817e-14, 2.127980007794583e-15, -1.629151584468762e-16]
+
+
+def chebyshev_compute(M, coefficients, p: SolverParameters | None = None):
+    """Compute_cheby (ChebyshevSolversModule.F90:83-186): three-term recurrence T_k = 2 M T_{k-1} - T_{k-2},
+    the products thresholded, the adds not. Returns (matrix, SolveInfo)."""
+    p = p or SolverParameters()
+    info = SolveInfo()
+    stats = MultiplyStats()
+    degree = len(coefficients)
+    ident = identity(M)
+    bal = M
+    if p.do_load_balancing:
+        ident = permute(ident, p.permutation)
+        bal = permute(bal, p.permutation)
+    tkm2 = ident
+    if degree == 1:
+        out = scale(tkm2, coefficients[0])
+    else:
+        tkm1 = bal
+        out = scale(tkm2, coefficients[0])
+        out = increment(tkm1, out, alpha=coefficients[1])
+        if degree > 2:
+            tk = multiply(bal, tkm1, alpha=2.0, thr=p.threshold, stats=stats)
+            tk = increment(tkm2, tk, alpha=-1.0)
+            out = increment(tk, out, alpha=coefficients[2])
+            for ii in range(4, degree + 1):
+                tkm2, tkm1 = tkm1, tk
+                tk = multiply(bal, tkm1, alpha=2.0, thr=p.threshold, stats=stats)
+                tk = increment(tkm2, tk, alpha=-1.0)
+                out = increment(tk, out, alpha=coefficients[ii - 1])
+    if p.do_load_balancing:
+        out = undo_permute(out, p.permutation)
+    info.flops = stats.flops
+    return out, info
+
+
+def compute_exponential(M, p: SolverParameters | None = None):
+    """ComputeExponential (ExponentialSolversModule.F90:37-148): spectral radius from PowerBounds with at most 10
+    iterations, scaling by a power of two, Chebyshev series of degree 15 with threshold/sigma, repeated squaring.
+    info.iterations = sigma_counter (squarings + 1). NOTE (reference behaviour, kept): PowerBounds leaves its loop in
+    iteration 1 with the value 0 when M(1,1) = 0 - the first Ritz value is M(1,1), the monitor's tight criterion
+    |0| <= converge_diff fires (ConvergenceMonitorModule.F90:121-129) and |aitken - ritz| = 0 < loose_cutoff
+    (EigenBoundsModule.F90:156-165) - so such a matrix is NOT scaled, whatever its spectral radius."""
+    p = p or SolverParameters()
+    psub = SolverParameters(**{**p.__dict__, "max_iterations": 10})
+    radius, _ = power_bounds(M, psub)
+    sigma_val, sigma_counter = 1.0, 1
+    while radius / sigma_val > 1.0:
+        sigma_val *= 2
+        sigma_counter += 1
+    sub = SolverParameters(**{**p.__dict__, "threshold": p.threshold / sigma_val})
+    out, info = chebyshev_compute(scale(M, 1.0 / sigma_val), EXP_CHEBYSHEV_COEFFICIENTS, sub)
+    stats = MultiplyStats()
+    if p.do_load_balancing:
+        out = permute(out, p.permutation)
+    for _ in range(1, sigma_counter):
+        out = multiply(out, out, thr=p.threshold, stats=stats)
+    if p.do_load_balancing:
+        out = undo_permute(out, p.permutation)
+    info.iterations = sigma_counter
+    info.flops += stats.flops
+    info.sigmas = [sigma_val]
+    return out, info
+
+
 def trs4(H, ISQ, trace_target, p: SolverParameters | None = None):
     """TRS4 (DensityMatrixSolversModule.F90:485-716)."""
     p = p or SolverParameters()

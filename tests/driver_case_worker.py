@@ -1,11 +1,9 @@
-"""WORKER of tests/test_gpu_drivers_pending.py (one case per process, so that an abort inside the library cannot take
-the test session down). Drivers of the C ABI that had no parity test of their own when the GPU budget of round 1 ran out: HPCP,
-PolarDecomposition, PowerBounds, McWeenyStep(S), EnergyDensityMatrix. The tests follow the reference's own
+"""WORKER of tests/test_gpu_drivers_more.py (one case per process, so that an abort inside the library cannot take
+the test session down). Cases: HPCP, PolarDecomposition, PowerBounds, McWeenyStep(S), EnergyDensityMatrix. The tests
+follow the reference's own
 (UnitTests/test_chemistry.py: test_hpcp; test_solvers.py: test_polarfunction :880, test_powermethod :826;
 test_chemistry.py: test_mcweeny_step, test_energy_density) at its tolerance (helpers.py THRESHOLD = 1e-4).
-
-They have NOT run on hardware yet: they are marked xfail(strict=False) so that a defect found by their first run
-shows up as XFAIL in the log instead of stopping the suite, and a pass as XPASS; round 2 removes the mark."""
+"""
 import os
 
 import numpy as np
@@ -110,4 +108,4 @@ if __name__ == "__main__":
     import ntpoly_b200.api as api
     api.ConstructGlobalProcessGrid(1, 1, 1)
     globals()["test_" + sys.argv[1]](api)
-    print("PENDING_CASE_OK", sys.argv[1], flush=True)
+    print("DRIVER_CASE_OK", sys.argv[1], flush=True)

@@ -6,8 +6,7 @@ The example is run with the command of the reference's ReadMe (Examples/PremadeM
 count of the shipped reference density (5) and must reproduce Density-Reference.mtx at the reference's own
 tolerance.
 
-First hardware run pending (written after the round-1 GPU budget was spent): non-strict xfail until then; skipped when
-the binary was not built."""
+Skipped when the binaries were not built (no reference checkout at build time)."""
 import os
 import subprocess
 
@@ -21,8 +20,7 @@ EXE_COMPLEX = os.path.join(ROOT, "oracle", "_ref", "example_ComplexMatrix")
 EXE_HYDROGEN = os.path.join(ROOT, "oracle", "_ref", "example_HydrogenAtom")
 GOLD = os.path.join(ROOT, "tests", "golden")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/example_PremadeMatrix was not built (no reference checkout at build time)"),
-              pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: first hardware run pending")]
+              pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/example_PremadeMatrix was not built (no reference checkout at build time)")]
 
 
 def test_reference_premade_example_runs_on_the_cuda_library(tmp_path):
@@ -39,25 +37,51 @@ def test_reference_premade_example_runs_on_the_cuda_library(tmp_path):
     assert np.linalg.norm(got - ref) <= 1e-4
 
 
-def test_reference_complex_example_runs_on_the_cuda_library(tmp_path):
+def test_reference_complex_example_runs_on_the_cuda_library(tmp_path, oracle):
     """Examples/ComplexMatrix (BASELINE config 5 at the shipped size): the example builds the Hermitian Guo matrix from the
-    directed graph through the triplet-list API, scales it by 0.5 and calls ComputeExponential; the file it writes must
-    be exp(0.5 G)"""
+    directed graph through the triplet-list API, scales it by 0.5 and calls ComputeExponential.
+
+    What the file must hold is what NTPoly itself computes for this input - and that is NOT exp(0.5 G): the shipped graph
+    has no self loop at node 1, so G(1,1) = 0, the first Ritz value of PowerBounds is 0, the convergence monitor's tight
+    criterion fires in iteration 1 (ConvergenceMonitorModule.F90:121-129, EigenBoundsModule.F90:156-165) and
+    ComputeExponential evaluates its degree-15 Chebyshev series on the UNSCALED matrix (spectral radius 25.8). The CPU
+    restatement (oracle.compute_exponential, pinned against scipy.linalg.expm on inputs that do get scaled:
+    tests/test_oracle_golden.py::test_exponential_restatement) reproduces that number for number; the library has to
+    match it (round 1 compared with expm and mis-reported a failure). A second run with a self loop added at node 1 -
+    the same front end, the same driver, now scaled by 32 and squared five times - must equal exp(0.5 G')."""
     import sys
     import scipy.linalg as la
+    import scipy.sparse as sp
     sys.path.insert(0, ROOT)
     from ntpoly_b200.workloads import guo_transform
-    out = str(tmp_path / "Exponential.mtx")
-    cmd = [EXE_COMPLEX, "--input_file", os.path.join(GOLD, "complex_input.mtx"), "--exponential_file", out,
-           "--process_rows", "1", "--process_columns", "1", "--process_slices", "1", "--threshold", "1e-6"]   # ReadMe.md:72-74
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env)
-    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
-    got = sio.mmread(out).toarray()
-    g = guo_transform(sio.mmread(os.path.join(GOLD, "complex_input.mtx")))
-    want = la.expm(0.5 * g.toarray())
+
+    def run(infile, outfile):
+        cmd = [EXE_COMPLEX, "--input_file", infile, "--exponential_file", outfile,
+               "--process_rows", "1", "--process_columns", "1", "--process_slices", "1", "--threshold", "1e-6"]   # ReadMe.md:72-74
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+        return sio.mmread(outfile).toarray()
+
+    O = oracle
+    a = sio.mmread(os.path.join(GOLD, "complex_input.mtx"))
+    got = run(os.path.join(GOLD, "complex_input.mtx"), str(tmp_path / "Exponential.mtx"))
+    g = guo_transform(a)
+    ref, info = O.compute_exponential(O.PSMatrix.from_scipy(sp.csc_matrix(0.5 * g), is_complex=True),
+                                      O.SolverParameters(threshold=1e-6))
+    assert info.iterations == 1                      # the reference does not scale this input (see above)
+    want = ref.todense()
     assert got.shape == want.shape
-    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-6
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-10
+    # with a self loop at node 1 the same program computes the exponential proper
+    a2 = sp.coo_matrix(a).tolil()
+    a2[0, 0] = 1.0
+    loop_file = str(tmp_path / "input_with_loop.mtx")
+    sio.mmwrite(loop_file, sp.coo_matrix(a2), field="real", symmetry="general")
+    got2 = run(loop_file, str(tmp_path / "Exponential2.mtx"))
+    g2 = guo_transform(sp.coo_matrix(a2))
+    want2 = la.expm(0.5 * g2.toarray())
+    assert np.linalg.norm(got2 - want2) / np.linalg.norm(want2) <= 1e-6
 
 
 def test_reference_hydrogen_example_runs_on_the_cuda_library(tmp_path, oracle):

@@ -242,3 +242,34 @@ def test_solvers_vs_scipy(oracle, fn, ref):
             out, _ = O.square_root(M, p)
             expect = (q * w ** 0.5) @ q.T
     assert np.linalg.norm(out.todense() - expect) / np.linalg.norm(expect) <= 1e-4
+
+
+def test_exponential_restatement(oracle):
+    """ComputeExponential (ExponentialSolversModule.F90:37-148), restated: pinned against scipy.linalg.expm the way the
+    reference's own test is (UnitTests/test_solvers.py test_exponential: relative error <= 1e-4), on a real symmetric
+    31x31 input and on the shipped complex example with a self loop at node 1 (radius 25.8 -> sigma 32, 5 squarings).
+    Also pins the reference quirk the shipped example runs into: M(1,1) = 0 -> PowerBounds returns 0 in iteration 1
+    -> no scaling."""
+    import scipy.linalg as la
+    import scipy.io as sio
+    import os
+    from ntpoly_b200.workloads import guo_transform
+    O = oracle
+    rng = np.random.default_rng(11)
+    n = 31
+    m = rng.uniform(0.0, 1.0, (n, n))
+    m = 0.5 * (m + m.T)
+    out, info = O.compute_exponential(O.PSMatrix.from_scipy(sp.csc_matrix(m)), O.SolverParameters(threshold=0.0))
+    expect = la.expm(m)
+    assert info.iterations > 1
+    assert np.linalg.norm(out.todense() - expect) / np.linalg.norm(expect) <= 1e-8
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "complex_input.mtx")
+    g = guo_transform(sio.mmread(gold))
+    shifted = sp.csc_matrix(0.5 * g + 0.3 * sp.identity(g.shape[0]))
+    out, info = O.compute_exponential(O.PSMatrix.from_scipy(shifted, is_complex=True), O.SolverParameters(threshold=1e-6))
+    expect = la.expm(shifted.toarray())
+    assert info.iterations == 6 and info.sigmas == [32.0]
+    assert np.linalg.norm(out.todense() - expect) / np.linalg.norm(expect) <= 1e-8
+    radius, pinfo = O.power_bounds(O.PSMatrix.from_scipy(sp.csc_matrix(0.5 * g), is_complex=True),
+                                   O.SolverParameters(max_iterations=10, threshold=1e-6))
+    assert radius == 0.0 and pinfo.iterations == 1
