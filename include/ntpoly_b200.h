@@ -325,6 +325,10 @@ double ntb_tile_builds(void);
 /* distributed products whose left operand was fetched as a tile halo (1 x C x 1 grids): {count, tile bytes received
  * from the peers (the rank's own tiles are used in place)} */
 void ntb_get_halo_counters(double *out2);
+/* peer memory over NVLink (column-split grids): {1 when every rank has mapped every other rank's slab, products that
+ * read the neighbours' operand tiles in place (no copy, no NCCL), barrier/exchange kernels enqueued, peak bytes of the
+ * peer-visible slab in use} */
+void ntb_get_peer_counters(double *out4);
 /* 1 (default): column-split grids use the tile halo exchange; 0: always the reference-style CSC panel gather */
 void ntb_set_halo_path(int on);
 /* 0 (default): PermuteMatrix / UndoPermuteMatrix relabel the indices on the device; 1: the reference's two products by

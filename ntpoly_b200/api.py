@@ -77,7 +77,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_StageArrays ntb_FillMatrixFromStaged_ps ntb_sorted_ingests ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_set_fused_shift ntb_get_halo_counters ntb_set_halo_path ntb_set_permute_gemm ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_set_fused_shift ntb_get_halo_counters ntb_get_peer_counters ntb_set_halo_path ntb_set_permute_gemm ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -953,6 +953,12 @@ def halo_counters():
     out = (c_double * 2)()
     lib().ntb_get_halo_counters(out)
     return {"products": int(out[0]), "bytes": float(out[1])}
+
+
+def peer_counters():
+    out = (c_double * 4)()
+    lib().ntb_get_peer_counters(out)
+    return {"ok": bool(out[0]), "products": int(out[1]), "exchanges": int(out[2]), "slab_peak_bytes": int(out[3])}
 
 
 def set_halo_path(on=True):

@@ -20,7 +20,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(LIBDIR, "libntpoly_b200.so")
 
-SOURCES = ["device.cu", "spgemm.cu", "spgemm_tile.cu", "ops.cu", "comm.cu", "psmatrix.cu", "solvers.cu", "smatrix.cu", "c_api.cu",
+SOURCES = ["device.cu", "peer.cu", "spgemm.cu", "spgemm_tile.cu", "ops.cu", "comm.cu", "psmatrix.cu", "solvers.cu", "smatrix.cu", "c_api.cu",
            "c_api_local.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

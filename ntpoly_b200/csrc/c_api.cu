@@ -1,6 +1,7 @@
 // extern "C" surface: NTPoly's `*_wrp` symbols over the CUDA hot path.
 // See include/ntpoly_b200.h for the per-section reference citations.
 #include "c_api_common.h"
+#include "peer.h"
 #include "ops.cuh"
 #include "solvers.h"
 #include <algorithm>
@@ -381,7 +382,7 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().peer_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
 // C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when
@@ -418,6 +419,10 @@ void ntb_get_deferred_counters(double* out2) { out2[0] = (double)rt().deferred_p
 void ntb_get_tile_counters(double* out2) { out2[0] = (double)rt().tile_products; out2[1] = rt().dmma_issued; }
 double ntb_tile_builds(void) { return (double)rt().tile_builds; }
 void ntb_get_halo_counters(double* out2) { out2[0] = (double)rt().halo_products; out2[1] = rt().halo_bytes; }
+void ntb_get_peer_counters(double* out4) {
+  out4[0] = ntb::peer().ok ? 1.0 : 0.0; out4[1] = (double)rt().peer_products; out4[2] = (double)ntb::peer().exchanges;
+  out4[3] = (double)ntb::shared_slab_peak();
+}
 void ntb_set_halo_path(int on) { ntb::set_halo_path(on); }
 void ntb_set_permute_gemm(int on) { ntb::set_permute_gemm(on); }
 double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }

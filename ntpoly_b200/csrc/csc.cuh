@@ -4,6 +4,7 @@
 #pragma once
 #include "device.cuh"
 #include <memory>
+#include <vector>
 #include <type_traits>
 
 namespace ntb {
@@ -25,11 +26,37 @@ struct ChunkTiles {
   const double* tval_view = nullptr;
 };
 constexpr long long HALO_TILE_BIAS = 1ll << 30;
+// One rank's left form as the other ranks of a column-split grid see it (peer.h): where its arrays lie in the owner's
+// peer-visible slab. Exactly one PeerPayload; ntiles / nnz sit in the two words a kernel can patch in.
+struct PeerLeftDesc {
+  long long off_colmeta, off_ent, off_kmeta, off_tval;   // byte offsets in the owner's slab
+  int ncc, nsuper;
+  int ok;                                    // the form exists, is worth the tensor cores and lies in the slab
+  int right_ok;                              // the same verdict on the publishing rank's RIGHT operand (decision exchange)
+  long long ntiles;
+  long long nnz;                             // entries of the block (panel fill for the rule table, algorithmic bytes)
+};
+static_assert(sizeof(PeerLeftDesc) == 64, "PeerLeftDesc is one peer payload");
+// The left operand of a tile product as the kernels see it: one piece per rank of the process row (1 on a single
+// rank). Chunk column q of the gathered operand is chunk column q % ncc_piece of piece q / ncc_piece; entries address
+// tiles relative to their own piece. Passed by value as a kernel parameter.
+struct LeftPieceView { const int4* colmeta; const int4* ent; const int4* kmeta; const double* tval; };
+struct LeftView {
+  int npieces = 1;
+  int ncc_piece = 0;
+  const double* tval2 = nullptr;             // copied halo tiles (NCCL fallback path): indices from HALO_TILE_BIAS on, piece 0
+  LeftPieceView piece[PEER_MAX];
+};
 // Both forms of one matrix, built on first use as a product operand or emitted together with a product's result.
 // Immutable once built, so copies of a matrix share them; any change of the entries drops them.
 struct TileForms {
   ChunkTiles left, right;                    // as the A (Y) operand / as the B (X) operand
   int has_left = 0, has_right = 0;           // 0 not built, 1 built, -1 cannot be built (pattern reach overflow)
+  // multi-GPU (column-split grids, peer.h): the left form's descriptors of EVERY rank once it has been published
+  // (by the product that wrote it, or at its first use as a left operand); the collective verdict on the right forms
+  std::vector<PeerLeftDesc> left_pub;
+  bool left_needs_barrier = false;           // the tiles were changed in place after publication (ScaleMatrix)
+  int right_all_ok = 0;                      // 0 unknown, 1 every rank's right form is usable, -1 not
 };
 
 template <typename T> struct LocalCsc;
@@ -137,9 +164,15 @@ void spgemm(const LocalCsc<T>& X, const LocalCsc<T>& Y, double alpha, double thr
 const ChunkTiles* tile_operand_form(const LocalCsc<double>& M, bool left);
 // product from tile forms alone: A = left form of the (possibly gathered) left operand, B = right form of the local
 // right operand. force: never decline (the caller has already committed collectively to this path).
-bool spgemm_tile_core(const ChunkTiles& A, const ChunkTiles& B, int ncols, int nrows, double alpha, double thr,
+// publish: on a column-split multi-GPU grid the product ends with a peer exchange that hands the descriptor of the
+// left form it has written to every rank (all ranks must pass the same value).
+bool spgemm_tile_core(const LeftView& A, const ChunkTiles& B, int ncols, int nrows, double alpha, double thr,
                       const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
-                      bool force, unsigned want = WANT_ALL);
+                      bool force, unsigned want = WANT_ALL, bool publish = false);
+// the one-piece view of a local (or NCCL-gathered) left form
+LeftView left_view_of(const ChunkTiles& A);
+// descriptor of a rank's own left form for publication (ok = 0 when an array lies outside the peer-visible slab)
+PeerLeftDesc left_desc_of(const ChunkTiles* L, long long nnz, bool usable);
 // column sums of |alpha*A + B| from the right tile forms of both blocks; false when either has none (use the CSC kernel)
 bool tile_diff_col_abs_sums(const LocalCsc<double>& A, const LocalCsc<double>& B, double alpha, double* d_colsum);
 // assemble the left form of a row of column blocks from per-rank pieces (see psmatrix.cu: halo gather)

@@ -1,5 +1,6 @@
 #include "device.cuh"
 #include <cstring>
+#include <deque>
 #include <map>
 #include <unordered_map>
 
@@ -66,6 +67,73 @@ size_t round_size(size_t bytes) {
 }
 }  // namespace
 
+
+// ---------------------------------------------------------------------------
+// Peer-visible slab (multi-GPU, see peer.cu): ONE big allocation per process that every other rank of the box has
+// mapped through CUDA IPC. Buffers that peers read in place over NVLink (the left tile forms of distributed products)
+// are carved out of it, so a peer addresses them as (its mapping of this slab) + offset. Allocation is host-side
+// first fit with coalescing. A freed block is QUARANTINED until the next peer barrier has been enqueued
+// (shared_slab_epoch): a peer may still be reading it, and every rank frees at the same point of the (SPMD) program,
+// so one barrier later nobody can be.
+// ---------------------------------------------------------------------------
+namespace {
+struct SharedSlab {
+  unsigned char* base = nullptr;
+  size_t bytes = 0;
+  std::map<size_t, size_t> avail;                    // offset -> size, coalesced, reusable now
+  std::unordered_map<size_t, size_t> live;           // offset -> size
+  struct Q { size_t off, size; unsigned long long epoch; };
+  std::deque<Q> quarantine;
+  unsigned long long epoch = 0;
+  size_t in_use = 0, peak = 0;
+  void insert_free(size_t off, size_t size) {
+    auto nx = avail.lower_bound(off);
+    if (nx != avail.begin()) {
+      auto pv = std::prev(nx);
+      if (pv->first + pv->second == off) { off = pv->first; size += pv->second; avail.erase(pv); }
+    }
+    if (nx != avail.end() && off + size == nx->first) { size += nx->second; avail.erase(nx); }
+    avail[off] = size;
+  }
+} g_slab;
+}  // namespace
+
+void shared_slab_attach(void* base, size_t bytes, size_t reserved_prefix) {
+  g_slab = SharedSlab();
+  g_slab.base = static_cast<unsigned char*>(base);
+  g_slab.bytes = bytes;
+  if (base && bytes > reserved_prefix) g_slab.avail[reserved_prefix] = bytes - reserved_prefix;
+}
+void shared_slab_detach() { g_slab = SharedSlab(); }
+void shared_slab_epoch() { ++g_slab.epoch; }
+bool is_shared_ptr(const void* p) {
+  const unsigned char* q = static_cast<const unsigned char*>(p);
+  return g_slab.base && q >= g_slab.base && q < g_slab.base + g_slab.bytes;
+}
+long long shared_offset(const void* p) {
+  return is_shared_ptr(p) ? (long long)(static_cast<const unsigned char*>(p) - g_slab.base) : -1;
+}
+size_t shared_slab_peak() { return g_slab.peak; }
+void* dmalloc_shared(size_t bytes) {
+  if (!g_slab.base) return dmalloc(bytes);
+  while (!g_slab.quarantine.empty() && g_slab.quarantine.front().epoch < g_slab.epoch) {
+    g_slab.insert_free(g_slab.quarantine.front().off, g_slab.quarantine.front().size);
+    g_slab.quarantine.pop_front();
+  }
+  const size_t need = ((bytes ? bytes : 1) + 255) & ~size_t(255);
+  auto best = g_slab.avail.end();
+  for (auto it = g_slab.avail.begin(); it != g_slab.avail.end(); ++it)
+    if (it->second >= need && (best == g_slab.avail.end() || it->second < best->second)) best = it;
+  if (best == g_slab.avail.end()) return dmalloc(bytes);         // slab full: an ordinary (not peer-visible) block
+  const size_t off = best->first, size = best->second;
+  g_slab.avail.erase(best);
+  if (size > need) g_slab.avail[off + need] = size - need;
+  g_slab.live[off] = need;
+  g_slab.in_use += need;
+  if (g_slab.in_use > g_slab.peak) g_slab.peak = g_slab.in_use;
+  return g_slab.base + off;
+}
+
 void* dmalloc(size_t bytes) {
   ensure_init();
   const size_t need = round_size(bytes);
@@ -91,6 +159,15 @@ void* dmalloc(size_t bytes) {
 }
 void dfree(void* p) {
   if (!p) return;
+  if (is_shared_ptr(p)) {
+    const size_t off = (size_t)(static_cast<unsigned char*>(p) - g_slab.base);
+    auto it = g_slab.live.find(off);
+    NTB_CHECK(it != g_slab.live.end(), "dfree of a slab pointer that is not live");
+    g_slab.quarantine.push_back({off, it->second, g_slab.epoch});
+    g_slab.in_use -= it->second;
+    g_slab.live.erase(it);
+    return;
+  }
   auto it = g_arena.capacity.find(p);
   NTB_CHECK(it != g_arena.capacity.end(), "dfree of a pointer the arena does not own");
   g_arena.free_blocks.emplace(it->second, p);
@@ -142,6 +219,21 @@ void readback_async(void* host, const void* dev, size_t bytes) {
   g_rt.launches++;
   g_rb_pending.push_back(PendingReadback{host, g_rb_used, bytes});
   g_rb_used += padded;
+}
+// A kernel of the caller stores `bytes` at the returned device address (mapped pinned host memory); they are handed to
+// `host` by the next stream_sync(), like readback_async().
+void* readback_reserve(void* host, size_t bytes) {
+  const size_t padded = (bytes + 15) & ~size_t(15);
+  NTB_CHECK(padded <= RB_SCRATCH, "readback_reserve: request exceeds the scratch");
+  if (g_rb_used + padded > RB_SCRATCH) stream_sync();
+  if (!g_rb_host) {
+    CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&g_rb_host), RB_SCRATCH, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_rb_dev), g_rb_host, 0));
+  }
+  void* d = g_rb_dev + g_rb_used;
+  g_rb_pending.push_back(PendingReadback{host, g_rb_used, bytes});
+  g_rb_used += padded;
+  return d;
 }
 void stream_sync() {
   CUDA_CHECK(cudaStreamSynchronize(g_rt.stream));

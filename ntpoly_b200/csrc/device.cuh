@@ -7,6 +7,8 @@
 
 namespace ntb {
 
+constexpr int PEER_MAX = 16;             // ranks of one box whose memory a kernel can address (peer.h)
+
 struct Runtime {
   int device = -1;
   cudaStream_t stream = nullptr;   // all kernels of the hot path are issued here
@@ -19,6 +21,7 @@ struct Runtime {
   unsigned long long tile_products = 0;  // local products that ran on the DMMA tile path
   unsigned long long tile_builds = 0;    // CSC -> tile-form conversions (0 per product once operands carry their forms)
   unsigned long long halo_products = 0;  // distributed products that fetched the left operand as a tile halo
+  unsigned long long peer_products = 0;  // ... of which read the halo tiles in place from the peers' memory (no copy, no NCCL)
   double halo_bytes = 0.0;               // tile bytes received from the peers for those halos
   double dmma_issued = 0.0;              // DMMA.8x8x4 instructions (x256 FMAs) issued by the tile path
   unsigned long long deferred_products = 0;      // tile products emitted without CSC entries (outer + right form only)
@@ -41,7 +44,16 @@ void stream_sync();
 // device -> host copy on the library stream whose result is valid after the next stream_sync(); small sizes bypass the
 // copy engines (see device.cu)
 void readback_async(void* host, const void* dev, size_t bytes);
+void* readback_reserve(void* host, size_t bytes);
 size_t arena_bytes_reserved();
+// peer-visible slab (device.cu / peer.cu): falls back to dmalloc when there is no slab or it is full
+void shared_slab_attach(void* base, size_t bytes, size_t reserved_prefix);
+void shared_slab_detach();
+void shared_slab_epoch();
+bool is_shared_ptr(const void* p);
+long long shared_offset(const void* p);      // byte offset inside the slab, -1 for any other pointer
+size_t shared_slab_peak();
+void* dmalloc_shared(size_t bytes);
 
 // RAII device array on the library stream
 template <typename T> struct DevBuf {
@@ -61,6 +73,12 @@ template <typename T> struct DevBuf {
     release();
     n = count;
     p = static_cast<T*>(dmalloc((count ? count : 1) * sizeof(T)));
+  }
+  // prefers the peer-visible slab (multi-GPU runs); an ordinary arena block otherwise
+  void alloc_shared(size_t count) {
+    release();
+    n = count;
+    p = static_cast<T*>(dmalloc_shared((count ? count : 1) * sizeof(T)));
   }
   void release() { if (p) { dfree(p); p = nullptr; n = 0; } }
   void zero() { CUDA_CHECK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), rt().stream)); }

@@ -4,6 +4,7 @@
 // so index/value loads are coalesced; the two sorted lists of a column are
 // combined by rank (binary search) instead of a serial merge.
 #include "ops.cuh"
+#include "peer.h"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace ntb {
@@ -170,6 +171,10 @@ template <typename T> void csc_scale(LocalCsc<T>& M, T c) {
   // cached tile forms: scaled in place when this matrix is their only owner, dropped otherwise
   if constexpr (!scalar_traits<T>::is_complex) {
     if (M.forms && M.forms.use_count() == 1) {
+      // a published left form is read in place by the other ranks (peer.h): they must have finished the products
+      // enqueued so far before the tiles change, and must not start the next one before the change is complete
+      const bool published = !M.forms->left_pub.empty() && M.forms->has_left == 1 && peer().ok;
+      if (published) { peer_barrier(); M.forms->left_needs_barrier = true; }
       for (ChunkTiles* t : {&M.forms->left, &M.forms->right}) {
         const int has = (t == &M.forms->left) ? M.forms->has_left : M.forms->has_right;
         const long long n = t->ntiles * 32;

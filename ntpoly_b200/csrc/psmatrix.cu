@@ -1,4 +1,5 @@
 #include "psmatrix.h"
+#include "peer.h"
 #include <chrono>
 #include <functional>
 #include "ops.cuh"
@@ -72,6 +73,8 @@ void grid_construct(ProcessGrid& g, int rows, int cols, int slices) {
     comm_set_shape(g.row, cols, g.my_col);
     g.column = comm_split(w.comm, g.my_slice * cols + g.my_col, g.rank);
     comm_set_shape(g.column, rows, g.my_row);
+    // column-split grids read the other ranks' operand tiles in place over NVLink (peer.h); collective, once per process
+    if (rows == 1 && slices == 1 && cols == w.size) g.peer_ok = peer_setup(w.comm);
   }
   g.constructed = true;
 }
@@ -637,6 +640,40 @@ void mat_filter(Matrix& M, double threshold) {
   if (M.is_complex) csc_filter<cplx>(M.c, threshold); else csc_filter<double>(M.r, threshold);
 }
 
+// Reduction of n <= 8 device doubles over `comm`, result on the host. On a column-split peer grid (peer.h) whose
+// communicator spans all ranks this is ONE small kernel - the barrier/exchange - riding on the read-back the caller
+// needs anyway, reduced on the host in rank order (run-to-run and rank-to-rank identical); NCCL otherwise.
+static void reduce_to_host(const ProcessGrid& g, CommHandle* comm, double* d_vals, int n, const RedOp* ops, double* h_out) {
+  const int np = comm_size(comm);
+  if (np > 1 && g.peer_ok && peer().ok && np == peer().n) {
+    std::vector<PeerPayload> all((size_t)np);
+    PeerPayload z{};
+    peer_exchange(z, all.data(), d_vals, n);
+    stream_sync();
+    for (int i = 0; i < n; ++i) {
+      double acc = 0.0;
+      for (int p = 0; p < np; ++p) {
+        double v;
+        std::memcpy(&v, &all[p].w[i], sizeof(double));
+        if (p == 0) acc = v;
+        else if (ops[i] == RedOp::Sum) acc += v;
+        else if (ops[i] == RedOp::Max) acc = std::max(acc, v);
+        else acc = std::min(acc, v);
+      }
+      h_out[i] = acc;
+    }
+    return;
+  }
+  for (int i = 0; i < n; ++i) comm_allreduce_f64(comm, d_vals + i, 1, ops[i]);
+  for (int i = 0; i < n; ++i) readback_async(&h_out[i], d_vals + i, sizeof(double));
+  stream_sync();
+}
+static double reduce_to_host(const ProcessGrid& g, CommHandle* comm, double* d_val, RedOp op) {
+  double h = 0.0;
+  reduce_to_host(g, comm, d_val, 1, &op, &h);
+  return h;
+}
+
 static void allreduce_host(CommHandle* comm, double* vals, int n, RedOp op) {
   if (comm_size(comm) == 1) return;
   DevBuf<double> d((size_t)n);
@@ -690,10 +727,7 @@ double mat_trace(const Matrix& M) {
   DevBuf<double> d(1);
   if (M.is_complex) csc_trace<cplx>(M.c.view(), M.start_row, M.start_col, d.get());
   else csc_trace<double>(M.r.view(), M.start_row, M.start_col, d.get());
-  comm_allreduce_f64(M.grid->within_slice, d.get(), 1, RedOp::Sum);
-  double h;
-  d2h(&h, d.get(), 1);
-  return h;
+  return reduce_to_host(*M.grid, M.grid->within_slice, d.get(), RedOp::Sum);
 }
 
 double mat_norm(const Matrix& M) {
@@ -703,10 +737,7 @@ double mat_norm(const Matrix& M) {
   else csc_col_abs_sums<double>(M.r.view(), colsum.get());
   comm_allreduce_f64(M.grid->column, colsum.get(), (size_t)M.local_cols, RedOp::Sum);
   reduce_max(colsum.get(), M.local_cols, d.get());
-  comm_allreduce_f64(M.grid->row, d.get(), 1, RedOp::Max);
-  double h;
-  d2h(&h, d.get(), 1);
-  return h;
+  return reduce_to_host(*M.grid, M.grid->row, d.get(), RedOp::Max);
 }
 
 // MatrixNorm(alpha*A + B) without forming the sum (see k_diff_col_abs); operands of equal type and layout
@@ -724,10 +755,7 @@ double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha) {
     csc_diff_col_abs_sums<double>(A.r.view(), B.r.view(), alpha, colsum.get());
   comm_allreduce_f64(B.grid->column, colsum.get(), (size_t)B.local_cols, RedOp::Sum);
   reduce_max(colsum.get(), B.local_cols, d.get());
-  comm_allreduce_f64(B.grid->row, d.get(), 1, RedOp::Max);
-  double h;
-  d2h(&h, d.get(), 1);
-  return h;
+  return reduce_to_host(*B.grid, B.grid->row, d.get(), RedOp::Max);
 }
 
 double mat_sigma(const Matrix& M) {
@@ -743,10 +771,9 @@ void mat_gershgorin(const Matrix& M, double* e_min, double* e_max) {
   comm_allreduce_f64(M.grid->column, dmax.get(), (size_t)M.local_cols, RedOp::Sum);
   reduce_min(dmin.get(), M.local_cols, d.get());
   reduce_max(dmax.get(), M.local_cols, d.get() + 1);
-  comm_allreduce_f64(M.grid->row, d.get(), 1, RedOp::Min);
-  comm_allreduce_f64(M.grid->row, d.get() + 1, 1, RedOp::Max);
+  const RedOp ops[2] = {RedOp::Min, RedOp::Max};
   double h[2];
-  d2h(h, d.get(), 2);
+  reduce_to_host(*M.grid, M.grid->row, d.get(), 2, ops, h);
   *e_min = h[0];
   *e_max = h[1];
 }
@@ -762,9 +789,9 @@ void mat_dot(const Matrix& A, const Matrix& B, double* re, double* im) {
   } else {
     csc_dot<double>(A.r.view(), B.r.view(), d.get());
   }
-  comm_allreduce_f64(A.grid->within_slice, d.get(), 2, RedOp::Sum);
+  const RedOp ops[2] = {RedOp::Sum, RedOp::Sum};
   double h[2];
-  d2h(h, d.get(), 2);
+  reduce_to_host(*A.grid, A.grid->within_slice, d.get(), 2, ops, h);
   *re = h[0];
   if (im) *im = h[1];
 }
@@ -857,6 +884,10 @@ __global__ void __launch_bounds__(256) k_col_len(const int* __restrict__ outer, 
 }
 
 struct HaloRecord { long long ok, nsuper, ntiles, nnzA, qlo, qhi, nnzB, ntilesB; };
+static long long halo_tile_limit() {
+  static const long long lim = [] { const char* e = std::getenv("NTB_HALO_TILE_LIMIT"); return e ? std::atoll(e) : (1ll << 26); }();
+  return lim;
+}
 __global__ void k_range_into_record(const int* __restrict__ r2, long long* __restrict__ qlo, long long* __restrict__ qhi) {
   if (threadIdx.x == 0) { *qlo = r2[0]; *qhi = r2[1]; }
 }
@@ -961,7 +992,17 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
     total_tiles += th - tl;
     if (p != me) halo_tiles += th - tl;
   }
-  NTB_CHECK(halo_tiles < (1ll << 26) && Lf->ntiles < HALO_TILE_BIAS - 64, "left operand too large for the halo exchange");
+  // the halo buffer is addressed with 32-bit tile indices from HALO_TILE_BIAS on: a left operand or a halo that does
+  // not fit DECLINES the path - on every rank alike, every rank evaluates every rank's sizes from the gathered records
+  for (int r = 0; r < C; ++r) {
+    long long ht = 0;
+    for (int p = 0; p < C; ++p) {
+      int a, b, tl, th;
+      run_of((int)rec[r].qlo, (int)rec[r].qhi, p, a, b, tl, th);
+      if (p != r) ht += th - tl;
+    }
+    if (ht >= halo_tile_limit() || rec[r].ntiles >= HALO_TILE_BIAS - 64) return false;
+  }
   G.ntiles = total_tiles;
   G.tval.alloc((size_t)std::max(halo_tiles, 1ll) * 32);
   G.tval_view = Lf->tval.get();
@@ -995,7 +1036,7 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   double useful = -1.0;
   if (count) { Bl.ensure_entries(); useful = useful_products_from_lengths(Bl, ylen_g.get()); }
   const auto t4 = now();
-  const bool done = spgemm_tile_core(G, *Rf, B.local_cols, A.local_rows, alpha, wthr, rv, out, useful, ds, true, want);
+  const bool done = spgemm_tile_core(left_view_of(G), *Rf, B.local_cols, A.local_rows, alpha, wthr, rv, out, useful, ds, true, want);
   const auto t5 = now();
   if (timing && me == 0)
     std::fprintf(stderr, "[halo] records %.3f  index gather %.3f  tiles %.3f (%.1f MB)  flops %.3f  product %.3f ms\n",
@@ -1013,6 +1054,93 @@ static bool halo_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   rt().alg_bytes += a_bytes + (double)Bl.bytes() + (double)out.bytes();
   rt().halo_products++;
   rt().halo_bytes += (double)halo_tiles * 256.0;
+  return true;
+}
+
+
+// ---------------------------------------------------------------------------
+// Tile-form product on a 1 x C x 1 grid WITHOUT any copy of the left operand (peer.h): every rank has mapped every
+// other rank's slab, the left forms live there, and the numeric kernel's bulk copies fetch the few A super-tiles of
+// the neighbouring ranks straight from the owner's HBM over NVLink, stage by stage, overlapped with the DMMAs of the
+// stages before - the reference's row-panel gather (comm_includes/ReduceAndComposeMatrix*.f90) fused into the product.
+// What the ranks need of each other is 64 bytes per left form: where its arrays lie (PeerLeftDesc). A product hands
+// out the descriptor of the left form it has written with the same small kernel that acts as the barrier between its
+// tile stores and the peers' reads (spgemm_tile_core, publish); a form built from CSC is published at its first use
+// here. Steady state of a solver loop: no NCCL call, no host decision, nothing but the product's own two read-backs.
+// Returns false ON EVERY RANK ALIKE when the product does not qualify (all verdicts come from exchanged records).
+static bool peer_tile_product(const Matrix& A, const Matrix& B, double alpha, double wthr, const RuleView& rv,
+                              const std::function<void()>& full_rules, const DiagShift* ds, LocalCsc<double>& out,
+                              GemmStats& st, unsigned want) {
+  ProcessGrid& g = *A.grid;
+  if (!g.peer_ok || !peer().ok || peer().n != g.C || !tile_path_on() || A.local_cols % 64 != 0 || !(wthr >= 0.0)) return false;
+  const int C = g.C;
+  const LocalCsc<double>& Al = A.r;
+  const LocalCsc<double>& Bl = B.r;
+  const int lcols = A.local_cols;
+  const ChunkTiles* Lf = tile_operand_form(Al, true);
+  const ChunkTiles* Rf = tile_operand_form(Bl, false);
+  TileForms& fa = *Al.forms;
+  TileForms& fb = *Bl.forms;
+  // forms built from CSC must be reasonably full (mostly-padding tiles are the scalar kernels' business); forms written
+  // by a product have fixed 64-tile slots, their tile count says nothing about the fill
+  auto dense_enough = [](const ChunkTiles* f, long long nnz) {
+    return f->emitted || (double)nnz >= 0.20 * 32.0 * (double)f->ntiles;
+  };
+  // a right form written by a (collective) product exists on every rank; one built from CSC needs a collective verdict
+  const bool right_known = (Rf && Rf->emitted) || fb.right_all_ok != 0;
+  if (fa.left_pub.empty() || !right_known) {
+    PeerLeftDesc mine = left_desc_of(Lf, Al.nnz, Lf && dense_enough(Lf, Al.nnz));
+    mine.right_ok = (Rf && dense_enough(Rf, Bl.nnz)) ? 1 : 0;
+    std::vector<PeerLeftDesc> all((size_t)C);
+    PeerPayload pl;
+    std::memcpy(&pl, &mine, sizeof(pl));
+    peer_exchange(pl, reinterpret_cast<PeerPayload*>(all.data()));
+    stream_sync();
+    bool rok = true;
+    for (int p = 0; p < C; ++p) rok = rok && all[p].right_ok != 0;
+    if (!(Rf && Rf->emitted)) fb.right_all_ok = rok ? 1 : -1;
+    else if (!rok) return false;
+    if (fa.left_pub.empty()) fa.left_pub = all;
+    fa.left_needs_barrier = false;                // the exchange was a barrier
+  }
+  if (!(Rf && Rf->emitted) && fb.right_all_ok != 1) return false;
+  long long nnzA = 0;
+  for (int p = 0; p < C; ++p) {
+    if (!fa.left_pub[p].ok) return false;
+    nnzA += fa.left_pub[p].nnz;
+  }
+  if (nnzA == 0) return false;
+  if (fa.left_needs_barrier) { peer_barrier(); fa.left_needs_barrier = false; }
+  // A row block of A's panel cannot be more than 10 % full when the whole panel holds fewer entries than 10 % of
+  // ONE row block: only past that bound is the per-block histogram (and its all-reduce) needed for the rule table
+  if ((double)nnzA > 0.1 * (double)A.row_block() * (double)Bl.rows) full_rules();
+
+  LeftView V;
+  V.npieces = C;
+  V.ncc_piece = lcols / 32;
+  for (int p = 0; p < C; ++p) {
+    const PeerLeftDesc& d = fa.left_pub[p];
+    const unsigned char* base = peer().base[p];
+    V.piece[p] = LeftPieceView{reinterpret_cast<const int4*>(base + d.off_colmeta), reinterpret_cast<const int4*>(base + d.off_ent),
+                               reinterpret_cast<const int4*>(base + d.off_kmeta), reinterpret_cast<const double*>(base + d.off_tval)};
+  }
+  // instrumentation (off in timed regions): useful products need the column lengths of the whole row panel of A
+  double useful = -1.0;
+  if (rt().count_flops) {
+    DevBuf<int> ylen((size_t)lcols), ylen_g((size_t)C * lcols);
+    NTB_LAUNCH(k_col_len, div_up(lcols, 256), 256, 0, Al.outer.get(), lcols, ylen.get());
+    comm_allgather_bytes(g.row, ylen.get(), ylen_g.get(), (size_t)lcols * sizeof(int));
+    Bl.ensure_entries();
+    useful = useful_products_from_lengths(Bl, ylen_g.get());
+  }
+  if (!spgemm_tile_core(V, *Rf, B.local_cols, A.local_rows, alpha, wthr, rv, out, useful, ds, true, want, true)) return false;
+  st.flops = rt().count_flops ? 2.0 * useful : 0.0;
+  st.shift_applied = ds && ds->sigma != 0.0;
+  // compulsory bytes: the rank's share of A (the few halo super-tiles read from the neighbours come on top), its B
+  // block and the kept C block
+  rt().alg_bytes += (double)Al.bytes() + (double)Bl.bytes() + (double)out.bytes();
+  rt().halo_products++;
+  rt().peer_products++;
   return true;
 }
 
@@ -1111,9 +1239,16 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
         colblock_fills(Bl, inner_dim, fb);
         set_rules(fa, fb);
       };
-      product_done = halo_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st,
+      product_done = peer_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st,
                                        want);
-      if (!product_done) { rv = RuleView(); }
+      if (!product_done) {
+        rv = RuleView();
+        // without a peer space (GPUs that cannot map each other, NTB_P2P=0): the tile halo is copied with NCCL
+        if (!(g.peer_ok && peer().ok))
+          product_done = halo_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st,
+                                           want);
+        if (!product_done) { rv = RuleView(); }
+      }
     }
   }
 

@@ -22,6 +22,7 @@ struct ProcessGrid {
   CommHandle* between_slice = nullptr;
   CommHandle* row = nullptr;      // same (slice,row): size C, my rank = my_col
   CommHandle* column = nullptr;   // same (slice,col): size R, my rank = my_row
+  bool peer_ok = false;           // column-split grid whose ranks have mapped each other's slabs (peer.h)
   bool constructed = false;
 };
 void grid_construct(ProcessGrid& g, int rows, int cols, int slices);

@@ -329,7 +329,7 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   if constexpr (!scalar_traits<T>::is_complex) {
     if (tile_path_enabled() && !rt().count_flops && ncols > 0 && Xl.nnz > 0 && Yl.nnz > 0 && Xl.forms && Yl.forms &&
         Xl.forms->has_right == 1 && Yl.forms->has_left == 1 &&
-        spgemm_tile_core(Yl.forms->left, Xl.forms->right, ncols, nrows, alpha, thr, rules, Z, -1.0, shift, false, want)) {
+        spgemm_tile_core(left_view_of(Yl.forms->left), Xl.forms->right, ncols, nrows, alpha, thr, rules, Z, -1.0, shift, false, want)) {
       if (stats) { stats->shift_applied = shift && shift->sigma != 0.0; stats->flops = 0.0; stats->tmp_entries = 0; }
       account_bytes(Z.nnz);
       return;

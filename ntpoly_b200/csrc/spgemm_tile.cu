@@ -25,7 +25,10 @@
 // by tile padding never survive the strict |v| > thr test, so results equal the scalar
 // path up to summation order.
 #include "csc.cuh"
+#include "peer.h"
 #include <chrono>
+#include <cstring>
+#include <vector>
 
 namespace ntb {
 
@@ -35,10 +38,19 @@ constexpr int IPL = MAXR / 32;               // bitmap words owned by a lane
 
 struct CtView {
   const int4* colmeta; const int4* ent; const double* tval; const int4* kmeta; int ncc;
-  const double* tval2;   // tiles with index >= HALO_TILE_BIAS (minus the slack of a virtual origin) live here (halo buffer)
 };
-__device__ __forceinline__ const double* tile_ptr(const CtView& V, long long tile) {
-  return (tile >= HALO_TILE_BIAS - 64) ? V.tval2 + (tile - HALO_TILE_BIAS) * 32 : V.tval + tile * 32;
+// ---- left operand = one piece per rank of the process row (csc.cuh: LeftView). Piece of chunk column q and its index there:
+__device__ __forceinline__ int lv_piece(const LeftView& A, int q, int& ql) {
+  if (A.npieces == 1) { ql = q; return 0; }
+  const int p = q / A.ncc_piece;
+  ql = q - p * A.ncc_piece;
+  return p;
+}
+// address of a tile of piece p (a peer address over NVLink when p is another rank); tiles with an index from
+// HALO_TILE_BIAS on (minus the slack of a virtual origin) are copied halo tiles of the NCCL fallback path
+__device__ __forceinline__ const double* lv_tile_ptr(const LeftView& A, int p, long long tile) {
+  if (A.tval2 != nullptr && tile >= HALO_TILE_BIAS - 64) return A.tval2 + (tile - HALO_TILE_BIAS) * 32;
+  return A.piece[p].tval + tile * 32;
 }
 
 // A: super-tile id = row/64, bit = ((col%32)/4)*8 + (row/8)%8, fragment lane = (row%8)*4 + col%4
@@ -186,8 +198,9 @@ static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
   const int ncc = T.ncc;
   const int nk = ISA ? div_up(M.cols, 4) : 0;
   DevBuf<int> scount((size_t)ncc), tcount((size_t)ncc), sptr((size_t)ncc + 1), tptr((size_t)ncc + 1), overflow(1);
-  T.colmeta.alloc((size_t)ncc);
-  if (ISA) T.kmeta.alloc((size_t)nk);
+  // a left form is what the other ranks of a column-split grid read in place: peer-visible slab when there is one
+  if (ISA) { T.colmeta.alloc_shared((size_t)ncc); T.kmeta.alloc_shared((size_t)nk); }
+  else T.colmeta.alloc((size_t)ncc);
   overflow.zero();
   const int grid = max(1, min(div_up(ncc, TW), kNumSMs * 8));
   NTB_LAUNCH((k_ct_build<ISA, false>), grid, TW * 32, 0, M, ncc, scount.get(), tcount.get(), T.colmeta.get(),
@@ -203,8 +216,8 @@ static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
   if (h[2]) return false;
   T.nsuper = h[0];
   T.ntiles = h[1];
-  T.ent.alloc((size_t)max(T.nsuper, 1));
-  T.tval.alloc((size_t)T.ntiles * 32);
+  if (ISA) { T.ent.alloc_shared((size_t)max(T.nsuper, 1)); T.tval.alloc_shared((size_t)T.ntiles * 32); }
+  else { T.ent.alloc((size_t)max(T.nsuper, 1)); T.tval.alloc((size_t)T.ntiles * 32); }
   T.tval.zero();
   NTB_LAUNCH((k_ct_build<ISA, true>), grid, TW * 32, 0, M, ncc, (int*)nullptr, (int*)nullptr, T.colmeta.get(),
              (int4*)nullptr, nk, (int*)nullptr, sptr.get(), tptr.get(), T.ent.get(), T.tval.get());
@@ -213,7 +226,7 @@ static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
 }
 
 // per output tile column J: row-tile window aligned to blocks of 8 row tiles, and the DMMA count
-__global__ void __launch_bounds__(256) k_tile_bounds(CtView A, CtView B, int nJ, int* __restrict__ imin8, int* __restrict__ nI8,
+__global__ void __launch_bounds__(256) k_tile_bounds(LeftView A, CtView B, int nJ, int* __restrict__ imin8, int* __restrict__ nI8,
                                                      unsigned long long* __restrict__ ndmma, int diag_on, int dd,
                                                      int ncols_diag, int nrows) {
   const int lane = threadIdx.x & 31;
@@ -228,10 +241,14 @@ __global__ void __launch_bounds__(256) k_tile_bounds(CtView A, CtView B, int nJ,
       const int4 en = B.ent[cm.x + e];
       const unsigned long long m = ((unsigned long long)(unsigned)en.w << 32) | (unsigned)en.z;
       unsigned byte = (unsigned)(m >> (jj * 8)) & 0xffu;
+      if (byte == 0u) continue;               // (an entry with an empty mask may carry an id past the last chunk column)
+      int ql;
+      const int pc = lv_piece(A, en.x, ql);
+      const int4* kmeta = A.piece[pc].kmeta + ql * 8;
       while (byte) {
         const int kk = __ffs(byte) - 1;
         byte &= byte - 1;
-        const int4 km = A.kmeta[en.x * 8 + kk];
+        const int4 km = kmeta[kk];
         if (km.y > 0) { mn = min(mn, km.z); mx = max(mx, km.w); mine += (unsigned long long)km.y; }
       }
     }
@@ -370,11 +387,11 @@ __device__ __forceinline__ unsigned or_bytes(unsigned long long m) {
 }
 
 // entry index of super-tile `id` in a chunk column (binary search unless the ids are one contiguous run), or -1
-__device__ __forceinline__ int ct_find(const CtView& A, const int4& ca, int id) {
+__device__ __forceinline__ int ct_find(const int4* __restrict__ ent, const int4& ca, int id) {
   if (ca.y <= 0 || id < ca.z || id > ca.w) return -1;
   if (ca.w - ca.z + 1 == ca.y) return ca.x + (id - ca.z);
   int l2 = 0, h2 = ca.y;
-  while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.ent[ca.x + mid].x < id) l2 = mid + 1; else h2 = mid; }
+  while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (ent[ca.x + mid].x < id) l2 = mid + 1; else h2 = mid; }
   return (l2 < ca.y) ? ca.x + l2 : -1;
 }
 // the (A super-tile, B super-tile) pair of one inner chunk: masks and tile offsets when they share an inner tile
@@ -426,7 +443,7 @@ struct ResultForms {
 };
 template <int NSTAGE, int MINB, int DENSE>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
-k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
+k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
                 int* __restrict__ task_counter, int* __restrict__ cnt, ResultForms out, int nrows, int ncols, EmitSpec es) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* slab = reinterpret_cast<double*>(smem);
@@ -453,6 +470,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
     int4 cmB_n = none, eb_n = none, ca_n = none, ea_n = none;
     unsigned long long mA_n = 0ull, mB_n = 0ull;
     int offA_n = 0, offB_n = 0;
+    int pc_n = 0;                                    // piece (rank of the process row) that holds this lane's A super-tile
     int gt0_n = 0, gt1_n = 0;
     auto advance = [&]() {
       switch (pstep) {
@@ -472,12 +490,20 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
         case 3:
           // an entry of a product-written form may carry an empty mask (and an id past the last chunk column of A)
           have_n = have_n && mask64(eb_n) != 0ull;
-          ca_n = have_n ? A.colmeta[eb_n.x] : none;
+          if (have_n) {
+            int ql;
+            pc_n = lv_piece(A, eb_n.x, ql);
+            ca_n = A.piece[pc_n].colmeta[ql];
+          } else {
+            pc_n = 0;
+            ca_n = none;
+          }
           break;
         case 4: {
-          const int idx = have_n ? ct_find(A, ca_n, tk_n.y) : -1;
+          const int4* entA = A.piece[pc_n].ent;
+          const int idx = have_n ? ct_find(entA, ca_n, tk_n.y) : -1;
           found_n = idx >= 0;
-          ea_n = found_n ? A.ent[idx] : none;
+          ea_n = found_n ? entA[idx] : none;
           break;
         }
         case 5:
@@ -486,7 +512,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
           // consumed, so that their bulk copies find them there (the DMMA warps were waiting 12 % of their time for
           // a full barrier, i.e. for HBM latency at the short band-edge stages)
           if (mA_n != 0ull) {
-            bulk_prefetch_l2(tile_ptr(A, (long long)offA_n + 8 * first_group(mA_n)), (unsigned)span_tiles(mA_n) * 256u);
+            bulk_prefetch_l2(lv_tile_ptr(A, pc_n, (long long)offA_n + 8 * first_group(mA_n)), (unsigned)span_tiles(mA_n) * 256u);
             bulk_prefetch_l2(B.tval + ((long long)offB_n + 8 * first_group(mB_n)) * 32, (unsigned)span_tiles(mB_n) * 256u);
           }
           break;
@@ -503,6 +529,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
       const int4 cmB = cmB_n;
       unsigned long long mA = mA_n, mB = mB_n;
       int offA = offA_n, offB = offB_n;
+      int pc = pc_n;
       if (!done) {
         if (lane == 0) task_raw = atomicAdd(task_counter, 1);
         pstep = 0;
@@ -514,9 +541,12 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
           bool have = e < cmB.y;
           const int4 eb = have ? B.ent[cmB.x + e] : none;
           have = have && mask64(eb) != 0ull;
-          const int4 ca = have ? A.colmeta[eb.x] : none;
-          const int idx = have ? ct_find(A, ca, Ib) : -1;
-          const int4 ea = (idx >= 0) ? A.ent[idx] : none;
+          int ql = 0;
+          pc = have ? lv_piece(A, eb.x, ql) : 0;
+          const int4* entA = A.piece[pc].ent;
+          const int4 ca = have ? A.piece[pc].colmeta[ql] : none;
+          const int idx = have ? ct_find(entA, ca, Ib) : -1;
+          const int4 ea = (idx >= 0) ? entA[idx] : none;
           ct_pair(ea, eb, Ib, idx >= 0, mA, mB, offA, offB);
         }
         unsigned todo = __ballot_sync(0xffffffffu, mA != 0ull);
@@ -528,6 +558,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
           const bool last = final_batch && todo == 0u;
           const unsigned long long sA = __shfl_sync(0xffffffffu, mA, l), sB = __shfl_sync(0xffffffffu, mB, l);
           const int oA = __shfl_sync(0xffffffffu, offA, l), oB = __shfl_sync(0xffffffffu, offB, l);
+          const int pA = __shfl_sync(0xffffffffu, pc, l);
           // digest the masks while the slot may still be busy
           const int gfA = first_group(sA), gfB = first_group(sB);
           unsigned desc = 0;
@@ -563,7 +594,7 @@ k_tile_numeric9(CtView A, CtView B, int nJ, const int* __restrict__ gtask_off, c
             const unsigned bA = (unsigned)span_tiles(sA) * 256u, bB = (unsigned)span_tiles(sB) * 256u;
             mbar_arrive_expect_tx(bar0 + 8 * st, bA + bB);
             const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
-            if (bA) bulk_g2s(slab_s, tile_ptr(A, (long long)oA + 8 * gfA), bA, bar0 + 8 * st);
+            if (bA) bulk_g2s(slab_s, lv_tile_ptr(A, pA, (long long)oA + 8 * gfA), bA, bar0 + 8 * st);
             if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + ((long long)oB + 8 * gfB) * 32, bB, bar0 + 8 * st);
           }
           __syncwarp();
@@ -908,7 +939,7 @@ void tile_materialize_entries(const LocalCsc<double>& M) {
   M.inner.alloc((size_t)M.nnz);
   M.val.alloc((size_t)M.nnz);
   if (M.nnz == 0 || M.cols == 0) return;
-  const CtView Rv{R.colmeta.get(), R.ent.get(), R.tval.get(), nullptr, R.ncc, nullptr};
+  const CtView Rv{R.colmeta.get(), R.ent.get(), R.tval.get(), nullptr, R.ncc};
   DevBuf<int> bad(1);
   bad.zero();
   NTB_LAUNCH(k_right_to_csc, max(1, min(div_up((long long)M.cols * 32, 256), kNumSMs * 16)), 256, 0, M.cols, Rv,
@@ -965,8 +996,8 @@ bool tile_diff_col_abs_sums(const LocalCsc<double>& A, const LocalCsc<double>& B
   const ChunkTiles& Ra = A.forms->right;
   const ChunkTiles& Rb = B.forms->right;
   if (A.cols != B.cols || A.rows != B.rows || Ra.ncc != Rb.ncc || A.cols == 0) return false;
-  const CtView Av{Ra.colmeta.get(), Ra.ent.get(), Ra.tval.get(), nullptr, Ra.ncc, nullptr};
-  const CtView Bv{Rb.colmeta.get(), Rb.ent.get(), Rb.tval.get(), nullptr, Rb.ncc, nullptr};
+  const CtView Av{Ra.colmeta.get(), Ra.ent.get(), Ra.tval.get(), nullptr, Ra.ncc};
+  const CtView Bv{Rb.colmeta.get(), Rb.ent.get(), Rb.tval.get(), nullptr, Rb.ncc};
   const int nJ = div_up(A.cols, 8);
   NTB_LAUNCH(k_form_diff_col_abs, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, nJ, A.cols,
              alpha, d_colsum);
@@ -1009,6 +1040,30 @@ void tile_fixup_gathered_left(ChunkTiles& G, const LeftPiece* pieces, int npiece
   }
 }
 
+// ---- how many tasks (64x64 output blocks) a product may have: 64 KB of slots each, at most a third of the device
+// memory, and the 32-bit tile index
+static long long tile_task_limit() {
+  static const long long lim = [] {
+    size_t free_b = 0, total_b = 0;
+    ensure_init();
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    long long l = (long long)(total_b / 3 / 65536);
+    if (const char* e = std::getenv("NTB_TILE_TASK_LIMIT")) l = std::atoll(e);      // tests
+    return std::min<long long>(l, (1ll << 31) / 128 - 1);
+  }();
+  return lim;
+}
+// a task that holds fewer than this many DMMAs on average is a scattered pattern: 64 KB of slots for a handful of
+// entries (the scalar kernels' business); a banded product has ~1000 per task, a 32x32 block pair alone 128
+constexpr long long MIN_DMMA_PER_TASK = 16;
+__global__ void k_task_guard(const int* __restrict__ ntasks, const unsigned long long* __restrict__ ndmma, long long limit,
+                             int* __restrict__ decline) {
+  if (threadIdx.x == 0) {
+    const long long t = *ntasks;
+    *decline = (t > limit || (long long)*ndmma < MIN_DMMA_PER_TASK * t) ? 1 : 0;
+  }
+}
+
 // returns false when the operands are not locally dense enough (caller falls back to the
 // scalar window kernels). useful_products = sum over B entries of the A column lengths.
 bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double alpha, double thr, const RuleView& rules,
@@ -1018,16 +1073,38 @@ bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double 
   if (!A || (!A->emitted && (double)Yl.nnz < 0.20 * 32.0 * (double)A->ntiles)) return false;   // tiles mostly padding
   const ChunkTiles* B = tile_operand_form(Xl, false);
   if (!B || (!B->emitted && (double)Xl.nnz < 0.20 * 32.0 * (double)B->ntiles)) return false;
-  return spgemm_tile_core(*A, *B, Xl.cols, Yl.rows, alpha, thr, rules, Z, useful_products, shift, false, want);
+  return spgemm_tile_core(left_view_of(*A), *B, Xl.cols, Yl.rows, alpha, thr, rules, Z, useful_products, shift, false, want);
 }
 
-bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncols, int nrows, double alpha, double thr,
+LeftView left_view_of(const ChunkTiles& A) {
+  LeftView v;
+  v.npieces = 1;
+  v.ncc_piece = A.ncc;
+  // a form gathered by the NCCL fallback path addresses the rank's own tiles in place (tval_view) and the copied halo
+  // tiles (tval) with indices from HALO_TILE_BIAS on
+  v.piece[0] = LeftPieceView{A.colmeta.get(), A.ent.get(), A.kmeta.get(), A.tval_view ? A.tval_view : A.tval.get()};
+  v.tval2 = A.tval_view ? A.tval.get() : nullptr;
+  return v;
+}
+PeerLeftDesc left_desc_of(const ChunkTiles* L, long long nnz, bool usable) {
+  PeerLeftDesc d{};
+  d.nnz = nnz;
+  if (!L) return d;
+  d.off_colmeta = shared_offset(L->colmeta.get());
+  d.off_ent = shared_offset(L->ent.get());
+  d.off_kmeta = shared_offset(L->kmeta.get());
+  d.off_tval = shared_offset(L->tval.get());
+  d.ncc = L->ncc; d.nsuper = L->nsuper; d.ntiles = L->ntiles;
+  d.ok = (usable && d.off_colmeta >= 0 && d.off_ent >= 0 && d.off_kmeta >= 0 && d.off_tval >= 0) ? 1 : 0;
+  return d;
+}
+
+bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, int nrows, double alpha, double thr,
                       const RuleView& rules, LocalCsc<double>& Z, double useful_products, const DiagShift* shift,
-                      bool force, unsigned want) {
+                      bool force, unsigned want, bool publish) {
   // the CSC entries are produced from the right form (kept entries = non-zero values)
   if (want & WANT_CSC) want |= WANT_RIGHT;
   if (!(want & (WANT_LEFT | WANT_RIGHT))) want |= WANT_RIGHT;
-  const ChunkTiles* A = &Aform;
   const ChunkTiles* B = &Bform;
   static const bool timing = std::getenv("NTB_TILE_TIMING") != nullptr;      // developer probe: wall time per phase
   auto now = [&]() { if (timing) stream_sync(); return std::chrono::steady_clock::now(); };
@@ -1035,9 +1112,7 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
     return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto t0 = now();
   const int nJ = div_up(ncols, 8), nG = B->ncc;
-  const CtView Av{A->colmeta.get(), A->ent.get(), A->tval_view ? A->tval_view : A->tval.get(), A->kmeta.get(), A->ncc,
-                  A->tval_view ? A->tval.get() : nullptr};
-  const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc, nullptr};
+  const CtView Bv{B->colmeta.get(), B->ent.get(), B->tval.get(), nullptr, B->ncc};
   EmitSpec es;
   es.alpha = alpha; es.thr = thr; es.rules = rules;
   es.sigma = shift ? shift->sigma : 0.0;
@@ -1055,10 +1130,32 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   int h_tasks = 0;
   readback_async(&h_ndmma, ndmma.get(), sizeof(h_ndmma));
   readback_async(&h_tasks, gtask_off.get() + nG, sizeof(int));
+  // The result is stored as fixed slots of 64 tiles per (task, super-tile): 64 KB per task for the two forms. A
+  // product whose tasks would not fit (a scattered pattern that touches many blocks with few entries each) is
+  // DECLINED - the caller then takes the scalar / gather path - never aborted. On a multi-GPU grid every rank must
+  // take the same branch: the verdicts travel with a peer exchange that rides on this read-back (no extra wait).
+  const long long task_limit = tile_task_limit();
+  const bool collective = publish || Av.npieces > 1;
+  std::vector<PeerPayload> verdicts;
+  DevBuf<int> d_decline;
+  if (collective) {
+    d_decline.alloc(1);
+    NTB_LAUNCH(k_task_guard, 1, 32, 0, gtask_off.get() + nG, ndmma.get(), task_limit, d_decline.get());
+    verdicts.resize((size_t)peer().n);
+    PeerPayload mine{};
+    peer_exchange(mine, verdicts.data(), nullptr, 0, d_decline.get());
+  }
   stream_sync();
-  // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
-  if (!force && useful_products >= 0.0 && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
-  NTB_CHECK((long long)h_tasks * 128 < (1ll << 31), "tile product: more than 2^31 tile slots in the result");
+  if (collective) {
+    for (const PeerPayload& v : verdicts) if (v.w[7] != 0ull) return false;       // on every rank alike
+  } else {
+    // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
+    if (!force && useful_products >= 0.0 && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
+    const bool too_big = (long long)h_tasks > task_limit;
+    const bool scattered = (long long)h_ndmma < MIN_DMMA_PER_TASK * (long long)h_tasks;
+    if (!force && (too_big || scattered)) return false;
+    NTB_CHECK(!too_big, "tile product: the result's tile slots exceed the device memory budget (NCCL fallback path)");
+  }
 
   const auto t1 = now();
   // ---- the result's tile forms: fixed slots of 64 tiles per (task, super-tile); index known up front
@@ -1072,15 +1169,16 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
   cnt.zero();
   task_counter.zero();
-  L.ent.alloc(ns); R.ent.alloc(ns);
-  L.colmeta.alloc((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
-  L.kmeta.alloc((size_t)nk);
+  // the left form is what the other ranks read in place when this result becomes a left operand: peer-visible slab
+  L.ent.alloc_shared(ns); R.ent.alloc(ns);
+  L.colmeta.alloc_shared((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
+  L.kmeta.alloc_shared((size_t)nk);
   L.coltile.alloc((size_t)nG * 2 + 1);
   L.ncc = div_up(ncols, 32); R.ncc = nG;
   L.nsuper = R.nsuper = 2 * h_tasks;
   L.ntiles = R.ntiles = (long long)h_tasks * 128;
   L.emitted = R.emitted = true;
-  if (wl) L.tval.alloc((size_t)max(L.ntiles, 1ll) * 32);     // never read outside present tiles: no memset
+  if (wl) L.tval.alloc_shared((size_t)max(L.ntiles, 1ll) * 32);     // never read outside present tiles: no memset
   if (wr) R.tval.alloc((size_t)max(R.ntiles, 1ll) * 32);
   if (h_tasks > 0)
     NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, gbmin.get(), gtask_off.get(), tasks.get());
@@ -1126,12 +1224,24 @@ bool spgemm_tile_core(const ChunkTiles& Aform, const ChunkTiles& Bform, int ncol
   if (wl) NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), L.ent.get(), L.kmeta.get());
   int h_nnz = 0;
   readback_async(&h_nnz, Z.outer.get() + ncols, sizeof(int));
+  // multi-GPU: hand the descriptor of the left form just written to every rank. The exchange is also the barrier that
+  // orders this rank's tile stores before any peer's reads, and it rides on the read-back of nnz.
+  std::vector<PeerLeftDesc> pub;
+  if (publish && wl) {
+    pub.resize((size_t)peer().n);
+    const PeerLeftDesc mine = left_desc_of(&L, 0, true);
+    static_assert(sizeof(PeerPayload) == sizeof(PeerLeftDesc), "payload size");
+    PeerPayload pl;
+    std::memcpy(&pl, &mine, sizeof(pl));
+    peer_exchange(pl, reinterpret_cast<PeerPayload*>(pub.data()), nullptr, 0, Z.outer.get() + ncols);
+  }
   stream_sync();
   const auto t4 = now();
   Z.alloc_entries(0);
   Z.nnz = h_nnz;
   forms->has_left = wl ? 1 : 0;                // a form that was not asked for is rebuilt from CSC if it is ever needed
   forms->has_right = wr ? 1 : 0;
+  if (!pub.empty()) forms->left_pub = std::move(pub);
   Z.forms = forms;
   if (h_nnz > 0) {
     if (want & WANT_CSC) tile_materialize_entries(Z);        // inner/val from the right form right away ...

@@ -34,6 +34,12 @@ def main():
     nt.init_world_from_torch()
     grids = {2: [(2, 1, 1), (1, 2, 1), (1, 1, 2)], 4: [(2, 2, 1), (1, 2, 2), (4, 1, 1), (1, 4, 1)],
              8: [(2, 2, 2), (4, 2, 1), (1, 2, 4), (1, 8, 1)]}[world]
+    if os.environ.get("NTB_WORKER_GRIDS"):            # e.g. "1x2x1": the fallback variants of tests/test_gpu_multi.py
+        grids = [tuple(int(x) for x in gs.split("x")) for gs in os.environ["NTB_WORKER_GRIDS"].split(",")]
+    # what a column-split grid is expected to do: "peer" (default: operand tiles of the neighbours read in place over
+    # NVLink), "nccl" (NTB_P2P=0: tile halo copied with ncclSend/Recv), "gather" (the tile path declines collectively,
+    # the reference-style CSC panel gather runs)
+    expect = os.environ.get("NTB_WORKER_EXPECT", "peer")
     for (R, C, S) in grids:
         nt.ConstructGlobalProcessGrid(R, C, S)
         g = O.Grid(R, C, S)
@@ -99,7 +105,11 @@ def main():
         compare_sparse(local_block(Cm), oracle_block(O, O.multiply(OA, OA, thr=1e-9), rank), 1e-9)
         column_split = (R == 1 and S == 1 and C > 1)
         # column-split grids fetch the left operand as a tile halo; the other grids gather CSC panels
-        assert nt.halo_counters()["products"] == (1 if column_split else 0), nt.halo_counters()
+        halo = column_split and expect != "gather"
+        assert nt.halo_counters()["products"] == (1 if halo else 0), nt.halo_counters()
+        if column_split:
+            pc = nt.peer_counters()
+            assert pc["ok"] == (os.environ.get("NTB_P2P") != "0") and pc["products"] == (1 if expect == "peer" else 0), pc
         # a product of products reads the tile forms emitted with Cm; check it against the oracle fed with the GPU's Cm
         parts = [None] * world
         dist.all_gather_object(parts, local_block(Cm))
@@ -110,7 +120,7 @@ def main():
         compare_sparse(local_block(D), oracle_block(O, O.multiply(OC, OA, alpha=-0.5, thr=1e-9), rank), 1e-9)
         D.Gemm(A, Cm, None, threshold=1e-9)
         compare_sparse(local_block(D), oracle_block(O, O.multiply(OA, OC, thr=1e-9), rank), 1e-9)
-        if column_split:
+        if halo:
             assert nt.halo_counters()["products"] == 3 and nt.tile_builds() == 2
         # fused identity shift across the grid == the two reference calls, bit for bit
         I = nt.Matrix_ps(n); I.FillIdentity()
