@@ -329,6 +329,12 @@ void ntb_get_halo_counters(double *out2);
  * read the neighbours' operand tiles in place (no copy, no NCCL), barrier/exchange kernels enqueued, peak bytes of the
  * peer-visible slab in use} */
 void ntb_get_peer_counters(double *out4);
+/* measured issue peak of the FP64 tensor-core instruction DMMA.8x8x4 on this GPU, TFLOP/s (best of `repeats` launches of
+ * a register-only micro-kernel): the denominator of the FP64-tensor roofline fraction, measured in the same run */
+double ntb_measure_dmma_peak_tflops(int repeats);
+/* host waits for the library stream since the last ntb_reset_counters (a sign iteration in tile space needs 3: the two
+ * products' task counts and the convergence norm) */
+double ntb_get_sync_count(void);
 /* 1 (default): column-split grids use the tile halo exchange; 0: always the reference-style CSC panel gather */
 void ntb_set_halo_path(int on);
 /* 0 (default): PermuteMatrix / UndoPermuteMatrix relabel the indices on the device; 1: the reference's two products by

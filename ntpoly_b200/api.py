@@ -77,7 +77,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_StageArrays ntb_FillMatrixFromStaged_ps ntb_sorted_ingests ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_set_fused_shift ntb_get_halo_counters ntb_get_peer_counters ntb_set_halo_path ntb_set_permute_gemm ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_set_fused_shift ntb_get_halo_counters ntb_get_peer_counters ntb_measure_dmma_peak_tflops ntb_get_sync_count ntb_set_halo_path ntb_set_permute_gemm ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -102,6 +102,8 @@ def lib():
         L.ntb_MatrixAlgorithmicBytes_ps.restype = c_longlong
         L.ntb_version.restype = c_char_p
         L.ntb_algorithmic_bytes.restype = c_double
+        L.ntb_measure_dmma_peak_tflops.restype = c_double
+        L.ntb_get_sync_count.restype = c_double
         L.ntb_set_stream.argtypes = [c_void_p]
         L.ntb_world_init.argtypes = [c_int, c_int, c_void_p]
         L.ntb_nccl_unique_id.argtypes = [c_void_p]
@@ -959,6 +961,16 @@ def peer_counters():
     out = (c_double * 4)()
     lib().ntb_get_peer_counters(out)
     return {"ok": bool(out[0]), "products": int(out[1]), "exchanges": int(out[2]), "slab_peak_bytes": int(out[3])}
+
+
+def sync_count():
+    """host waits for the library stream since the last reset_counters()"""
+    return int(lib().ntb_get_sync_count())
+
+
+def measure_dmma_peak_tflops(repeats=3):
+    """issue peak of DMMA.8x8x4 on this GPU (TFLOP/s), measured now"""
+    return float(lib().ntb_measure_dmma_peak_tflops(c_int(repeats)))
 
 
 def set_halo_path(on=True):

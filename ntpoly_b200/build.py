@@ -21,7 +21,7 @@ OBJDIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(LIBDIR, "libntpoly_b200.so")
 
 SOURCES = ["device.cu", "peer.cu", "spgemm.cu", "spgemm_tile.cu", "ops.cu", "comm.cu", "psmatrix.cu", "solvers.cu", "smatrix.cu", "c_api.cu",
-           "c_api_local.cu"]
+           "c_api_local.cu", "micro.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -10,6 +10,7 @@
 #include <sstream>
 #include <string>
 
+namespace ntb { double measure_dmma_peak_tflops(int repeats); }
 using namespace ntb;
 
 using namespace ntb::capi;
@@ -127,6 +128,7 @@ void WriteMatrixToMatrixMarket_ps_wrp(const int* ih, const char* file_name, cons
     DevBuf<unsigned char> dval((size_t)nloc * vsz), aval((size_t)tot * vsz);
     if (nloc) {
       h2d(drow.get(), rows.data(), (size_t)nloc); h2d(dcol.get(), cols.data(), (size_t)nloc);
+      readback_flush();
       CUDA_CHECK(cudaMemcpyAsync(dval.get(), M.is_complex ? (const void*)vc.data() : (const void*)vr.data(), (size_t)nloc * vsz, cudaMemcpyHostToDevice, rt().stream));
     }
     comm_group_start();
@@ -382,7 +384,7 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().peer_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().syncs = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().peer_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
 // C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when
@@ -423,6 +425,8 @@ void ntb_get_peer_counters(double* out4) {
   out4[0] = ntb::peer().ok ? 1.0 : 0.0; out4[1] = (double)rt().peer_products; out4[2] = (double)ntb::peer().exchanges;
   out4[3] = (double)ntb::shared_slab_peak();
 }
+double ntb_get_sync_count(void) { return (double)rt().syncs; }
+double ntb_measure_dmma_peak_tflops(int repeats) { return ntb::measure_dmma_peak_tflops(repeats > 0 ? repeats : 3); }
 void ntb_set_halo_path(int on) { ntb::set_halo_path(on); }
 void ntb_set_permute_gemm(int on) { ntb::set_permute_gemm(on); }
 double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }

@@ -157,20 +157,24 @@ int comm_rank(const CommHandle* c) { return c ? c->rank : 0; }
 void comm_set_shape(CommHandle* c, int size, int rank) { if (c) { c->size = size; c->rank = rank; } }
 
 void comm_allreduce_f64(CommHandle* c, double* d_buf, size_t count, RedOp op) {
+  readback_flush();
   if (!c || c->size <= 1 || count == 0) return;
   ncclRedOp_t o = op == RedOp::Sum ? ncclSum : (op == RedOp::Max ? ncclMax : ncclMin);
   NCCL_CHECK(g_nccl.AllReduce(d_buf, d_buf, count, ncclDouble, o, c->comm, rt().stream));
 }
 void comm_allgather_bytes(CommHandle* c, const void* d_send, void* d_recv, size_t bytes) {
+  readback_flush();
   if (!c || c->size <= 1) {
     if (d_send != d_recv) CUDA_CHECK(cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, rt().stream));
     return;
   }
   NCCL_CHECK(g_nccl.AllGather(d_send, d_recv, bytes, ncclChar, c->comm, rt().stream));
 }
-void comm_group_start() { if (g_nccl.lib) NCCL_CHECK(g_nccl.GroupStart()); }
+void comm_group_start() {
+  readback_flush(); if (g_nccl.lib) NCCL_CHECK(g_nccl.GroupStart()); }
 void comm_group_end() { if (g_nccl.lib) NCCL_CHECK(g_nccl.GroupEnd()); }
 void comm_broadcast_bytes(CommHandle* c, const void* d_send, void* d_recv, size_t bytes, int root) {
+  readback_flush();
   if (!c || c->size <= 1) {
     if (d_send != d_recv && bytes) CUDA_CHECK(cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, rt().stream));
     return;
@@ -179,10 +183,12 @@ void comm_broadcast_bytes(CommHandle* c, const void* d_send, void* d_recv, size_
   NCCL_CHECK(g_nccl.Broadcast(d_send, d_recv, bytes, ncclChar, root, c->comm, rt().stream));
 }
 void comm_send_bytes(CommHandle* c, const void* d_buf, size_t bytes, int peer) {
+  readback_flush();
   NTB_CHECK(c != nullptr, "send on a null communicator");
   NCCL_CHECK(g_nccl.Send(d_buf, bytes, ncclChar, peer, c->comm, rt().stream));
 }
 void comm_recv_bytes(CommHandle* c, void* d_buf, size_t bytes, int peer) {
+  readback_flush();
   NTB_CHECK(c != nullptr, "recv on a null communicator");
   NCCL_CHECK(g_nccl.Recv(d_buf, bytes, ncclChar, peer, c->comm, rt().stream));
 }

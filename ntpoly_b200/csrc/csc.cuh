@@ -55,6 +55,8 @@ struct TileForms {
   // multi-GPU (column-split grids, peer.h): the left form's descriptors of EVERY rank once it has been published
   // (by the product that wrote it, or at its first use as a left operand); the collective verdict on the right forms
   std::vector<PeerLeftDesc> left_pub;
+  std::vector<PeerLeftDesc> pub_landing;     // where the exchange of the publishing product lands (valid after a sync)
+  bool pub_pending = false;                  // published, descriptors on their way (they arrive with the next stream_sync)
   bool left_needs_barrier = false;           // the tiles were changed in place after publication (ScaleMatrix)
   int right_all_ok = 0;                      // 0 unknown, 1 every rank's right form is usable, -1 not
 };
@@ -66,7 +68,7 @@ void tile_materialize_entries(const LocalCsc<double>& M);
 template <typename T> struct LocalCsc {
   int rows = 0;
   int cols = 0;
-  long long nnz = 0;
+  LazyCount nnz;      // known on the host, or on its way (deferred tile products: device.cuh LazyCount)
   DevBuf<int> outer;  // [cols+1]
   mutable DevBuf<int> inner;  // [nnz]
   mutable DevBuf<T> val;      // [nnz]
@@ -120,6 +122,19 @@ template <typename T> struct LocalCsc {
     return (size_t)nnz * (sizeof(T) + 4) + ((size_t)cols + 1) * 4;
   }
 };
+
+// algorithmic bytes of one local product: bytes(X) + bytes(Y, unless it is X) + bytes(Z kept), added to
+// rt().alg_bytes now or - when a count is still on its way from the device - inside the next stream_sync()
+inline void account_product_bytes(const LazyCount& x, int xcols, const LazyCount& y, int ycols, bool count_y,
+                                  const LazyCount& z, int zcols, size_t elem_bytes) {
+  auto fx = x.later(), fy = y.later(), fz = z.later();
+  auto add = [fx, fy, fz, xcols, ycols, zcols, count_y, elem_bytes] {
+    auto b = [elem_bytes](long long nnz, int cols) { return (double)nnz * (double)(elem_bytes + 4) + ((double)cols + 1) * 4; };
+    rt().alg_bytes += b(fx(), xcols) + b(fz(), zcols) + (count_y ? b(fy(), ycols) : 0.0);
+  };
+  if (x.pending() || y.pending() || z.pending()) on_next_sync(add);
+  else add();
+}
 
 // Threshold-rule table of the local product. The reference decides per local
 // block pair whether the product runs through its dense branch, which tests

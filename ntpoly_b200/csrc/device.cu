@@ -1,6 +1,7 @@
 #include "device.cuh"
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <unordered_map>
 
@@ -189,23 +190,40 @@ unsigned char* g_rb_dev = nullptr;                   // the same memory as seen 
 size_t g_rb_used = 0;
 std::vector<PendingReadback> g_rb_pending;
 
-__global__ void __launch_bounds__(128) k_readback(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst,
-                                                  unsigned bytes, int words) {
-  if (words) {
-    const unsigned n = bytes >> 2;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
-      reinterpret_cast<unsigned*>(dst)[i] = reinterpret_cast<const unsigned*>(src)[i];
-  } else {
-    for (unsigned i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+// consecutive read-backs (no kernel of the library launched in between) travel in ONE launch: up to RB_SEG segments
+constexpr int RB_SEG = 8;
+struct ReadbackBatch { const unsigned char* src[RB_SEG]; unsigned char* dst[RB_SEG]; unsigned bytes[RB_SEG]; int n; };
+__global__ void __launch_bounds__(128) k_readback(ReadbackBatch b) {
+  for (int s = 0; s < b.n; ++s) {
+    const unsigned char* src = b.src[s];
+    unsigned char* dst = b.dst[s];
+    const unsigned bytes = b.bytes[s];
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes) & 3u) == 0) {
+      const unsigned n = bytes >> 2;
+      for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
+        reinterpret_cast<unsigned*>(dst)[i] = reinterpret_cast<const unsigned*>(src)[i];
+    } else {
+      for (unsigned i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    }
   }
   __threadfence_system();
 }
+ReadbackBatch g_rb_batch{};
+unsigned long long g_rb_batch_launches = 0;       // rt().launches when the open batch got its last segment
 }  // namespace
+void readback_flush() {
+  if (g_rb_batch.n == 0) return;
+  k_readback<<<1, 128, 0, g_rt.stream>>>(g_rb_batch);
+  CUDA_CHECK(cudaGetLastError());
+  g_rt.launches++;
+  g_rb_batch.n = 0;
+}
 
 void readback_async(void* host, const void* dev, size_t bytes) {
   if (bytes == 0) return;
   const size_t padded = (bytes + 15) & ~size_t(15);
   if (bytes > RB_MAX || g_rb_used + padded > RB_SCRATCH) {          // bulk, or scratch exhausted: the copy engine
+    readback_flush();
     CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g_rt.stream));
     return;
   }
@@ -213,10 +231,14 @@ void readback_async(void* host, const void* dev, size_t bytes) {
     CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&g_rb_host), RB_SCRATCH, cudaHostAllocMapped));
     CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_rb_dev), g_rb_host, 0));
   }
-  const int words = ((reinterpret_cast<uintptr_t>(dev) & 3u) == 0 && (bytes & 3u) == 0) ? 1 : 0;
-  k_readback<<<1, 128, 0, g_rt.stream>>>(static_cast<const unsigned char*>(dev), g_rb_dev + g_rb_used, (unsigned)bytes, words);
-  CUDA_CHECK(cudaGetLastError());
-  g_rt.launches++;
+  // a segment may join the open batch only if nothing was launched since (the batch's copy runs where its LAST
+  // segment was enqueued; a kernel in between could have changed an earlier segment's source)
+  if (g_rb_batch.n == RB_SEG || (g_rb_batch.n > 0 && g_rb_batch_launches != g_rt.launches)) readback_flush();
+  g_rb_batch.src[g_rb_batch.n] = static_cast<const unsigned char*>(dev);
+  g_rb_batch.dst[g_rb_batch.n] = g_rb_dev + g_rb_used;
+  g_rb_batch.bytes[g_rb_batch.n] = (unsigned)bytes;
+  g_rb_batch.n++;
+  g_rb_batch_launches = g_rt.launches;
   g_rb_pending.push_back(PendingReadback{host, g_rb_used, bytes});
   g_rb_used += padded;
 }
@@ -235,13 +257,24 @@ void* readback_reserve(void* host, size_t bytes) {
   g_rb_used += padded;
   return d;
 }
+namespace {
+std::vector<std::function<void()>> g_sync_hooks;
+}
+void on_next_sync(std::function<void()> fn) { g_sync_hooks.push_back(std::move(fn)); }
 void stream_sync() {
+  readback_flush();
   CUDA_CHECK(cudaStreamSynchronize(g_rt.stream));
   if (!g_rb_pending.empty()) {
     for (const PendingReadback& r : g_rb_pending) std::memcpy(r.host, g_rb_host + r.off, r.bytes);
     g_rb_pending.clear();
   }
   g_rb_used = 0;
+  g_rt.syncs++;
+  if (!g_sync_hooks.empty()) {                   // the read-backs they wait for have landed
+    std::vector<std::function<void()>> hooks;
+    hooks.swap(g_sync_hooks);
+    for (auto& h : hooks) h();
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -334,9 +367,51 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_final(const int* __restrict__ i
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = partial[nblocks];
 }
 
+// small inputs: one block does the whole scan (one launch instead of three; the scans of the hot path are over a few
+// thousand groups or a rank's columns, and at that size the launches cost more than the work)
+constexpr int SCAN1_T = 1024;
+constexpr int SCAN1_MAX = 1 << 16;
+template <typename Out>
+__global__ void __launch_bounds__(SCAN1_T) k_scan_single(const int* __restrict__ in, Out* __restrict__ out, int n) {
+  __shared__ Out sw[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (n + SCAN1_T - 1) / SCAN1_T;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  Out s = 0;
+  for (int i = lo; i < hi; ++i) s += (Out)in[i];
+  Out inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const Out o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) sw[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const Out w = sw[lane];
+    Out winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const Out o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    sw[lane] = winc - w;
+    if (lane == 31) sw[32] = winc;
+  }
+  __syncthreads();
+  Out ex = sw[warp] + inc - s;
+  for (int i = lo; i < hi; ++i) { out[i] = ex; ex += (Out)in[i]; }
+  if (threadIdx.x == 0) out[n] = sw[32];
+}
+
 template <typename Out> static void scan_impl(const int* in, Out* out, int n) {
   if (n <= 0) {
+    readback_flush();
     CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(Out), rt().stream));
+    return;
+  }
+  if (n <= SCAN1_MAX && static_cast<const void*>(in) != static_cast<const void*>(out)) {
+    NTB_LAUNCH((k_scan_single<Out>), 1, SCAN1_T, 0, in, out, n);
     return;
   }
   int nblocks = div_up(n, SCAN_TILE);

@@ -2,6 +2,8 @@
 // accounting and device-wide scans used by every kernel family.
 #pragma once
 #include "common.cuh"
+#include <functional>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -15,6 +17,7 @@ struct Runtime {
   bool owns_stream = false;
   bool inited = false;
   unsigned long long launches = 0; // kernels launched by this library (bench: gpu_launches)
+  unsigned long long syncs = 0;    // host waits for the library stream (stream_sync)
   double flops_useful = 0.0;       // 2*sum_{(i,k) in A} nnz(B(k,:)) accumulated over multiplies
   unsigned long long multiplies = 0;
   unsigned long long dense_rule_blocks = 0;
@@ -44,6 +47,14 @@ void stream_sync();
 // device -> host copy on the library stream whose result is valid after the next stream_sync(); small sizes bypass the
 // copy engines (see device.cu)
 void readback_async(void* host, const void* dev, size_t bytes);
+// Consecutive readback_async() calls travel in one launch; the batch is launched before ANY later work of the library
+// stream (NTB_LAUNCH, memsets, copies, collectives call this), so a read-back still sees what it saw when it was a
+// launch of its own.
+void readback_flush();
+// fn runs inside the next stream_sync(), after the read-backs enqueued so far have landed in their host addresses:
+// how a product finishes its bookkeeping (entry count, published descriptors, byte accounting) WITHOUT a wait of its
+// own - the values arrive with whatever wait comes next (the following product's task count, a norm)
+void on_next_sync(std::function<void()> fn);
 void* readback_reserve(void* host, size_t bytes);
 size_t arena_bytes_reserved();
 // peer-visible slab (device.cu / peer.cu): falls back to dmalloc when there is no slab or it is full
@@ -81,8 +92,36 @@ template <typename T> struct DevBuf {
     p = static_cast<T*>(dmalloc_shared((count ? count : 1) * sizeof(T)));
   }
   void release() { if (p) { dfree(p); p = nullptr; n = 0; } }
-  void zero() { CUDA_CHECK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), rt().stream)); }
+  void zero() { readback_flush(); CUDA_CHECK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), rt().stream)); }
   T* get() const { return p; }
+};
+
+// An entry count that may still be on its way from the device: a tile product whose entries are deferred enqueues the
+// read-back of its count and returns; the value lands with the next stream_sync() of anybody. Reading the count
+// (implicit conversion) waits only if it has not landed yet. Copies share the landing cell.
+struct PendingCount { int raw = 0; bool arrived = false; };
+struct LazyCount {
+  mutable long long v = 0;
+  mutable std::shared_ptr<PendingCount> pend;
+  LazyCount() = default;
+  LazyCount(long long x) : v(x) {}
+  LazyCount& operator=(long long x) { v = x; pend.reset(); return *this; }
+  void settle() const {
+    if (!pend) return;
+    if (!pend->arrived) stream_sync();
+    v = pend->raw;
+    pend.reset();
+  }
+  operator long long() const { settle(); return v; }
+  bool pending() const { return pend && !pend->arrived; }
+  // false only when the count is known to be zero
+  bool maybe_nonzero() const { return pending() ? true : (long long)(*this) > 0; }
+  // a reader for later (inside an on_next_sync hook, when the value has landed)
+  std::function<long long()> later() const {
+    if (!pend) { const long long x = v; return [x] { return x; }; }
+    std::shared_ptr<PendingCount> p = pend;
+    return [p] { return (long long)p->raw; };
+  }
 };
 
 template <typename T> inline void d2h(T* host, const T* dev, size_t count) {
@@ -90,14 +129,17 @@ template <typename T> inline void d2h(T* host, const T* dev, size_t count) {
   stream_sync();
 }
 template <typename T> inline void h2d(T* dev, const T* host, size_t count) {
+  readback_flush();
   CUDA_CHECK(cudaMemcpyAsync(dev, host, count * sizeof(T), cudaMemcpyHostToDevice, rt().stream));
 }
 template <typename T> inline void d2d(T* dst, const T* src, size_t count) {
+  readback_flush();
   if (count) CUDA_CHECK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToDevice, rt().stream));
 }
 
 #define NTB_LAUNCH(kernel, grid, block, smem, ...)                              \
   do {                                                                          \
+    ::ntb::readback_flush();                                                    \
     kernel<<<(grid), (block), (smem), ::ntb::rt().stream>>>(__VA_ARGS__);       \
     ::ntb::rt().launches++;                                                     \
     CUDA_CHECK(cudaGetLastError());                                             \

@@ -114,6 +114,7 @@ void csc_increment(const CscView<T>& A, LocalCsc<T>& B, double alpha, double thr
   out.alloc_entries(h_nnz);
   NTB_LAUNCH((k_increment<T, true>), warp_grid(cols), 256, 0, A, Bv, alpha, thr, rb, (int*)nullptr, opos.get(),
              out.outer.get(), out.inner.get(), out.val.get());
+  readback_flush();
   CUDA_CHECK(cudaMemcpyAsync(out.outer.get() + cols, opos.get() + total, sizeof(int), cudaMemcpyDeviceToDevice, rt().stream));
   B.swap(out);
 }
@@ -156,6 +157,7 @@ template <typename T> void csc_pairwise(const CscView<T>& A, const CscView<T>& B
   C.alloc_entries(h_nnz);
   NTB_LAUNCH((k_pairwise<T, true>), warp_grid(cols), 256, 0, A, B, (int*)nullptr, opos.get(), C.outer.get(),
              C.inner.get(), C.val.get());
+  readback_flush();
   CUDA_CHECK(cudaMemcpyAsync(C.outer.get() + cols, opos.get() + nnzA, sizeof(int), cudaMemcpyDeviceToDevice, rt().stream));
 }
 
@@ -234,6 +236,7 @@ static void select_impl(const CscView<T>& M, long long nnz, int out_rows, double
   res.alloc_entries(h_nnz);
   NTB_LAUNCH((k_select<T, MODE, true>), warp_grid(cols), 256, 0, M, thr, rb, S, s, (int*)nullptr, opos.get(),
              res.outer.get(), res.inner.get(), res.val.get());
+  readback_flush();
   CUDA_CHECK(cudaMemcpyAsync(res.outer.get() + cols, opos.get() + nnz, sizeof(int), cudaMemcpyDeviceToDevice, rt().stream));
   out.swap(res);
 }
@@ -638,6 +641,7 @@ void csc_from_device_triplets(int rows, int cols, const int* d_row, const int* d
   const int g = min(div_up(n, 256), kNumSMs * 16);
   NTB_LAUNCH(k_make_keys, g, 256, 0, d_col, d_row, n, keys.get(), perm.get());
   size_t tmp_bytes = 0;
+  readback_flush();
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.get(), keys_sorted.get(), perm.get(), perm_sorted.get(),
                                   (int)n, 0, 64, rt().stream);
   DevBuf<unsigned char> tmp(tmp_bytes);

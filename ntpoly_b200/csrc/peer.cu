@@ -108,6 +108,7 @@ bool peer_setup(CommHandle* wc) {
   mine.device = rt().device;
   mine.bytes = g_slab_bytes;
   if (g_slab) {
+    readback_flush();
     CUDA_CHECK(cudaMemsetAsync(g_slab, 0, CTRL_BYTES, rt().stream));            // flags and inbox start at zero
     if (cudaIpcGetMemHandle(&mine.handle, g_slab) != cudaSuccess) { cudaGetLastError(); ok_local = 0.0; }
   }
@@ -160,6 +161,7 @@ void peer_exchange(const PeerPayload& mine, PeerPayload* out, const void* dev8, 
   unsigned long long* host_out =
       out ? static_cast<unsigned long long*>(readback_reserve(out, sizeof(PeerPayload) * g_peer.n)) : nullptr;
   NTB_CHECK(n8 >= 0 && n8 <= 8, "peer_exchange: at most 8 words");
+  readback_flush();
   k_peer_exchange<<<1, 128, 0, rt().stream>>>(c, mine, static_cast<const unsigned long long*>(dev8), dev8 ? n8 : 0,
                                               dev_i32_w7, epoch, (int)(epoch % RING), host_out);
   CUDA_CHECK(cudaGetLastError());

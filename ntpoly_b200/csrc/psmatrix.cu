@@ -264,6 +264,7 @@ template <> const LocalCsc<cplx>& loc<cplx>(const Matrix& M) { return M.c; }
 // transfer of a copy stream. With 4 MB pieces it waits for at most one piece (< 0.1 ms).
 static void copy_in_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
   constexpr size_t PIECE = 4u << 20;
+  readback_flush();
   for (size_t off = 0; off < bytes; off += PIECE)
     CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off,
                                std::min(PIECE, bytes - off), kind, stream));
@@ -1088,6 +1089,7 @@ static bool peer_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   };
   // a right form written by a (collective) product exists on every rank; one built from CSC needs a collective verdict
   const bool right_known = (Rf && Rf->emitted) || fb.right_all_ok != 0;
+  if (fa.left_pub.empty() && fa.pub_pending) stream_sync();      // published by the product that wrote it; descriptors on their way
   if (fa.left_pub.empty() || !right_known) {
     PeerLeftDesc mine = left_desc_of(Lf, Al.nnz, Lf && dense_enough(Lf, Al.nnz));
     mine.right_ok = (Rf && dense_enough(Rf, Bl.nnz)) ? 1 : 0;
@@ -1138,7 +1140,7 @@ static bool peer_tile_product(const Matrix& A, const Matrix& B, double alpha, do
   st.shift_applied = ds && ds->sigma != 0.0;
   // compulsory bytes: the rank's share of A (the few halo super-tiles read from the neighbours come on top), its B
   // block and the kept C block
-  rt().alg_bytes += (double)Al.bytes() + (double)Bl.bytes() + (double)out.bytes();
+  account_product_bytes(Bl.nnz, Bl.cols, Al.nnz, Al.cols, true, out.nnz, out.cols, sizeof(double));
   rt().halo_products++;
   rt().peer_products++;
   return true;

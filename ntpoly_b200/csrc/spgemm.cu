@@ -327,11 +327,12 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   // ---- operands that already carry their tile forms (results of earlier tile products): with the flop accounting
   // switched off nothing needs the CSC entries, which may even be deferred (LocalCsc::deferred)
   if constexpr (!scalar_traits<T>::is_complex) {
-    if (tile_path_enabled() && !rt().count_flops && ncols > 0 && Xl.nnz > 0 && Yl.nnz > 0 && Xl.forms && Yl.forms &&
+    if (tile_path_enabled() && !rt().count_flops && ncols > 0 && Xl.nnz.maybe_nonzero() && Yl.nnz.maybe_nonzero() && Xl.forms && Yl.forms &&
         Xl.forms->has_right == 1 && Yl.forms->has_left == 1 &&
         spgemm_tile_core(left_view_of(Yl.forms->left), Xl.forms->right, ncols, nrows, alpha, thr, rules, Z, -1.0, shift, false, want)) {
       if (stats) { stats->shift_applied = shift && shift->sigma != 0.0; stats->flops = 0.0; stats->tmp_entries = 0; }
-      account_bytes(Z.nnz);
+      // (the counts of a deferred product, or of deferred operands, may still be on their way: accounted when they land)
+      account_product_bytes(Xl.nnz, Xl.cols, Yl.nnz, Yl.cols, Yl.outer.get() != Xl.outer.get(), Z.nnz, ncols, sizeof(T));
       return;
     }
   }

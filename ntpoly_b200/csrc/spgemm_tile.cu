@@ -1222,35 +1222,53 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
   Z.outer.alloc((size_t)ncols + 1);
   exclusive_scan(cnt.get(), Z.outer.get(), ncols);
   if (wl) NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), L.ent.get(), L.kmeta.get());
-  int h_nnz = 0;
-  readback_async(&h_nnz, Z.outer.get() + ncols, sizeof(int));
+  forms->has_left = wl ? 1 : 0;                // a form that was not asked for is rebuilt from CSC if it is ever needed
+  forms->has_right = wr ? 1 : 0;
   // multi-GPU: hand the descriptor of the left form just written to every rank. The exchange is also the barrier that
-  // orders this rank's tile stores before any peer's reads, and it rides on the read-back of nnz.
-  std::vector<PeerLeftDesc> pub;
-  if (publish && wl) {
-    pub.resize((size_t)peer().n);
+  // orders this rank's tile stores before any peer's reads.
+  const bool pub = publish && wl;
+  if (pub) {
+    forms->pub_landing.assign((size_t)peer().n, PeerLeftDesc{});
+    forms->pub_pending = true;
     const PeerLeftDesc mine = left_desc_of(&L, 0, true);
     static_assert(sizeof(PeerPayload) == sizeof(PeerLeftDesc), "payload size");
     PeerPayload pl;
     std::memcpy(&pl, &mine, sizeof(pl));
-    peer_exchange(pl, reinterpret_cast<PeerPayload*>(pub.data()), nullptr, 0, Z.outer.get() + ncols);
+    peer_exchange(pl, reinterpret_cast<PeerPayload*>(forms->pub_landing.data()), nullptr, 0, Z.outer.get() + ncols);
   }
-  stream_sync();
-  const auto t4 = now();
-  Z.alloc_entries(0);
-  Z.nnz = h_nnz;
-  forms->has_left = wl ? 1 : 0;                // a form that was not asked for is rebuilt from CSC if it is ever needed
-  forms->has_right = wr ? 1 : 0;
-  if (!pub.empty()) forms->left_pub = std::move(pub);
-  Z.forms = forms;
-  if (h_nnz > 0) {
-    if (want & WANT_CSC) tile_materialize_entries(Z);        // inner/val from the right form right away ...
-    else { Z.deferred = true; rt().deferred_products++; }    // ... or on first use
+  auto land_pub = [forms] {
+    if (forms->pub_pending) { forms->left_pub = std::move(forms->pub_landing); forms->pub_landing.clear(); forms->pub_pending = false; }
+  };
+  auto t4 = t3;
+  if (want & WANT_CSC) {
+    // the caller reads the entries: count now, entries from the right form right away
+    int h_nnz = 0;
+    readback_async(&h_nnz, Z.outer.get() + ncols, sizeof(int));
+    stream_sync();
+    land_pub();
+    t4 = now();
+    Z.alloc_entries(0);
+    Z.nnz = h_nnz;
+    Z.forms = forms;
+    if (h_nnz > 0) tile_materialize_entries(Z);
+  } else {
+    // DEFERRED product (a driver intermediate, an iterate that lives in tile space): nobody needs the entry count
+    // before the next wait of the library stream - the next product's task count, a norm - so it is not waited for
+    // here. The count, the published descriptors and the byte accounting land inside that wait (on_next_sync).
+    auto pc = std::make_shared<PendingCount>();
+    readback_async(&pc->raw, Z.outer.get() + ncols, sizeof(int));
+    on_next_sync([pc, land_pub] { pc->arrived = true; land_pub(); });
+    t4 = now();
+    Z.alloc_entries(0);
+    Z.nnz.pend = pc;
+    Z.forms = forms;
+    Z.deferred = true;
+    rt().deferred_products++;
   }
   const auto t5 = now();
   if (timing)
     std::fprintf(stderr, "[tile] bounds %.3f  layout %.3f  numeric %.3f  index %.3f  csc %.3f ms  (tasks %d, nnz %d)\n",
-                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), h_tasks, h_nnz);
+                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), h_tasks, Z.nnz.pending() ? -1 : (int)(long long)Z.nnz);
   rt().tile_products++;
   rt().dmma_issued += (double)h_ndmma;
   return true;

@@ -64,6 +64,45 @@ def block_sparse(n: int = 65536, block: int = 32, neighbours: int = 20, band_blo
     return sp.csc_matrix(m)
 
 
+def block_sparse_hamiltonian(n: int = 65536, block: int = 32, neighbours: int = 20, band_blocks: int = 64,
+                             seed: int = 1234, coupling: float = 0.35, decay: float = 8.0) -> sp.csc_matrix:
+    """c3: block-sparse LINEAR-SCALING Hamiltonian (an insulator): dense block x block tiles, ~neighbours tiles per
+    block row inside a block band (1 % block fill at n = 65536), Gaussian couplings that decay with the block
+    distance, and on-site energies -1 / +1 for the first / second half of every block's orbitals, so that the
+    spectrum has a gap of ~1.4 at half filling (n/2 electrons) and the density matrix decays: ~1800 entries per row
+    above 1e-6 against ~640 of H (measured at n = 4096). `block_sparse` above has no gap - its density matrix is
+    dense, purification of it is not a linear-scaling workload - and stays for the pattern tests."""
+    rng = np.random.default_rng(seed)
+    nb = n // block
+    bi, bj = [], []
+    half = max(1, neighbours // 2)
+    for i in range(nb):
+        hi = min(nb - 1, i + band_blocks)
+        cand = np.arange(i + 1, hi + 1)
+        take = min(half, len(cand))
+        if take:
+            sel = rng.choice(cand, size=take, replace=False)
+            bi += [i] * take
+            bj += list(sel)
+    bi = np.asarray(bi, np.int64)
+    bj = np.asarray(bj, np.int64)
+    nblk = len(bi)
+    vals = rng.standard_normal((nblk, block, block)) * (coupling / np.sqrt(block * neighbours))
+    vals *= np.exp(-np.abs(bi - bj) / decay)[:, None, None]
+    ii = (bi[:, None, None] * block + np.arange(block)[None, :, None]).repeat(block, axis=2)
+    jj = (bj[:, None, None] * block + np.arange(block)[None, None, :]).repeat(block, axis=1)
+    upper = sp.coo_matrix((vals.ravel(), (ii.ravel(), jj.ravel())), shape=(n, n))
+    dvals = rng.standard_normal((nb, block, block)) * (0.5 * coupling / np.sqrt(block))
+    dvals = 0.5 * (dvals + dvals.transpose(0, 2, 1))
+    dvals += np.diag(np.where(np.arange(block) < block // 2, -1.0, 1.0))[None, :, :]
+    di = (np.arange(nb)[:, None, None] * block + np.arange(block)[None, :, None]).repeat(block, axis=2)
+    dj = (np.arange(nb)[:, None, None] * block + np.arange(block)[None, None, :]).repeat(block, axis=1)
+    diag = sp.coo_matrix((dvals.ravel(), (di.ravel(), dj.ravel())), shape=(n, n))
+    m = (upper + upper.T + diag).tocsc()
+    m.sort_indices()
+    return sp.csc_matrix(m)
+
+
 def guo_transform(a: sp.spmatrix) -> sp.csc_matrix:
     """Hermitian matrix of a directed graph as built by the reference example
     (Examples/ComplexMatrix/main.f90:109-160): S = symmetrised adjacency pattern,

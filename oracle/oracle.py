@@ -442,6 +442,9 @@ class MultiplyStats:
     branches: list = field(default_factory=list)
 
 
+TOTAL_STATS = None          # set to a MultiplyStats to count every multiply (bench.py, cpu_baseline of whole solves)
+
+
 def useful_flops(A: PSMatrix, B: PSMatrix) -> float:
     """F = 2 * sum_{(i,k) in pattern(A)} nnz(B(k,:)); x4 if complex."""
     brow = np.diff(sp.csr_matrix(B.mat).indptr)
@@ -495,6 +498,8 @@ def multiply(A: PSMatrix, B: PSMatrix, C: PSMatrix | None = None, alpha=1.0, bet
     AB = PSMatrix(A.n, g, cplx, grid[0][0] if (nI == 1 and nJ == 1) else sp.bmat(grid, format="csc"))
     if stats is not None:
         stats.flops += useful_flops(A, B)
+    if TOTAL_STATS is not None:          # bench.py: the useful flops of a whole driver (its multiplies take no stats)
+        TOTAL_STATS.flops += useful_flops(A, B)
     if C is None or abs(beta) < np.finfo(np.float64).tiny:     # MatrixMultiply.f90:324-329
         return AB
     return increment(AB, scale(C, beta))
