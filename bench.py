@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
     a = ap.parse_args()
-    defaults = {"c1": (8192, 1e-8), "c3": (65536, 1e-6), "c4": (262144, 1e-6), "c5": (4096, 1e-6)}
+    defaults = {"c1": (8192, 1e-8), "c3": (65536, 1e-6), "c4": (262144, 1e-6), "c5": (2048, 1e-6)}
     if a.n == 0:
         a.n = defaults[a.config][0]
     if a.threshold == 0.0:
@@ -220,7 +220,7 @@ def cpu_workload(args, sample: bool):
         return O, stepf, (f"the first 2 purification iterations of the same TRS4 solve on the N={n} instance of the "
                           f"generator (1/{args.n // n} of the block rows; the pattern is a block band, work per block row is "
                           "size independent)")
-    n = min(args.n, 2048)
+    n = min(args.n, 512)
     g = W.complex_hermitian_graph(n)
     shift = float(np.asarray(abs(g).sum(axis=0)).max()) + 1.0
     A = O.PSMatrix.from_scipy(sp.csc_matrix(g + sp.identity(n) * shift), is_complex=True)
@@ -329,8 +329,9 @@ class Env:
         if self.world > 1:
             # NCCL's log (communicator sizes: the driver checks that N ranks took part) goes to stderr: NCCL writes to
             # file descriptor 1, which now points at stderr; the JSON line goes to the saved original stdout
-            os.environ.setdefault("NCCL_DEBUG", "INFO")
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+                os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "INFO")
+                os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         nt.init_world_from_torch()
         assert self.world == args.gpus or self.world == 1, "launch with torchrun --nproc-per-node == --gpus"
@@ -424,6 +425,7 @@ def timed_steps(env, step, steps, flush=None):
         ms_total = sum(a.elapsed_time(b) for a, b in pairs)
     clocks = sampler.stop()
     prof = nt.profile_read()
+    prof["phases"] = nt.profile_read_phases()
     nt.profile_enable(False)
     return ms_total, clocks, prof
 
@@ -440,6 +442,9 @@ def roofline_of(env, prof, alg_bytes, flops_local, ms_total_local, peaks, kernel
     r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
          "kernel": kernel, "launches_timed": prof["products"], "peak_source": peak_src,
          "numeric_share_of_step": nms / ms_total_local if ms_total_local > 0 else 0.0,
+         "step_ms_by_phase": dict({k: v / max(env.args.steps, 1) for k, v in prof.get("phases", {}).items()},
+                                  numeric_ms=nms / max(env.args.steps, 1),
+                                  unaccounted_ms=(ms_total_local - nms - sum(prof.get("phases", {}).values())) / max(env.args.steps, 1)),
          "fp64_tflops_useful": tf}
     if peaks:
         r["fp64_tensor_peak_tflops"] = peaks["dmma_issue_tflops"]
@@ -879,9 +884,8 @@ def run_c5(env):
             nt.ExponentialSolvers.ComputeExponential(Eh, Ee, p)
             return Ai.get_arrays(), Ee.get_arrays()
 
-        e2e_step()
         env.barrier()
-        k = 2
+        k = 1
         t0 = time.perf_counter()
         for _ in range(k):
             o1, o2 = e2e_step()

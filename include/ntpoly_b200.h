@@ -335,11 +335,20 @@ double ntb_measure_dmma_peak_tflops(int repeats);
 /* host waits for the library stream since the last ntb_reset_counters (a sign iteration in tile space needs 3: the two
  * products' task counts and the convergence norm) */
 double ntb_get_sync_count(void);
+/* device milliseconds per phase of the hot path accumulated while ntb_profile_enable(1) was on, then cleared:
+ * out8[0] symbolic phases of the tile products, [2] their tails (outer index, per-K meta, publication), [3] convergence
+ * norms / scalars, [4] tile-space combines (the numeric kernels themselves: ntb_profile_read) */
+void ntb_profile_read_phases(double *out8);
 /* 1 (default): column-split grids use the tile halo exchange; 0: always the reference-style CSC panel gather */
 void ntb_set_halo_path(int on);
 /* 0 (default): PermuteMatrix / UndoPermuteMatrix relabel the indices on the device; 1: the reference's two products by
  * permutation matrices (LoadBalancerModule.F90:38-47, 77-86). Same result bit for bit. */
 void ntb_set_permute_gemm(int on);
+/* 1 (default): TRS2 / TRS4 evaluate 2X - X^2, Fx + sigma*Gx, Tr(X2 Fx), Tr(X2 Gx), Tr(XH), Tr(X) straight from the tile
+ * forms of iterates that came out of tile products; 0: the reference's call sequence on CSC entries.
+ * Same results up to the summation order of the scalars. ntb_tile_combines: tile-space combinations since the reset. */
+void ntb_set_fused_steps(int on);
+double ntb_tile_combines(void);
 /* C = alpha*A*B (thresholded), then IncrementMatrix(Identity, C, sigma) with threshold 0 — the call pair of
  * SignSolversModule.F90:226-229 / SquareRootSolversModule.F90 as one entry point. */
 void ntb_MatrixMultiplyShift_ps(const int *ih_matA, const int *ih_matB, int *ih_matC, const double *alpha,

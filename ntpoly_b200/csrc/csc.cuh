@@ -188,6 +188,16 @@ bool spgemm_tile_core(const LeftView& A, const ChunkTiles& B, int ncols, int nro
 LeftView left_view_of(const ChunkTiles& A);
 // descriptor of a rank's own left form for publication (ok = 0 when an array lies outside the peer-visible slab)
 PeerLeftDesc left_desc_of(const ChunkTiles* L, long long nnz, bool usable);
+// ---- tile-space helpers of the fused driver steps (spgemm_tile.cu, end): scalars and linear combinations straight
+// from the right tile forms of iterates whose CSC entries are deferred. All return false when an operand has no
+// usable right form (the caller then takes the reference's CSC call sequence).
+// mode 0: d_out[0] = sum A.*B;  mode 1 (TRS4, A = X^2, B = X): d_out[0] = sum X2.*Fx, d_out[1] = sum X2.*Gx;
+// mode 2: d_out[0] = trace(A) (B = nullptr). Identity / diagonal: local row of column c is c + dd, for c < ncols_diag.
+bool tile_form_scalars(int mode, const LocalCsc<double>& A, const LocalCsc<double>* B, int dd, int ncols_diag, double* d_out);
+// mode 0: Z = alpha*P + beta*Q with the sparse add's threshold on matched entries;  mode 1 (TRS4, P = X^2, Q = X):
+// Z = Fx + sigma*Gx. Z is a tile-space result like a product's (forms per `want`, deferred entries).
+bool tile_combine(const LocalCsc<double>& P, const LocalCsc<double>& Q, int mode, double alpha, double beta, double thr,
+                  double sigma, int dd, int ncols_diag, LocalCsc<double>& Z, unsigned want, bool publish);
 // column sums of |alpha*A + B| from the right tile forms of both blocks; false when either has none (use the CSC kernel)
 bool tile_diff_col_abs_sums(const LocalCsc<double>& A, const LocalCsc<double>& B, double alpha, double* d_colsum);
 // assemble the left form of a row of column blocks from per-rank pieces (see psmatrix.cu: halo gather)

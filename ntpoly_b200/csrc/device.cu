@@ -29,6 +29,22 @@ void ensure_init() {
   g_rt.inited = true;
 }
 
+PhaseScope::PhaseScope(int tag) {
+  if (!g_rt.profile) return;
+  Runtime::PhaseEv ev{tag, nullptr, nullptr};
+  CUDA_CHECK(cudaEventCreate(&ev.e0));
+  CUDA_CHECK(cudaEventCreate(&ev.e1));
+  readback_flush();
+  CUDA_CHECK(cudaEventRecord(ev.e0, g_rt.stream));
+  idx = (int)g_rt.phase_events.size();
+  g_rt.phase_events.push_back(ev);
+}
+PhaseScope::~PhaseScope() {
+  if (idx < 0 || idx >= (int)g_rt.phase_events.size()) return;
+  readback_flush();
+  cudaEventRecord(g_rt.phase_events[(size_t)idx].e1, g_rt.stream);
+}
+
 void set_stream(cudaStream_t s) {
   ensure_init();
   if (g_rt.stream) CUDA_CHECK(cudaStreamSynchronize(g_rt.stream));

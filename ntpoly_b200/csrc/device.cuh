@@ -22,6 +22,7 @@ struct Runtime {
   unsigned long long multiplies = 0;
   unsigned long long dense_rule_blocks = 0;
   unsigned long long tile_products = 0;  // local products that ran on the DMMA tile path
+  unsigned long long tile_combines = 0;  // tile-space linear combinations (fused driver steps: no CSC round trip)
   unsigned long long tile_builds = 0;    // CSC -> tile-form conversions (0 per product once operands carry their forms)
   unsigned long long halo_products = 0;  // distributed products that fetched the left operand as a tile halo
   unsigned long long peer_products = 0;  // ... of which read the halo tiles in place from the peers' memory (no copy, no NCCL)
@@ -35,6 +36,17 @@ struct Runtime {
   // optional device timing of the dominant (numeric SpGEMM) kernels, for bench.py's roofline
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  // ... and of the phases around them (bench.py: where the rest of a step goes): tag, begin, end
+  struct PhaseEv { int tag; cudaEvent_t e0, e1; };
+  std::vector<PhaseEv> phase_events;
+};
+// device time of a phase of the hot path, only while rt().profile is on: PhaseScope p(tag) brackets what is enqueued
+// during its lifetime with two events. Tags: 0 symbolic phase of a tile product (bounds ... task count), 2 its tail
+// (outer scan, per-K meta, publication), 3 convergence norm / scalars, 4 tile-space combine
+struct PhaseScope {
+  int idx = -1;
+  explicit PhaseScope(int tag);
+  ~PhaseScope();
 };
 Runtime& rt();
 void ensure_init();

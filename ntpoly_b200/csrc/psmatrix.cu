@@ -725,6 +725,10 @@ void mat_increment(const Matrix& A, Matrix& B, double alpha, double threshold) {
 }
 
 double mat_trace(const Matrix& M) {
+  if (!M.is_complex && M.r.deferred) {            // an iterate that lives in tile space: no CSC round trip
+    double t;
+    if (mat_tile_scalars(2, M, nullptr, &t)) return t;
+  }
   DevBuf<double> d(1);
   if (M.is_complex) csc_trace<cplx>(M.c.view(), M.start_row, M.start_col, d.get());
   else csc_trace<double>(M.r.view(), M.start_row, M.start_col, d.get());
@@ -750,6 +754,7 @@ double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha) {
     mat_increment(A, t, alpha, 0.0);
     return mat_norm(t);
   }
+  PhaseScope ph(3);
   DevBuf<double> colsum((size_t)B.local_cols), d(1);
   if (A.is_complex) csc_diff_col_abs_sums<cplx>(A.c.view(), B.c.view(), alpha, colsum.get());
   else if (!(tile_path_on() && tile_diff_col_abs_sums(A.r, B.r, alpha, colsum.get())))   // iterates that live as tile forms
@@ -757,6 +762,46 @@ double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha) {
   comm_allreduce_f64(B.grid->column, colsum.get(), (size_t)B.local_cols, RedOp::Sum);
   reduce_max(colsum.get(), B.local_cols, d.get());
   return reduce_to_host(*B.grid, B.grid->row, d.get(), RedOp::Max);
+}
+
+// ---- fused driver steps in tile space -----------------------------------------------------------------------------
+static bool tile_space_operand(const Matrix& M) {
+  return M.constructed && !M.is_complex && M.r.forms && M.r.forms->has_right == 1;
+}
+bool mat_tile_scalars(int mode, const Matrix& A, const Matrix* B, double* out) {
+  if (!tile_path_on() || !tile_space_operand(A) || (B && (!tile_space_operand(*B) || B->grid != A.grid || B->logical_dim != A.logical_dim)))
+    return false;
+  // only worth it (and only collective-safe) for iterates that came out of tile products: those exist on every rank
+  if (!A.r.forms->right.emitted && !(B && B->r.forms->right.emitted)) return false;
+  // (ranks may disagree on a form built from CSC; harmless where the reduction is ONE peer exchange whatever each rank
+  // contributes, not where it is a sequence of NCCL calls)
+  if (A.grid->size > 1 && !(A.grid->peer_ok && peer().ok)) return false;
+  PhaseScope ph(3);
+  const int nout = (mode == 1) ? 2 : 1;
+  DevBuf<double> d(2);
+  const int dd = A.start_col - A.start_row;
+  const int ncd = std::max(0, std::min(A.local_cols, A.actual_dim - A.start_col));
+  if (!tile_form_scalars(mode, A.r, B ? &B->r : nullptr, dd, ncd, d.get())) return false;
+  const RedOp ops[2] = {RedOp::Sum, RedOp::Sum};
+  reduce_to_host(*A.grid, A.grid->within_slice, d.get(), nout, ops, out);
+  return true;
+}
+bool mat_tile_combine(const Matrix& P, const Matrix& Q, int mode, double alpha, double beta, double thr, double sigma,
+                      Matrix& Out, unsigned want) {
+  if (!tile_path_on() || !tile_space_operand(P) || !tile_space_operand(Q) || P.grid != Q.grid || P.logical_dim != Q.logical_dim)
+    return false;
+  if (!P.r.forms->right.emitted) return false;          // P is the product of the step (X^2): always a tile-space result
+  ProcessGrid& g = *P.grid;
+  const bool multi = g.size > 1;
+  if (multi && !(g.peer_ok && peer().ok)) return false;  // (general grids keep the reference's call sequence)
+  PhaseScope ph(4);
+  Matrix res;
+  mat_construct_empty(res, P.actual_dim, P.grid, false);
+  const int dd = P.start_col - P.start_row;
+  const int ncd = std::max(0, std::min(P.local_cols, P.actual_dim - P.start_col));
+  if (!tile_combine(P.r, Q.r, mode, alpha, beta, thr, sigma, dd, ncd, res.r, want, multi)) return false;
+  Out = std::move(res);
+  return true;
 }
 
 double mat_sigma(const Matrix& M) {
@@ -780,6 +825,15 @@ void mat_gershgorin(const Matrix& M, double* e_min, double* e_max) {
 }
 
 void mat_dot(const Matrix& A, const Matrix& B, double* re, double* im) {
+  if (!A.is_complex && !B.is_complex && (A.r.deferred || B.r.deferred) && A.r.nnz.maybe_nonzero() && B.r.nnz.maybe_nonzero()) {
+    // an iterate that lives in tile space (e.g. Tr(X H) of a purification): from the right forms, the other
+    // operand's form is built once and cached
+    if (!A.r.forms) A.r.forms = std::make_shared<TileForms>();
+    if (!B.r.forms) B.r.forms = std::make_shared<TileForms>();
+    const bool ok = tile_operand_form(A.r, false) != nullptr && tile_operand_form(B.r, false) != nullptr;
+    double t;
+    if (ok && mat_tile_scalars(0, A, &B, &t)) { *re = t; if (im) *im = 0.0; return; }
+  }
   DevBuf<double> d(2);
   if (A.is_complex || B.is_complex) {
     Matrix ta, tb;
@@ -1280,9 +1334,14 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
       const double inner_dim = (double)Xsrc->rows;
       std::vector<double> cnt, fa(nI), fb;
       rowblock_counts(*Ysrc, cnt);
-      for (int i = 0; i < nI; ++i) fa[i] = cnt[i] / ((double)rb * inner_dim);
-      colblock_fills(*Xsrc, inner_dim, fb);
-      set_rules(fa, fb);
+      bool any_a = false;
+      for (int i = 0; i < nI; ++i) { fa[i] = cnt[i] / ((double)rb * inner_dim); any_a = any_a || fa[i] > 0.1; }
+      // the dense rule needs BOTH panels more than 10 % full: when no row block of A's panel is, B's fills are not
+      // needed (and B's entry count - a deferred product's may still be on its way - is not waited for)
+      if (any_a) {
+        colblock_fills(*Xsrc, inner_dim, fb);
+        set_rules(fa, fb);
+      }
     }
     // ---- local product
     // deferred entries only for a plain replacement of C on a single slice

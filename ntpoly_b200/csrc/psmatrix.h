@@ -125,6 +125,12 @@ void mat_scale_c(Matrix& M, cplx c);
 double mat_trace(const Matrix& M);
 double mat_norm(const Matrix& M);
 double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha);   // MatrixNorm(alpha*A + B), sum not formed
+// ---- tile-space helpers of the fused driver steps (csc.cuh: tile_form_scalars / tile_combine) on distributed
+// matrices; false (on every rank alike) when the operands do not live as tile forms - the caller then issues the
+// reference's own call sequence. mode as in csc.cuh; out receives 1 (modes 0, 2) or 2 (mode 1) reduced scalars.
+bool mat_tile_scalars(int mode, const Matrix& A, const Matrix* B, double* out);
+bool mat_tile_combine(const Matrix& P, const Matrix& Q, int mode, double alpha, double beta, double thr, double sigma,
+                      Matrix& Out, unsigned want);
 double mat_sigma(const Matrix& M);
 void mat_dot(const Matrix& A, const Matrix& B, double* re, double* im);
 void mat_pairwise(const Matrix& A, const Matrix& B, Matrix& C);

@@ -81,6 +81,14 @@ bool Monitor::converged(bool be_verbose) const {              // :122-191
 // (out = PR*in*PC resp. PC*in*PR); the same matrix is obtained here by relabelling the indices on the device
 // (psmatrix.cu: mat_relabel): in(r,c) lands at (rev[r], rev[c]) for PermuteMatrix and at (fwd[r], fwd[c]) for
 // UndoPermuteMatrix. NTB_PERMUTE_GEMM=1 / ntb_set_permute_gemm(1) selects the reference's two products instead.
+// 1 (default): TRS2 / TRS4 evaluate their per-iteration helpers in tile space (csc.cuh: tile_combine,
+// tile_form_scalars); 0 (NTB_FUSED_STEPS=0): always the reference's call sequence on CSC entries
+static int g_fused_steps = -1;
+void set_fused_steps(int on) { g_fused_steps = on ? 1 : 0; }
+static bool fused_steps_enabled() {
+  if (g_fused_steps < 0) { const char* e = std::getenv("NTB_FUSED_STEPS"); g_fused_steps = (e && e[0] == '0') ? 0 : 1; }
+  return g_fused_steps == 1;
+}
 static int g_permute_gemm = -1;
 void set_permute_gemm(int on) { g_permute_gemm = on ? 1 : 0; }
 static bool permute_gemm() {
@@ -171,10 +179,18 @@ void solve_trs2(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, dou
   for (II = 1; II <= p.max_iterations; ++II) {
     const double tv = mat_trace(X);
     sigma[II] = (trace - tv < 0.0) ? -1.0 : 1.0;
-    mat_multiply(X, X, X2, 1.0, 0.0, p.threshold, &s.pool);
+    // X^2 stays in tile space (both forms, entries deferred) when the product runs on the tile path
+    mat_multiply(X, X, X2, 1.0, 0.0, p.threshold, &s.pool, WANT_LEFT | WANT_RIGHT);
     if (sigma[II] > 0.0) {
-      mat_scale(X, 2.0);
-      mat_increment(X2, X, -1.0, p.threshold);
+      // 2X - X^2 (ScaleMatrix(X, 2); IncrementMatrix(X2, X, -1, threshold)): straight from the tile forms when both
+      // iterates live there, the reference's two calls otherwise
+      Matrix T;
+      if (fused_steps_enabled() && mat_tile_combine(X2, X, 0, -1.0, 2.0, p.threshold, 0.0, T, WANT_LEFT | WANT_RIGHT)) {
+        std::swap(X, T);
+      } else {
+        mat_scale(X, 2.0);
+        mat_increment(X2, X, -1.0, p.threshold);
+      }
     } else {
       mat_copy(X2, X);
     }
@@ -273,30 +289,61 @@ void solve_trs4(const Matrix& H, const Matrix& ISQ, double trace, Matrix& K, dou
   double energy = 0.0;
   int II = 1;
   for (II = 1; II <= p.max_iterations; ++II) {
-    mat_multiply(X, X, X2, 1.0, 0.0, p.threshold, &s.pool);
-    mat_copy(X2, Fx);
-    mat_scale(Fx, -3.0);
-    mat_increment(X, Fx, 4.0, 0.0);
-    mat_copy(s.IMat, Gx);
-    mat_increment(X, Gx, -2.0, 0.0);
-    mat_increment(X2, Gx, 1.0, 0.0);
-    const double tfx = dot_real(X2, Fx);
-    const double tgx = dot_real(X2, Gx);
+    // X^2 stays in tile space (both forms, entries deferred) when the product runs on the tile path
+    mat_multiply(X, X, X2, 1.0, 0.0, p.threshold, &s.pool, WANT_LEFT | WANT_RIGHT);
+    // Fused step: Tr(X2 Fx), Tr(X2 Gx) and Fx + sigma Gx are evaluated entry by entry from the tile
+    // forms of X2 and X with the reference's rounding sequence - Fx, Gx are never formed, nothing leaves tile space.
+    // Otherwise (complex, scattered, general grids): the reference's call sequence below.
+    double tfx = 0.0, tgx = 0.0;
+    double both[2];
+    const bool fused = fused_steps_enabled() && mat_tile_scalars(1, X2, &X, both);
+    if (fused) {
+      tfx = both[0]; tgx = both[1];
+    } else {
+      mat_copy(X2, Fx);
+      mat_scale(Fx, -3.0);
+      mat_increment(X, Fx, 4.0, 0.0);
+      mat_copy(s.IMat, Gx);
+      mat_increment(X, Gx, -2.0, 0.0);
+      mat_increment(X2, Gx, 1.0, 0.0);
+      tfx = dot_real(X2, Fx);
+      tgx = dot_real(X2, Gx);
+    }
     sigma[II] = (std::fabs(tgx) < 1.0e-14) ? 0.5 * (sigma_max - sigma_min) : (trace - tfx) / tgx;
     if (sigma[II] > sigma_max) {
-      mat_copy(X, T);
-      mat_scale(T, 2.0);
-      mat_increment(X2, T, -1.0, 0.0);
+      if (!(fused && mat_tile_combine(X2, X, 0, -1.0, 2.0, 0.0, 0.0, T, WANT_LEFT | WANT_RIGHT))) {
+        mat_copy(X, T);
+        mat_scale(T, 2.0);
+        mat_increment(X2, T, -1.0, 0.0);
+      }
     } else if (sigma[II] < sigma_min) {
       mat_copy(X2, T);
     } else {
-      mat_scale(Gx, sigma[II]);
-      mat_increment(Fx, Gx, 1.0, 0.0);
-      mat_multiply(X2, Gx, T, 1.0, 0.0, p.threshold, &s.pool);
+      bool done = false;
+      if (fused) {
+        Matrix FG;                               // Fx + sigma*Gx, needed as a right operand only
+        if (mat_tile_combine(X2, X, 1, 0.0, 0.0, 0.0, sigma[II], FG, WANT_RIGHT)) {
+          mat_multiply(X2, FG, T, 1.0, 0.0, p.threshold, &s.pool, WANT_LEFT | WANT_RIGHT);
+          done = true;
+        }
+      }
+      if (!done) {
+        if (fused) {                             // (the combine declined: form Fx, Gx after all)
+          mat_copy(X2, Fx);
+          mat_scale(Fx, -3.0);
+          mat_increment(X, Fx, 4.0, 0.0);
+          mat_copy(s.IMat, Gx);
+          mat_increment(X, Gx, -2.0, 0.0);
+          mat_increment(X2, Gx, 1.0, 0.0);
+        }
+        mat_scale(Gx, sigma[II]);
+        mat_increment(Fx, Gx, 1.0, 0.0);
+        mat_multiply(X2, Gx, T, 1.0, 0.0, p.threshold, &s.pool);
+      }
     }
     // reference :624-625 first forms X_k - TempMat and then overwrites it with TempMat;
     // the discarded difference has no effect on any result and is not computed here.
-    mat_copy(T, X);
+    std::swap(X, T);                             // (the reference copies TempMat into X; T is scratch)
     const double old = energy;
     energy = dot_real(X, s.WH);
     mon.append(energy - old);

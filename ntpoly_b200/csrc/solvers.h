@@ -48,7 +48,8 @@ struct SolveRecord {
 };
 SolveRecord& last_solve();
 
-void set_permute_gemm(int on);   // 1: PermuteMatrix as two products with permutation matrices (reference form), 0 (default): index relabelling
+void set_permute_gemm(int on);
+void set_fused_steps(int on);   // 1: PermuteMatrix as two products with permutation matrices (reference form), 0 (default): index relabelling
 void permute_matrix(const Matrix& in, Matrix& out, const Permutation& p, MemoryPool* pool);
 void undo_permute_matrix(const Matrix& in, Matrix& out, const Permutation& p, MemoryPool* pool);
 

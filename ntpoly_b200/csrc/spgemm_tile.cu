@@ -25,6 +25,7 @@
 // by tile padding never survive the strict |v| > thr test, so results equal the scalar
 // path up to summation order.
 #include "csc.cuh"
+#include "ops.cuh"
 #include "peer.h"
 #include <chrono>
 #include <cstring>
@@ -441,6 +442,71 @@ struct ResultForms {
   int4* entR; double* tvalR;                 // right form: slot 2*task + h
   unsigned want;                             // WANT_LEFT | WANT_RIGHT
 };
+// ---- the finished strip of a task goes STRAIGHT INTO THE TWO TILE FORMS OF THE RESULT (shared by the numeric kernel's
+// epilogue and the tile-space combine kernel). acc[ii][0..1]: the lane's two values of row tile ii (C-fragment layout:
+// row lane/4, columns 2*(lane%4), +1), zero where the result has no entry; km bit ii: the lane keeps an entry of row
+// tile ii; c0/c1: its kept entries in its two columns (j0, j0 + 1).
+__device__ __forceinline__ void emit_strip(double (&acc)[8][2], unsigned km, int c0, int c1, int lane, int wj, int task,
+                                           int gt0, int gtn, int j0, int* __restrict__ cnt, const ResultForms& out) {
+  const int r = lane >> 2, cc = (lane & 3) * 2;
+  // presence bytes of the strip's tiles in the two forms of the RESULT: right form = (rows 0-31 / 32-63) x inner
+  // tiles of 4 rows (lanes 0-15 hold rows 0-3 of a row tile, lanes 16-31 rows 4-7); left form = (columns 0-3 /
+  // 4-7) x row tiles (lanes with lane%4 < 2 hold columns 0-3)
+  unsigned x = km;
+  x = (x | (x << 4)) & 0x0f0fu;
+  x = (x | (x << 2)) & 0x3333u;
+  x = (x | (x << 1)) & 0x5555u;                  // bit ii -> bit 2*ii
+  const unsigned bR = __reduce_or_sync(0xffffffffu, (lane & 16) ? (x << 1) : x);
+  const unsigned bL = __reduce_or_sync(0xffffffffu, (lane & 2) ? (km << 8) : km);
+  if (bL == 0u) return;                        // nothing of this strip survives
+#pragma unroll
+  for (int d = 4; d < 32; d <<= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+  }
+  if (lane < 4) {
+    if (c0) atomicAdd(&cnt[j0], c0);
+    if (c1) atomicAdd(&cnt[j0 + 1], c1);
+  }
+  const int slotL = 2 * gt0 + (wj >> 2) * gtn + (task - gt0);
+  if (out.want & WANT_RIGHT) {
+    // 4x8 tiles (h, jj = wj, kk): rows 32h + 4kk + row%4, fragment position (col%8)*4 + row%4. Row tile ii holds
+    // inner tiles kk = 2(ii%4) (rows 0-3: lanes 0-15) and 2(ii%4)+1 (rows 4-7: lanes 16-31) of super-tile h = ii/4
+    const unsigned half = (unsigned)lane >> 4;
+    double* base = out.tvalR + ((long long)task * 2 * 64 + 8 * wj) * 32 + cc * 4 + (r & 3);
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const unsigned byte = (bR >> (8 * (ii >> 2))) & 0xffu;
+      const unsigned kk = 2u * (ii & 3) + half;
+      if ((byte >> kk) & 1u) {
+        double* t = base + ((ii >> 2) * 64 + __popc(byte & ((1u << kk) - 1u))) * 32;
+        t[0] = acc[ii][0];
+        t[4] = acc[ii][1];
+      }
+    }
+  }
+  if (out.want & WANT_LEFT) {
+    // 8x4 tiles (kk' = 2(wj%4) + ch, ii) of super-tile (Ib, chunk column 2g + wj/4): columns 4ch + col%4, fragment
+    // position (row%8)*4 + col%4; lanes with lane%4 < 2 hold ch = 0
+    const unsigned ch = ((unsigned)lane & 3u) >> 1;
+    const unsigned byte = (bL >> (8 * ch)) & 0xffu;
+    double* base = out.tvalL + ((long long)slotL * 64 + 8 * (2 * (wj & 3) + (int)ch)) * 32 + r * 4 + (cc & 3);
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+      if ((byte >> ii) & 1u)
+        *reinterpret_cast<double2*>(base + __popc(byte & ((1u << ii) - 1u)) * 32) = make_double2(acc[ii][0], acc[ii][1]);
+  }
+  if (lane == 0) {
+    // presence masks: byte wj of the two right-form entries, bytes 2(wj%4), 2(wj%4)+1 of the left-form entry
+    // (little endian: .z/.w of the int4 are the low / high word of the 64-bit mask)
+    unsigned char* mR = reinterpret_cast<unsigned char*>(out.entR + (size_t)task * 2) + 8;
+    mR[wj] = (unsigned char)(bR & 0xffu);
+    mR[16 + wj] = (unsigned char)((bR >> 8) & 0xffu);
+    unsigned char* mL = reinterpret_cast<unsigned char*>(out.entL + slotL) + 8 + 2 * (wj & 3);
+    mL[0] = (unsigned char)(bL & 0xffu);
+    mL[1] = (unsigned char)((bL >> 8) & 0xffu);
+  }
+}
 template <int NSTAGE, int MINB, int DENSE>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
 k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
@@ -780,63 +846,7 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
       c1 += k1 ? 1 : 0;
       km |= ((k0 || k1) ? 1u : 0u) << ii;
     }
-    // presence bytes of the strip's tiles in the two forms of the RESULT: right form = (rows 0-31 / 32-63) x inner
-    // tiles of 4 rows (lanes 0-15 hold rows 0-3 of a row tile, lanes 16-31 rows 4-7); left form = (columns 0-3 /
-    // 4-7) x row tiles (lanes with lane%4 < 2 hold columns 0-3)
-    unsigned x = km;
-    x = (x | (x << 4)) & 0x0f0fu;
-    x = (x | (x << 2)) & 0x3333u;
-    x = (x | (x << 1)) & 0x5555u;                  // bit ii -> bit 2*ii
-    const unsigned bR = __reduce_or_sync(0xffffffffu, (lane & 16) ? (x << 1) : x);
-    const unsigned bL = __reduce_or_sync(0xffffffffu, (lane & 2) ? (km << 8) : km);
-    if (bL == 0u) continue;                        // nothing of this strip survives
-#pragma unroll
-    for (int d = 4; d < 32; d <<= 1) {
-      c0 += __shfl_xor_sync(0xffffffffu, c0, d);
-      c1 += __shfl_xor_sync(0xffffffffu, c1, d);
-    }
-    if (lane < 4) {
-      if (c0) atomicAdd(&cnt[j0], c0);
-      if (c1) atomicAdd(&cnt[j0 + 1], c1);
-    }
-    const int slotL = 2 * gt0 + (wj >> 2) * gtn + (task - gt0);
-    if (out.want & WANT_RIGHT) {
-      // 4x8 tiles (h, jj = wj, kk): rows 32h + 4kk + row%4, fragment position (col%8)*4 + row%4. Row tile ii holds
-      // inner tiles kk = 2(ii%4) (rows 0-3: lanes 0-15) and 2(ii%4)+1 (rows 4-7: lanes 16-31) of super-tile h = ii/4
-      const unsigned half = (unsigned)lane >> 4;
-      double* base = out.tvalR + ((long long)task * 2 * 64 + 8 * wj) * 32 + cc * 4 + (r & 3);
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        const unsigned byte = (bR >> (8 * (ii >> 2))) & 0xffu;
-        const unsigned kk = 2u * (ii & 3) + half;
-        if ((byte >> kk) & 1u) {
-          double* t = base + ((ii >> 2) * 64 + __popc(byte & ((1u << kk) - 1u))) * 32;
-          t[0] = acc[ii][0];
-          t[4] = acc[ii][1];
-        }
-      }
-    }
-    if (out.want & WANT_LEFT) {
-      // 8x4 tiles (kk' = 2(wj%4) + ch, ii) of super-tile (Ib, chunk column 2g + wj/4): columns 4ch + col%4, fragment
-      // position (row%8)*4 + col%4; lanes with lane%4 < 2 hold ch = 0
-      const unsigned ch = ((unsigned)lane & 3u) >> 1;
-      const unsigned byte = (bL >> (8 * ch)) & 0xffu;
-      double* base = out.tvalL + ((long long)slotL * 64 + 8 * (2 * (wj & 3) + (int)ch)) * 32 + r * 4 + (cc & 3);
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii)
-        if ((byte >> ii) & 1u)
-          *reinterpret_cast<double2*>(base + __popc(byte & ((1u << ii) - 1u)) * 32) = make_double2(acc[ii][0], acc[ii][1]);
-    }
-    if (lane == 0) {
-      // presence masks: byte wj of the two right-form entries, bytes 2(wj%4), 2(wj%4)+1 of the left-form entry
-      // (little endian: .z/.w of the int4 are the low / high word of the 64-bit mask)
-      unsigned char* mR = reinterpret_cast<unsigned char*>(out.entR + (size_t)task * 2) + 8;
-      mR[wj] = (unsigned char)(bR & 0xffu);
-      mR[16 + wj] = (unsigned char)((bR >> 8) & 0xffu);
-      unsigned char* mL = reinterpret_cast<unsigned char*>(out.entL + slotL) + 8 + 2 * (wj & 3);
-      mL[0] = (unsigned char)(bL & 0xffu);
-      mL[1] = (unsigned char)((bL >> 8) & 0xffu);
-    }
+    emit_strip(acc, km, c0, c1, lane, wj, task, gt0, gtn, j0, cnt, out);
   }
 }
 
@@ -1076,6 +1086,101 @@ bool spgemm_tile(const LocalCsc<double>& Xl, const LocalCsc<double>& Yl, double 
   return spgemm_tile_core(left_view_of(*A), *B, Xl.cols, Yl.rows, alpha, thr, rules, Z, useful_products, shift, false, want);
 }
 
+// ---- everything a tile-space result needs around the kernel that computes its strips (the numeric SpGEMM kernel, or
+// the combine kernel of the fused driver steps): task table, index of the two forms with fixed slots, outer index from
+// the kept-entry counts, per-K meta of the left form, publication on multi-GPU grids, (lazy) entry count.
+using StripLauncher = std::function<void(const int2* tasks, int ntasks, int* task_counter, int* cnt, const ResultForms& out)>;
+static void tile_emit_result(int nJ, int nG, const int* gbmin_p, const int* gtask_off_p, int h_tasks, int ncols, int nrows,
+                             unsigned want, bool publish, LocalCsc<double>& Z, const StripLauncher& launch, bool profile) {
+  // ---- the result's tile forms: fixed slots of 64 tiles per (task, super-tile); index known up front
+  auto forms = std::make_shared<TileForms>();
+  ChunkTiles& L = forms->left;
+  ChunkTiles& R = forms->right;
+  const bool wl = (want & WANT_LEFT) != 0, wr = (want & WANT_RIGHT) != 0;
+  const size_t ns = (size_t)max(h_tasks, 1) * 2;
+  const int nk = div_up(ncols, 4);
+  DevBuf<int2> tasks((size_t)max(h_tasks, 1));
+  DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
+  cnt.zero();
+  task_counter.zero();
+  // the left form is what the other ranks read in place when this result becomes a left operand: peer-visible slab
+  L.ent.alloc_shared(ns); R.ent.alloc(ns);
+  L.colmeta.alloc_shared((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
+  L.kmeta.alloc_shared((size_t)nk);
+  L.coltile.alloc((size_t)nG * 2 + 1);
+  L.ncc = div_up(ncols, 32); R.ncc = nG;
+  L.nsuper = R.nsuper = 2 * h_tasks;
+  L.ntiles = R.ntiles = (long long)h_tasks * 128;
+  L.emitted = R.emitted = true;
+  if (wl) L.tval.alloc_shared((size_t)max(L.ntiles, 1ll) * 32);     // never read outside present tiles: no memset
+  if (wr) R.tval.alloc((size_t)max(R.ntiles, 1ll) * 32);
+  if (h_tasks > 0)
+    NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, gbmin_p, gtask_off_p, tasks.get());
+  NTB_LAUNCH(k_forms_layout, div_up(h_tasks + nG, 256), 256, 0, h_tasks, nG, tasks.get(), gtask_off_p, L.ent.get(),
+             R.ent.get(), L.colmeta.get(), R.colmeta.get(), L.coltile.get());
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (profile && rt().profile) {
+    CUDA_CHECK(cudaEventCreate(&ev0));
+    CUDA_CHECK(cudaEventCreate(&ev1));
+    CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
+  }
+  if (h_tasks > 0) {
+    const ResultForms out{L.ent.get(), L.tval.get(), R.ent.get(), R.tval.get(), want & (WANT_LEFT | WANT_RIGHT)};
+    launch(tasks.get(), h_tasks, task_counter.get(), cnt.get(), out);
+  }
+  if (profile && rt().profile) {
+    CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
+    rt().prof_events.emplace_back(ev0, ev1);
+  }
+  // ---- outer index of the result (kept-entry counts came from the numeric kernel); per-K meta of the left form
+  std::unique_ptr<PhaseScope> ph_tail(new PhaseScope(2));
+  Z.rows = nrows; Z.cols = ncols;
+  Z.outer.alloc((size_t)ncols + 1);
+  exclusive_scan(cnt.get(), Z.outer.get(), ncols);
+  if (wl) NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off_p, L.ent.get(), L.kmeta.get());
+  forms->has_left = wl ? 1 : 0;                // a form that was not asked for is rebuilt from CSC if it is ever needed
+  forms->has_right = wr ? 1 : 0;
+  // multi-GPU: hand the descriptor of the left form just written to every rank. The exchange is also the barrier that
+  // orders this rank's tile stores before any peer's reads.
+  const bool pub = publish && wl;
+  if (pub) {
+    forms->pub_landing.assign((size_t)peer().n, PeerLeftDesc{});
+    forms->pub_pending = true;
+    const PeerLeftDesc mine = left_desc_of(&L, 0, true);
+    static_assert(sizeof(PeerPayload) == sizeof(PeerLeftDesc), "payload size");
+    PeerPayload pl;
+    std::memcpy(&pl, &mine, sizeof(pl));
+    peer_exchange(pl, reinterpret_cast<PeerPayload*>(forms->pub_landing.data()), nullptr, 0, Z.outer.get() + ncols);
+  }
+  auto land_pub = [forms] {
+    if (forms->pub_pending) { forms->left_pub = std::move(forms->pub_landing); forms->pub_landing.clear(); forms->pub_pending = false; }
+  };
+  ph_tail.reset();
+  if (want & WANT_CSC) {
+    // the caller reads the entries: count now, entries from the right form right away
+    int h_nnz = 0;
+    readback_async(&h_nnz, Z.outer.get() + ncols, sizeof(int));
+    stream_sync();
+    land_pub();
+    Z.alloc_entries(0);
+    Z.nnz = h_nnz;
+    Z.forms = forms;
+    if (h_nnz > 0) tile_materialize_entries(Z);
+  } else {
+    // DEFERRED product (a driver intermediate, an iterate that lives in tile space): nobody needs the entry count
+    // before the next wait of the library stream - the next product's task count, a norm - so it is not waited for
+    // here. The count, the published descriptors and the byte accounting land inside that wait (on_next_sync).
+    auto pc = std::make_shared<PendingCount>();
+    readback_async(&pc->raw, Z.outer.get() + ncols, sizeof(int));
+    on_next_sync([pc, land_pub] { pc->arrived = true; land_pub(); });
+    Z.alloc_entries(0);
+    Z.nnz.pend = pc;
+    Z.forms = forms;
+    Z.deferred = true;
+    rt().deferred_products++;
+  }
+}
+
 LeftView left_view_of(const ChunkTiles& A) {
   LeftView v;
   v.npieces = 1;
@@ -1119,6 +1224,7 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
   es.dd = shift ? shift->dd : 0;
   es.ncols_diag = shift ? shift->ncols_diag : 0;
   // ---- symbolic: row-tile window of every tile column -> 64-row blocks of every group -> task table
+  std::unique_ptr<PhaseScope> ph_sym(new PhaseScope(0));
   DevBuf<int> imin8((size_t)nJ), nI8((size_t)nJ), gbmin((size_t)nG), gnb((size_t)nG), gtask_off((size_t)nG + 1);
   DevBuf<unsigned long long> ndmma(1);
   ndmma.zero();
@@ -1145,6 +1251,7 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
     PeerPayload mine{};
     peer_exchange(mine, verdicts.data(), nullptr, 0, d_decline.get());
   }
+  ph_sym.reset();
   stream_sync();
   if (collective) {
     for (const PeerPayload& v : verdicts) if (v.w[7] != 0ull) return false;       // on every rank alike
@@ -1157,52 +1264,17 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
     NTB_CHECK(!too_big, "tile product: the result's tile slots exceed the device memory budget (NCCL fallback path)");
   }
 
-  const auto t1 = now();
-  // ---- the result's tile forms: fixed slots of 64 tiles per (task, super-tile); index known up front
-  auto forms = std::make_shared<TileForms>();
-  ChunkTiles& L = forms->left;
-  ChunkTiles& R = forms->right;
-  const bool wl = (want & WANT_LEFT) != 0, wr = (want & WANT_RIGHT) != 0;
-  const size_t ns = (size_t)max(h_tasks, 1) * 2;
-  const int nk = div_up(ncols, 4);
-  DevBuf<int2> tasks((size_t)max(h_tasks, 1));
-  DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
-  cnt.zero();
-  task_counter.zero();
-  // the left form is what the other ranks read in place when this result becomes a left operand: peer-visible slab
-  L.ent.alloc_shared(ns); R.ent.alloc(ns);
-  L.colmeta.alloc_shared((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
-  L.kmeta.alloc_shared((size_t)nk);
-  L.coltile.alloc((size_t)nG * 2 + 1);
-  L.ncc = div_up(ncols, 32); R.ncc = nG;
-  L.nsuper = R.nsuper = 2 * h_tasks;
-  L.ntiles = R.ntiles = (long long)h_tasks * 128;
-  L.emitted = R.emitted = true;
-  if (wl) L.tval.alloc_shared((size_t)max(L.ntiles, 1ll) * 32);     // never read outside present tiles: no memset
-  if (wr) R.tval.alloc((size_t)max(R.ntiles, 1ll) * 32);
-  if (h_tasks > 0)
-    NTB_LAUNCH(k_task_table, div_up((long long)nG * 32, 256), 256, 0, nG, gbmin.get(), gtask_off.get(), tasks.get());
-  NTB_LAUNCH(k_forms_layout, div_up(h_tasks + nG, 256), 256, 0, h_tasks, nG, tasks.get(), gtask_off.get(), L.ent.get(),
-             R.ent.get(), L.colmeta.get(), R.colmeta.get(), L.coltile.get());
-  const auto t2 = now();
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (rt().profile) {
-    CUDA_CHECK(cudaEventCreate(&ev0));
-    CUDA_CHECK(cudaEventCreate(&ev1));
-    CUDA_CHECK(cudaEventRecord(ev0, rt().stream));
-  }
-  if (h_tasks > 0) {
+  auto launch_numeric = [&](const int2* tasks_p, int ntasks_l, int* task_counter_p, int* cnt_p, const ResultForms& out) {
     // pipeline shape: 3 stages x 2 CTAs per SM (default) or 2 stages x 3 CTAs per SM (NTB_NUMERIC_SHAPE=23)
     static const int shape = [] { const char* e = std::getenv("NTB_NUMERIC_SHAPE"); return e ? std::atoi(e) : 32; }();
-    const ResultForms out{L.ent.get(), L.tval.get(), R.ent.get(), R.tval.get(), want & (WANT_LEFT | WANT_RIGHT)};
     auto launch = [&](auto kern, int nstage, int per_sm) {
       static bool attr_set = false;
       if (!attr_set) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem9(nstage)));
         attr_set = true;
       }
-      NTB_LAUNCH(kern, min(h_tasks, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, gtask_off.get(),
-                 tasks.get(), h_tasks, task_counter.get(), cnt.get(), out, nrows, ncols, es);
+      NTB_LAUNCH(kern, min(ntasks_l, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, gtask_off.get(),
+                 tasks_p, ntasks_l, task_counter_p, cnt_p, out, nrows, ncols, es);
     };
     // fast paths of the DMMA warps: NTB_DENSE_STAGE=0 generic loop only, 1 (default) dense-stage block, 2 also the
     // A-complete block (experimental)
@@ -1211,66 +1283,259 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
     else if (dense >= 2) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 2>, NSTAGE_DEFAULT, 2);
     else if (dense == 1) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 1>, NSTAGE_DEFAULT, 2);
     else launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 0>, NSTAGE_DEFAULT, 2);
-  }
-  if (rt().profile) {
-    CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
-    rt().prof_events.emplace_back(ev0, ev1);
-  }
-  const auto t3 = now();
-  // ---- outer index of the result (kept-entry counts came from the numeric kernel); per-K meta of the left form
-  Z.rows = nrows; Z.cols = ncols;
-  Z.outer.alloc((size_t)ncols + 1);
-  exclusive_scan(cnt.get(), Z.outer.get(), ncols);
-  if (wl) NTB_LAUNCH(k_forms_kmeta, div_up(nk, 256), 256, 0, nk, nG, tasks.get(), gtask_off.get(), L.ent.get(), L.kmeta.get());
-  forms->has_left = wl ? 1 : 0;                // a form that was not asked for is rebuilt from CSC if it is ever needed
-  forms->has_right = wr ? 1 : 0;
-  // multi-GPU: hand the descriptor of the left form just written to every rank. The exchange is also the barrier that
-  // orders this rank's tile stores before any peer's reads.
-  const bool pub = publish && wl;
-  if (pub) {
-    forms->pub_landing.assign((size_t)peer().n, PeerLeftDesc{});
-    forms->pub_pending = true;
-    const PeerLeftDesc mine = left_desc_of(&L, 0, true);
-    static_assert(sizeof(PeerPayload) == sizeof(PeerLeftDesc), "payload size");
-    PeerPayload pl;
-    std::memcpy(&pl, &mine, sizeof(pl));
-    peer_exchange(pl, reinterpret_cast<PeerPayload*>(forms->pub_landing.data()), nullptr, 0, Z.outer.get() + ncols);
-  }
-  auto land_pub = [forms] {
-    if (forms->pub_pending) { forms->left_pub = std::move(forms->pub_landing); forms->pub_landing.clear(); forms->pub_pending = false; }
   };
-  auto t4 = t3;
-  if (want & WANT_CSC) {
-    // the caller reads the entries: count now, entries from the right form right away
-    int h_nnz = 0;
-    readback_async(&h_nnz, Z.outer.get() + ncols, sizeof(int));
-    stream_sync();
-    land_pub();
-    t4 = now();
-    Z.alloc_entries(0);
-    Z.nnz = h_nnz;
-    Z.forms = forms;
-    if (h_nnz > 0) tile_materialize_entries(Z);
-  } else {
-    // DEFERRED product (a driver intermediate, an iterate that lives in tile space): nobody needs the entry count
-    // before the next wait of the library stream - the next product's task count, a norm - so it is not waited for
-    // here. The count, the published descriptors and the byte accounting land inside that wait (on_next_sync).
-    auto pc = std::make_shared<PendingCount>();
-    readback_async(&pc->raw, Z.outer.get() + ncols, sizeof(int));
-    on_next_sync([pc, land_pub] { pc->arrived = true; land_pub(); });
-    t4 = now();
-    Z.alloc_entries(0);
-    Z.nnz.pend = pc;
-    Z.forms = forms;
-    Z.deferred = true;
-    rt().deferred_products++;
-  }
-  const auto t5 = now();
-  if (timing)
-    std::fprintf(stderr, "[tile] bounds %.3f  layout %.3f  numeric %.3f  index %.3f  csc %.3f ms  (tasks %d, nnz %d)\n",
-                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), h_tasks, Z.nnz.pending() ? -1 : (int)(long long)Z.nnz);
+  tile_emit_result(nJ, nG, gbmin.get(), gtask_off.get(), h_tasks, ncols, nrows, want, publish, Z, launch_numeric, true);
   rt().tile_products++;
   rt().dmma_issued += (double)h_ndmma;
+  return true;
+}
+
+
+// =====================================================================================================================
+// TILE-SPACE HELPERS OF THE DRIVERS' FUSED STEPS. A purification iterate that came out of a tile
+// product lives as tile forms with deferred CSC entries; the reference's per-iteration helpers on it -
+//   TRS4: Fx = 4X - 3X^2, Gx = I - 2X + X^2, Tr(X^2 Fx), Tr(X^2 Gx), Fx + sigma Gx   (DensityMatrixSolversModule.F90:591-625)
+//   TRS2: 2X - X^2 with threshold                                                      (:394-400)
+//   energy Tr(X H), Tr(X)
+// are evaluated here straight from the right tile forms, entry by entry with the reference's own rounding sequence
+// (scale, then alpha*a + b with one rounding: ops.cu k_increment), and a combined matrix is written as a tile-space
+// result of its own (both forms, fixed slots, deferred entries) through the same emit_strip as a product. Nothing is
+// converted to CSC and back, no form is rebuilt with k_ct_build. Entries that are exactly zero do not exist in tile
+// space; the reference may keep such an entry (its value is 0 either way).
+// =====================================================================================================================
+struct CombineSpec {
+  int mode;              // 0: alpha*P + (beta*Q), matched entries kept iff |v| > thr;  1: TRS4  Fx + sigma*Gx from P = X^2, Q = X
+  double alpha, beta, thr, sigma;
+  int dd, ncols_diag;    // identity: local row of the diagonal entry of local column c is c + dd, for c < ncols_diag
+};
+__device__ __forceinline__ int4 rf_entry(const CtView& R, int g, int id) {
+  const int4 cm = R.colmeta[g];
+  const int idx = ct_find(R.ent, cm, id);
+  return idx >= 0 ? R.ent[idx] : make_int4(id, 0, 0, 0);
+}
+// element `pos` of tile (tile column jj, inner tile kk) of a right-form super-tile, 0 when the tile is absent
+__device__ __forceinline__ double rf_load(const CtView& R, const int4& en, int jj, unsigned kk, int pos) {
+  const unsigned byte = (unsigned)(mask64(en) >> (8 * jj)) & 0xffu;
+  if (((byte >> kk) & 1u) == 0u) return 0.0;
+  return R.tval[((long long)en.y + 8 * jj + __popc(byte & ((1u << kk) - 1u))) * 32 + pos];
+}
+// the reference's Fx, Gx of one entry (x2 = X^2(i,j), x = X(i,j), diag = 1 on the diagonal): Fx = copy X2, scale -3,
+// increment by 4 X; Gx = copy I, increment by -2 X, increment by X2
+__device__ __forceinline__ void trs4_fg(double x2, double x, double diag, double& fx, double& gx) {
+  fx = fma(4.0, x, __dmul_rn(-3.0, x2));
+  gx = fma(1.0, x2, fma(-2.0, x, diag));
+}
+__device__ __forceinline__ double combine_value(const CombineSpec& sp, double p, double q, int row, int col, bool& keep) {
+  if (sp.mode == 0) {
+    const double t = __dmul_rn(sp.beta, q);
+    const double v = fma(sp.alpha, p, t);
+    keep = (p != 0.0 && q != 0.0) ? (fabs(v) > sp.thr) : (v != 0.0);
+    return keep ? v : 0.0;
+  }
+  const double diag = (row == col + sp.dd && col < sp.ncols_diag) ? 1.0 : 0.0;
+  double fx, gx;
+  trs4_fg(p, q, diag, fx, gx);
+  const double v = fma(1.0, fx, __dmul_rn(sp.sigma, gx));
+  keep = v != 0.0;
+  return v;
+}
+
+// groups of 64 columns: hull of the 64-row blocks that P, Q (right forms) and the diagonal touch
+__global__ void __launch_bounds__(256) k_hull_bounds(CtView P, CtView Q, int nG, int with_diag, int dd, int ncols_diag, int nrows,
+                                                     int* __restrict__ gbmin, int* __restrict__ gnb) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nG) return;
+  int mn = INT_MAX, mx = -1;
+  const int4 cp = P.colmeta[g], cq = Q.colmeta[g];
+  if (cp.y > 0) { mn = min(mn, cp.z >> 1); mx = max(mx, cp.w >> 1); }
+  if (cq.y > 0) { mn = min(mn, cq.z >> 1); mx = max(mx, cq.w >> 1); }
+  if (with_diag && g * 64 < ncols_diag) {
+    const int r0 = g * 64 + dd, r1 = min(g * 64 + 63, ncols_diag - 1) + dd;
+    if (r1 >= 0 && r0 < nrows) { mn = min(mn, max(r0, 0) >> 6); mx = max(mx, min(r1, nrows - 1) >> 6); }
+  }
+  gbmin[g] = (mx >= 0) ? mn : 0;
+  gnb[g] = (mx >= 0) ? (mx - mn + 1) : 0;
+}
+
+// one CTA per task (64x64 block), warp w = tile column w: the strip is combined from the operands' right forms in
+// the accumulator layout of a product and goes through emit_strip
+__global__ void __launch_bounds__(256)
+k_form_combine(CtView P, CtView Q, CombineSpec sp, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks,
+               int ntasks, int* __restrict__ cnt, ResultForms out, int nrows, int ncols) {
+  const int lane = threadIdx.x & 31, wj = threadIdx.x >> 5;
+  const int r = lane >> 2, cc = (lane & 3) * 2;
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int2 tk = tasks[task];
+    const int g = tk.x, Ib = tk.y;
+    const int J = g * 8 + wj;
+    if (J >= nJ) continue;
+    const int gt0 = gtask_off[g], gtn = gtask_off[g + 1] - gt0;
+    const int j0 = J * 8 + cc;
+    const bool in0 = j0 < ncols, in1 = j0 + 1 < ncols;
+    double acc[8][2];
+    int c0 = 0, c1 = 0;
+    unsigned km = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int4 ep = rf_entry(P, g, 2 * Ib + h), eq = rf_entry(Q, g, 2 * Ib + h);
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const int ii = 4 * h + i4;
+        const unsigned kk = 2u * i4 + ((unsigned)r >> 2);
+        const int pos = cc * 4 + (r & 3);
+        const int row = (Ib * 8 + ii) * 8 + r;
+        const double p0 = rf_load(P, ep, wj, kk, pos), p1 = rf_load(P, ep, wj, kk, pos + 4);
+        const double q0 = rf_load(Q, eq, wj, kk, pos), q1 = rf_load(Q, eq, wj, kk, pos + 4);
+        bool k0 = false, k1 = false;
+        double f0 = 0.0, f1 = 0.0;
+        if (row < nrows) {
+          if (in0) f0 = combine_value(sp, p0, q0, row, j0, k0);
+          if (in1) f1 = combine_value(sp, p1, q1, row, j0 + 1, k1);
+        }
+        acc[ii][0] = k0 ? f0 : 0.0;
+        acc[ii][1] = k1 ? f1 : 0.0;
+        c0 += k0 ? 1 : 0;
+        c1 += k1 ? 1 : 0;
+        km |= ((k0 || k1) ? 1u : 0u) << ii;
+      }
+    }
+    emit_strip(acc, km, c0, c1, lane, wj, task, gt0, gtn, j0, cnt, out);
+  }
+}
+
+// Scalars over two right forms, one warp per tile column (8 matrix columns), merge of the two id-sorted super-tile
+// lists like k_form_diff_col_abs; per-tile-column partial sums, reduced afterwards in a fixed order.
+//   MODE 0: part[J] = sum p*q                                   (DotMatrix)
+//   MODE 1: part[J] = sum x2*Fx, part[nJ + J] = sum x2*Gx        (TRS4, P = X^2, Q = X)
+//   MODE 2: part[J] = sum of the diagonal entries of P           (MatrixTrace; Q unused)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_form_scalars(CtView A, CtView B, int nJ, int ncols, int nrows, int dd, int ncols_diag, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const int4 none = make_int4(INT_MAX, 0, 0, 0);
+  for (int J = gw; J < nJ; J += nw) {
+    const int q = J >> 3, sh = (J & 7) * 8;
+    const int4 ca = A.colmeta[q], cb = (MODE == 2) ? make_int4(0, 0, 0, -1) : B.colmeta[q];
+    int ia = 0, ib = 0;
+    int4 ea = (ca.y > 0) ? A.ent[ca.x] : none, eb = (cb.y > 0) ? B.ent[cb.x] : none;
+    const int col = J * 8 + (lane >> 2);
+    double s1 = 0.0, s2 = 0.0;
+    while (ea.x != INT_MAX || eb.x != INT_MAX) {
+      const int id = min(ea.x, eb.x);
+      const bool ta = ea.x == id, tb = eb.x == id;
+      const unsigned long long wa = ta ? mask64(ea) : 0ull, wb = tb ? mask64(eb) : 0ull;
+      const unsigned ma = (unsigned)(wa >> sh) & 0xffu, mb = (unsigned)(wb >> sh) & 0xffu;
+      const long long ba = (long long)ea.y + sh, bb = (long long)eb.y + sh;
+      unsigned m = (MODE == 0) ? (ma & mb) : ma;                 // every mode is a sum over entries of A (x B)
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1u;
+        const unsigned below = (1u << kk) - 1u;
+        const double a = A.tval[(ba + __popc(ma & below)) * 32 + lane];
+        double b = 0.0;
+        if (MODE != 2 && ((mb >> kk) & 1u)) b = B.tval[(bb + __popc(mb & below)) * 32 + lane];
+        const int row = id * 32 + kk * 4 + (lane & 3);
+        if (MODE == 0) s1 = fma(a, b, s1);
+        else if (MODE == 1) {
+          const double diag = (row == col + dd && col < ncols_diag) ? 1.0 : 0.0;
+          double fx, gx;
+          trs4_fg(a, b, diag, fx, gx);
+          s1 = fma(a, fx, s1);
+          s2 = fma(a, gx, s2);
+        } else if (row == col + dd && col < ncols_diag) s1 += a;
+      }
+      if (ta) { ++ia; ea = (ia < ca.y) ? A.ent[ca.x + ia] : none; }
+      if (tb) { ++ib; eb = (ib < cb.y) ? B.ent[cb.x + ib] : none; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      if (MODE == 1) s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) { part[J] = s1; if (MODE == 1) part[nJ + J] = s2; }
+  }
+}
+
+static CtView right_view(const ChunkTiles& R) { return CtView{R.colmeta.get(), R.ent.get(), R.tval.get(), nullptr, R.ncc}; }
+static const ChunkTiles* usable_right_form(const LocalCsc<double>& M) {
+  if (M.cols == 0) return nullptr;
+  const ChunkTiles* R = tile_operand_form(M, false);
+  if (!R) return nullptr;
+  // a form built from CSC must be reasonably full (see spgemm_tile); one written by a product is what it is
+  if (!R->emitted && (double)(long long)M.nnz < 0.20 * 32.0 * (double)R->ntiles) return nullptr;
+  return R;
+}
+
+// d_out[0..nout) = the scalars of `mode` (see k_form_scalars) over this rank's block; false: no usable right forms
+bool tile_form_scalars(int mode, const LocalCsc<double>& A, const LocalCsc<double>* B, int dd, int ncols_diag, double* d_out) {
+  if (!tile_path_on()) return false;
+  const ChunkTiles* Ra = usable_right_form(A);
+  const ChunkTiles* Rb = B ? usable_right_form(*B) : Ra;
+  if (!Ra || !Rb) return false;
+  if (B && (A.cols != B->cols || A.rows != B->rows || Ra->ncc != Rb->ncc)) return false;
+  const int nJ = div_up(A.cols, 8), nout = (mode == 1) ? 2 : 1;
+  DevBuf<double> part((size_t)nJ * nout);
+  const int grid = max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16));
+  const CtView Av = right_view(*Ra), Bv = right_view(*Rb);
+  if (mode == 0) NTB_LAUNCH((k_form_scalars<0>), grid, 256, 0, Av, Bv, nJ, A.cols, A.rows, dd, ncols_diag, part.get());
+  else if (mode == 1) NTB_LAUNCH((k_form_scalars<1>), grid, 256, 0, Av, Bv, nJ, A.cols, A.rows, dd, ncols_diag, part.get());
+  else NTB_LAUNCH((k_form_scalars<2>), grid, 256, 0, Av, Bv, nJ, A.cols, A.rows, dd, ncols_diag, part.get());
+  for (int k = 0; k < nout; ++k) reduce_sum(part.get() + (size_t)k * nJ, nJ, d_out + k);
+  return true;
+}
+
+// Z = combine(P, Q) as a tile-space result (see CombineSpec); false when an operand has no usable right form, or -
+// on a column-split multi-GPU grid: on every rank alike - when the result's slots would not fit
+bool tile_combine(const LocalCsc<double>& P, const LocalCsc<double>& Q, int mode, double alpha, double beta, double thr,
+                  double sigma, int dd, int ncols_diag, LocalCsc<double>& Z, unsigned want, bool publish) {
+  if (!tile_path_on() || P.cols != Q.cols || P.rows != Q.rows) return false;
+  if (publish) {
+    // every rank must take the same branch: only product-written forms (they exist on every rank or on none) qualify
+    if (!(P.forms && P.forms->has_right == 1 && P.forms->right.emitted && Q.forms && Q.forms->has_right == 1 &&
+          Q.forms->right.emitted)) return false;
+  }
+  const ChunkTiles* Rp = usable_right_form(P);
+  const ChunkTiles* Rq = usable_right_form(Q);
+  if (!Rp || !Rq || Rp->ncc != Rq->ncc) return false;
+  if (want & WANT_CSC) want |= WANT_RIGHT;
+  if (!(want & (WANT_LEFT | WANT_RIGHT))) want |= WANT_RIGHT;
+  const int ncols = P.cols, nrows = P.rows;
+  const int nJ = div_up(ncols, 8), nG = Rp->ncc;
+  const CtView Pv = right_view(*Rp), Qv = right_view(*Rq);
+  CombineSpec sp{mode, alpha, beta, thr, sigma, dd, ncols_diag};
+  DevBuf<int> gbmin((size_t)nG), gnb((size_t)nG), gtask_off((size_t)nG + 1);
+  NTB_LAUNCH(k_hull_bounds, div_up(nG, 256), 256, 0, Pv, Qv, nG, mode == 1 ? 1 : 0, dd, ncols_diag, nrows, gbmin.get(), gnb.get());
+  exclusive_scan(gnb.get(), gtask_off.get(), nG);
+  int h_tasks = 0;
+  readback_async(&h_tasks, gtask_off.get() + nG, sizeof(int));
+  const long long task_limit = tile_task_limit();
+  std::vector<PeerPayload> verdicts;
+  DevBuf<int> d_decline;
+  DevBuf<unsigned long long> d_big;
+  if (publish) {
+    d_decline.alloc(1);
+    d_big.alloc(1);
+    const unsigned long long big = ~0ull >> 1;          // (the combine has no DMMA count: the scattered test never fires)
+    h2d(d_big.get(), &big, 1);
+    NTB_LAUNCH(k_task_guard, 1, 32, 0, gtask_off.get() + nG, d_big.get(), task_limit, d_decline.get());
+    verdicts.resize((size_t)peer().n);
+    PeerPayload mine{};
+    peer_exchange(mine, verdicts.data(), nullptr, 0, d_decline.get());
+  }
+  stream_sync();
+  if (publish) {
+    for (const PeerPayload& v : verdicts) if (v.w[7] != 0ull) return false;
+  } else if ((long long)h_tasks > task_limit) {
+    return false;
+  }
+  auto launch = [&](const int2* tasks_p, int ntasks_l, int* /*task_counter*/, int* cnt_p, const ResultForms& out) {
+    NTB_LAUNCH(k_form_combine, min(ntasks_l, kNumSMs * 16), 256, 0, Pv, Qv, sp, nJ, gtask_off.get(), tasks_p, ntasks_l, cnt_p,
+               out, nrows, ncols);
+  };
+  tile_emit_result(nJ, nG, gbmin.get(), gtask_off.get(), h_tasks, ncols, nrows, want, publish, Z, launch, false);
+  rt().tile_combines++;
   return true;
 }
 
