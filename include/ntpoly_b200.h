@@ -363,6 +363,17 @@ double ntb_SignIteration(int *ih_X, const int *ih_identity, int *ih_T1, int *ih_
  * ||X_next - X||. SignFunction_wrp runs this and then exchanges the contents of X and X_next. */
 double ntb_SignStep(const int *ih_X, const int *ih_identity, int *ih_T1, int *ih_Xnext, const double *alpha_k,
                     const double *threshold, int *ih_memory_pool);
+/* Tile-space helpers of the fused TRS2 / TRS4 steps (DensityMatrixSolversModule.F90:394-400, 591-625), exposed for their
+ * parity tests. Operands must be real matrices that live as tile forms (results of tile products); return 1 when the
+ * helper ran, 0 when the caller has to issue the reference's call sequence instead.
+ *   ntb_TileCombine_ps  mode 0: Out = alpha*P + beta*Q, a matched entry kept iff |v| > threshold (ScaleMatrix(Q, beta);
+ *                       IncrementMatrix(P, Q, alpha, threshold));  mode 1 (P = X^2, Q = X): Out = Fx + sigma*Gx with
+ *                       Fx = 4X - 3X^2, Gx = I - 2X + X^2
+ *   ntb_TileScalars_ps  mode 0: out2[0] = DotMatrix(A, B);  mode 1 (A = X^2, B = X): out2 = {DotMatrix(X2, Fx),
+ *                       DotMatrix(X2, Gx)};  mode 2: out2[0] = MatrixTrace(A) (B = NULL) */
+int ntb_TileCombine_ps(const int *ih_P, const int *ih_Q, int mode, double alpha, double beta, double threshold, double sigma,
+                       int *ih_Out);
+int ntb_TileScalars_ps(int mode, const int *ih_A, const int *ih_B, double *out2);
 /* Instrumentation, 0 by default: when 1 every multiply also counts its useful products
  * F = sum over the entries (k,j) of B of nnz(A(:,k)) (counters [2], ntb_last_solve [4]); one extra sweep over B and
  * one read-back per product. When 0 the counts are only taken where the path choice needs them. */

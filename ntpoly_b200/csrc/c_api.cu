@@ -416,6 +416,16 @@ double ntb_SignStep(const int* ih_x, const int* ih_identity, int* ih_t1, int* ih
   return sign_step(*get<Matrix>(ih_x), *get<Matrix>(ih_identity), *get<Matrix>(ih_t1), *get<Matrix>(ih_xnext), unused,
                    *alpha_k, *threshold, false, pool);
 }
+// tile-space helpers of the fused driver steps, exposed for their parity tests: 1 when the operands live as tile forms
+// and the helper ran, 0 when the caller has to issue the reference's call sequence
+int ntb_TileCombine_ps(const int* ih_p, const int* ih_q, int mode, double alpha, double beta, double threshold, double sigma,
+                       int* ih_out) {
+  return mat_tile_combine(*get<Matrix>(ih_p), *get<Matrix>(ih_q), mode, alpha, beta, threshold, sigma, *get<Matrix>(ih_out),
+                          WANT_LEFT | WANT_RIGHT) ? 1 : 0;
+}
+int ntb_TileScalars_ps(int mode, const int* ih_a, const int* ih_b, double* out2) {
+  return mat_tile_scalars(mode, *get<Matrix>(ih_a), ih_b ? get<Matrix>(ih_b) : nullptr, out2) ? 1 : 0;
+}
 void ntb_set_flop_counting(int on) { ensure_init(); rt().count_flops = on != 0; }
 void ntb_get_deferred_counters(double* out2) { out2[0] = (double)rt().deferred_products; out2[1] = (double)rt().deferred_materialized; }
 void ntb_get_tile_counters(double* out2) { out2[0] = (double)rt().tile_products; out2[1] = rt().dmma_issued; }

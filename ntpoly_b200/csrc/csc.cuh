@@ -196,8 +196,9 @@ PeerLeftDesc left_desc_of(const ChunkTiles* L, long long nnz, bool usable);
 bool tile_form_scalars(int mode, const LocalCsc<double>& A, const LocalCsc<double>* B, int dd, int ncols_diag, double* d_out);
 // mode 0: Z = alpha*P + beta*Q with the sparse add's threshold on matched entries;  mode 1 (TRS4, P = X^2, Q = X):
 // Z = Fx + sigma*Gx. Z is a tile-space result like a product's (forms per `want`, deferred entries).
+// rb: height of the reference's local row blocks (the untested tail of the sparse add is per row block).
 bool tile_combine(const LocalCsc<double>& P, const LocalCsc<double>& Q, int mode, double alpha, double beta, double thr,
-                  double sigma, int dd, int ncols_diag, LocalCsc<double>& Z, unsigned want, bool publish);
+                  double sigma, int dd, int ncols_diag, int rb, LocalCsc<double>& Z, unsigned want, bool publish);
 // column sums of |alpha*A + B| from the right tile forms of both blocks; false when either has none (use the CSC kernel)
 bool tile_diff_col_abs_sums(const LocalCsc<double>& A, const LocalCsc<double>& B, double alpha, double* d_colsum);
 // assemble the left form of a row of column blocks from per-rank pieces (see psmatrix.cu: halo gather)

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_final(const int* __restrict__ i
 // small inputs: one block does the whole scan (one launch instead of three; the scans of the hot path are over a few
 // thousand groups or a rank's columns, and at that size the launches cost more than the work)
 constexpr int SCAN1_T = 1024;
-constexpr int SCAN1_MAX = 1 << 16;
+constexpr int SCAN1_MAX = 1 << 13;     // beyond that the per-thread chunks are long and their loads uncoalesced: three launches win
 template <typename Out>
 __global__ void __launch_bounds__(SCAN1_T) k_scan_single(const int* __restrict__ in, Out* __restrict__ out, int n) {
   __shared__ Out sw[33];

@@ -799,7 +799,7 @@ bool mat_tile_combine(const Matrix& P, const Matrix& Q, int mode, double alpha, 
   mat_construct_empty(res, P.actual_dim, P.grid, false);
   const int dd = P.start_col - P.start_row;
   const int ncd = std::max(0, std::min(P.local_cols, P.actual_dim - P.start_col));
-  if (!tile_combine(P.r, Q.r, mode, alpha, beta, thr, sigma, dd, ncd, res.r, want, multi)) return false;
+  if (!tile_combine(P.r, Q.r, mode, alpha, beta, thr, sigma, dd, ncd, P.row_block(), res.r, want, multi)) return false;
   Out = std::move(res);
   return true;
 }

@@ -1307,11 +1307,18 @@ struct CombineSpec {
   int mode;              // 0: alpha*P + (beta*Q), matched entries kept iff |v| > thr;  1: TRS4  Fx + sigma*Gx from P = X^2, Q = X
   double alpha, beta, thr, sigma;
   int dd, ncols_diag;    // identity: local row of the diagonal entry of local column c is c + dd, for c < ncols_diag
+  // mode 0 with thr > 0: the sparse add's rule for UNMATCHED entries (AddSparseVectors.f90:21-70, ops.cu k_increment):
+  // kept without a test when the other operand has no entry further down in the same row segment of the column (the
+  // reference's untested tail), otherwise iff |w| > thr. lastP / lastQ[seg * ncols + col]: last row with an entry.
+  const int* lastP; const int* lastQ;
+  int rb, ncols;
 };
 __device__ __forceinline__ int4 rf_entry(const CtView& R, int g, int id) {
   const int4 cm = R.colmeta[g];
-  const int idx = ct_find(R.ent, cm, id);
-  return idx >= 0 ? R.ent[idx] : make_int4(id, 0, 0, 0);
+  const int idx = ct_find(R.ent, cm, id);            // (lower bound: the entry found may belong to a later id)
+  if (idx < 0) return make_int4(id, 0, 0, 0);
+  const int4 en = R.ent[idx];
+  return en.x == id ? en : make_int4(id, 0, 0, 0);
 }
 // element `pos` of tile (tile column jj, inner tile kk) of a right-form super-tile, 0 when the tile is absent
 __device__ __forceinline__ double rf_load(const CtView& R, const int4& en, int jj, unsigned kk, int pos) {
@@ -1329,7 +1336,13 @@ __device__ __forceinline__ double combine_value(const CombineSpec& sp, double p,
   if (sp.mode == 0) {
     const double t = __dmul_rn(sp.beta, q);
     const double v = fma(sp.alpha, p, t);
-    keep = (p != 0.0 && q != 0.0) ? (fabs(v) > sp.thr) : (v != 0.0);
+    if (p != 0.0 && q != 0.0) keep = fabs(v) > sp.thr;
+    else if (v == 0.0) keep = false;
+    else if (sp.lastP == nullptr || fabs(v) > sp.thr) keep = true;
+    else {                                       // unmatched and not above the threshold: only the untested tail survives
+      const int* other = (p != 0.0) ? sp.lastQ : sp.lastP;
+      keep = other[(size_t)(row / sp.rb) * sp.ncols + col] < row;
+    }
     return keep ? v : 0.0;
   }
   const double diag = (row == col + sp.dd && col < sp.ncols_diag) ? 1.0 : 0.0;
@@ -1355,6 +1368,33 @@ __global__ void __launch_bounds__(256) k_hull_bounds(CtView P, CtView Q, int nG,
   }
   gbmin[g] = (mx >= 0) ? mn : 0;
   gnb[g] = (mx >= 0) ? (mx - mn + 1) : 0;
+}
+
+// last[seg * ncols + col] = largest row of a non-zero entry of the right form in row segment seg (rb rows) of column
+// col; the array starts at -1. One warp per tile column.
+__global__ void __launch_bounds__(256) k_form_last_rows(CtView R, int nJ, int ncols, int rb, int* __restrict__ last) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int J = gw; J < nJ; J += nw) {
+    const int4 cm = R.colmeta[J >> 3];
+    const int sh = (J & 7) * 8;
+    const int col = J * 8 + (lane >> 2);
+    for (int e = 0; e < cm.y; ++e) {
+      const int4 en = R.ent[cm.x + e];
+      const unsigned byte = (unsigned)(mask64(en) >> sh) & 0xffu;
+      unsigned m = byte;
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1u;
+        const double v = R.tval[((long long)en.y + sh + __popc(byte & ((1u << kk) - 1u))) * 32 + lane];
+        if (v != 0.0 && col < ncols) {
+          const int row = en.x * 32 + kk * 4 + (lane & 3);
+          atomicMax(&last[(size_t)(row / rb) * ncols + col], row);
+        }
+      }
+    }
+  }
 }
 
 // one CTA per task (64x64 block), warp w = tile column w: the strip is combined from the operands' right forms in
@@ -1489,8 +1529,12 @@ bool tile_form_scalars(int mode, const LocalCsc<double>& A, const LocalCsc<doubl
 // Z = combine(P, Q) as a tile-space result (see CombineSpec); false when an operand has no usable right form, or -
 // on a column-split multi-GPU grid: on every rank alike - when the result's slots would not fit
 bool tile_combine(const LocalCsc<double>& P, const LocalCsc<double>& Q, int mode, double alpha, double beta, double thr,
-                  double sigma, int dd, int ncols_diag, LocalCsc<double>& Z, unsigned want, bool publish) {
+                  double sigma, int dd, int ncols_diag, int rb, LocalCsc<double>& Z, unsigned want, bool publish) {
   if (!tile_path_on() || P.cols != Q.cols || P.rows != Q.rows) return false;
+  if (rb <= 0) rb = P.rows > 0 ? P.rows : 1;
+  const int nseg = div_up(std::max(P.rows, 1), rb);
+  const bool tails = mode == 0 && thr > 0.0;
+  if (tails && (long long)nseg * P.cols > (1ll << 28)) return false;      // (a grid with very many row blocks per rank)
   if (publish) {
     // every rank must take the same branch: only product-written forms (they exist on every rank or on none) qualify
     if (!(P.forms && P.forms->has_right == 1 && P.forms->right.emitted && Q.forms && Q.forms->has_right == 1 &&
@@ -1504,7 +1548,19 @@ bool tile_combine(const LocalCsc<double>& P, const LocalCsc<double>& Q, int mode
   const int ncols = P.cols, nrows = P.rows;
   const int nJ = div_up(ncols, 8), nG = Rp->ncc;
   const CtView Pv = right_view(*Rp), Qv = right_view(*Rq);
-  CombineSpec sp{mode, alpha, beta, thr, sigma, dd, ncols_diag};
+  CombineSpec sp{mode, alpha, beta, thr, sigma, dd, ncols_diag, nullptr, nullptr, rb, ncols};
+  DevBuf<int> lastP, lastQ;
+  if (tails) {
+    const size_t cells = (size_t)nseg * ncols;
+    lastP.alloc(cells); lastQ.alloc(cells);
+    readback_flush();
+    CUDA_CHECK(cudaMemsetAsync(lastP.get(), 0xff, cells * sizeof(int), rt().stream));
+    CUDA_CHECK(cudaMemsetAsync(lastQ.get(), 0xff, cells * sizeof(int), rt().stream));
+    const int grid = max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16));
+    NTB_LAUNCH(k_form_last_rows, grid, 256, 0, Pv, nJ, ncols, rb, lastP.get());
+    NTB_LAUNCH(k_form_last_rows, grid, 256, 0, Qv, nJ, ncols, rb, lastQ.get());
+    sp.lastP = lastP.get(); sp.lastQ = lastQ.get();
+  }
   DevBuf<int> gbmin((size_t)nG), gnb((size_t)nG), gtask_off((size_t)nG + 1);
   NTB_LAUNCH(k_hull_bounds, div_up(nG, 256), 256, 0, Pv, Qv, nG, mode == 1 ? 1 : 0, dd, ncols_diag, nrows, gbmin.get(), gnb.get());
   exclusive_scan(gnb.get(), gtask_off.get(), nG);
