@@ -349,6 +349,9 @@ void ntb_set_permute_gemm(int on);
  * Same results up to the summation order of the scalars. ntb_tile_combines: tile-space combinations since the reset. */
 void ntb_set_fused_steps(int on);
 double ntb_tile_combines(void);
+/* output columns of local products served by the shared-memory hash accumulator (scattered patterns: wide row window,
+ * few products) since the reset; NTB_HASH_BIN=0 in the environment sends them back to the window kernels */
+double ntb_hash_columns(void);
 /* C = alpha*A*B (thresholded), then IncrementMatrix(Identity, C, sigma) with threshold 0 — the call pair of
  * SignSolversModule.F90:226-229 / SquareRootSolversModule.F90 as one entry point. */
 void ntb_MatrixMultiplyShift_ps(const int *ih_matA, const int *ih_matB, int *ih_matC, const double *alpha,

@@ -14,6 +14,9 @@
 //   numeric      bin 1-4: one WARP per column, dense window accumulator in shared memory
 //                bin 5  : one CTA per column, shared-memory window up to ~200 KB
 //                bin 6  : one CTA per column, window in a per-CTA global slab (L2 resident)
+//                bin 7  : one warp per column, SHARED-MEMORY HASH accumulator: scattered columns whose row window
+//                         is wide but whose product count is small (graph-like patterns, permuted / load-balanced
+//                         matrices) - work proportional to the products, not to the window
 //                each: accumulate in k order, then sweep the window in row order applying
 //                the drop rule (|alpha*v|>thr or dense-branch |v|>thr) -> sorted, filtered,
 //                alpha-scaled entries written to a staging area at a bound-derived offset
@@ -36,7 +39,10 @@ static bool tile_path_enabled() {
 
 bool tile_path_on() { return tile_path_enabled(); }
 
-constexpr int NBINS = 7;       // 0: empty column, 1..4 warp windows, 5 CTA window, 6 global slab
+constexpr int NBINS = 8;       // 0: empty column, 1..4 warp windows, 5 CTA window, 6 global slab, 7 warp hash
+constexpr int HASH_UB = 1024;  // bin 7: at most this many products per column ...
+constexpr int HASH_H = 2048;   // ... in a table of this many slots per warp (load factor <= 1/2)
+constexpr int HASH_WARPS = 4;  // warps (= columns in flight) per CTA of the hash kernel
 constexpr int WARPS = 8;       // warps per CTA in the warp-window kernels
 constexpr int CTA_T = 256;     // threads per CTA in the CTA-window kernels
 constexpr size_t SMEM_BUDGET = 200 * 1024;
@@ -87,10 +93,12 @@ __global__ void __launch_bounds__(256) k_bounds(CscView<T> X, CscView<T> Y, int*
       cap[j] = (int)min((unsigned long long)w, ub);
       int b = 0;
       if (w > 0) {
-        b = NBINS - 1;
+        b = 6;
 #pragma unroll
-        for (int t = NBINS - 2; t >= 1; --t)
+        for (int t = 5; t >= 1; --t)
           if (w <= cfg.wmax[t]) b = t;
+        // a wide window with few products: the hash accumulator (sweeping the window would cost more than the products)
+        if (cfg.wmax[7] > 0 && w > cfg.wmax[4] && ub <= (unsigned long long)HASH_UB && ub * 4ull < (unsigned long long)w) b = 7;
       }
       binid[j] = b;
       my_flops += ub;
@@ -255,6 +263,129 @@ k_numeric_cta(CscView<T> X, CscView<T> Y, const int* __restrict__ list, const in
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// bin 7: one warp per output column, hash accumulator in shared memory. Four phases, all deterministic:
+//   A  symbolic: the rows of every Y(:,k), k in X(:,j), are inserted into an open-addressing table (keys only);
+//   B  the distinct rows are compacted, sorted (bitonic, in shared memory) and every table slot learns the RANK of
+//      its row in that order;
+//   C  numeric: k ascending like the reference; the rows of one Y(:,k) are distinct, so the lanes of the warp update
+//      distinct accumulators acc[rank] - no atomics, the summation order per entry is the reference's;
+//   D  ordered sweep over the ranks: threshold rule, alpha, emit - sorted output for free, as in the window kernels.
+// Replaces the O(window) sweep per column of bins 5/6 for scattered patterns (the reference's bucketed hash_index,
+// sparse_includes/MultiplyBlock.f90:20-33, has the same purpose).
+template <typename T> struct HashSmem {
+  int keys[HASH_H];
+  int rank[HASH_H];
+  int sorted[HASH_UB];
+  T acc[HASH_UB];
+};
+__device__ __forceinline__ unsigned hash_slot(int r) { return ((unsigned)r * 2654435761u) >> (32 - 11); }
+static_assert(HASH_H == (1 << 11), "hash_slot assumes 2^11 slots");
+
+template <typename T>
+__global__ void __launch_bounds__(HASH_WARPS * 32)
+k_numeric_hash(CscView<T> X, CscView<T> Y, const int* __restrict__ list, const int* __restrict__ nlist_p,
+               const long long* __restrict__ tmp_off, double alpha, double thr, RuleView rules,
+               int* __restrict__ tmp_idx, T* __restrict__ tmp_val, int* __restrict__ cnt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  HashSmem<T>& S = reinterpret_cast<HashSmem<T>*>(smem_raw)[warp];
+  const int nlist = *nlist_p;
+  for (int li = blockIdx.x * HASH_WARPS + warp; li < nlist; li += gridDim.x * HASH_WARPS) {
+    const int j = list[li];
+    for (int t = lane; t < HASH_H; t += 32) S.keys[t] = -1;
+    __syncwarp();
+    const int xs = X.outer[j], xe = X.outer[j + 1];
+    // ---- A: keys
+    for (int p = xs; p < xe; ++p) {
+      const int k = X.inner[p];
+      const int s = Y.outer[k], e = Y.outer[k + 1];
+      for (int q = s + lane; q < e; q += 32) {
+        const int r = Y.inner[q];
+        unsigned slot = hash_slot(r);
+        for (;;) {
+          const int old = atomicCAS(&S.keys[slot], -1, r);
+          if (old == -1 || old == r) break;
+          slot = (slot + 1u) & (HASH_H - 1);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- B: compact, sort, ranks
+    int nd = 0;
+    for (int t0 = 0; t0 < HASH_H; t0 += 32) {
+      const int key = S.keys[t0 + lane];
+      const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
+      if (key >= 0) S.sorted[nd + __popc(m & ((1u << lane) - 1u))] = key;
+      nd += __popc(m);
+    }
+    int np2 = 32;
+    while (np2 < nd) np2 <<= 1;
+    for (int t = nd + lane; t < np2; t += 32) S.sorted[t] = INT_MAX;
+    __syncwarp();
+    for (int kk = 2; kk <= np2; kk <<= 1)
+      for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+        for (int t = lane; t < np2; t += 32) {
+          const int partner = t ^ jj;
+          if (partner > t) {
+            const int a = S.sorted[t], b = S.sorted[partner];
+            const bool up = (t & kk) == 0;
+            if ((a > b) == up) { S.sorted[t] = b; S.sorted[partner] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    for (int t = lane; t < nd; t += 32) {
+      const int r = S.sorted[t];
+      unsigned slot = hash_slot(r);
+      while (S.keys[slot] != r) slot = (slot + 1u) & (HASH_H - 1);
+      S.rank[slot] = t;
+      S.acc[t] = zero_of<T>();
+    }
+    __syncwarp();
+    // ---- C: numeric, k ascending
+    for (int p = xs; p < xe; ++p) {
+      const int k = X.inner[p];
+      const T b = X.val[p];
+      const int s = Y.outer[k], e = Y.outer[k + 1];
+      for (int q = s + lane; q < e; q += 32) {
+        const int r = Y.inner[q];
+        unsigned slot = hash_slot(r);
+        while (S.keys[slot] != r) slot = (slot + 1u) & (HASH_H - 1);
+        const int a = S.rank[slot];
+        S.acc[a] = s_fma(Y.val[q], b, S.acc[a]);
+      }
+      __syncwarp();
+    }
+    // ---- D: ordered sweep
+    const long long off = tmp_off[j];
+    int count = 0;
+    for (int t0 = 0; t0 < nd; t0 += 32) {
+      const int t = t0 + lane;
+      bool keep = false;
+      T v = zero_of<T>();
+      int row = 0;
+      if (t < nd) {
+        v = S.acc[t];
+        row = S.sorted[t];
+        const T sv = s_scale(alpha, v);
+        keep = keep_entry(s_abs(sv), s_abs(v), thr, rule_for(rules, row, j));
+        v = sv;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const long long pos = off + count + __popc(m & ((1u << lane) - 1));
+        tmp_idx[pos] = row;
+        tmp_val[pos] = v;
+      }
+      count += __popc(m);
+    }
+    if (lane == 0) cnt[j] = count;
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_compact(int ncols, const long long* __restrict__ tmp_off,
@@ -351,6 +482,8 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   for (int b = 1; b <= 4; ++b) cfg.wmax[b] = per_warp_elems[b];
   cfg.wmax[5] = (int)(SMEM_BUDGET / sizeof(T));
   cfg.wmax[6] = INT_MAX;
+  static const bool hash_on = [] { const char* e = std::getenv("NTB_HASH_BIN"); return !(e && e[0] == '0'); }();
+  cfg.wmax[7] = hash_on ? 1 : 0;             // (a switch, not a width: bin 7 is chosen by product count, see k_bounds)
 
   // ---- tile path first: it needs only the useful-product count, not the per-column windows
   if constexpr (!scalar_traits<T>::is_complex) {
@@ -433,6 +566,14 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
     NTB_LAUNCH((k_numeric_cta<T, false>), blocks, CTA_T, SMEM_BUDGET, X, Y, lists.get() + (size_t)5 * ncols,
                bin_count.get() + 5, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
                tmp_val.get(), cnt.get(), (T*)nullptr);
+  }
+  if (h_bins[7] > 0) {
+    const size_t smem = sizeof(HashSmem<T>) * HASH_WARPS;
+    CUDA_CHECK(cudaFuncSetAttribute((k_numeric_hash<T>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = min(div_up(h_bins[7], HASH_WARPS), kNumSMs * 8);
+    NTB_LAUNCH((k_numeric_hash<T>), blocks, HASH_WARPS * 32, smem, X, Y, lists.get() + (size_t)7 * ncols, bin_count.get() + 7,
+               tmp_off.get(), alpha, thr, rules, tmp_idx.get(), tmp_val.get(), cnt.get());
+    rt().hash_columns += (unsigned long long)h_bins[7];
   }
   DevBuf<T> slab;
   if (h_bins[6] > 0) {

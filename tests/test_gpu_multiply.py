@@ -331,3 +331,25 @@ def test_flop_counting_is_optional_instrumentation(nt, oracle):
     E.Gemm(C, A, None, threshold=thr)
     assert nt.tile_counters()["tile_products"] == 1
     assert _bits_equal(D, E)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_scattered_columns_use_the_hash_accumulator(nt, oracle, cplx):
+    """graph-like pattern (c5 in small: directed ER graph, ~25 entries per row, rows anywhere in 0..N): every output
+    column has a row window as wide as the matrix but only ~600 products - served by the shared-memory hash accumulator
+    (bin 7), result identical to the oracle (same k-ascending summation order per entry)"""
+    from ntpoly_b200.workloads import complex_hermitian_graph
+    n = 16384
+    g = complex_hermitian_graph(n)
+    if not cplx:
+        g = sp.csc_matrix(g.real + g.imag)
+    A = nt.Matrix_ps(n, is_complex=cplx)
+    A.fill_from_scipy(g)
+    C = nt.Matrix_ps(n)
+    nt.reset_counters()
+    C.Gemm(A, A, None, alpha=0.7, threshold=1e-6)
+    assert nt.hash_columns() > 0.9 * n
+    OA = oracle.PSMatrix.from_scipy(g, is_complex=cplx)
+    ref = oracle.multiply(OA, OA, alpha=0.7, thr=1e-6)
+    compare_sparse(C.to_scipy(), ref.to_scipy(), 1e-6, tol=1e-13)
+    assert C.GetSize() == ref.nnz()
