@@ -197,7 +197,7 @@ static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
   T.emitted = false;
   T.ncc = div_up(M.cols, G::CW);
   const int ncc = T.ncc;
-  const int nk = ISA ? div_up(M.cols, 4) : 0;
+  const int nk = ISA ? T.ncc * 8 : 0;          // eight per-K records per chunk column, the last one padded (k_tile_bounds reads whole lines)
   DevBuf<int> scount((size_t)ncc), tcount((size_t)ncc), sptr((size_t)ncc + 1), tptr((size_t)ncc + 1), overflow(1);
   // a left form is what the other ranks of a column-split grid read in place: peer-visible slab when there is one
   if (ISA) { T.colmeta.alloc_shared((size_t)ncc); T.kmeta.alloc_shared((size_t)nk); }
@@ -246,12 +246,15 @@ __global__ void __launch_bounds__(256) k_tile_bounds(LeftView A, CtView B, int n
       int ql;
       const int pc = lv_piece(A, en.x, ql);
       const int4* kmeta = A.piece[pc].kmeta + ql * 8;
-      while (byte) {
-        const int kk = __ffs(byte) - 1;
-        byte &= byte - 1;
-        const int4 km = kmeta[kk];
-        if (km.y > 0) { mn = min(mn, km.z); mx = max(mx, km.w); mine += (unsigned long long)km.y; }
-      }
+      // the eight per-K records of the chunk column are one 128-byte line: load them all up front, independent of
+      // each other - ONE memory latency per entry instead of one per inner tile (it matters when the line lives in a
+      // neighbouring rank's memory, a few microseconds away over NVLink)
+      int4 km[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) km[kk] = kmeta[kk];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        if (((byte >> kk) & 1u) && km[kk].y > 0) { mn = min(mn, km[kk].z); mx = max(mx, km[kk].w); mine += (unsigned long long)km[kk].y; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -541,9 +544,13 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
     auto advance = [&]() {
       switch (pstep) {
         case 0: {
-          const int t = __shfl_sync(0xffffffffu, task_raw, 0);
-          tid_n = t;
+          int t = __shfl_sync(0xffffffffu, task_raw, 0);
           valid_n = t < ntasks;
+          // Multi-GPU: the tasks at both ends of the rank's column range read A super-tiles of the neighbouring ranks
+          // over NVLink (higher latency); handed out LAST they would be the kernel's tail. Hand out the task list
+          // from both ends towards the middle instead.
+          if (valid_n && A.npieces > 1) t = (t & 1) ? ntasks - 1 - (t >> 1) : (t >> 1);
+          tid_n = t;
           tk_n = valid_n ? tasks[t] : make_int2(0, 0);
           break;
         }
@@ -1067,10 +1074,76 @@ static long long tile_task_limit() {
 // entries (the scalar kernels' business); a banded product has ~1000 per task, a 32x32 block pair alone 128
 constexpr long long MIN_DMMA_PER_TASK = 16;
 __global__ void k_task_guard(const int* __restrict__ ntasks, const unsigned long long* __restrict__ ndmma, long long limit,
-                             int* __restrict__ decline) {
+                             unsigned long long* __restrict__ out3) {
   if (threadIdx.x == 0) {
     const long long t = *ntasks;
-    *decline = (t > limit || (long long)*ndmma < MIN_DMMA_PER_TASK * t) ? 1 : 0;
+    const unsigned long long nd = *ndmma;
+    out3[0] = (unsigned long long)t;
+    out3[1] = nd;
+    out3[2] = (t > limit || (long long)nd < MIN_DMMA_PER_TASK * t) ? 1ull : 0ull;
+  }
+}
+
+// The symbolic phase after k_tile_bounds in ONE launch (a single block; a rank has a few thousand groups at most): 64-row
+// block range of every group (k_group_bounds), exclusive scan into the task offsets, and the plan's three numbers
+// out3 = {tasks, DMMA count, decline verdict} which travel to the host in one piece (with the peer exchange on a
+// multi-GPU grid). Three launches and a read-back kernel less per product - at 8 GPUs a product is short enough for
+// that to show.
+constexpr int PLAN_T = 1024, PLAN_MAX_GROUPS = PLAN_T * 8;
+__global__ void __launch_bounds__(PLAN_T)
+k_group_plan(int nJ, int nG, const int* __restrict__ imin8, const int* __restrict__ nI8, int* __restrict__ gbmin,
+             int* __restrict__ gtask_off, const unsigned long long* __restrict__ ndmma, long long limit,
+             unsigned long long* __restrict__ out3) {
+  __shared__ int sw[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (nG + PLAN_T - 1) / PLAN_T;
+  const int g0 = min(nG, (int)threadIdx.x * per), g1 = min(nG, g0 + per);
+  int nb[8];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = g0 + i;
+    nb[i] = 0;
+    if (i < per && g < g1) {
+      int mn = INT_MAX, mx = -1;
+      for (int J = g * 8; J < min(nJ, g * 8 + 8); ++J)
+        if (nI8[J] > 0) { mn = min(mn, imin8[J] >> 3); mx = max(mx, ((imin8[J] + nI8[J]) >> 3) - 1); }
+      gbmin[g] = (mx >= 0) ? mn : 0;
+      nb[i] = (mx >= 0) ? (mx - mn + 1) : 0;
+      s += nb[i];
+    }
+  }
+  int inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) sw[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = sw[lane];
+    int winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    sw[lane] = winc - w;
+    if (lane == 31) sw[32] = winc;
+  }
+  __syncthreads();
+  int ex = sw[warp] + inc - s;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per && g0 + i < g1) { gtask_off[g0 + i] = ex; ex += nb[i]; }
+  if (threadIdx.x == 0) {
+    const long long t = sw[32];
+    gtask_off[nG] = (int)t;
+    const unsigned long long nd = *ndmma;
+    out3[0] = (unsigned long long)t;
+    out3[1] = nd;
+    out3[2] = (t > limit || (long long)nd < MIN_DMMA_PER_TASK * t) ? 1ull : 0ull;
   }
 }
 
@@ -1098,11 +1171,11 @@ static void tile_emit_result(int nJ, int nG, const int* gbmin_p, const int* gtas
   ChunkTiles& R = forms->right;
   const bool wl = (want & WANT_LEFT) != 0, wr = (want & WANT_RIGHT) != 0;
   const size_t ns = (size_t)max(h_tasks, 1) * 2;
-  const int nk = div_up(ncols, 4);
+  const int nk = div_up(ncols, 32) * 8;        // whole 8-record lines per chunk column (k_tile_bounds)
   DevBuf<int2> tasks((size_t)max(h_tasks, 1));
-  DevBuf<int> cnt((size_t)nJ * 8), task_counter(1);
+  DevBuf<int> cnt((size_t)nJ * 8 + 1);            // kept-entry counts per column + the task counter: one memset
   cnt.zero();
-  task_counter.zero();
+  int* const task_counter_p = cnt.get() + (size_t)nJ * 8;
   // the left form is what the other ranks read in place when this result becomes a left operand: peer-visible slab
   L.ent.alloc_shared(ns); R.ent.alloc(ns);
   L.colmeta.alloc_shared((size_t)nG * 2); R.colmeta.alloc((size_t)nG);
@@ -1126,7 +1199,7 @@ static void tile_emit_result(int nJ, int nG, const int* gbmin_p, const int* gtas
   }
   if (h_tasks > 0) {
     const ResultForms out{L.ent.get(), L.tval.get(), R.ent.get(), R.tval.get(), want & (WANT_LEFT | WANT_RIGHT)};
-    launch(tasks.get(), h_tasks, task_counter.get(), cnt.get(), out);
+    launch(tasks.get(), h_tasks, task_counter_p, cnt.get(), out);
   }
   if (profile && rt().profile) {
     CUDA_CHECK(cudaEventRecord(ev1, rt().stream));
@@ -1230,31 +1303,37 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
   ndmma.zero();
   NTB_LAUNCH(k_tile_bounds, max(1, min(div_up((long long)nJ * 32, 256), kNumSMs * 16)), 256, 0, Av, Bv, nJ, imin8.get(),
              nI8.get(), ndmma.get(), es.sigma != 0.0 ? 1 : 0, es.dd, es.ncols_diag, nrows);
-  NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), gbmin.get(), gnb.get());
-  exclusive_scan(gnb.get(), gtask_off.get(), nG);
-  unsigned long long h_ndmma = 0;
-  int h_tasks = 0;
-  readback_async(&h_ndmma, ndmma.get(), sizeof(h_ndmma));
-  readback_async(&h_tasks, gtask_off.get() + nG, sizeof(int));
   // The result is stored as fixed slots of 64 tiles per (task, super-tile): 64 KB per task for the two forms. A
   // product whose tasks would not fit (a scattered pattern that touches many blocks with few entries each) is
   // DECLINED - the caller then takes the scalar / gather path - never aborted. On a multi-GPU grid every rank must
   // take the same branch: the verdicts travel with a peer exchange that rides on this read-back (no extra wait).
   const long long task_limit = tile_task_limit();
   const bool collective = publish || Av.npieces > 1;
+  DevBuf<unsigned long long> plan(3);
+  if (nG <= PLAN_MAX_GROUPS) {
+    NTB_LAUNCH(k_group_plan, 1, PLAN_T, 0, nJ, nG, imin8.get(), nI8.get(), gbmin.get(), gtask_off.get(), ndmma.get(), task_limit,
+               plan.get());
+  } else {
+    NTB_LAUNCH(k_group_bounds, div_up(nG, 256), 256, 0, nJ, nG, imin8.get(), nI8.get(), gbmin.get(), gnb.get());
+    exclusive_scan(gnb.get(), gtask_off.get(), nG);
+    NTB_LAUNCH(k_task_guard, 1, 32, 0, gtask_off.get() + nG, ndmma.get(), task_limit, plan.get());
+  }
+  unsigned long long h_plan[3] = {0, 0, 0};
   std::vector<PeerPayload> verdicts;
-  DevBuf<int> d_decline;
   if (collective) {
-    d_decline.alloc(1);
-    NTB_LAUNCH(k_task_guard, 1, 32, 0, gtask_off.get() + nG, ndmma.get(), task_limit, d_decline.get());
     verdicts.resize((size_t)peer().n);
     PeerPayload mine{};
-    peer_exchange(mine, verdicts.data(), nullptr, 0, d_decline.get());
+    peer_exchange(mine, verdicts.data(), plan.get(), 3);      // every rank's {tasks, DMMAs, verdict}, own included
+  } else {
+    readback_async(h_plan, plan.get(), sizeof(h_plan));
   }
   ph_sym.reset();
   stream_sync();
+  if (collective) for (int i = 0; i < 3; ++i) h_plan[i] = verdicts[(size_t)peer().me].w[i];
+  const unsigned long long h_ndmma = h_plan[1];
+  const int h_tasks = (int)h_plan[0];
   if (collective) {
-    for (const PeerPayload& v : verdicts) if (v.w[7] != 0ull) return false;       // on every rank alike
+    for (const PeerPayload& v : verdicts) if (v.w[2] != 0ull) return false;       // on every rank alike
   } else {
     // tensor-core work must not dwarf the useful work (256 FMAs per DMMA)
     if (!force && useful_products >= 0.0 && (double)h_ndmma * 256.0 > 12.0 * useful_products) return false;
@@ -1565,24 +1644,25 @@ bool tile_combine(const LocalCsc<double>& P, const LocalCsc<double>& Q, int mode
   NTB_LAUNCH(k_hull_bounds, div_up(nG, 256), 256, 0, Pv, Qv, nG, mode == 1 ? 1 : 0, dd, ncols_diag, nrows, gbmin.get(), gnb.get());
   exclusive_scan(gnb.get(), gtask_off.get(), nG);
   int h_tasks = 0;
-  readback_async(&h_tasks, gtask_off.get() + nG, sizeof(int));
   const long long task_limit = tile_task_limit();
   std::vector<PeerPayload> verdicts;
-  DevBuf<int> d_decline;
-  DevBuf<unsigned long long> d_big;
+  DevBuf<unsigned long long> d_big, plan;
   if (publish) {
-    d_decline.alloc(1);
     d_big.alloc(1);
+    plan.alloc(3);
     const unsigned long long big = ~0ull >> 1;          // (the combine has no DMMA count: the scattered test never fires)
     h2d(d_big.get(), &big, 1);
-    NTB_LAUNCH(k_task_guard, 1, 32, 0, gtask_off.get() + nG, d_big.get(), task_limit, d_decline.get());
+    NTB_LAUNCH(k_task_guard, 1, 32, 0, gtask_off.get() + nG, d_big.get(), task_limit, plan.get());
     verdicts.resize((size_t)peer().n);
     PeerPayload mine{};
-    peer_exchange(mine, verdicts.data(), nullptr, 0, d_decline.get());
+    peer_exchange(mine, verdicts.data(), plan.get(), 3);
+  } else {
+    readback_async(&h_tasks, gtask_off.get() + nG, sizeof(int));
   }
   stream_sync();
   if (publish) {
-    for (const PeerPayload& v : verdicts) if (v.w[7] != 0ull) return false;
+    h_tasks = (int)verdicts[(size_t)peer().me].w[0];
+    for (const PeerPayload& v : verdicts) if (v.w[2] != 0ull) return false;
   } else if ((long long)h_tasks > task_limit) {
     return false;
   }
