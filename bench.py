@@ -63,8 +63,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
+    ap.add_argument("--c5-scale", type=float, default=0.0125,
+                    help="c5: the exponential's input is G*scale + 0.01*I (the reference example scales its 512-node graph by 0.5 "
+                         "and gets a DENSE exponential; at N=32768 the scale keeps exp(G*scale) sparse above the threshold)")
     a = ap.parse_args()
-    defaults = {"c1": (8192, 1e-8), "c3": (65536, 1e-6), "c4": (262144, 1e-6), "c5": (2048, 1e-6)}
+    defaults = {"c1": (8192, 1e-8), "c3": (65536, 1e-6), "c4": (262144, 1e-6), "c5": (32768, 1e-6)}
     if a.n == 0:
         a.n = defaults[a.config][0]
     if a.threshold == 0.0:
@@ -82,8 +85,8 @@ def workload_name(args):
     if args.config == "c3":
         return (f"TRS4 purification (whole solve = one step), block-sparse insulator N={n}, 32x32 blocks, 20 blocks per block "
                 f"row, trace N/2, thr={thr:g}, converge 1e-5, identity overlap")
-    return (f"complex Hermitian path (Guo-transformed directed ER graph, ~25 nnz/row) N={n}: Hotelling inverse of G + s*I "
-            f"plus Chebyshev-16 exponential of G/8, thr={thr:g} (whole pair of solves = one step)")
+    return (f"complex Hermitian path (Guo-transformed directed ER graph, ~25 nnz/row) N={n}: Hotelling inverse of G + (8*||G||_1 + 1)*I "
+            f"plus Chebyshev-16 exponential of {args.c5_scale:g}*G, thr={thr:g} (whole pair of solves = one step)")
 
 
 def config_of(args, world):
@@ -809,9 +812,13 @@ def run_c5(env):
 
     def build(nn):
         g = complex_hermitian_graph(nn)
-        shift = float(np.asarray(abs(g).sum(axis=0)).max()) + 1.0
-        a = sp.csc_matrix(g + sp.identity(nn) * shift)          # Hotelling input: positive definite shifted copy
-        e = sp.csc_matrix(g * 0.125 + sp.identity(nn) * 0.01)   # exponential input (non-zero (1,1): PowerBounds scales it)
+        # Hotelling input: positive definite shifted copy, G + s*I with s = 8*||G||_1 + 1. (With s = ||G||_1 + 1 the
+        # iteration cannot converge at thr = 1e-6: the dropped terms (G/s)^k, k >= 3, have a 1-norm of ~0.1-0.2, the
+        # residual ||I - X*A||_1 stagnates there above the monitor's loose cutoff 1e-2 and the solve runs into
+        # max_iterations - measured, gpurun_out/r2c16_probe_inv*.log; the reference's monitor behaves the same.)
+        shift = 8.0 * float(np.asarray(abs(g).sum(axis=0)).max()) + 1.0
+        a = sp.csc_matrix(g + sp.identity(nn) * shift)
+        e = sp.csc_matrix(g * (args.c5_scale if nn == n else 0.125) + sp.identity(nn) * 0.01)   # exponential input (non-zero (1,1): PowerBounds scales it)
         return a, e
 
     def params():

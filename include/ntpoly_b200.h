@@ -352,6 +352,11 @@ double ntb_tile_combines(void);
 /* output columns of local products served by the shared-memory hash accumulator (scattered patterns: wide row window,
  * few products) since the reset; NTB_HASH_BIN=0 in the environment sends them back to the window kernels */
 double ntb_hash_columns(void);
+/* complex local products that ran on the FP64 tensor-core tile path since the reset: a complex product C = A*B is one
+ * real tile product of the embeddings A^ = [[Re A, -Im A], [Im A, Re A]] (rows and columns interleaved) and
+ * B^ = (Re B; Im B) (rows interleaved) - the reference's ZGEMM dense branch (DMatrixModule.F90:517-593) at tile
+ * granularity; NTB_COMPLEX_TILE=0 in the environment keeps complex products on the scalar window / hash kernels */
+double ntb_complex_tile_products(void);
 /* C = alpha*A*B (thresholded), then IncrementMatrix(Identity, C, sigma) with threshold 0 — the call pair of
  * SignSolversModule.F90:226-229 / SquareRootSolversModule.F90 as one entry point. */
 void ntb_MatrixMultiplyShift_ps(const int *ih_matA, const int *ih_matB, int *ih_matC, const double *alpha,

@@ -77,7 +77,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_StageArrays ntb_FillMatrixFromStaged_ps ntb_sorted_ingests ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_set_fused_shift ntb_get_halo_counters ntb_get_peer_counters ntb_measure_dmma_peak_tflops ntb_get_sync_count ntb_profile_read_phases ntb_set_halo_path ntb_set_permute_gemm ntb_TileCombine_ps ntb_TileScalars_ps ntb_set_fused_steps ntb_tile_combines ntb_hash_columns ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_set_fused_shift ntb_get_halo_counters ntb_get_peer_counters ntb_measure_dmma_peak_tflops ntb_get_sync_count ntb_profile_read_phases ntb_set_halo_path ntb_set_permute_gemm ntb_TileCombine_ps ntb_TileScalars_ps ntb_set_fused_steps ntb_tile_combines ntb_hash_columns ntb_complex_tile_products ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -106,6 +106,7 @@ def lib():
         L.ntb_get_sync_count.restype = c_double
         L.ntb_tile_combines.restype = c_double
         L.ntb_hash_columns.restype = c_double
+        L.ntb_complex_tile_products.restype = c_double
         L.ntb_set_stream.argtypes = [c_void_p]
         L.ntb_world_init.argtypes = [c_int, c_int, c_void_p]
         L.ntb_nccl_unique_id.argtypes = [c_void_p]
@@ -999,6 +1000,10 @@ def hash_columns():
     return int(lib().ntb_hash_columns())
 
 
+def complex_tile_products():
+    return int(lib().ntb_complex_tile_products())
+
+
 def tile_combines():
     return int(lib().ntb_tile_combines())
 
@@ -1074,7 +1079,8 @@ def profile_read():
 def profile_read_phases():
     out = (c_double * 8)()
     lib().ntb_profile_read_phases(out)
-    return {"symbolic_ms": float(out[0]), "tail_ms": float(out[2]), "scalars_ms": float(out[3]), "combine_ms": float(out[4])}
+    return {"symbolic_ms": float(out[0]), "tail_ms": float(out[2]), "scalars_ms": float(out[3]), "combine_ms": float(out[4]),
+            "panel_gather_ms": float(out[5]), "operand_tile_build_ms": float(out[6]), "slice_sum_ms": float(out[7])}
 
 
 def last_solve():

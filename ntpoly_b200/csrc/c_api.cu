@@ -384,7 +384,7 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().syncs = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().tile_combines = 0; rt().hash_columns = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().peer_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().syncs = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().tile_combines = 0; rt().hash_columns = 0; rt().complex_tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().peer_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
 // C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when
@@ -442,6 +442,7 @@ void ntb_set_permute_gemm(int on) { ntb::set_permute_gemm(on); }
 void ntb_set_fused_steps(int on) { ntb::set_fused_steps(on); }
 double ntb_tile_combines(void) { return (double)rt().tile_combines; }
 double ntb_hash_columns(void) { return (double)rt().hash_columns; }
+double ntb_complex_tile_products(void) { return (double)rt().complex_tile_products; }
 double ntb_algorithmic_bytes(void) { return rt().alg_bytes; }
 void ntb_profile_enable(int on) { ensure_init(); rt().profile = on != 0; }
 void ntb_profile_read(double* out2) {

@@ -1312,6 +1312,7 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
     // every path below except the single-rank tile product reads the CSC entries of both operands
     if (S > 1 || comm_size(g.row) > 1 || comm_size(g.column) > 1 || nI > 1) { Al.ensure_entries(); Bl.ensure_entries(); }
     // ---- A task: my slice's column blocks, gathered along the process row (:94-145)
+    std::unique_ptr<PhaseScope> ph_gather(new PhaseScope(5));     // slice selection, panel gathers, stacking
     LocalCsc<T> Asel, Ypanel;
     const LocalCsc<T>* Ysrc = &Al;
     if (S > 1) { csc_select_col_blocks<T>(Al.view(), cb, S, g.my_slice, Asel); Ysrc = &Asel; }
@@ -1330,6 +1331,7 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
       Xsrc = &Xpanel;
     }
     NTB_CHECK(Ysrc->cols == Xsrc->rows, "multiply: gathered panels disagree on the inner dimension");
+    ph_gather.reset();
     {
       const double inner_dim = (double)Xsrc->rows;
       std::vector<double> cnt, fa(nI), fb;
@@ -1352,7 +1354,10 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
   rt().multiplies++;
 
   // ---- between-slice sum (:234-261)
-  if (S > 1) reduce_and_sum<T>(loc<T>(AB), g.between_slice, threshold, rb);
+  if (S > 1) {
+    PhaseScope ph_sum(7);
+    reduce_and_sum<T>(loc<T>(AB), g.between_slice, threshold, rb);
+  }
 
   // ---- C = AB  or  C = beta*C + AB (:324-329)
   if (std::fabs(beta) < 2.2250738585072014e-308 || !C.constructed) {

@@ -265,6 +265,119 @@ k_numeric_cta(CscView<T> X, CscView<T> Y, const int* __restrict__ list, const in
 
 
 // ---------------------------------------------------------------------------
+// bins 5/6, HEAVY columns (many products into a wide window: the iterates of graph-like / permuted matrices, c5): the
+// k loop of k_numeric_cta is serial with a block-wide barrier per k, which leaves the CTA idle when the Y columns
+// are short (25 entries under 256 threads) or when there are thousands of k. Here every warp takes 32 consecutive k at
+// a time (coalesced loads of the X entries and of the Y column bounds) and sends its products to the accumulator window
+// with floating-point atomic adds (RED.ADD.F64 in L2 for the global slab, shared-memory atomics for bin 5). The sum of
+// an entry is then formed in arrival order instead of k-ascending order: still within rounding of the reference (the
+// parity bound is 1e-10 relative), but no longer bit-reproducible from run to run for these columns -
+// NTB_ATOMIC_BINS=0 selects the serial kernel. The ordered sweep (threshold rule, alpha, sorted emit) is unchanged.
+// (global slab: RED.E.ADD.F64 - a reduction without a return value, so the warp does not wait for the round trip to L2;
+// atomicAdd() with an unused result still compiled to ATOMG here)
+template <bool GLOBAL> __device__ __forceinline__ void acc_add1(double* a, double v) {
+  if (GLOBAL) asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
+  else atomicAdd(a, v);
+}
+template <bool GLOBAL> __device__ __forceinline__ void acc_add(double* a, double v) { acc_add1<GLOBAL>(a, v); }
+template <bool GLOBAL> __device__ __forceinline__ void acc_add(cplx* a, cplx v) { acc_add1<GLOBAL>(&a->x, v.x); acc_add1<GLOBAL>(&a->y, v.y); }
+__device__ __forceinline__ double ld_acc(const double* a, bool global) { return global ? __ldcg(a) : *a; }
+__device__ __forceinline__ cplx ld_acc(const cplx* a, bool global) {
+  if (!global) return *a;
+  const double2 t = __ldcg(reinterpret_cast<const double2*>(a));
+  return cplx{t.x, t.y};
+}
+template <typename T, bool GLOBAL_SLAB>
+__global__ void __launch_bounds__(CTA_T)
+k_numeric_cta_atomic(CscView<T> X, CscView<T> Y, const int* __restrict__ list, const int* __restrict__ nlist_p,
+                     const int* __restrict__ lo, const int* __restrict__ wid, const long long* __restrict__ tmp_off,
+                     double alpha, double thr, RuleView rules, int* __restrict__ tmp_idx, T* __restrict__ tmp_val,
+                     int* __restrict__ cnt, T* __restrict__ slab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_warp_cnt[CTA_T / 32];
+  __shared__ int s_running;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nlist = *nlist_p;
+  for (int li = blockIdx.x; li < nlist; li += gridDim.x) {
+    const int j = list[li];
+    const int base = lo[j];
+    const int w = wid[j];
+    T* acc = GLOBAL_SLAB ? (slab + (size_t)blockIdx.x * Y.rows + base) : reinterpret_cast<T*>(smem_raw);
+    if (!GLOBAL_SLAB) {
+      for (int t = threadIdx.x; t < w; t += CTA_T) acc[t] = zero_of<T>();
+    }
+    __syncthreads();
+    const int xs = X.outer[j], xe = X.outer[j + 1];
+    for (int p0 = xs + warp * 32; p0 < xe; p0 += CTA_T) {
+      const int p = p0 + lane;
+      int ys = 0, ye = 0;
+      T xv = zero_of<T>();
+      if (p < xe) {
+        const int k = X.inner[p];
+        xv = X.val[p];
+        ys = Y.outer[k];
+        ye = Y.outer[k + 1];
+      }
+      const int nv = min(32, xe - p0);
+      // short Y columns (<= 16 entries on average): one lane per X entry walks its own column (no idle lanes);
+      // otherwise the warp strides over one column at a time
+      const int total = __reduce_add_sync(0xffffffffu, ye - ys);
+      if (total <= 16 * nv) {
+        for (int q = ys; q < ye; ++q) acc_add<GLOBAL_SLAB>(&acc[Y.inner[q] - base], s_mul(Y.val[q], xv));
+      } else {
+        for (int t = 0; t < nv; ++t) {
+          const int s0 = shfl(ys, t), e0 = shfl(ye, t);
+          const T b = shfl(xv, t);
+          for (int q = s0 + lane; q < e0; q += 32) acc_add<GLOBAL_SLAB>(&acc[Y.inner[q] - base], s_mul(Y.val[q], b));
+        }
+      }
+    }
+    if (GLOBAL_SLAB) __threadfence();
+    __syncthreads();
+    // ordered sweep in two passes without block-wide barriers in the loops: warp w owns the contiguous rows
+    // [w*seg, (w+1)*seg) of the window, counts its kept entries (independent loads, nothing serialises them), the
+    // eight counts are prefixed once, and the second pass re-reads the segment (L2 / shared memory), emits in row
+    // order at the warp's offset and clears the slab. (One barrier per 256 rows held the sweep of a 32768-row window
+    // at ~200 us per column - more than the products of a column with a few thousand of them.)
+    const long long off = tmp_off[j];
+    const int seg = ((w + CTA_T - 1) / CTA_T) * 32;
+    const int r0 = min(w, warp * seg), r1 = min(w, r0 + seg);
+    auto kept = [&](int t, T& sv) {
+      const T v = ld_acc(&acc[t], GLOBAL_SLAB);
+      sv = s_scale(alpha, v);
+      return keep_entry(s_abs(sv), s_abs(v), thr, rule_for(rules, base + t, j));
+    };
+    int mine = 0;
+    for (int t = r0 + lane; t < r1; t += 32) { T sv; mine += kept(t, sv) ? 1 : 0; }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) s_warp_cnt[warp] = mine;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int ww = 0; ww < CTA_T / 32; ++ww) { const int c = s_warp_cnt[ww]; total += c; if (ww < warp) before += c; }
+    for (int t0 = r0; t0 < r1; t0 += 32) {
+      const int t = t0 + lane;
+      bool keep = false;
+      T sv = zero_of<T>();
+      if (t < r1) {
+        keep = kept(t, sv);
+        if (GLOBAL_SLAB) acc[t] = zero_of<T>();
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const long long pos = off + before + __popc(m & ((1u << lane) - 1));
+        tmp_idx[pos] = base + t;
+        tmp_val[pos] = sv;
+      }
+      before += __popc(m);
+    }
+    if (threadIdx.x == 0) s_running = total;
+    if (threadIdx.x == 0) cnt[j] = s_running;
+    if (GLOBAL_SLAB) __threadfence();
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // bin 7: one warp per output column, hash accumulator in shared memory. Four phases, all deterministic:
 //   A  symbolic: the rows of every Y(:,k), k in X(:,j), are inserted into an open-addressing table (keys only);
 //   B  the distinct rows are compacted, sorted (bitonic, in shared memory) and every table slot learns the RANK of
@@ -440,6 +553,135 @@ double useful_products_from_lengths(const LocalCsc<double>& X, const int* d_ylen
 }
 
 // ---------------------------------------------------------------------------
+// COMPLEX128 ON THE FP64 TENSOR CORES (the reference's ZGEMM dense branch, DMatrixModule.F90:517-593, at tile
+// granularity). A complex product C = A*B is ONE real product of twice the size with exactly the 8 real flops per
+// complex multiply-add that the arithmetic needs - no 2x redundancy as with the full real embedding of both operands:
+//     B^ = rows (2k, 2k+1) <- (Re, Im) of row k of B                           (2n x m, "stacked" form)
+//     A^ = [[Re A, -Im A], [Im A, Re A]] with rows AND columns interleaved     (2n x 2n, embedded form)
+//     C^ = A^ * B^ = stacked form of C:  C^(2i,j) = Re C(i,j),  C^(2i+1,j) = Im C(i,j)
+// The interleaving keeps a complex 4x2 block inside one real 8x4 tile, so locally dense complex blocks (filled-in
+// exponentials / inverses, banded or block-sparse Hermitian matrices) fill the tiles of k_tile_numeric9 as well as real
+// ones do. The real product runs with threshold 0 (it keeps every non-zero); the reference's rule on the COMPLEX
+// magnitude (|alpha*v| > thr, or |v| > thr under the dense-block rule) is applied when the pairs are zipped back.
+__global__ void __launch_bounds__(256) k_embed_right(CscView<cplx> X, long long nnz, int* __restrict__ outer_h,
+                                                     int* __restrict__ inner_h, double* __restrict__ val_h) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
+    const int k = X.inner[p];
+    const cplx v = X.val[p];
+    *reinterpret_cast<int2*>(inner_h + 2 * p) = make_int2(2 * k, 2 * k + 1);
+    *reinterpret_cast<double2*>(val_h + 2 * p) = make_double2(v.x, v.y);
+  }
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j <= X.cols; j += stride) outer_h[j] = 2 * X.outer[j];
+}
+// one warp per column k of Y: real columns 2k = (Re, Im) and 2k+1 = (-Im, Re)
+__global__ void __launch_bounds__(256) k_embed_left(CscView<cplx> Y, int* __restrict__ outer_h, int* __restrict__ inner_h,
+                                                    double* __restrict__ val_h) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int k = gw; k < Y.cols; k += nw) {
+    const int s = Y.outer[k], e = Y.outer[k + 1];
+    const long long b0 = 4ll * s, b1 = 2ll * s + 2ll * e;
+    if (lane == 0) { outer_h[2 * k] = (int)b0; outer_h[2 * k + 1] = (int)b1; if (k == Y.cols - 1) outer_h[2 * k + 2] = 4 * e; }
+    for (int p = s + lane; p < e; p += 32) {
+      const int i = Y.inner[p];
+      const cplx a = Y.val[p];
+      const long long q = 2ll * (p - s);
+      *reinterpret_cast<int2*>(inner_h + b0 + q) = make_int2(2 * i, 2 * i + 1);
+      *reinterpret_cast<double2*>(val_h + b0 + q) = make_double2(a.x, a.y);
+      *reinterpret_cast<int2*>(inner_h + b1 + q) = make_int2(2 * i, 2 * i + 1);
+      *reinterpret_cast<double2*>(val_h + b1 + q) = make_double2(-a.y, a.x);
+    }
+  }
+}
+// stacked real result -> complex CSC with the threshold rule on the complex magnitude. One warp per column; an entry of
+// the real column opens a complex entry when its predecessor belongs to another complex row. FILL=false counts.
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_zip_complex(CscView<double> Zh, double alpha, double thr, RuleView rules,
+                                                     int* __restrict__ cnt, const int* __restrict__ outer,
+                                                     int* __restrict__ inner, cplx* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int j = gw; j < Zh.cols; j += nw) {
+    const int s = Zh.outer[j], e = Zh.outer[j + 1];
+    int count = 0;
+    const int dst = FILL ? outer[j] : 0;
+    for (int p0 = s; p0 < e; p0 += 32) {
+      const int p = p0 + lane;
+      bool keep = false;
+      int row = 0;
+      cplx v = cplx{0.0, 0.0};
+      if (p < e) {
+        const int r = Zh.inner[p];
+        const bool head = (p == s) || ((Zh.inner[p - 1] >> 1) != (r >> 1));
+        if (head) {
+          row = r >> 1;
+          if (r & 1) v.y = Zh.val[p];
+          else {
+            v.x = Zh.val[p];
+            if (p + 1 < e && Zh.inner[p + 1] == r + 1) v.y = Zh.val[p + 1];
+          }
+          const cplx sv = s_scale(alpha, v);
+          keep = keep_entry(s_abs(sv), s_abs(v), thr, rule_for(rules, row, j));
+          v = sv;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (FILL && keep) {
+        const int pos = dst + count + __popc(m & ((1u << lane) - 1));
+        inner[pos] = row;
+        val[pos] = v;
+      }
+      count += __popc(m);
+    }
+    if (!FILL && lane == 0) cnt[j] = count;
+  }
+}
+
+static bool complex_tile_enabled() {
+  static const bool on = [] { const char* e = std::getenv("NTB_COMPLEX_TILE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+// C = A*B for complex blocks through the real tile product of the embeddings; false = declined (scattered pattern, too
+// large for 32-bit entry counts, tile path off) - the caller then runs the scalar window / hash kernels
+static bool spgemm_complex_tiles(const LocalCsc<cplx>& Xl, const LocalCsc<cplx>& Yl, double alpha, double thr,
+                                 const RuleView& rules, LocalCsc<cplx>& Z, double useful_products) {
+  const long long nx = Xl.nnz, ny = Yl.nnz;
+  if (nx <= 0 || ny <= 0 || 4 * ny >= (1ll << 31) || 2 * nx >= (1ll << 31) || Yl.rows >= (1 << 30) || Yl.cols >= (1 << 30)) return false;
+  const CscView<cplx> X = Xl.view(), Y = Yl.view();
+  LocalCsc<double> Xh, Yh, Zh;
+  Xh.rows = 2 * Xl.rows; Xh.cols = Xl.cols;
+  Xh.outer.alloc((size_t)Xl.cols + 1);
+  Xh.alloc_entries(2 * nx);
+  NTB_LAUNCH(k_embed_right, min(div_up(nx, 256 * 4), kNumSMs * 16), 256, 0, X, nx, Xh.outer.get(), Xh.inner.get(), Xh.val.get());
+  Yh.rows = 2 * Yl.rows; Yh.cols = 2 * Yl.cols;
+  Yh.outer.alloc((size_t)2 * Yl.cols + 1);
+  Yh.alloc_entries(4 * ny);
+  NTB_LAUNCH(k_embed_left, max(1, min(div_up((long long)Yl.cols * 32, 256), kNumSMs * 16)), 256, 0, Y, Yh.outer.get(), Yh.inner.get(),
+             Yh.val.get());
+  // 4 real products per complex one; threshold 0 keeps every non-zero of the real product
+  if (!spgemm_tile(Xh, Yh, 1.0, 0.0, RuleView{}, Zh, 4.0 * useful_products, nullptr, WANT_CSC)) return false;
+  const int ncols = Xl.cols;
+  const CscView<double> Zv = Zh.view();
+  Z.rows = Yl.rows;
+  Z.cols = ncols;
+  Z.outer.alloc((size_t)ncols + 1);
+  DevBuf<int> cnt((size_t)ncols);
+  const int blocks = max(1, min(div_up((long long)ncols * 32, 256), kNumSMs * 16));
+  NTB_LAUNCH((k_zip_complex<false>), blocks, 256, 0, Zv, alpha, thr, rules, cnt.get(), (const int*)nullptr, (int*)nullptr, (cplx*)nullptr);
+  exclusive_scan(cnt.get(), Z.outer.get(), ncols);
+  int h_nnz = 0;
+  d2h(&h_nnz, Z.outer.get() + ncols, 1);
+  Z.alloc_entries(h_nnz);
+  if (h_nnz > 0)
+    NTB_LAUNCH((k_zip_complex<true>), blocks, 256, 0, Zv, alpha, thr, rules, (int*)nullptr, Z.outer.get(), Z.inner.get(), Z.val.get());
+  rt().complex_tile_products++;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 template <typename T>
 void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double thr, const RuleView& rules,
             LocalCsc<T>& Z, GemmStats* stats, const DiagShift* shift, unsigned want) {
@@ -506,6 +748,26 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
     }
   }
 
+  // ---- complex operands: the same tile path through the real embeddings when the blocks are locally dense
+  if constexpr (scalar_traits<T>::is_complex) {
+    if (tile_path_enabled() && complex_tile_enabled() && Xl.nnz > 0 && Yl.nnz > 0 && !(shift && shift->sigma != 0.0)) {
+      DevBuf<unsigned long long> fl(1);
+      fl.zero();
+      NTB_LAUNCH((k_useful_products<T>), min(div_up(Xl.nnz, 256 * 8), kNumSMs * 16), 256, 0, X, Y, Xl.nnz, fl.get());
+      unsigned long long h_fl = 0;
+      d2h(&h_fl, fl.get(), 1);
+      // worth it only when columns are long enough to fill tiles
+      if ((double)h_fl >= 16.0 * (double)ncols && spgemm_complex_tiles(Xl, Yl, alpha, thr, rules, Z, (double)h_fl)) {
+        if (stats) { stats->flops = 8.0 * (double)h_fl; stats->tmp_entries = 0; }
+        account_bytes(Z.nnz);
+        return;
+      }
+      Z.rows = nrows;
+      Z.cols = ncols;
+      Z.outer.alloc((size_t)ncols + 1);
+    }
+  }
+
   DevBuf<int> lo(ncols), wid(ncols), cap(ncols), binid(ncols), cnt(ncols);
   DevBuf<int> lists((size_t)NBINS * ncols);
   DevBuf<int> bin_count(NBINS);
@@ -560,12 +822,20 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
                bin_count.get() + b, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
                tmp_val.get(), cnt.get(), cfg.wmax[b]);
   }
+  static const bool atomic_bins = [] { const char* e = std::getenv("NTB_ATOMIC_BINS"); return !(e && e[0] == '0'); }();
   if (h_bins[5] > 0) {
-    CUDA_CHECK(cudaFuncSetAttribute((k_numeric_cta<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     int blocks = min(h_bins[5], kNumSMs * 4);
-    NTB_LAUNCH((k_numeric_cta<T, false>), blocks, CTA_T, SMEM_BUDGET, X, Y, lists.get() + (size_t)5 * ncols,
-               bin_count.get() + 5, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
-               tmp_val.get(), cnt.get(), (T*)nullptr);
+    if (atomic_bins) {
+      CUDA_CHECK(cudaFuncSetAttribute((k_numeric_cta_atomic<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+      NTB_LAUNCH((k_numeric_cta_atomic<T, false>), blocks, CTA_T, SMEM_BUDGET, X, Y, lists.get() + (size_t)5 * ncols,
+                 bin_count.get() + 5, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
+                 tmp_val.get(), cnt.get(), (T*)nullptr);
+    } else {
+      CUDA_CHECK(cudaFuncSetAttribute((k_numeric_cta<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+      NTB_LAUNCH((k_numeric_cta<T, false>), blocks, CTA_T, SMEM_BUDGET, X, Y, lists.get() + (size_t)5 * ncols,
+                 bin_count.get() + 5, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
+                 tmp_val.get(), cnt.get(), (T*)nullptr);
+    }
   }
   if (h_bins[7] > 0) {
     const size_t smem = sizeof(HashSmem<T>) * HASH_WARPS;
@@ -577,12 +847,19 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   }
   DevBuf<T> slab;
   if (h_bins[6] > 0) {
-    int blocks = min(h_bins[6], kNumSMs * 2);
+    // the slabs of all resident CTAs should stay in L2 (126 MB): at most ~96 MB of accumulator windows
+    const long long l2_fit = max(1ll, (96ll << 20) / ((long long)nrows * (long long)sizeof(T)));
+    int blocks = (int)min((long long)min(h_bins[6], kNumSMs * 4), atomic_bins ? max((long long)kNumSMs, l2_fit) : (long long)kNumSMs * 2);
     slab.alloc((size_t)blocks * nrows);
     slab.zero();
-    NTB_LAUNCH((k_numeric_cta<T, true>), blocks, CTA_T, 0, X, Y, lists.get() + (size_t)6 * ncols,
-               bin_count.get() + 6, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
-               tmp_val.get(), cnt.get(), slab.get());
+    if (atomic_bins)
+      NTB_LAUNCH((k_numeric_cta_atomic<T, true>), blocks, CTA_T, 0, X, Y, lists.get() + (size_t)6 * ncols,
+                 bin_count.get() + 6, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
+                 tmp_val.get(), cnt.get(), slab.get());
+    else
+      NTB_LAUNCH((k_numeric_cta<T, true>), blocks, CTA_T, 0, X, Y, lists.get() + (size_t)6 * ncols,
+                 bin_count.get() + 6, lo.get(), wid.get(), tmp_off.get(), alpha, thr, rules, tmp_idx.get(),
+                 tmp_val.get(), cnt.get(), slab.get());
   }
 
   if (rt().profile) {

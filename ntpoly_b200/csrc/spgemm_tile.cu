@@ -194,6 +194,7 @@ k_ct_build(CscView<double> M, int ncc, int* __restrict__ scount, int* __restrict
 template <bool ISA>
 static bool build_chunk_tiles(const CscView<double>& M, ChunkTiles& T) {
   using G = CtGeom<ISA>;
+  PhaseScope ph_build(6);                    // CSC -> tile form of an operand that carries none (first use, gathered panel)
   T.emitted = false;
   T.ncc = div_up(M.cols, G::CW);
   const int ncc = T.ncc;
@@ -439,6 +440,17 @@ __device__ __forceinline__ void ct_pair(const int4& ea, const int4& eb, int Ib, 
 // second pass; the next product reads these forms as they are.
 constexpr int META9 = 128;
 constexpr int numeric_smem9(int nstage) { return nstage * STAGE_BYTES + nstage * META9 + 2 * nstage * 8; }
+// BYTE-GRANULAR RING (template parameter RING): the stage descriptors and barriers live in RING_SLOTS slots of their
+// own, the tiles in one circular buffer of RING_BYTES from which every stage takes exactly the bytes of its two tile
+// spans. A band-edge stage holds ~20 of 64 tiles per operand, so the same shared memory keeps 6-8 stages in flight
+// instead of 3: the bulk copies of short stages are issued several stage times ahead (the DMMA warps spent 9 % of
+// their samples waiting for a full barrier with the 3 x 32 KB ring, profiles/r02a_numeric_source_top.txt), and the
+// eight DMMA warps of a CTA may drift up to RING_SLOTS stages apart, which evens out the unequal work of the tile
+// columns at a band edge. +128 of a slot's descriptor: int2 {byte offset of the A span, of the B span} in the buffer.
+constexpr int RING_SLOTS = 8;
+constexpr int RING_BYTES = 110 * 1024;
+constexpr int META_RING = 144;
+constexpr int numeric_smem_ring() { return RING_BYTES + RING_SLOTS * META_RING + 2 * RING_SLOTS * 8; }
 // where the strip of a task goes
 struct ResultForms {
   int4* entL; double* tvalL;                 // left form: slot s <-> entry s, tiles s*64 ...
@@ -510,14 +522,17 @@ __device__ __forceinline__ void emit_strip(double (&acc)[8][2], unsigned km, int
     mL[1] = (unsigned char)((bL >> 8) & 0xffu);
   }
 }
-template <int NSTAGE, int MINB, int DENSE>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block
+template <int NSTAGE_, int MINB, int DENSE, bool RING = false>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
 k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
                 int* __restrict__ task_counter, int* __restrict__ cnt, ResultForms out, int nrows, int ncols, EmitSpec es) {
+  constexpr int NSTAGE = RING ? RING_SLOTS : NSTAGE_;                       // descriptor slots / barrier pairs
+  constexpr int MSZ = RING ? META_RING : META9;
+  constexpr int DATA_BYTES = RING ? RING_BYTES : NSTAGE_ * STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem[];
   double* slab = reinterpret_cast<double*>(smem);
-  unsigned char* meta = smem + NSTAGE * STAGE_BYTES;
-  const unsigned bar0 = smem_u32(smem + NSTAGE * STAGE_BYTES + NSTAGE * META9);   // full[s] at +8s, empty[s] at +8(NSTAGE+s)
+  unsigned char* meta = smem + DATA_BYTES;
+  const unsigned bar0 = smem_u32(smem + DATA_BYTES + NSTAGE * MSZ);   // full[s] at +8s, empty[s] at +8(NSTAGE+s)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * (NSTAGE + s), CW); }
@@ -541,6 +556,11 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
     int offA_n = 0, offB_n = 0;
     int pc_n = 0;                                    // piece (rank of the process row) that holds this lane's A super-tile
     int gt0_n = 0, gt1_n = 0;
+    // byte ring (RING): next free byte, bytes in flight (padding at the wrap included), oldest slot in flight, slots in
+    // flight, parity of the empty barrier that releases the use in flight of every slot; lane l < RING_SLOTS keeps the
+    // bytes charged to slot l
+    unsigned rg_head = 0, rg_used = 0, rg_par = 0, rg_mine = 0;
+    int rg_tail = 0, rg_nout = 0;
     auto advance = [&]() {
       switch (pstep) {
         case 0: {
@@ -625,15 +645,27 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
         unsigned todo = __ballot_sync(0xffffffffu, mA != 0ull);
         const bool final_batch = (bb == nb - 1);
         if (todo == 0u && final_batch) todo = 1u;
+        // Everything about a stage that depends only on ITS OWN pair of masks is computed here by the lane that looked
+        // the pair up - 32 stages at once instead of once per stage by the whole warp: span and first group of both
+        // super-tiles, the bytes of the two bulk copies, their source addresses. (The copy warp is a single warp whose
+        // per-stage instruction count bounds how fast short band-edge stages can be handed out: with ~270 instructions
+        // per stage the DMMA warps spent 9 % of their samples waiting for a full barrier whatever the depth of the
+        // ring, profiles/r02a_numeric_source_top.txt and the byte-ring A/B of round 2.) The lane then also issues the
+        // copies of its stage itself; only the two masks and the first groups travel by shuffle.
+        const int gfA_l = first_group(mA), gfB_l = first_group(mB);
+        const unsigned bA_l = (unsigned)span_tiles(mA) * 256u, bB_l = (unsigned)span_tiles(mB) * 256u;
+        const unsigned flags_l = ((mA == ~0ull) ? 4u : 0u) | (nonzero_bytes(mA) << 8);
+        const double* srcA_l = lv_tile_ptr(A, pc, (long long)offA + 8 * gfA_l);
+        const double* srcB_l = B.tval + ((long long)offB + 8 * gfB_l) * 32;
+        const int gf_l = gfA_l | (gfB_l << 3);
         while (todo) {
           const int l = __ffs(todo) - 1;
           todo &= todo - 1;
           const bool last = final_batch && todo == 0u;
           const unsigned long long sA = __shfl_sync(0xffffffffu, mA, l), sB = __shfl_sync(0xffffffffu, mB, l);
-          const int oA = __shfl_sync(0xffffffffu, offA, l), oB = __shfl_sync(0xffffffffu, offB, l);
-          const int pA = __shfl_sync(0xffffffffu, pc, l);
+          const int gf = __shfl_sync(0xffffffffu, gf_l, l);
+          const int gfA = gf & 7, gfB = gf >> 3;
           // digest the masks while the slot may still be busy
-          const int gfA = first_group(sA), gfB = first_group(sB);
           unsigned desc = 0;
           if (lane < 8) {
             const unsigned ma = (unsigned)(sA >> (8 * lane)) & 0xffu;
@@ -651,24 +683,43 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
           const unsigned bbyte = (unsigned)(sB >> (8 * (lane >> 2))) & 0xffu;
           const unsigned b0 = (unsigned)(8 * ((lane >> 2) - gfB)) + (unsigned)__popc(bbyte & ((1u << (2 * (lane & 3))) - 1u));
           const unsigned b1 = b0 + ((bbyte >> (2 * (lane & 3))) & 1u);
-          const unsigned nzA = nonzero_bytes(sA);
-          mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
-          unsigned char* mt = meta + st * META9;
+          unsigned roff = 0;
+          if (RING) {
+            // room for bA + bB contiguous bytes and a free slot: release the oldest stages in flight until there is
+            const unsigned need = __shfl_sync(0xffffffffu, bA_l + bB_l, l);
+            bool wrap = rg_head + need > (unsigned)RING_BYTES;             // (the head may sit exactly at the end: pad 0)
+            unsigned pad = wrap ? (unsigned)RING_BYTES - rg_head : 0u;
+            while (rg_nout == NSTAGE || rg_used + pad + need > (unsigned)RING_BYTES) {
+              mbar_wait(bar0 + 8 * (NSTAGE + rg_tail), (rg_par >> rg_tail) & 1u);
+              rg_par ^= 1u << rg_tail;
+              rg_used -= __shfl_sync(0xffffffffu, rg_mine, rg_tail);
+              rg_tail = (rg_tail + 1 == NSTAGE) ? 0 : rg_tail + 1;
+              if (--rg_nout == 0) { rg_head = 0; rg_used = 0; pad = 0; wrap = false; }
+            }
+            if (wrap) rg_head = 0;
+            roff = rg_head;
+            rg_head += need;
+            rg_used += pad + need;
+            if (lane == st) rg_mine = pad + need;
+            ++rg_nout;
+          } else {
+            mbar_wait(bar0 + 8 * (NSTAGE + st), ph ^ 1u);        // consumers have released this slot
+          }
+          unsigned char* mt = meta + st * MSZ;
           if (lane < 8) reinterpret_cast<unsigned*>(mt + 16)[lane] = desc;
           reinterpret_cast<unsigned short*>(mt + 64)[lane] = (unsigned short)((b0 & 0xffu) | ((b1 & 0xffu) << 8));
-          if (lane == 0) {
-            *reinterpret_cast<unsigned long long*>(mt + 48) = sB;
+          if (lane == l) {
+            if (RING) *reinterpret_cast<int2*>(mt + 128) = make_int2((int)roff, (int)(roff + bA_l));
+            *reinterpret_cast<unsigned long long*>(mt + 48) = mB;
             *reinterpret_cast<int2*>(mt + 56) = make_int2(gt0, gtn);
-            *reinterpret_cast<int4*>(mt) = make_int4((int)((last ? 1u : 0u) | (done ? 2u : 0u) | ((sA == ~0ull) ? 4u : 0u) | (nzA << 8)),
-                                                     g, Ib, task);
+            *reinterpret_cast<int4*>(mt) = make_int4((int)((last ? 1u : 0u) | (done ? 2u : 0u) | flags_l), g, Ib, task);
           }
           __syncwarp();                                        // the other lanes' meta stores happen before the arrive
-          if (lane == 0) {
-            const unsigned bA = (unsigned)span_tiles(sA) * 256u, bB = (unsigned)span_tiles(sB) * 256u;
-            mbar_arrive_expect_tx(bar0 + 8 * st, bA + bB);
-            const unsigned slab_s = smem_u32(slab + (size_t)st * STAGE_DOUBLES);
-            if (bA) bulk_g2s(slab_s, lv_tile_ptr(A, pA, (long long)oA + 8 * gfA), bA, bar0 + 8 * st);
-            if (bB) bulk_g2s(slab_s + SLAB_DOUBLES * 8, B.tval + ((long long)oB + 8 * gfB) * 32, bB, bar0 + 8 * st);
+          if (lane == l) {
+            mbar_arrive_expect_tx(bar0 + 8 * st, bA_l + bB_l);
+            const unsigned slab_s = RING ? smem_u32(smem) + roff : smem_u32(slab + (size_t)st * STAGE_DOUBLES);
+            if (bA_l) bulk_g2s(slab_s, srcA_l, bA_l, bar0 + 8 * st);
+            if (bB_l) bulk_g2s(slab_s + (RING ? bA_l : (unsigned)SLAB_DOUBLES * 8u), srcB_l, bB_l, bar0 + 8 * st);
           }
           __syncwarp();
           if (++st == NSTAGE) { st = 0; ph ^= 1u; }
@@ -692,8 +743,11 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
     int gt0 = 0, gtn = 0;
     do {
       mbar_wait(bar0 + 8 * st, ph);
-      const unsigned char* mt = meta + st * META9;
+      const unsigned char* mt = meta + st * MSZ;
       const int4 mi = *reinterpret_cast<const int4*>(mt);
+      // the stage's A span and B span (doubles from the start of shared memory)
+      int offAd = st * STAGE_DOUBLES, offBd = st * STAGE_DOUBLES + SLAB_DOUBLES;
+      if (RING) { const int2 ro = *reinterpret_cast<const int2*>(mt + 128); offAd = ro.x >> 3; offBd = ro.y >> 3; }
       fl = (unsigned)mi.x & 0xffu; g = mi.y; Ib = mi.z; task = mi.w;
       { const int2 gt = *reinterpret_cast<const int2*>(mt + 56); gt0 = gt.x; gtn = gt.y; }
       const unsigned mb = mt[48 + wj];
@@ -705,8 +759,8 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
         // DMMAs need no mask arithmetic, no branches and no per-tile address chain (the generic loop below spends
         // ~13 instructions per DMMA, this block ~2), and ptxas is free to hoist the loads of the next inner tile
         // above the DMMAs of the current one. Same accumulation order as the generic loop: bit-identical results.
-        const double* Ad = slab + (size_t)st * STAGE_DOUBLES + lane;
-        const double* Bd = Ad + SLAB_DOUBLES + (unsigned)mt[64 + 8 * wj] * 32;
+        const double* Ad = slab + offAd + lane;
+        const double* Bd = slab + offBd + lane + (unsigned)mt[64 + 8 * wj] * 32;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const double bv = Bd[kk * 32];
@@ -718,8 +772,8 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
         // compile-time offsets from one pointer that advances by a constant; only the B tile index comes from the stage
         // descriptor. One short non-unrolled loop over the present inner tiles.
         const unsigned long long bo = *reinterpret_cast<const unsigned long long*>(mt + 64 + 8 * wj);
-        const double* Ad = slab + (size_t)st * STAGE_DOUBLES + lane;
-        const double* Bd = Ad + SLAB_DOUBLES;
+        const double* Ad = slab + offAd + lane;
+        const double* Bd = slab + offBd + lane;
 #pragma unroll 1
         for (int kk = 0; (mb >> kk) != 0u; ++kk, Ad += 8 * 32) {
           if (((mb >> kk) & 1u) == 0u) continue;
@@ -730,8 +784,8 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
       } else if (live != 0u) {
         const unsigned long long bo = *reinterpret_cast<const unsigned long long*>(mt + 64 + 8 * wj);
         const unsigned* adesc = reinterpret_cast<const unsigned*>(mt + 16);
-        const double* As = slab + (size_t)st * STAGE_DOUBLES + lane;
-        const double* Bs = As + SLAB_DOUBLES;
+        const double* As = slab + offAd + lane;
+        const double* Bs = slab + offBd + lane;
         unsigned dn = adesc[0];
 #pragma unroll 1
         for (int kk = 0; (live >> kk) != 0u; ++kk) {
@@ -825,6 +879,22 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
     const bool norules = es.rules.tbl == nullptr;
     int c0 = 0, c1 = 0;
     unsigned km = 0;                               // bit ii: this lane keeps an entry of row tile ii
+    // INTERIOR STRIP (nearly all of them): no edge of the matrix, no shifted diagonal, no rule table - the sparse rule
+    // |alpha*v| > thr on 16 values and nothing else (the general loop below spends ~25 instructions per row tile on
+    // tests that are the same for every strip away from the edges); same arithmetic, bit-identical results
+    const bool interior = norules && !on_diag && (I0 + 8) * 8 <= nrows && J * 8 + 8 <= ncols;
+    if (interior) {
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const double s0 = es.alpha * acc[ii][0], s1 = es.alpha * acc[ii][1];
+        const bool k0 = fabs(s0) > es.thr, k1 = fabs(s1) > es.thr;
+        acc[ii][0] = k0 ? s0 : 0.0;
+        acc[ii][1] = k1 ? s1 : 0.0;
+        c0 += k0 ? 1 : 0;
+        c1 += k1 ? 1 : 0;
+        km |= ((k0 || k1) ? 1u : 0u) << ii;
+      }
+    } else
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
       const double v0 = acc[ii][0], v1 = acc[ii][1];
@@ -1358,6 +1428,22 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
     // fast paths of the DMMA warps: NTB_DENSE_STAGE=0 generic loop only, 1 (default) dense-stage block, 2 also the
     // A-complete block (experimental)
     static const int dense = [] { const char* e = std::getenv("NTB_DENSE_STAGE"); return e ? std::atoi(e) : 1; }();
+    // default: the fixed ring of 3 x 32 KB stages; NTB_RING=1: the byte-granular ring (RING_SLOTS stages in flight) -
+    // measured 2-3 % SLOWER on the c4 step in both A/B runs of round 2 (profiles/README.md): the stages are not late
+    // because the ring is shallow but because one copy warp hands them out, and the deeper ring costs an extra
+    // descriptor load per stage and L1 capacity
+    static const int ring = [] { const char* e = std::getenv("NTB_RING"); return e ? std::atoi(e) : 0; }();
+    if (ring != 0 && shape != 23 && dense == 1) {
+      auto kern = k_tile_numeric9<NSTAGE_DEFAULT, 2, 1, true>;
+      static bool ring_attr_set = false;
+      if (!ring_attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem_ring()));
+        ring_attr_set = true;
+      }
+      NTB_LAUNCH(kern, min(ntasks_l, kNumSMs * 2), NUMERIC_THREADS, numeric_smem_ring(), Av, Bv, nJ, gtask_off.get(),
+                 tasks_p, ntasks_l, task_counter_p, cnt_p, out, nrows, ncols, es);
+      return;
+    }
     if (shape == 23) launch(k_tile_numeric9<2, 3, 0>, 2, 3);
     else if (dense >= 2) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 2>, NSTAGE_DEFAULT, 2);
     else if (dense == 1) launch(k_tile_numeric9<NSTAGE_DEFAULT, 2, 1>, NSTAGE_DEFAULT, 2);

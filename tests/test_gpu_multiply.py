@@ -353,3 +353,58 @@ def test_scattered_columns_use_the_hash_accumulator(nt, oracle, cplx):
     ref = oracle.multiply(OA, OA, alpha=0.7, thr=1e-6)
     compare_sparse(C.to_scipy(), ref.to_scipy(), 1e-6, tol=1e-13)
     assert C.GetSize() == ref.nnz()
+
+
+# ---- complex128 on the FP64 tensor cores (real embedding, spgemm.cu: spgemm_complex_tiles) ---------------------------
+def _complex_banded(n, hb, seed):
+    rng = np.random.default_rng(seed)
+    m = banded(n, half_bandwidth=hb).astype(np.complex128)
+    ph = sp.csc_matrix(m)
+    ph.data = ph.data * np.exp(1j * rng.uniform(0, 2 * np.pi, ph.nnz))
+    return sp.csc_matrix((ph + ph.conj().T) * 0.5)           # Hermitian band
+
+
+@pytest.mark.parametrize("n,hb,thr,alpha", [(1536, 40, 1e-8, 1.0), (1001, 13, 1e-5, -0.6), (640, 100, 0.0, 1.0)])
+def test_complex_tile_path_matches_scalar_path_and_oracle(nt, oracle, n, hb, thr, alpha):
+    """locally dense complex operands (Hermitian band): one real DMMA tile product of the embeddings
+    [[Re A, -Im A], [Im A, Re A]] x (Re B; Im B), threshold on the complex magnitude when the pairs are zipped back -
+    against the oracle and against the scalar complex kernels, sizes that are not tile multiples included"""
+    a = _complex_banded(n, hb, 5)
+    b = _complex_banded(n, hb, 6)
+    A, B, C1, C2 = to_gpu(nt, a), to_gpu(nt, b), nt.Matrix_ps(n), nt.Matrix_ps(n)
+    nt.set_tile_path(True)
+    nt.reset_counters()
+    C1.Gemm(A, B, None, alpha=alpha, threshold=thr)
+    assert nt.complex_tile_products() == 1, "the complex banded product did not take the tile path"
+    nt.set_tile_path(False)
+    nt.reset_counters()
+    C2.Gemm(A, B, None, alpha=alpha, threshold=thr)
+    assert nt.complex_tile_products() == 0
+    nt.set_tile_path(True)
+    ref = oracle.multiply(oracle.PSMatrix.from_scipy(a, is_complex=True), oracle.PSMatrix.from_scipy(b, is_complex=True),
+                          alpha=alpha, thr=thr)
+    compare_sparse(C1.to_scipy(), ref.to_scipy(), thr)
+    compare_sparse(C2.to_scipy(), ref.to_scipy(), thr)
+    compare_sparse(C1.to_scipy(), C2.to_scipy(), thr)
+
+
+def test_complex_dense_product_takes_the_tile_path(nt, oracle):
+    """the filled-in regime of the ComplexMatrix example (a dense exponential times itself): complex dense x dense"""
+    n = 300
+    rng = np.random.default_rng(9)
+    a = sp.csc_matrix(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    A, C = to_gpu(nt, a), nt.Matrix_ps(n)
+    nt.reset_counters()
+    C.Gemm(A, A, None, threshold=1e-9)
+    assert nt.complex_tile_products() == 1
+    compare_sparse(C.to_scipy(), a @ a, 1e-9)
+
+
+def test_complex_scattered_product_stays_on_scalar_kernels(nt):
+    n = 4096
+    a = random_sparse(n, 0.002, 78, True)
+    A, C = to_gpu(nt, a), nt.Matrix_ps(n)
+    nt.reset_counters()
+    C.Gemm(A, A)
+    assert nt.complex_tile_products() == 0
+    compare_sparse(C.to_scipy(), a @ a)
