@@ -25,7 +25,7 @@ from ctypes import POINTER, byref, c_bool, c_char_p, c_double, c_int, c_long, c_
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libntpoly_b200.so")
+LIB_PATH = os.environ.get("NTB_LIB") or os.path.join(_HERE, "lib", "libntpoly_b200.so")   # (NTB_LIB: A/B runs of a kernel variant)
 SIZE_wrp = 12
 _lib = None
 

@@ -409,6 +409,47 @@ __device__ __forceinline__ void ct_pair(const int4& ea, const int4& eb, int Ib, 
   }
 }
 
+// ---- stage plan: the look-ups of every task, done up front by a kernel of their own ----------------------------------
+// The copy warp of the numeric kernel used to find the stages of a task itself: task -> B's chunk-column record ->
+// B's entries -> A's chunk-column record -> (binary search) A's entry: five DEPENDENT loads per task, ~3-4 us of L2
+// latency that one task of look-ahead cannot hide at the band edges, where a task is consumed in 1-2 us (the DMMA
+// warps spent 10 % of their samples waiting for the first stages of a task, profiles/r02f_numeric_source_top.txt).
+// Here one warp per task does the same chain with the whole task list in flight at once and leaves, per task,
+//     hd[2t]   = {g, Ib, first task of the group, first task of the next group}
+//     hd[2t+1] = {B chunk column: first entry, entry count, 0, 0}
+//     rec[(32t + l)*2]     = {mask A lo, hi, mask B lo, hi}   for B entry l < 32 of the chunk column (zero: no stage)
+//     rec[(32t + l)*2 + 1] = {first tile of the A super-tile, of the B super-tile, piece of A, 0}
+// so that the copy warp needs ONE round trip (all addresses follow from the task id) instead of five.
+__global__ void __launch_bounds__(256)
+k_task_stages(LeftView A, CtView B, const int2* __restrict__ tasks, int ntasks, const int* __restrict__ gtask_off,
+              int4* __restrict__ hd, int4* __restrict__ rec) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= ntasks) return;
+  const int4 none = make_int4(0, 0, 0, -1);
+  const int2 tk = tasks[t];
+  const int4 cmB = B.colmeta[tk.x];
+  if (lane == 0) {
+    hd[2 * t] = make_int4(tk.x, tk.y, gtask_off[tk.x], gtask_off[tk.x + 1]);
+    hd[2 * t + 1] = make_int4(cmB.x, cmB.y, 0, 0);
+  }
+  bool have = lane < cmB.y;
+  const int4 eb = have ? B.ent[cmB.x + lane] : none;
+  have = have && mask64(eb) != 0ull;      // an entry of a product-written form may carry an empty mask
+  int ql = 0;
+  const int pc = have ? lv_piece(A, eb.x, ql) : 0;
+  const int4* entA = A.piece[pc].ent;
+  const int4 ca = have ? A.piece[pc].colmeta[ql] : none;
+  const int idx = have ? ct_find(entA, ca, tk.y) : -1;
+  const int4 ea = (idx >= 0) ? entA[idx] : none;
+  unsigned long long mA, mB;
+  int offA, offB;
+  ct_pair(ea, eb, tk.y, idx >= 0, mA, mB, offA, offB);
+  int4* r = rec + ((size_t)t * 32 + lane) * 2;
+  r[0] = make_int4((int)(unsigned)mA, (int)(unsigned)(mA >> 32), (int)(unsigned)mB, (int)(unsigned)(mB >> 32));
+  r[1] = make_int4(offA, offB, pc, 0);
+}
+
 // ---- the numeric kernel -------------------------------------------------------------------------------------------
 // Persistent CTAs (2 per SM); task = 64x64 output block (8 tile columns x 8 row tiles), handed out by an atomic counter.
 //
@@ -524,7 +565,7 @@ __device__ __forceinline__ void emit_strip(double (&acc)[8][2], unsigned km, int
 }
 template <int NSTAGE_, int MINB, int DENSE, bool RING = false>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
-k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off, const int2* __restrict__ tasks, int ntasks,
+k_tile_numeric9(LeftView A, CtView B, int nJ, const int4* __restrict__ plan_hd, const int4* __restrict__ plan_rec, int ntasks,
                 int* __restrict__ task_counter, int* __restrict__ cnt, ResultForms out, int nrows, int ncols, EmitSpec es) {
   constexpr int NSTAGE = RING ? RING_SLOTS : NSTAGE_;                       // descriptor slots / barrier pairs
   constexpr int MSZ = RING ? META_RING : META9;
@@ -548,10 +589,10 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
     const int4 none = make_int4(0, 0, 0, -1);
     int task_raw = 0;
     int pstep = 0;
-    bool valid_n = false, have_n = false, found_n = false;
+    bool valid_n = false;
     int tid_n = 0;
     int2 tk_n = make_int2(0, 0);
-    int4 cmB_n = none, eb_n = none, ca_n = none, ea_n = none;
+    int4 cmB_n = none;
     unsigned long long mA_n = 0ull, mB_n = 0ull;
     int offA_n = 0, offB_n = 0;
     int pc_n = 0;                                    // piece (rank of the process row) that holds this lane's A super-tile
@@ -561,6 +602,7 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
     // bytes charged to slot l
     unsigned rg_head = 0, rg_used = 0, rg_par = 0, rg_mine = 0;
     int rg_tail = 0, rg_nout = 0;
+    int4 hd0_n = none, hd1_n = none, r0_n = none, r1_n = none;
     auto advance = [&]() {
       switch (pstep) {
         case 0: {
@@ -571,39 +613,29 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
           // from both ends towards the middle instead.
           if (valid_n && A.npieces > 1) t = (t & 1) ? ntasks - 1 - (t >> 1) : (t >> 1);
           tid_n = t;
-          tk_n = valid_n ? tasks[t] : make_int2(0, 0);
+          // the task's stage plan (k_task_stages): four independent loads, every address follows from the task id
+          if (valid_n) {
+            hd0_n = plan_hd[2 * t];
+            hd1_n = plan_hd[2 * t + 1];
+            const int4* r = plan_rec + ((size_t)t * 32 + lane) * 2;
+            r0_n = r[0];
+            r1_n = r[1];
+          }
           break;
         }
         case 1:
-          cmB_n = valid_n ? B.colmeta[tk_n.x] : none;
-          gt0_n = valid_n ? gtask_off[tk_n.x] : 0;
-          gt1_n = valid_n ? gtask_off[tk_n.x + 1] : 0;
-          break;
-        case 2: have_n = valid_n && lane < cmB_n.y; eb_n = have_n ? B.ent[cmB_n.x + lane] : none; break;
-        case 3:
-          // an entry of a product-written form may carry an empty mask (and an id past the last chunk column of A)
-          have_n = have_n && mask64(eb_n) != 0ull;
-          if (have_n) {
-            int ql;
-            pc_n = lv_piece(A, eb_n.x, ql);
-            ca_n = A.piece[pc_n].colmeta[ql];
+          if (valid_n) {
+            tk_n = make_int2(hd0_n.x, hd0_n.y);
+            gt0_n = hd0_n.z; gt1_n = hd0_n.w;
+            cmB_n = make_int4(hd1_n.x, hd1_n.y, 0, 0);
+            mA_n = ((unsigned long long)(unsigned)r0_n.y << 32) | (unsigned)r0_n.x;
+            mB_n = ((unsigned long long)(unsigned)r0_n.w << 32) | (unsigned)r0_n.z;
+            offA_n = r1_n.x; offB_n = r1_n.y; pc_n = r1_n.z;
           } else {
-            pc_n = 0;
-            ca_n = none;
+            tk_n = make_int2(0, 0); gt0_n = 0; gt1_n = 0; cmB_n = none; mA_n = 0ull; mB_n = 0ull; offA_n = 0; offB_n = 0; pc_n = 0;
           }
-          break;
-        case 4: {
-          const int4* entA = A.piece[pc_n].ent;
-          const int idx = have_n ? ct_find(entA, ca_n, tk_n.y) : -1;
-          found_n = idx >= 0;
-          ea_n = found_n ? entA[idx] : none;
-          break;
-        }
-        case 5:
-          ct_pair(ea_n, eb_n, tk_n.y, found_n, mA_n, mB_n, offA_n, offB_n);
           // the stages of the NEXT task are now known: pull their tiles into L2 while this task is still being
-          // consumed, so that their bulk copies find them there (the DMMA warps were waiting 12 % of their time for
-          // a full barrier, i.e. for HBM latency at the short band-edge stages)
+          // consumed, so that their bulk copies find them there
           if (mA_n != 0ull) {
             bulk_prefetch_l2(lv_tile_ptr(A, pc_n, (long long)offA_n + 8 * first_group(mA_n)), (unsigned)span_tiles(mA_n) * 256u);
             bulk_prefetch_l2(B.tval + ((long long)offB_n + 8 * first_group(mB_n)) * 32, (unsigned)span_tiles(mB_n) * 256u);
@@ -614,7 +646,7 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
       ++pstep;
     };
     if (lane == 0) task_raw = atomicAdd(task_counter, 1);
-    while (pstep < 6) advance();
+    while (pstep < 2) advance();
     for (;;) {
       const bool done = !valid_n;
       const int g = tk_n.x, Ib = tk_n.y, task = tid_n;
@@ -723,11 +755,11 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int* __restrict__ gtask_off,
           }
           __syncwarp();
           if (++st == NSTAGE) { st = 0; ph ^= 1u; }
-          if (!done) { advance(); advance(); }                 // two links per stage: the L2 prefetch of the next task goes out early
+          if (!done && pstep < 2) advance();                   // one link per stage: the L2 prefetch of the next task goes out early
         }
       }
       if (done) break;
-      while (pstep < 6) advance();
+      while (pstep < 2) advance();
     }
     return;
   }
@@ -1414,6 +1446,10 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
   }
 
   auto launch_numeric = [&](const int2* tasks_p, int ntasks_l, int* task_counter_p, int* cnt_p, const ResultForms& out) {
+    // the stage plan of every task (k_task_stages): what the copy warps would otherwise look up one task at a time
+    DevBuf<int4> plan_hd((size_t)ntasks_l * 2), plan_rec((size_t)ntasks_l * 64);
+    NTB_LAUNCH(k_task_stages, div_up((long long)ntasks_l * 32, 256), 256, 0, Av, Bv, tasks_p, ntasks_l, gtask_off.get(), plan_hd.get(),
+               plan_rec.get());
     // pipeline shape: 3 stages x 2 CTAs per SM (default) or 2 stages x 3 CTAs per SM (NTB_NUMERIC_SHAPE=23)
     static const int shape = [] { const char* e = std::getenv("NTB_NUMERIC_SHAPE"); return e ? std::atoi(e) : 32; }();
     auto launch = [&](auto kern, int nstage, int per_sm) {
@@ -1422,8 +1458,8 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem9(nstage)));
         attr_set = true;
       }
-      NTB_LAUNCH(kern, min(ntasks_l, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, gtask_off.get(),
-                 tasks_p, ntasks_l, task_counter_p, cnt_p, out, nrows, ncols, es);
+      NTB_LAUNCH(kern, min(ntasks_l, kNumSMs * per_sm), NUMERIC_THREADS, numeric_smem9(nstage), Av, Bv, nJ, plan_hd.get(),
+                 plan_rec.get(), ntasks_l, task_counter_p, cnt_p, out, nrows, ncols, es);
     };
     // fast paths of the DMMA warps: NTB_DENSE_STAGE=0 generic loop only, 1 (default) dense-stage block, 2 also the
     // A-complete block (experimental)
@@ -1440,8 +1476,8 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem_ring()));
         ring_attr_set = true;
       }
-      NTB_LAUNCH(kern, min(ntasks_l, kNumSMs * 2), NUMERIC_THREADS, numeric_smem_ring(), Av, Bv, nJ, gtask_off.get(),
-                 tasks_p, ntasks_l, task_counter_p, cnt_p, out, nrows, ncols, es);
+      NTB_LAUNCH(kern, min(ntasks_l, kNumSMs * 2), NUMERIC_THREADS, numeric_smem_ring(), Av, Bv, nJ, plan_hd.get(),
+                 plan_rec.get(), ntasks_l, task_counter_p, cnt_p, out, nrows, ncols, es);
       return;
     }
     if (shape == 23) launch(k_tile_numeric9<2, 3, 0>, 2, 3);
