@@ -225,11 +225,13 @@ def cpu_workload(args, sample: bool):
         return O, stepf, (f"the first 2 purification iterations of the same TRS4 solve on the N={n} instance of the "
                           f"generator (1/{args.n // n} of the block rows; the pattern is a block band, work per block row is "
                           "size independent)")
-    n = min(args.n, 512)
+    # c5 on the CPU: the same generator, shift rule and scale on a smaller graph (the restatement's complex scattered
+    # products run at ~1 GFLOP/s: N=32768 would take many minutes per solve)
+    n = min(args.n, 2048 if sample else 4096)
     g = W.complex_hermitian_graph(n)
-    shift = float(np.asarray(abs(g).sum(axis=0)).max()) + 1.0
+    shift = 8.0 * float(np.asarray(abs(g).sum(axis=0)).max()) + 1.0
     A = O.PSMatrix.from_scipy(sp.csc_matrix(g + sp.identity(n) * shift), is_complex=True)
-    G = O.PSMatrix.from_scipy(sp.csc_matrix(g * 0.125 + sp.identity(n) * 0.01), is_complex=True)
+    G = O.PSMatrix.from_scipy(sp.csc_matrix(g * args.c5_scale + sp.identity(n) * 0.01), is_complex=True)
     p = O.SolverParameters(converge_diff=1e-5, threshold=thr)
 
     def stepf(st):

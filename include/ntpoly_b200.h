@@ -284,8 +284,9 @@ long long ntb_GetMatrixLocalSize_ps(const int *ih_this);
 void ntb_GetMatrixArrays_ps(const int *ih_this, int *rows, int *cols, double *vals);
 /* The same for a real matrix without waiting for the device-to-host copies (they run on a second stream and overlap
  * whatever is enqueued next, e.g. the ingest of the next matrix); returns the local entry count. The host arrays
- * (pinned memory, or the copies serialise) are complete after ntb_EgressWait(). */
-long long ntb_GetMatrixArraysAsync_ps(const int *ih_this, int *rows, int *cols, double *vals);
+ * (pinned memory, or the copies serialise) are complete after ntb_EgressWait(). capacity = entries the three host
+ * arrays can hold: when the block has more, NOTHING is copied and minus the required count is returned. */
+long long ntb_GetMatrixArraysAsync_ps(const int *ih_this, long long capacity, int *rows, int *cols, double *vals);
 void ntb_EgressWait(void);
 /* Ingest in two halves, so that the host-to-device copies of the NEXT matrix overlap the work on the current one:
  * ntb_StageArrays only enqueues the copies of a real 1-based global list (pinned host arrays, valid until the fill) on a

@@ -789,8 +789,11 @@ class Matrix_ps:
     def get_arrays_async(self, out):
         """real matrices: like get_arrays(out=...) but the device-to-host copies run on a second stream; the (pinned)
         buffers are complete after egress_wait()"""
-        n = int(lib().ntb_GetMatrixArraysAsync_ps(self.ih, _ip(out[0]), _ip(out[1]),
+        cap = min(len(out[0]), len(out[1]), len(out[2]))
+        n = int(lib().ntb_GetMatrixArraysAsync_ps(self.ih, c_longlong(cap), _ip(out[0]), _ip(out[1]),
                                                   out[2].ctypes.data_as(POINTER(c_double))))
+        if n < 0:
+            raise ValueError(f"get_arrays_async: the buffers hold {cap} entries, the local block has {-n}")
         return tuple(a[:n] for a in out)
 
     def fill_from_scipy(self, m):

@@ -351,8 +351,11 @@ void ntb_GetMatrixArrays_ps(const int* ih, int* rows, int* cols, double* vals) {
   if (M.is_complex) mat_get_triplets(M, rows, cols, nullptr, reinterpret_cast<cplx*>(vals));
   else mat_get_triplets(M, rows, cols, vals, nullptr);
 }
-long long ntb_GetMatrixArraysAsync_ps(const int* ih, int* rows, int* cols, double* vals) {
-  return mat_get_triplets_async(*get<Matrix>(ih), rows, cols, vals);
+long long ntb_GetMatrixArraysAsync_ps(const int* ih, long long capacity, int* rows, int* cols, double* vals) {
+  const Matrix& M = *get<Matrix>(ih);
+  const long long need = M.local_nnz();
+  if (need > capacity) return -need;          // the caller's buffers are too small: nothing is written
+  return mat_get_triplets_async(M, rows, cols, vals);
 }
 void ntb_EgressWait(void) { mat_egress_wait(); }
 void ntb_StageArrays(int* ih_stage, long long n, const int* rows, const int* cols, const double* vals) {

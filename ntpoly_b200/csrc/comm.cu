@@ -1,4 +1,8 @@
 #include "comm.h"
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <ctime>
 #include "device.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
@@ -112,20 +116,28 @@ void world_init_from_env() {
   std::string path = std::string("/tmp/ntpoly_b200_ncclid_") + (port ? port : "0");
   if (const char* p = std::getenv("NTB_RENDEZVOUS_FILE")) path = p;
   unsigned char id[128];
+  // A file left behind by a run that crashed must never be taken for this launch's id (a reader would then hang in
+  // ncclCommInitRank): rank 0 removes whatever is there and creates the file exclusively (0600, no symlink followed),
+  // readers accept only a file written at most two minutes before their own start (the ranks of one launch start within seconds of each other; what a crashed run left behind is older, or removed by rank 0 first).
+  const time_t started = time(nullptr);
   if (rank == 0) {
     world_get_unique_id(id);
-    std::string tmp = path + ".tmp";
-    FILE* f = std::fopen(tmp.c_str(), "wb");
-    NTB_CHECK(f != nullptr, "cannot write NCCL rendezvous file");
-    std::fwrite(id, 1, 128, f);
-    std::fclose(f);
-    std::rename(tmp.c_str(), path.c_str());
+    ::unlink(path.c_str());
+    std::string tmp = path + ".tmp." + std::to_string((long long)getpid());
+    ::unlink(tmp.c_str());
+    const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+    NTB_CHECK(fd >= 0, "cannot create the NCCL rendezvous file");
+    NTB_CHECK(::write(fd, id, 128) == 128, "cannot write the NCCL rendezvous file");
+    ::close(fd);
+    NTB_CHECK(std::rename(tmp.c_str(), path.c_str()) == 0, "cannot publish the NCCL rendezvous file");
   } else {
     for (int tries = 0;; ++tries) {
-      FILE* f = std::fopen(path.c_str(), "rb");
-      if (f) {
-        size_t n = std::fread(id, 1, 128, f);
-        std::fclose(f);
+      struct stat sb;
+      const int fd = ::open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+      if (fd >= 0) {
+        const bool fresh = ::fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_mtime + 120 >= started;
+        const ssize_t n = fresh ? ::read(fd, id, 128) : 0;
+        ::close(fd);
         if (n == 128) break;
       }
       NTB_CHECK(tries < 6000, "timed out waiting for the NCCL rendezvous file");

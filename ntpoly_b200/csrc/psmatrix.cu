@@ -505,7 +505,9 @@ long long mat_get_triplets(const Matrix& M, int* rows, int* cols, double* vals_r
 // copy of the next input: PCIe is full duplex). The staged device arrays live until mat_egress_wait().
 namespace {
 struct PendingEgress { DevBuf<int> row, col; DevBuf<double> val; };
-std::vector<PendingEgress> g_pending_egress;
+// (never destroyed: at process exit the blocks of an egress nobody waited for would otherwise be handed back to a
+// device arena whose own static destructor may already have run)
+std::vector<PendingEgress>& g_pending_egress = *new std::vector<PendingEgress>();
 cudaStream_t g_copy_stream = nullptr;
 cudaEvent_t g_egress_ready = nullptr;
 }  // namespace

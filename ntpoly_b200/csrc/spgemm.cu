@@ -53,6 +53,18 @@ __device__ __forceinline__ bool keep_entry(double mag_scaled, double mag_raw, do
   return (dense_rule ? mag_raw : mag_scaled) > thr;
 }
 
+// |v| for the drop test of the heavy-column kernel: sqrt(x^2 + y^2) while the squares are comfortably inside the
+// double range, hypot() otherwise (the library routine is ~60 instructions and was most of the 8e9 instructions of
+// a c5 sweep launch, profiles/r02g_c5_atomic_slab.keys.txt); differs from hypot() by an ulp at most, i.e. only for
+// entries that sit on the threshold itself
+__device__ __forceinline__ double mag_fast(double v) { return fabs(v); }
+__device__ __forceinline__ double mag_fast(cplx v) {
+  const double m2 = v.x * v.x + v.y * v.y;
+  return (m2 > 1e-280 && m2 < 1e280) ? sqrt(m2) : hypot(v.x, v.y);
+}
+__device__ __forceinline__ bool is_zero(double v) { return v == 0.0; }
+__device__ __forceinline__ bool is_zero(cplx v) { return v.x == 0.0 && v.y == 0.0; }
+
 __device__ __forceinline__ bool rule_for(const RuleView& r, int inner_idx, int outer_idx) {
   if (r.tbl == nullptr) return false;
   return r.tbl[(inner_idx / r.rb) * r.nJ + (outer_idx / r.cb)] != 0;
@@ -308,7 +320,24 @@ k_numeric_cta_atomic(CscView<T> X, CscView<T> Y, const int* __restrict__ list, c
     }
     __syncthreads();
     const int xs = X.outer[j], xe = X.outer[j + 1];
-    for (int p0 = xs + warp * 32; p0 < xe; p0 += CTA_T) {
+    // entries s0 + start, + stride, ... of one Y column, four at a time: the loads of a group are issued before its
+    // first reduction (a single load per iteration left the warp waiting one L2 latency per product)
+    auto walk = [&](int s0, int e0, T b, int start, int stride) {
+      int q = s0 + start;
+      for (; q + 3 * stride < e0; q += 4 * stride) {
+        const int i0 = Y.inner[q], i1 = Y.inner[q + stride], i2 = Y.inner[q + 2 * stride], i3 = Y.inner[q + 3 * stride];
+        const T v0 = Y.val[q], v1 = Y.val[q + stride], v2 = Y.val[q + 2 * stride], v3 = Y.val[q + 3 * stride];
+        acc_add<GLOBAL_SLAB>(&acc[i0 - base], s_mul(v0, b));
+        acc_add<GLOBAL_SLAB>(&acc[i1 - base], s_mul(v1, b));
+        acc_add<GLOBAL_SLAB>(&acc[i2 - base], s_mul(v2, b));
+        acc_add<GLOBAL_SLAB>(&acc[i3 - base], s_mul(v3, b));
+      }
+      for (; q < e0; q += stride) acc_add<GLOBAL_SLAB>(&acc[Y.inner[q] - base], s_mul(Y.val[q], b));
+    };
+    // a SHORT X column (c5: 26 entries of G against 650-entry columns of the iterate) would occupy one warp only:
+    // then all eight warps take the same 32 k and share every Y column, 256 entries per sweep
+    const bool shared_k = (xe - xs) <= 64;
+    for (int p0 = xs + (shared_k ? 0 : warp * 32); p0 < xe; p0 += (shared_k ? 32 : CTA_T)) {
       const int p = p0 + lane;
       int ys = 0, ye = 0;
       T xv = zero_of<T>();
@@ -320,55 +349,68 @@ k_numeric_cta_atomic(CscView<T> X, CscView<T> Y, const int* __restrict__ list, c
       }
       const int nv = min(32, xe - p0);
       // short Y columns (<= 16 entries on average): one lane per X entry walks its own column (no idle lanes);
-      // otherwise the warp strides over one column at a time
+      // otherwise the warp (or the CTA) strides over one column at a time
       const int total = __reduce_add_sync(0xffffffffu, ye - ys);
       if (total <= 16 * nv) {
-        for (int q = ys; q < ye; ++q) acc_add<GLOBAL_SLAB>(&acc[Y.inner[q] - base], s_mul(Y.val[q], xv));
+        if (!shared_k || warp == 0) walk(ys, ye, xv, 0, 1);
       } else {
         for (int t = 0; t < nv; ++t) {
           const int s0 = shfl(ys, t), e0 = shfl(ye, t);
           const T b = shfl(xv, t);
-          for (int q = s0 + lane; q < e0; q += 32) acc_add<GLOBAL_SLAB>(&acc[Y.inner[q] - base], s_mul(Y.val[q], b));
+          if (shared_k) walk(s0, e0, b, (int)threadIdx.x, CTA_T);
+          else walk(s0, e0, b, lane, 32);
         }
       }
     }
     if (GLOBAL_SLAB) __threadfence();
     __syncthreads();
     // ordered sweep in two passes without block-wide barriers in the loops: warp w owns the contiguous rows
-    // [w*seg, (w+1)*seg) of the window, counts its kept entries (independent loads, nothing serialises them), the
-    // eight counts are prefixed once, and the second pass re-reads the segment (L2 / shared memory), emits in row
-    // order at the warp's offset and clears the slab. (One barrier per 256 rows held the sweep of a 32768-row window
+    // [w*seg, (w+1)*seg) of the window, counts its kept entries, the eight counts are prefixed once, and the second
+    // pass re-reads the segment (L2 / shared memory), emits in row order at the warp's offset and clears the slab.
+    // Four 32-row groups per iteration, loads first. (One barrier per 256 rows held the sweep of a 32768-row window
     // at ~200 us per column - more than the products of a column with a few thousand of them.)
     const long long off = tmp_off[j];
     const int seg = ((w + CTA_T - 1) / CTA_T) * 32;
     const int r0 = min(w, warp * seg), r1 = min(w, r0 + seg);
-    auto kept = [&](int t, T& sv) {
-      const T v = ld_acc(&acc[t], GLOBAL_SLAB);
+    auto kept = [&](T v, int t, T& sv) {
       sv = s_scale(alpha, v);
-      return keep_entry(s_abs(sv), s_abs(v), thr, rule_for(rules, base + t, j));
+      if (is_zero(v)) return false;            // an untouched row of the window (|0| > thr is false for every thr >= 0)
+      return keep_entry(mag_fast(sv), mag_fast(v), thr, rule_for(rules, base + t, j));
     };
     int mine = 0;
-    for (int t = r0 + lane; t < r1; t += 32) { T sv; mine += kept(t, sv) ? 1 : 0; }
+    for (int t0 = r0; t0 < r1; t0 += 128) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int t = t0 + 32 * u + lane; v[u] = (t < r1) ? ld_acc(&acc[t], GLOBAL_SLAB) : zero_of<T>(); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int t = t0 + 32 * u + lane; T sv; if (t < r1 && kept(v[u], t, sv)) ++mine; }
+    }
     mine = __reduce_add_sync(0xffffffffu, mine);
     if (lane == 0) s_warp_cnt[warp] = mine;
     __syncthreads();
     int before = 0, total = 0;
     for (int ww = 0; ww < CTA_T / 32; ++ww) { const int c = s_warp_cnt[ww]; total += c; if (ww < warp) before += c; }
-    for (int t0 = r0; t0 < r1; t0 += 32) {
-      const int t = t0 + lane;
-      bool keep = false;
-      T sv = zero_of<T>();
-      if (t < r1) {
-        keep = kept(t, sv);
-        if (GLOBAL_SLAB) acc[t] = zero_of<T>();
+    for (int t0 = r0; t0 < r1; t0 += 128) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int t = t0 + 32 * u + lane; v[u] = (t < r1) ? ld_acc(&acc[t], GLOBAL_SLAB) : zero_of<T>(); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + 32 * u + lane;
+        bool keep = false;
+        T sv = zero_of<T>();
+        if (t < r1) {
+          keep = kept(v[u], t, sv);
+          if (GLOBAL_SLAB) acc[t] = zero_of<T>();
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const long long pos = off + before + __popc(m & ((1u << lane) - 1));
+          tmp_idx[pos] = base + t;
+          tmp_val[pos] = sv;
+        }
+        before += __popc(m);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const long long pos = off + before + __popc(m & ((1u << lane) - 1));
-        tmp_idx[pos] = base + t;
-        tmp_val[pos] = sv;
-      }
-      before += __popc(m);
     }
     if (threadIdx.x == 0) s_running = total;
     if (threadIdx.x == 0) cnt[j] = s_running;

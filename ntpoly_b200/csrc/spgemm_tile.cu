@@ -1197,23 +1197,38 @@ k_group_plan(int nJ, int nG, const int* __restrict__ imin8, const int* __restric
              int* __restrict__ gtask_off, const unsigned long long* __restrict__ ndmma, long long limit,
              unsigned long long* __restrict__ out3) {
   __shared__ int sw[33];
+  __shared__ int s_nb[PLAN_MAX_GROUPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // phase 1: the per-tile-column windows are read with coalesced, independent loads (one J per thread and sweep) and
+  // reduced over the 8 tile columns of a group inside 8 consecutive lanes (a single block walking its groups one
+  // after the other paid a memory latency per tile column: 39 us per product on the c4 step)
+  for (int J0 = 0; J0 < nG * 8; J0 += PLAN_T) {
+    const int J = J0 + (int)threadIdx.x;
+    int mn = INT_MAX, mx = -1;
+    if (J < nJ) {
+      const int n8 = nI8[J], i8 = imin8[J];
+      if (n8 > 0) { mn = i8 >> 3; mx = ((i8 + n8) >> 3) - 1; }
+    }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    const int g = J >> 3;
+    if ((threadIdx.x & 7) == 0 && g < nG) {
+      gbmin[g] = (mx >= 0) ? mn : 0;
+      s_nb[g] = (mx >= 0) ? (mx - mn + 1) : 0;
+    }
+  }
+  __syncthreads();
   const int per = (nG + PLAN_T - 1) / PLAN_T;
   const int g0 = min(nG, (int)threadIdx.x * per), g1 = min(nG, g0 + per);
   int nb[8];
   int s = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int g = g0 + i;
-    nb[i] = 0;
-    if (i < per && g < g1) {
-      int mn = INT_MAX, mx = -1;
-      for (int J = g * 8; J < min(nJ, g * 8 + 8); ++J)
-        if (nI8[J] > 0) { mn = min(mn, imin8[J] >> 3); mx = max(mx, ((imin8[J] + nI8[J]) >> 3) - 1); }
-      gbmin[g] = (mx >= 0) ? mn : 0;
-      nb[i] = (mx >= 0) ? (mx - mn + 1) : 0;
-      s += nb[i];
-    }
+    nb[i] = (i < per && g0 + i < g1) ? s_nb[g0 + i] : 0;
+    s += nb[i];
   }
   int inc = s;
 #pragma unroll
