@@ -98,6 +98,19 @@ void csc_increment(const CscView<T>& A, LocalCsc<T>& B, double alpha, double thr
     d2h(&h, A.outer + cols, 1);
     nnzA = h;
   }
+  // adding into an EMPTY block is a copy: every entry of A is an untested tail of the merge (kept whatever the
+  // threshold) and 1.0 * a is a bit for bit - the first of the S adds of the between-slice sum, FillFromTripletList
+  // style accumulations, Increment into a freshly constructed matrix
+  if (B.nnz == 0 && alpha == 1.0) {
+    LocalCsc<T> out;
+    out.rows = A.rows; out.cols = cols;
+    out.outer.alloc((size_t)cols + 1);
+    out.alloc_entries(nnzA);
+    d2d(out.outer.get(), A.outer, (size_t)cols + 1);
+    if (nnzA > 0) { d2d(out.inner.get(), A.inner, (size_t)nnzA); d2d(out.val.get(), A.val, (size_t)nnzA); }
+    B.swap(out);
+    return;
+  }
   const long long total = nnzA + B.nnz;
   NTB_CHECK(total < (1ll << 31), "increment: more than 2^31 entries in a local block");
   if (rb <= 0) rb = A.rows > 0 ? A.rows : 1;

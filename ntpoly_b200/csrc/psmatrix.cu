@@ -790,9 +790,12 @@ bool mat_tile_scalars(int mode, const Matrix& A, const Matrix* B, double* out) {
 }
 bool mat_tile_combine(const Matrix& P, const Matrix& Q, int mode, double alpha, double beta, double thr, double sigma,
                       Matrix& Out, unsigned want) {
-  if (!tile_path_on() || !tile_space_operand(P) || !tile_space_operand(Q) || P.grid != Q.grid || P.logical_dim != Q.logical_dim)
-    return false;
-  if (!P.r.forms->right.emitted) return false;          // P is the product of the step (X^2): always a tile-space result
+  if (!tile_path_on() || !tile_space_operand(P) || P.grid != Q.grid || P.logical_dim != Q.logical_dim) return false;
+  if (!P.r.forms->right.emitted) return false;          // P is the product of the step (X^2, T_k): always a tile-space result
+  // Q may still be a plain CSC block on a single rank (the first steps of a recurrence: Identity, the input): its
+  // right form is built and cached like a product operand's
+  if (!tile_space_operand(Q) && Q.constructed && !Q.is_complex && P.grid->size == 1 && Q.r.nnz > 0) tile_operand_form(Q.r, false);
+  if (!tile_space_operand(Q)) return false;
   ProcessGrid& g = *P.grid;
   const bool multi = g.size > 1;
   if (multi && !(g.peer_ok && peer().ok)) return false;  // (general grids keep the reference's call sequence)

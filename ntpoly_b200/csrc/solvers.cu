@@ -815,6 +815,23 @@ static void chebyshev_compute(const Matrix& In, Matrix& Out, const std::vector<d
     permute_matrix(Bal, Bal, p.balance_permutation, &pool);
   }
   mat_copy(Identity, Tkm2);
+  // One step of the recurrence, T_k = 2*Bal*T_{k-1} - T_{k-2}, Res += c_k*T_k (ChebyshevSolversModule.F90:146-163:
+  // MatrixMultiply, IncrementMatrix(Tkm2, Tk, -1), IncrementMatrix(Tk, Res, c_k), both adds with threshold 0). When
+  // the product runs on the tile path (real, locally dense iterates, one rank) the two adds are combined straight
+  // from the tile forms (k_form_combine through the product's emit_strip) and the iterates never leave tile space:
+  // 1*Tk + (-1)*Tkm2 and c*Tk + 1*Res are the same sums as the reference's (-1)*Tkm2 + Tk and c*Tk + Res (the add is
+  // commutative, and with threshold 0 the rule "kept iff non-zero, or an untested tail" does not depend on which list
+  // is called A), except that a tail entry that is EXACTLY zero does not exist in a tile form.
+  auto step = [&](double c) {
+    const bool fuse = fused_steps_enabled() && !Bal.is_complex && Bal.grid->size == 1;
+    mat_multiply(Bal, Tkm1, Tk, 2.0, 0.0, p.threshold, &pool, fuse ? WANT_RIGHT : WANT_ALL);   // (T_k is only ever a right operand)
+    Matrix T;
+    if (fuse && mat_tile_combine(Tk, Tkm2, 0, 1.0, -1.0, 0.0, 0.0, T, WANT_RIGHT)) std::swap(Tk, T);
+    else mat_increment(Tkm2, Tk, -1.0, 0.0);
+    Matrix R;
+    if (fuse && mat_tile_combine(Tk, Res, 0, c, 1.0, 0.0, 0.0, R, WANT_RIGHT)) std::swap(Res, R);
+    else mat_increment(Tk, Res, c, 0.0);
+  };
   if (degree == 1) {
     mat_copy(Tkm2, Res);
     mat_scale(Res, coef[0]);
@@ -824,15 +841,11 @@ static void chebyshev_compute(const Matrix& In, Matrix& Out, const std::vector<d
     mat_scale(Res, coef[0]);
     mat_increment(Tkm1, Res, coef[1], 0.0);
     if (degree > 2) {
-      mat_multiply(Bal, Tkm1, Tk, 2.0, 0.0, p.threshold, &pool);
-      mat_increment(Tkm2, Tk, -1.0, 0.0);
-      mat_increment(Tk, Res, coef[2], 0.0);
+      step(coef[2]);
       for (int ii = 4; ii <= degree; ++ii) {
         mat_copy(Tkm1, Tkm2);
         mat_copy(Tk, Tkm1);
-        mat_multiply(Bal, Tkm1, Tk, 2.0, 0.0, p.threshold, &pool);
-        mat_increment(Tkm2, Tk, -1.0, 0.0);
-        mat_increment(Tk, Res, coef[ii - 1], 0.0);
+        step(coef[ii - 1]);
       }
     }
   }

@@ -334,3 +334,30 @@ def test_fused_steps_equal_the_reference_call_sequence(nt, oracle, solver):
     assert res[True][0] == pytest.approx(info.energy, rel=1e-8)
     assert res[True][5] == pytest.approx(n // 2, abs=1e-2)
     compare_sparse(res[True][3], Kref.to_scipy(), thr, tol=1e-6)
+
+
+def test_chebyshev_recurrence_in_tile_space_equals_the_reference_call_sequence(nt, oracle):
+    """ComputeExponential of a real banded matrix (ChebyshevSolversModule.F90:146-163): with the fused steps the
+    recurrence T_k = 2*Bal*T_{k-1} - T_{k-2}, Res += c_k*T_k is combined straight from the tile forms (the two sparse
+    adds per step never see CSC); against the same driver issuing the reference's calls, the oracle and scipy's expm"""
+    import scipy.linalg as la
+    n, thr = 1536, 1e-9
+    m = banded(n, half_bandwidth=24, scale=0.2)
+    m = sp.csc_matrix(m * 0.4)                      # spectral radius < 1: PowerBounds does not scale it away
+    M = to_gpu(nt, m)
+    res = {}
+    for fused in (True, False):
+        nt.set_fused_steps(fused)
+        nt.reset_counters()
+        E = nt.Matrix_ps(n)
+        nt.ExponentialSolvers.ComputeExponential(M, E, params(nt, 1e-9, thr))
+        res[fused] = (E.to_scipy(), nt.tile_combines(), nt.last_solve()["loop_counter"])
+    nt.set_fused_steps(True)
+    assert res[True][1] >= 20 and res[False][1] == 0            # 14 steps x 2 combines (the first ones may decline)
+    assert res[True][2] == res[False][2]
+    compare_sparse(res[True][0], res[False][0], thr, tol=1e-9)
+    ref, info = oracle.compute_exponential(oracle.PSMatrix.from_scipy(m), oracle.SolverParameters(converge_diff=1e-9, threshold=thr))
+    assert res[True][2] == info.iterations
+    compare_sparse(res[True][0], ref.to_scipy(), thr, tol=1e-8)
+    want = la.expm(m.toarray())
+    assert np.linalg.norm(res[True][0].toarray() - want) / np.linalg.norm(want) < 1e-6
