@@ -308,16 +308,22 @@ template <typename T> struct PartList {
   int row_off[MAX_PARTS];
   int n;
 };
-template <typename T>
-__global__ void __launch_bounds__(256) k_stack_count(PartList<T> P, int cols, int* __restrict__ cnt) {
+// the same list in device memory: any number of parts (a process column of more than MAX_PARTS ranks)
+template <typename T> struct PartRef {
+  const CscView<T>* part;
+  const int* row_off;
+  int n;
+};
+template <typename T, typename L>
+__global__ void __launch_bounds__(256) k_stack_count(L P, int cols, int* __restrict__ cnt) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
   int c = 0;
   for (int q = 0; q < P.n; ++q) c += P.part[q].outer[j + 1] - P.part[q].outer[j];
   cnt[j] = c;
 }
-template <typename T>
-__global__ void __launch_bounds__(256) k_stack_fill(PartList<T> P, int cols, const int* __restrict__ out_outer,
+template <typename T, typename L>
+__global__ void __launch_bounds__(256) k_stack_fill(L P, int cols, const int* __restrict__ out_outer,
                                                     int* __restrict__ out_inner, T* __restrict__ out_val) {
   WARP_COL_LOOP(cols) {
     int o = out_outer[j];
@@ -333,20 +339,36 @@ __global__ void __launch_bounds__(256) k_stack_fill(PartList<T> P, int cols, con
 }
 template <typename T>
 void csc_stack_rows(const CscView<T>* parts, const int* row_offsets, int n, int total_rows, LocalCsc<T>& out) {
-  NTB_CHECK(n >= 1 && n <= MAX_PARTS, "stack_rows: too many parts");
-  PartList<T> P;
-  P.n = n;
-  for (int q = 0; q < n; ++q) { P.part[q] = parts[q]; P.row_off[q] = row_offsets[q]; }
+  NTB_CHECK(n >= 1, "stack_rows: no parts");
   const int cols = parts[0].cols;
   DevBuf<int> cnt((size_t)cols);
-  NTB_LAUNCH((k_stack_count<T>), div_up(cols, 256), 256, 0, P, cols, cnt.get());
   out.rows = total_rows; out.cols = cols;
   out.outer.alloc((size_t)cols + 1);
-  exclusive_scan(cnt.get(), out.outer.get(), cols);
-  int h_nnz = 0;
-  d2h(&h_nnz, out.outer.get() + cols, 1);
-  out.alloc_entries(h_nnz);
-  NTB_LAUNCH((k_stack_fill<T>), warp_grid(cols), 256, 0, P, cols, out.outer.get(), out.inner.get(), out.val.get());
+  auto run = [&](auto P) {
+    using L = decltype(P);
+    NTB_LAUNCH((k_stack_count<T, L>), div_up(cols, 256), 256, 0, P, cols, cnt.get());
+    exclusive_scan(cnt.get(), out.outer.get(), cols);
+    int h_nnz = 0;
+    d2h(&h_nnz, out.outer.get() + cols, 1);
+    out.alloc_entries(h_nnz);
+    NTB_LAUNCH((k_stack_fill<T, L>), warp_grid(cols), 256, 0, P, cols, out.outer.get(), out.inner.get(), out.val.get());
+  };
+  // (NTB_STACK_INLINE_PARTS: tests force the device-memory list on grids with two process rows)
+  static const int inline_parts = [] { const char* e = std::getenv("NTB_STACK_INLINE_PARTS"); return e ? std::min(std::atoi(e), MAX_PARTS) : MAX_PARTS; }();
+  if (n <= inline_parts) {                    // the list travels as a kernel argument
+    PartList<T> P;
+    P.n = n;
+    for (int q = 0; q < n; ++q) { P.part[q] = parts[q]; P.row_off[q] = row_offsets[q]; }
+    run(P);
+  } else {                                    // more parts than fit into the argument: the list lives in device memory
+    DevBuf<CscView<T>> d_parts((size_t)n);
+    DevBuf<int> d_off((size_t)n);
+    h2d(d_parts.get(), parts, (size_t)n);
+    h2d(d_off.get(), row_offsets, (size_t)n);
+    stream_sync();                            // (the caller's host arrays are the h2d sources)
+    run(PartRef<T>{d_parts.get(), d_off.get(), n});
+    stream_sync();                            // d_parts / d_off go back to the arena behind the kernels (stream order), nothing else to wait for
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -42,6 +42,9 @@ def test_process_grids(nproc):
     # the same for the NCCL halo: a halo beyond the buffer's index range declines collectively
     ("nccl_halo_declines", {"NTB_P2P": "0", "NTB_HALO_TILE_LIMIT": "1", "NTB_WORKER_GRIDS": "1x2x1",
                             "NTB_WORKER_EXPECT": "gather"}),
+    # a process column with more ranks than a kernel argument can list (> 16 in production): the part list of the
+    # stacked B panel lives in device memory - forced here on two process rows
+    ("device_part_list", {"NTB_STACK_INLINE_PARTS": "1", "NTB_WORKER_GRIDS": "2x1x1"}),
 ])
 def test_column_split_fallbacks(name, env):
     _run(2, env, 29640)
