@@ -27,6 +27,14 @@ def test_async_egress_matches_blocking(nt):
         assert np.array_equal(out0[k], ref[k]) and np.array_equal(out1[k], ref[k])
     assert np.array_equal(out0[2], ref[2]) and np.array_equal(out1[2], 2.0 * ref[2])
     nt.egress_wait()                              # idempotent
+    # buffers that cannot hold the block: nothing is written, the required count comes back (the call used to
+    # trust the caller's buffers)
+    small = tuple(x[: len(ref[0]) - 1] for x in bufs[0])
+    before = [x.copy() for x in bufs[0]]
+    with pytest.raises(ValueError, match=str(len(ref[0]))):
+        C.get_arrays_async(small)
+    nt.egress_wait()
+    assert all(np.array_equal(x, y) for x, y in zip(before, bufs[0]))
 
 
 def test_sorted_list_ingest_equals_sorting_ingest(nt):
