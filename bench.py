@@ -43,8 +43,8 @@ METRICS = {"c4": "spgemm_useful_gflops_per_sign_iteration", "c1": "spgemm_useful
            "c3": "spgemm_useful_gflops_per_trs4_purification", "c5": "spgemm_useful_gflops_complex_inverse_exponential"}
 ALPHA_MAX = 1.69770248526
 # dram read+write bytes of one numeric launch (mean of the step's two products) from `ncu --set full` of the SHIPPED
-# kernel on the c4 step: profiles/r02a_numeric.keys.txt (918 MB + 411 MB and 963 MB + 765 MB). Only quoted for c4 on 1 GPU.
-NCU_TRAFFIC_C4 = 0.5 * ((922.55e6 + 410.95e6) + (963.47e6 + 764.79e6))
+# kernel on the c4 step: profiles/r02h_numeric.keys.txt (951 MB + 410 MB and 992 MB + 765 MB). Only quoted for c4 on 1 GPU.
+NCU_TRAFFIC_C4 = 0.5 * ((950.65e6 + 410.02e6) + (991.55e6 + 764.95e6))
 
 
 def parse():
@@ -650,7 +650,7 @@ def run_c4(env):
     roof = None
     if rank == 0:
         extra["traffic_source"] = ("ncu --set full of the shipped kernel, mean of the step's two launches "
-                                   "(profiles/r02a_numeric.keys.txt)") if world == 1 and n == 262144 else None
+                                   "(profiles/r02h_numeric.keys.txt)") if world == 1 and n == 262144 else None
         roof = roofline_of(env, prof, alg_bytes, flops_per_step_local * args.steps, ms_local, peaks,
                            "k_tile_numeric9 (numeric SpGEMM incl. threshold and tile-form output, one launch per product)", extra)
         if world == 1 and n == 262144:
