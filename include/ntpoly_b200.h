@@ -321,6 +321,11 @@ void ntb_get_tile_counters(double *out2);
 void ntb_set_tile_path(int on);
 /* 1 (default): MatrixMultiplyShift fuses the identity shift into the product's emit pass; 0: two reference calls */
 void ntb_set_fused_shift(int on);
+/* 1 (default): the sign / polar iteration takes ||X_new - X|| out of the epilogue of the product that computes X_new
+ * (tile path, one rank or a column-split grid) instead of a separate pass over both iterates; 0 (NTB_FUSED_NORM=0):
+ * always the separate norm kernel. ntb_fused_norms: norms obtained that way since the reset. */
+void ntb_set_fused_norm(int on);
+double ntb_fused_norms(void);
 /* CSC -> tile-form conversions since the last reset (0 per product once operands carry their tile forms) */
 double ntb_tile_builds(void);
 /* distributed products whose left operand was fetched as a tile halo (1 x C x 1 grids): {count, tile bytes received

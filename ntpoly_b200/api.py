@@ -77,7 +77,7 @@ ntb_TripletList_r_set ntb_TripletList_r_get ntb_TripletList_c_set ntb_TripletLis
 ntb_FillMatrixFromArrays_ps ntb_GetMatrixLocalSize_ps ntb_GetMatrixArrays_ps ntb_GetMatrixArraysAsync_ps ntb_EgressWait ntb_StageArrays ntb_FillMatrixFromStaged_ps ntb_sorted_ingests ntb_ConstructEmptyMatrixComplex_ps
 ntb_MatrixIsComplex_ps ntb_FilterMatrix_ps ntb_ScaleMatrixComplex_ps ntb_InverseSquareRootOrder_wrp
 ntb_SquareRootOrder_wrp ntb_ConstructRandomPermutationSeeded ntb_SetPermutation ntb_get_counters
-ntb_set_fused_shift ntb_get_halo_counters ntb_get_peer_counters ntb_measure_dmma_peak_tflops ntb_get_sync_count ntb_profile_read_phases ntb_set_halo_path ntb_set_permute_gemm ntb_TileCombine_ps ntb_TileScalars_ps ntb_set_fused_steps ntb_tile_combines ntb_hash_columns ntb_complex_tile_products ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
+ntb_set_fused_shift ntb_set_fused_norm ntb_fused_norms ntb_get_halo_counters ntb_get_peer_counters ntb_measure_dmma_peak_tflops ntb_get_sync_count ntb_profile_read_phases ntb_set_halo_path ntb_set_permute_gemm ntb_TileCombine_ps ntb_TileScalars_ps ntb_set_fused_steps ntb_tile_combines ntb_hash_columns ntb_complex_tile_products ntb_tile_builds ntb_MatrixMultiplyShift_ps ntb_SignIteration ntb_SignStep ntb_set_flop_counting ntb_get_deferred_counters ntb_grid_layout ntb_default_grid ntb_reset_counters ntb_get_tile_counters ntb_set_tile_path ntb_algorithmic_bytes ntb_profile_enable ntb_profile_read ntb_last_solve ntb_MatrixAlgorithmicBytes_ps ntb_version
 """.split()
 
 
@@ -106,6 +106,7 @@ def lib():
         L.ntb_get_sync_count.restype = c_double
         L.ntb_tile_combines.restype = c_double
         L.ntb_hash_columns.restype = c_double
+        L.ntb_fused_norms.restype = c_double
         L.ntb_complex_tile_products.restype = c_double
         L.ntb_set_stream.argtypes = [c_void_p]
         L.ntb_world_init.argtypes = [c_int, c_int, c_void_p]
@@ -1017,6 +1018,14 @@ def set_permute_gemm(on=True):
 
 def set_fused_shift(on=True):
     lib().ntb_set_fused_shift(c_int(1 if on else 0))
+
+
+def set_fused_norm(on=True):
+    lib().ntb_set_fused_norm(c_int(1 if on else 0))
+
+
+def fused_norms():
+    return int(lib().ntb_fused_norms())
 
 
 def sign_iteration(X, identity, T1, T2, alpha_k, threshold, memory_pool=None):

@@ -387,9 +387,11 @@ void ntb_SetPermutation(int* ih, const int* n, const int* lookup) {
 void ntb_get_counters(double* out4) {
   out4[0] = (double)rt().launches; out4[1] = (double)rt().multiplies; out4[2] = rt().flops_useful; out4[3] = (double)rt().dense_rule_blocks;
 }
-void ntb_reset_counters(void) { rt().launches = 0; rt().syncs = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().tile_combines = 0; rt().hash_columns = 0; rt().complex_tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().peer_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
+void ntb_reset_counters(void) { rt().launches = 0; rt().syncs = 0; rt().multiplies = 0; rt().flops_useful = 0.0; rt().dense_rule_blocks = 0; rt().alg_bytes = 0.0; rt().tile_products = 0; rt().tile_combines = 0; rt().hash_columns = 0; rt().fused_norms = 0; rt().complex_tile_products = 0; rt().dmma_issued = 0.0; rt().tile_builds = 0; rt().halo_products = 0; rt().peer_products = 0; rt().halo_bytes = 0.0; rt().deferred_products = 0; rt().deferred_materialized = 0; rt().sorted_ingests = 0; }
 void ntb_set_tile_path(int on) { ntb::set_tile_path(on); }
 void ntb_set_fused_shift(int on) { ntb::set_fused_shift(on); }
+void ntb_set_fused_norm(int on) { ntb::set_fused_norm(on); }
+double ntb_fused_norms(void) { return (double)rt().fused_norms; }
 // C = alpha*A*B (thresholded) then IncrementMatrix(Identity, C, sigma): the two reference calls as one (fused when
 // the product runs on the tile path)
 void ntb_MatrixMultiplyShift_ps(const int* ih_a, const int* ih_b, int* ih_c, const double* alpha, const double* threshold,

@@ -166,6 +166,14 @@ struct DiagShift {
   double sigma = 0.0;
   int dd = 0;            // local row of the diagonal entry of local column 0
   int ncols_diag = 0;    // local columns whose global index is below the actual (unpadded) dimension
+  // Optional second fusion (tile path only, one rank or a column-split grid): column sums of |Z - Y| where Y is the
+  // LEFT operand of the product (same rows / local columns as Z) - the drivers' "IncrementMatrix(Xnew, X, -1);
+  // MatrixNorm(X)" right after X*T (SignSolversModule.F90:230-234) without reading either iterate again: the epilogue of
+  // the numeric kernel has the finished strip in registers and fetches the matching tiles of Y's left form (they
+  // were this product's A operand a moment ago: L2). diff_colsum: device array [columns of Z]; diff_applied is set
+  // by the product when it has filled it (the caller runs the separate norm kernel otherwise).
+  double* diff_colsum = nullptr;
+  mutable bool diff_applied = false;
 };
 // What the caller needs of a product (tile path only; every other path delivers plain CSC): the CSC entries and/or
 // the tile forms of the result. Without WANT_CSC the entries are deferred (LocalCsc::deferred) and WANT_RIGHT is implied.

@@ -23,6 +23,7 @@ struct Runtime {
   unsigned long long dense_rule_blocks = 0;
   unsigned long long tile_products = 0;  // local products that ran on the DMMA tile path
   unsigned long long complex_tile_products = 0;  // complex local products that ran on the DMMA tile path (real embedding)
+  unsigned long long fused_norms = 0;    // difference norms that came out of a product's epilogue (no separate pass)
   unsigned long long hash_columns = 0;   // output columns served by the shared-memory hash accumulator (scattered patterns)
   unsigned long long tile_combines = 0;  // tile-space linear combinations (fused driver steps: no CSC round trip)
   unsigned long long tile_builds = 0;    // CSC -> tile-form conversions (0 per product once operands carry their forms)

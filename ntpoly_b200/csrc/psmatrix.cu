@@ -1221,7 +1221,7 @@ static bool fused_shift_enabled() {
 // returns true when the optional diagonal shift `sigma` (C = alpha*A*B + sigma*I, see DiagShift) was fused
 template <typename T>
 static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double beta, double threshold,
-                       double sigma = 0.0, unsigned want = WANT_ALL) {
+                       double sigma = 0.0, unsigned want = WANT_ALL, double* diff_colsum = nullptr, bool* diff_applied = nullptr) {
   ProcessGrid& g = *A.grid;
   const int S = g.S;
   const double wthr = (S > 1) ? threshold / (S * 1000) : threshold;      // MatrixMultiply.f90:25-29
@@ -1237,6 +1237,14 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
     ds.dd = A.start_col - A.start_row;        // same block coordinates for A, B and the product
     ds.ncols_diag = std::max(0, std::min(A.local_cols, A.actual_dim - A.start_col));
   }
+  // fused |AB - A| column sums (DiagShift::diff_colsum): whole columns must be local (one process row), one slice,
+  // plain replacement of C
+  const bool want_diff = diff_colsum != nullptr && S == 1 && g.R == 1 && std::fabs(beta) < 2.2250738585072014e-308;
+  if (want_diff) ds.diff_colsum = diff_colsum;
+  const DiagShift* const ds_p = (want_shift || want_diff) ? &ds : nullptr;
+  DiagShift ds_plain = ds;                    // (paths that cannot take the second fusion)
+  ds_plain.diff_colsum = nullptr;
+  const DiagShift* const ds_plain_p = want_shift ? &ds_plain : nullptr;
   // per local block pair: dense or sparse threshold rule (GemmMatrix.f90:49-61) from the panel fills
   DevBuf<unsigned char> d_rule;
   RuleView rv;
@@ -1300,14 +1308,12 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
         colblock_fills(Bl, inner_dim, fb);
         set_rules(fa, fb);
       };
-      product_done = peer_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st,
-                                       want);
+      product_done = peer_tile_product(A, B, alpha, wthr, rv, full_rules, ds_p, loc<double>(AB), st, want);
       if (!product_done) {
         rv = RuleView();
         // without a peer space (GPUs that cannot map each other, NTB_P2P=0): the tile halo is copied with NCCL
         if (!(g.peer_ok && peer().ok))
-          product_done = halo_tile_product(A, B, alpha, wthr, rv, full_rules, want_shift ? &ds : nullptr, loc<double>(AB), st,
-                                           want);
+          product_done = halo_tile_product(A, B, alpha, wthr, rv, full_rules, ds_plain_p, loc<double>(AB), st, want);
         if (!product_done) { rv = RuleView(); }
       }
     }
@@ -1353,8 +1359,11 @@ static bool multiply_t(const Matrix& A, const Matrix& B, Matrix& C, double alpha
     // ---- local product
     // deferred entries only for a plain replacement of C on a single slice
     const unsigned w = (S == 1 && (std::fabs(beta) < 2.2250738585072014e-308 || !C.constructed)) ? want : WANT_ALL;
-    spgemm<T>(*Xsrc, *Ysrc, alpha, wthr, rv, loc<T>(AB), &st, want_shift ? &ds : nullptr, w);
+    // (the second fusion only where the left operand is the rank's own block, not a gathered panel)
+    const bool local_operands = comm_size(g.row) == 1 && comm_size(g.column) == 1;
+    spgemm<T>(*Xsrc, *Ysrc, alpha, wthr, rv, loc<T>(AB), &st, local_operands ? ds_p : ds_plain_p, w);
   }
+  if (diff_applied) *diff_applied = ds.diff_applied;
   rt().flops_useful += st.flops;
   rt().multiplies++;
 
@@ -1406,6 +1415,38 @@ void mat_multiply_shift(const Matrix& A, const Matrix& B, Matrix& C, double alph
     mat_multiply(A, B, C, alpha, 0.0, threshold, pool);
   }
   mat_increment(Identity, C, sigma, 0.0);
+}
+
+// C = alpha*A*B (thresholded) and, in the same pass when the product runs on the tile path, MatrixNorm(C - A): the pair
+// "Gemm; IncrementMatrix(C, A, -1); MatrixNorm(A)" of the sign / polar iteration (SignSolversModule.F90:230-234) with
+// the difference taken in the product's epilogue (csc.cuh: DiagShift::diff_colsum). Always computes C; returns true
+// and the norm when the fusion applied, false when the caller still has to call mat_diff_norm(C, A, -1).
+static int g_fused_norm = -1;
+void set_fused_norm(int on) { g_fused_norm = on ? 1 : 0; }
+static bool fused_norm_enabled() {
+  if (g_fused_norm < 0) { const char* e = std::getenv("NTB_FUSED_NORM"); g_fused_norm = (e && e[0] == '0') ? 0 : 1; }
+  return g_fused_norm == 1;
+}
+bool mat_multiply_diffnorm(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double threshold, MemoryPool* pool,
+                           unsigned want, double* norm_out) {
+  NTB_CHECK(A.constructed && B.constructed, "MatrixMultiply on an unconstructed matrix");
+  if (A.is_complex || B.is_complex || !fused_norm_enabled() || !tile_path_on() || &A == &C) {
+    mat_multiply(A, B, C, alpha, 0.0, threshold, pool, want);
+    return false;
+  }
+  NTB_CHECK(A.logical_dim == B.logical_dim && A.grid == B.grid, "MatrixMultiply: operands live on different grids/sizes");
+  if (pool) { pool->rows = A.local_rows; pool->cols = A.local_cols; pool->is_complex = false; pool->constructed = true; }
+  DevBuf<double> colsum((size_t)std::max(A.local_cols, 1)), d(1);
+  bool applied = false;
+  ProcessGrid* grid = A.grid;
+  const int lcols = A.local_cols;
+  multiply_t<double>(A, B, C, alpha, 0.0, threshold, 0.0, want, colsum.get(), &applied);
+  if (!applied) return false;
+  PhaseScope ph(3);
+  reduce_max(colsum.get(), lcols, d.get());
+  *norm_out = reduce_to_host(*grid, grid->row, d.get(), RedOp::Max);
+  rt().fused_norms++;
+  return true;
 }
 
 void mat_similarity_transform(const Matrix& A, const Matrix& P, const Matrix& PInv, Matrix& Res, MemoryPool* pool,

@@ -125,6 +125,10 @@ void mat_scale_c(Matrix& M, cplx c);
 double mat_trace(const Matrix& M);
 double mat_norm(const Matrix& M);
 double mat_diff_norm(const Matrix& A, const Matrix& B, double alpha);   // MatrixNorm(alpha*A + B), sum not formed
+// C = alpha*A*B and MatrixNorm(C - A) from the product's own epilogue when it runs on the tile path (true: *norm_out set)
+bool mat_multiply_diffnorm(const Matrix& A, const Matrix& B, Matrix& C, double alpha, double threshold, MemoryPool* pool,
+                           unsigned want, double* norm_out);
+void set_fused_norm(int on);
 // ---- tile-space helpers of the fused driver steps (csc.cuh: tile_form_scalars / tile_combine) on distributed
 // matrices; false (on every rank alike) when the operands do not live as tile forms - the caller then issues the
 // reference's own call sequence. mode as in csc.cuh; out receives 1 (modes 0, 2) or 2 (mode 1) reduced scalars.

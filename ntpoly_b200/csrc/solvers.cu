@@ -548,8 +548,10 @@ double sign_step(const Matrix& X, const Matrix& Identity, Matrix& T1, Matrix& Xn
   }
   // the next iterate is read by the norm below and by the products of the next pass, all of which work on tile
   // forms: its CSC entries stay deferred until somebody asks for them (the caller reading the result)
-  mat_multiply(X, T1, Xn, 0.5 * alpha_k, 0.0, threshold, pool, WANT_LEFT | WANT_RIGHT);
-  // reference: IncrementMatrix(T2, X, -1); norm = MatrixNorm(X); CopyMatrix(T2, X) — X - T2 is never needed itself
+  // reference: IncrementMatrix(T2, X, -1); norm = MatrixNorm(X); CopyMatrix(T2, X) — X - T2 is never needed itself,
+  // and on the tile path not even a second pass over the two iterates: ||Xn - X|| comes out of the product's epilogue
+  double norm_value = 0.0;
+  if (mat_multiply_diffnorm(X, T1, Xn, 0.5 * alpha_k, threshold, pool, WANT_LEFT | WANT_RIGHT, &norm_value)) return norm_value;
   return mat_diff_norm(Xn, X, -1.0);
 }
 // ... and in place, as the drivers use it: X becomes the next iterate by exchanging it with the work matrix T2

@@ -308,6 +308,11 @@ struct EmitSpec {
   double alpha, thr, sigma;
   int dd, ncols_diag;
   RuleView rules;
+  // fused difference norm (csc.cuh: DiagShift::diff_colsum): per (task, column of the block) sum of |z - y| over the
+  // 64 rows of the block, y from the left operand's own left form (piece diff_piece of the LeftView)
+  double* diff_partial = nullptr;     // [tasks * 64]
+  const int4* diff_self = nullptr;    // [tasks * 2] {first tile, found, mask lo, mask hi} of y's super-tile (row block, chunk column 2g + c)
+  int diff_piece = 0;
 };
 template <bool RULES>
 __device__ __forceinline__ double final_value(const EmitSpec& e, double v, int row, int col, bool& keep) {
@@ -422,13 +427,26 @@ __device__ __forceinline__ void ct_pair(const int4& ea, const int4& eb, int Ib, 
 // so that the copy warp needs ONE round trip (all addresses follow from the task id) instead of five.
 __global__ void __launch_bounds__(256)
 k_task_stages(LeftView A, CtView B, const int2* __restrict__ tasks, int ntasks, const int* __restrict__ gtask_off,
-              int4* __restrict__ hd, int4* __restrict__ rec) {
+              int4* __restrict__ hd, int4* __restrict__ rec, int4* __restrict__ self, int self_q0, int ncc_total) {
   const int lane = threadIdx.x & 31;
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= ntasks) return;
   const int4 none = make_int4(0, 0, 0, -1);
   const int2 tk = tasks[t];
   const int4 cmB = B.colmeta[tk.x];
+  // fused difference norm: where the left operand's OWN block under this output block lies (its two chunk columns)
+  if (self != nullptr && lane < 2) {
+    const int q = self_q0 + 2 * tk.x + lane;
+    int4 rec2 = make_int4(0, 0, 0, 0);
+    if (q < ncc_total) {
+      int ql;
+      const int pc = lv_piece(A, q, ql);
+      const int4* entA = A.piece[pc].ent;
+      const int idx = ct_find(entA, A.piece[pc].colmeta[ql], tk.y);
+      if (idx >= 0) { const int4 ea = entA[idx]; if (ea.x == tk.y) rec2 = make_int4(ea.y, 1, ea.z, ea.w); }     // (mask in .z/.w like an entry: mask64)
+    }
+    self[2 * t + lane] = rec2;
+  }
   if (lane == 0) {
     hd[2 * t] = make_int4(tk.x, tk.y, gtask_off[tk.x], gtask_off[tk.x + 1]);
     hd[2 * t + 1] = make_int4(cmB.x, cmB.y, 0, 0);
@@ -563,7 +581,7 @@ __device__ __forceinline__ void emit_strip(double (&acc)[8][2], unsigned km, int
     mL[1] = (unsigned char)((bL >> 8) & 0xffu);
   }
 }
-template <int NSTAGE_, int MINB, int DENSE, bool RING = false>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block
+template <int NSTAGE_, int MINB, int DENSE, bool RING = false, bool DIFF = false>   // DENSE: 0 generic loop only, 1 + dense-stage block, 2 + A-complete block; DIFF: fused |Z - Y| column sums
 __global__ void __launch_bounds__(NUMERIC_THREADS, MINB)
 k_tile_numeric9(LeftView A, CtView B, int nJ, const int4* __restrict__ plan_hd, const int4* __restrict__ plan_rec, int ntasks,
                 int* __restrict__ task_counter, int* __restrict__ cnt, ResultForms out, int nrows, int ncols, EmitSpec es) {
@@ -784,6 +802,21 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int4* __restrict__ plan_hd, 
       { const int2 gt = *reinterpret_cast<const int2*>(mt + 56); gt0 = gt.x; gtn = gt.y; }
       const unsigned mb = mt[48 + wj];
       const unsigned live = mb & ((unsigned)mi.x >> 8) & 0xffu;
+      if (DIFF && (fl & 3u) == 1u) {
+        // fused difference norm: at the start of the task's LAST stage, request the left operand's own tiles under
+        // this strip into L1 ahead of the epilogue's loads (holding the 16 values in registers instead spills).
+        // Measured: it does not matter where the request is issued - the +0.08 ms of the fused epilogue are the
+        // 0.45 GB of these tiles coming from HBM again (the form does not stay in L2), not latency; a "y stage"
+        // through the TMA ring would overlap them with the DMMAs.
+        const int4 se = es.diff_self[2 * task + (wj >> 2)];
+        const int ccq = (lane & 3) * 2;
+        const int kkA = 2 * (wj & 3) + (ccq >> 2);
+        const unsigned byte = (unsigned)(mask64(se) >> (8 * kkA)) & 0xffu;
+        const double* tb = lv_tile_ptr(A, es.diff_piece, (long long)se.x + 8 * kkA) + (lane >> 2) * 4 + (ccq & 3);
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii)
+          if ((byte >> ii) & 1u) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + __popc(byte & ((1u << ii) - 1u)) * 32));
+      }
       if (DENSE >= 1 && (fl & 4u) != 0u && mb == 0xffu) {
         // DENSE STAGE: all 64 tiles of the A super-tile and all 8 inner tiles of this warp's B tile column are present
         // (the interior of a band or of a filled-in block). Every fragment sits at a compile-time offset from two
@@ -955,8 +988,44 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int4* __restrict__ plan_hd, 
       c1 += k1 ? 1 : 0;
       km |= ((k0 || k1) ? 1u : 0u) << ii;
     }
+    if (DIFF) {
+      // |z - y| over the strip, y = the left operand's own entries at these positions: tiles (kk, ii) of its
+      // super-tile (row block Ib, chunk column 2g + wj/4), kk = 2 (wj % 4) + (0 for the lane's columns 0-3, 1 for
+      // 4-7); in A-fragment order the lane's two values (row r, columns cc % 4, + 1) are one aligned 16-byte load.
+      // The eight column sums of the strip go to this task's cells of the partial array (reduced over the tasks of
+      // a group in task order afterwards: deterministic).
+      const int4 se = es.diff_self[2 * task + (wj >> 2)];
+      const int kkA = 2 * (wj & 3) + (cc >> 2);
+      const unsigned byte = (unsigned)(mask64(se) >> (8 * kkA)) & 0xffu;
+      const double* tb = lv_tile_ptr(A, es.diff_piece, (long long)se.x + 8 * kkA) + r * 4 + (cc & 3);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        double2 y = make_double2(0.0, 0.0);
+        if ((byte >> ii) & 1u) y = *reinterpret_cast<const double2*>(tb + __popc(byte & ((1u << ii) - 1u)) * 32);
+        s0 += fabs(acc[ii][0] - y.x);
+        s1 += fabs(acc[ii][1] - y.y);
+      }
+#pragma unroll
+      for (int d = 4; d < 32; d <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      }
+      if (lane < 4) *reinterpret_cast<double2*>(es.diff_partial + (size_t)task * 64 + 8 * wj + cc) = make_double2(s0, s1);
+    }
     emit_strip(acc, km, c0, c1, lane, wj, task, gt0, gtn, j0, cnt, out);
   }
+}
+
+// fused difference norm: column sums from the per-task partials, tasks of a group in ascending order
+__global__ void __launch_bounds__(256)
+k_diff_partial_reduce(int ncols, const int* __restrict__ gtask_off, const double* __restrict__ partial, double* __restrict__ colsum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  const int g = j >> 6;
+  double s = 0.0;
+  for (int t = gtask_off[g]; t < gtask_off[g + 1]; ++t) s += partial[(size_t)t * 64 + (j & 63)];
+  colsum[j] = s;
 }
 
 // ---- index of the result's tile forms: known BEFORE the numeric kernel runs ------------------------------------------
@@ -1463,10 +1532,41 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
   auto launch_numeric = [&](const int2* tasks_p, int ntasks_l, int* task_counter_p, int* cnt_p, const ResultForms& out) {
     // the stage plan of every task (k_task_stages): what the copy warps would otherwise look up one task at a time
     DevBuf<int4> plan_hd((size_t)ntasks_l * 2), plan_rec((size_t)ntasks_l * 64);
-    NTB_LAUNCH(k_task_stages, div_up((long long)ntasks_l * 32, 256), 256, 0, Av, Bv, tasks_p, ntasks_l, gtask_off.get(), plan_hd.get(),
-               plan_rec.get());
-    // pipeline shape: 3 stages x 2 CTAs per SM (default) or 2 stages x 3 CTAs per SM (NTB_NUMERIC_SHAPE=23)
+    // fused difference norm (DiagShift::diff_colsum): only with the default kernel shape, on one rank or on the peer
+    // path (the rank's own columns of the left operand are piece `me` of the view); otherwise the caller's norm kernel runs
     static const int shape = [] { const char* e = std::getenv("NTB_NUMERIC_SHAPE"); return e ? std::atoi(e) : 32; }();
+    static const int dense = [] { const char* e = std::getenv("NTB_DENSE_STAGE"); return e ? std::atoi(e) : 1; }();
+    static const int ring = [] { const char* e = std::getenv("NTB_RING"); return e ? std::atoi(e) : 0; }();
+    const bool diff = shift && shift->diff_colsum && shape != 23 && dense == 1 && ring == 0 && Av.tval2 == nullptr &&
+                      (Av.npieces == 1 || (peer().ok && peer().n == Av.npieces));
+    EmitSpec esl = es;
+    DevBuf<int4> plan_self;
+    DevBuf<double> diff_partial;
+    const int self_piece = (Av.npieces > 1) ? peer().me : 0;
+    if (diff) {
+      plan_self.alloc((size_t)ntasks_l * 2);
+      diff_partial.alloc((size_t)ntasks_l * 64);
+      diff_partial.zero();
+      esl.diff_partial = diff_partial.get();
+      esl.diff_self = plan_self.get();
+      esl.diff_piece = self_piece;
+    }
+    NTB_LAUNCH(k_task_stages, div_up((long long)ntasks_l * 32, 256), 256, 0, Av, Bv, tasks_p, ntasks_l, gtask_off.get(), plan_hd.get(),
+               plan_rec.get(), diff ? plan_self.get() : (int4*)nullptr, self_piece * Av.ncc_piece, Av.npieces * Av.ncc_piece);
+    if (diff) {
+      auto kern = k_tile_numeric9<NSTAGE_DEFAULT, 2, 1, false, true>;
+      static bool diff_attr_set = false;
+      if (!diff_attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, numeric_smem9(NSTAGE_DEFAULT)));
+        diff_attr_set = true;
+      }
+      NTB_LAUNCH(kern, min(ntasks_l, kNumSMs * 2), NUMERIC_THREADS, numeric_smem9(NSTAGE_DEFAULT), Av, Bv, nJ, plan_hd.get(),
+                 plan_rec.get(), ntasks_l, task_counter_p, cnt_p, out, nrows, ncols, esl);
+      NTB_LAUNCH(k_diff_partial_reduce, div_up(ncols, 256), 256, 0, ncols, gtask_off.get(), diff_partial.get(), shift->diff_colsum);
+      shift->diff_applied = true;
+      return;
+    }
+    // pipeline shape: 3 stages x 2 CTAs per SM (default) or 2 stages x 3 CTAs per SM (NTB_NUMERIC_SHAPE=23)
     auto launch = [&](auto kern, int nstage, int per_sm) {
       static bool attr_set = false;
       if (!attr_set) {
@@ -1478,12 +1578,10 @@ bool spgemm_tile_core(const LeftView& Av, const ChunkTiles& Bform, int ncols, in
     };
     // fast paths of the DMMA warps: NTB_DENSE_STAGE=0 generic loop only, 1 (default) dense-stage block, 2 also the
     // A-complete block (experimental)
-    static const int dense = [] { const char* e = std::getenv("NTB_DENSE_STAGE"); return e ? std::atoi(e) : 1; }();
     // default: the fixed ring of 3 x 32 KB stages; NTB_RING=1: the byte-granular ring (RING_SLOTS stages in flight) -
     // measured 2-3 % SLOWER on the c4 step in both A/B runs of round 2 (profiles/README.md): the stages are not late
     // because the ring is shallow but because one copy warp hands them out, and the deeper ring costs an extra
     // descriptor load per stage and L1 capacity
-    static const int ring = [] { const char* e = std::getenv("NTB_RING"); return e ? std::atoi(e) : 0; }();
     if (ring != 0 && shape != 23 && dense == 1) {
       auto kern = k_tile_numeric9<NSTAGE_DEFAULT, 2, 1, true>;
       static bool ring_attr_set = false;

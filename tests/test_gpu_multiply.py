@@ -408,3 +408,33 @@ def test_complex_scattered_product_stays_on_scalar_kernels(nt):
     C.Gemm(A, A)
     assert nt.complex_tile_products() == 0
     compare_sparse(C.to_scipy(), a @ a)
+
+
+@pytest.mark.parametrize("n,hb,thr", [(2048, 40, 1e-7), (1111, 25, 0.0), (3000, 82, 1e-6)])
+def test_difference_norm_from_the_product_epilogue(nt, n, hb, thr):
+    """||X_new - X|| of the sign iteration comes out of the epilogue of the product that computes X_new (the left
+    operand's own tiles are fetched for the finished strip): same value as the separate pass over the two iterates,
+    same X_new bit for bit, deterministic; sizes that are not multiples of 64 included"""
+    ak = 1.3
+    rng = np.random.default_rng(3)
+    x = banded(n, half_bandwidth=hb) * 0.3
+    # an unsymmetric perturbation, so that rows and columns cannot be confused anywhere
+    x = sp.csc_matrix(x + sp.diags([rng.uniform(-0.05, 0.05, n - 3)], [3], shape=(n, n)))
+    X, I = to_gpu(nt, x), nt.Matrix_ps(n)
+    I.FillIdentity()
+    res = {}
+    for fused in (True, False):
+        nt.set_fused_norm(fused)
+        T1, X1 = nt.Matrix_ps(n), nt.Matrix_ps(n)
+        nt.reset_counters()
+        nv = nt.sign_step(X, I, T1, X1, ak, thr)
+        nv_again = nt.sign_step(X, I, T1, X1, ak, thr)
+        res[fused] = (nv, nv_again, nt.fused_norms(), X1)
+    nt.set_fused_norm(True)
+    assert res[True][2] == 2 and res[False][2] == 0
+    assert res[True][0] == res[True][1]                                   # deterministic
+    assert res[True][0] == pytest.approx(res[False][0], rel=1e-13)
+    assert _bits_equal(res[True][3], res[False][3])
+    D = nt.Matrix_ps(X)
+    D.Increment(res[True][3], -1.0)
+    assert res[True][0] == pytest.approx(D.Norm(), rel=1e-13)            # the reference's two calls on CSC entries
