@@ -43,8 +43,8 @@ METRICS = {"c4": "spgemm_useful_gflops_per_sign_iteration", "c1": "spgemm_useful
            "c3": "spgemm_useful_gflops_per_trs4_purification", "c5": "spgemm_useful_gflops_complex_inverse_exponential"}
 ALPHA_MAX = 1.69770248526
 # dram read+write bytes of one numeric launch (mean of the step's two products) from `ncu --set full` of the SHIPPED
-# kernel on the c4 step: profiles/r02h_numeric.keys.txt (951 MB + 410 MB and 992 MB + 765 MB). Only quoted for c4 on 1 GPU.
-NCU_TRAFFIC_C4 = 0.5 * ((950.65e6 + 410.02e6) + (991.55e6 + 764.95e6))
+# kernel on the c4 step: profiles/r02h_numeric.keys.txt (951 MB + 410 MB and 993 MB + 779 MB). Only quoted for c4 on 1 GPU.
+NCU_TRAFFIC_C4 = 0.5 * ((951.27e6 + 410.40e6) + (992.53e6 + 779.18e6))
 
 
 def parse():
