@@ -807,8 +807,8 @@ k_tile_numeric9(LeftView A, CtView B, int nJ, const int4* __restrict__ plan_hd, 
         // this strip into L1 ahead of the epilogue's loads (holding the 16 values in registers instead spills).
         // Measured: it does not matter where the request is issued. The fused epilogue costs +0.1 ms per launch
         // (ncu: 995 vs 892 us) with UNCHANGED dram bytes - the tiles come from L2 - i.e. one more dependent round
-        // trip (self record -> tile loads -> sums) in every warp's epilogue, ~1 us per task; carrying the tiles
-        // through the TMA ring as a last "y stage" would hide it.
+        // trip (self record -> tile loads -> sums) in every warp's epilogue, ~1 us per task. Carrying the tiles
+        // through the TMA ring as a last "y stage" of the task was tried as well: same time (profiles/README.md).
         const int4 se = es.diff_self[2 * task + (wj >> 2)];
         const int ccq = (lane & 3) * 2;
         const int kkA = 2 * (wj & 3) + (ccq >> 2);
