@@ -889,8 +889,11 @@ void spgemm(const LocalCsc<T>& Xl, const LocalCsc<T>& Yl, double alpha, double t
   }
   DevBuf<T> slab;
   if (h_bins[6] > 0) {
-    // the slabs of all resident CTAs should stay in L2 (126 MB): at most ~96 MB of accumulator windows
-    const long long l2_fit = max(1ll, (96ll << 20) / ((long long)nrows * (long long)sizeof(T)));
+    // How many accumulator windows (one per CTA) are in flight. Measured on c5 (N=32768 complex, 512 KB per window;
+    // gpurun_out/r2c35*): 48 MB of windows 971 ms per step, 96 MB 890, 192 MB 745, 288 / 512 MB the same - more
+    // columns in flight beat keeping every window inside the 126 MB L2, up to ~2.6 CTAs per SM
+    static const long long slab_mb = [] { const char* e = std::getenv("NTB_SLAB_L2_MB"); return e ? std::max(1ll, std::atoll(e)) : 192ll; }();
+    const long long l2_fit = max(1ll, (slab_mb << 20) / ((long long)nrows * (long long)sizeof(T)));
     int blocks = (int)min((long long)min(h_bins[6], kNumSMs * 4), atomic_bins ? max((long long)kNumSMs, l2_fit) : (long long)kNumSMs * 2);
     slab.alloc((size_t)blocks * nrows);
     slab.zero();
