@@ -273,3 +273,34 @@ def test_exponential_restatement(oracle):
     radius, pinfo = O.power_bounds(O.PSMatrix.from_scipy(sp.csc_matrix(0.5 * g), is_complex=True),
                                    O.SolverParameters(max_iterations=10, threshold=1e-6))
     assert radius == 0.0 and pinfo.iterations == 1
+
+
+def test_hotelling_on_the_c5_graph_needs_the_larger_shift(oracle):
+    """Why bench.py's c5 inverts G + (8*||G||_1 + 1)*I and not G + (||G||_1 + 1)*I: at thr 1e-6
+    the dropped terms of the smaller shift keep the residual ||I - X*A||_1 above the monitor's loose cutoff 1e-2, the
+    automatic exit never fires and the solve runs into max_iterations; with the larger shift it leaves through the
+    stagnation rule after 8-10 iterations. The reference's monitor (restated in oracle.Monitor) decides both."""
+    from ntpoly_b200.workloads import complex_hermitian_graph
+    O = oracle
+    n = 768
+    g = complex_hermitian_graph(n)
+    n1 = float(np.asarray(abs(g).sum(axis=0)).max())
+    p = O.SolverParameters(converge_diff=1e-5, threshold=1e-6, max_iterations=14)
+    _, slow = O.invert(O.PSMatrix.from_scipy(sp.csc_matrix(g + sp.identity(n) * (n1 + 1.0)), is_complex=True), p)
+    assert slow.iterations == 15 and slow.history[-1] > 1e-2          # ran into max_iterations, residual stagnating
+    assert abs(slow.history[-1] - slow.history[-2]) < 1e-3
+    inv, fast = O.invert(O.PSMatrix.from_scipy(sp.csc_matrix(g + sp.identity(n) * (8.0 * n1 + 1.0)), is_complex=True), p)
+    assert fast.iterations <= 10 and 1e-5 < fast.history[-1] < 1e-2   # left through the stagnation rule
+    a = (g + sp.identity(n) * (8.0 * n1 + 1.0)).toarray()
+    assert np.abs(inv.todense() @ a - np.eye(n)).sum(axis=0).max() < 1e-2
+
+
+def test_chebyshev_low_order_coefficients_behind_the_c5_scale():
+    """the reference evaluates exp through T_0..T_15, and T_k has LARGE low-order coefficients
+    (x^3 in T_15: 560, x^4 in T_14: 1568), so the iterates T_k(scale*G) of a graph matrix fill in unless
+    560*scale^3 stays below the threshold - the reason for bench.py's --c5-scale 0.001 at N = 32768."""
+    from numpy.polynomial import chebyshev as C
+    t15 = C.cheb2poly([0] * 15 + [1])
+    t14 = C.cheb2poly([0] * 14 + [1])
+    assert abs(t15[3]) == 560 and abs(t14[4]) == 1568
+    assert 560 * 0.001 ** 3 < 1e-6 < 560 * 0.005 ** 3
