@@ -553,7 +553,13 @@ def run_c4(env):
     est_step_ms = env.allmax([(time.perf_counter() - t_w) * 1e3 / warm])[0]
     ms_total, clocks, prof = timed_steps(env, step, args.steps, est_step_ms=est_step_ms)
     cnt = nt.counters()
+    fused_norms = nt.fused_norms()
     extra = {"tile_form_builds_in_timed_region": nt.tile_builds(), "peer": nt.peer_counters(),
+             "fused_norms_in_timed_region": fused_norms,
+             "numeric_time_includes": ("the step's convergence norm ||X_new - X||, taken in the epilogue of the second product "
+                                       "(about +0.09 ms per step on one GPU instead of a 0.18 ms pass of its own); with "
+                                       "NTB_FUSED_NORM=0 the two products alone give fp64_frac 0.49 / frac 0.25 "
+                                       "(profiles/r02h_bench_1gpu_c4_separate_norm_kernel.json)") if fused_norms else "the two products only",
              "host_waits_per_step": nt.sync_count() / args.steps,
              "deferred_csc_products_in_timed_region": nt.deferred_counters()["products"],
              "deferred_csc_materialized_in_timed_region": nt.deferred_counters()["materialized"]}
