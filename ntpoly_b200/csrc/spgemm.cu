@@ -13,7 +13,9 @@
 //   k_binlists   columns -> bins by window size (accumulator kind), chunk-contiguous
 //   numeric      bin 1-4: one WARP per column, dense window accumulator in shared memory
 //                bin 5  : one CTA per column, shared-memory window up to ~200 KB
-//                bin 6  : one CTA per column, window in a per-CTA global slab (L2 resident)
+//                bin 6  : one CTA per column, window in a per-CTA global slab
+//                         (bins 5/6 by default through k_numeric_cta_atomic: 32 k per warp, floating-point atomics into
+//                         the window, barrier-free ordered sweep; NTB_ATOMIC_BINS=0: the serial-k kernel k_numeric_cta)
 //                bin 7  : one warp per column, SHARED-MEMORY HASH accumulator: scattered columns whose row window
 //                         is wide but whose product count is small (graph-like patterns, permuted / load-balanced
 //                         matrices) - work proportional to the products, not to the window
@@ -21,8 +23,9 @@
 //                the drop rule (|alpha*v|>thr or dense-branch |v|>thr) -> sorted, filtered,
 //                alpha-scaled entries written to a staging area at a bound-derived offset
 //   scan + k_compact   exact CSC of the kept entries
-// The window sweep makes sort and filter free: no hash tables, no atomics, and the
-// summation order per element is the reference's (k ascending).
+// The window sweep makes sort and filter free. Bins 1-4 and 7 (and the serial-k variant of 5/6) use no atomics and sum
+// every element in the reference's order (k ascending); complex operands that are locally dense take the FP64
+// tensor-core tile path through their real embeddings instead (spgemm_complex_tiles below).
 #include "csc.cuh"
 
 namespace ntb {
